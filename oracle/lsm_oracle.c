@@ -1,0 +1,402 @@
+/*
+ * TEST INFRASTRUCTURE — plain-C CPU restatement of the reference's audio -> spikes -> LSM ->
+ * features path.  Never linked into or called by the product library; only tests/, bench.py's
+ * cpu_baseline / --impl reference legs and __graft_entry__.smoke() load it.
+ *
+ * PARITY STATUS: "parity unpinned" for the three third-party packages the reference delegates
+ * to (gammatone==1.0.3, librosa==0.11.0, snn_reservoir_py==2.0.0: not vendored, not installable,
+ * the reference has no tests).  Pinned pieces: the IIR recurrence (bit-exact vs scipy.signal.lfilter),
+ * the window mean (numpy, F-ordered segment => sequential sum), zoom (bit-exact vs
+ * scipy.ndimage.zoom order=1), the hysteresis encoder and w_critico (bit-exact vs the reference's
+ * own functions run verbatim) — see tests/test_oracle_*.py and tests/golden/make_golden.py.
+ *
+ * Every floating-point result here is a fixed sequence of IEEE-754 binary64/binary32
+ * +,-,*,/,sqrt operations (compile with -ffp-contract=off, no -ffast-math), so it is the same on
+ * any machine and the CUDA kernels can reproduce it bit for bit with __dadd_rn/__dmul_rn.
+ * The single deviation from "what numpy would do" is log10: numpy calls the platform libm
+ * (or SVML), whose last bit differs between machines; we use the fdlibm/FreeBSD algorithm
+ * below (< 1 ulp) on both CPU and GPU.
+ *
+ * Build: make -C oracle   (gcc -O2 -ffp-contract=off -pthread -shared -fPIC)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <pthread.h>
+#include <stdatomic.h>
+#include <unistd.h>
+
+/* Utterances are independent (create_dataset.py:143, extract_lsm_features.py:78 are plain
+ * per-sample loops), so the multi-core baseline is a dynamic parallel-for over utterances. */
+typedef void (*utt_fn)(void *ctx, int b, void *scratch);
+typedef struct {
+    utt_fn fn; void *ctx; int B; atomic_int next;
+    void *(*mk)(void *ctx); void (*rm)(void *scratch);
+} pf_job;
+
+static void *pf_worker(void *arg)
+{
+    pf_job *j = (pf_job *)arg;
+    void *scratch = j->mk(j->ctx);
+    for (;;) {
+        int b = atomic_fetch_add(&j->next, 1);
+        if (b >= j->B) break;
+        j->fn(j->ctx, b, scratch);
+    }
+    j->rm(scratch);
+    return NULL;
+}
+
+static void parallel_for(pf_job *j, int nthreads)
+{
+    if (nthreads <= 0) nthreads = (int)sysconf(_SC_NPROCESSORS_ONLN);
+    if (nthreads > j->B) nthreads = j->B;
+    if (nthreads < 1) nthreads = 1;
+    atomic_store(&j->next, 0);
+    if (nthreads == 1) { pf_worker(j); return; }
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
+    for (int i = 0; i < nthreads; ++i) pthread_create(&th[i], NULL, pf_worker, j);
+    for (int i = 0; i < nthreads; ++i) pthread_join(th[i], NULL);
+    free(th);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Deterministic log10 for finite x > 0 (normal numbers; the path only feeds it sqrt(mean)+1e-9).
+ * fdlibm e_log.c kernel + FreeBSD e_log10.c hi/lo recombination, basic operations only.      */
+static const double
+    LG1 = 6.666666666666735130e-01, LG2 = 3.999999999940941908e-01,
+    LG3 = 2.857142874366239149e-01, LG4 = 2.222219843214978396e-01,
+    LG5 = 1.818357216161805012e-01, LG6 = 1.531383769920937332e-01,
+    LG7 = 1.479819860511658591e-01,
+    IVLN10HI = 4.34294481878168880939e-01,  /* 0x3fdbcb7b15200000 */
+    IVLN10LO = 2.50829467116452752298e-11,  /* 0x3dbb9438ca9aadd5 */
+    LOG10_2HI = 3.01029995663611771306e-01, /* 0x3FD34413509F6000 */
+    LOG10_2LO = 3.69423907715893078616e-13; /* 0x3D59FEF311F12B36 */
+
+double oracle_log10(double x)
+{
+    uint64_t ix;
+    memcpy(&ix, &x, 8);
+    int32_t hx = (int32_t)(ix >> 32);
+    int32_t k = 0;
+    if (hx < 0x00100000) {           /* subnormal: scale up (not reached on this path) */
+        x *= 18014398509481984.0;    /* 2**54 */
+        memcpy(&ix, &x, 8);
+        hx = (int32_t)(ix >> 32);
+        k -= 54;
+    }
+    k += (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    int32_t i = (hx + 0x95f64) & 0x100000;
+    /* normalise x or x/2 so that sqrt(2)/2 < x < sqrt(2) */
+    ix = ((uint64_t)(uint32_t)(hx | (i ^ 0x3ff00000)) << 32) | (ix & 0xffffffffu);
+    memcpy(&x, &ix, 8);
+    k += (i >> 20);
+    double f = x - 1.0;
+    double hfsq = 0.5 * f * f;
+    double s = f / (2.0 + f);
+    double z = s * s;
+    double w = z * z;
+    double t1 = w * (LG2 + w * (LG4 + w * LG6));
+    double t2 = z * (LG1 + w * (LG3 + w * (LG5 + w * LG7)));
+    double R = t2 + t1;
+    double hi = f - hfsq;
+    uint64_t ih;
+    memcpy(&ih, &hi, 8);
+    ih &= 0xffffffff00000000ull;
+    memcpy(&hi, &ih, 8);
+    double lo = (f - hi) - hfsq + s * (hfsq + R);
+    double val_hi = hi * IVLN10HI;
+    double dk = (double)k;
+    double y2 = dk * LOG10_2HI;
+    double val_lo = dk * LOG10_2LO + (lo + hi) * IVLN10LO + lo * IVLN10HI;
+    double ww = y2 + val_hi;
+    val_lo += (y2 - ww) + val_hi;
+    val_hi = ww;
+    return val_lo + val_hi;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 1, gammatone branch: create_dataset.py:49-78 + gammatone.gtgram.
+ * coefs: [C][10] rows {A0,A11,A12,A13,A14,A2,B0,B1,B2,gain}, row 0 = lowest centre frequency.
+ * spec: out [C][ncols] = sqrt(mean(window of (y4/gain)^2))                                   */
+static void gammatone_energy(const float *pcm, int L, const double *coefs, int C,
+                             int nwin, int hop, int ncols, double *spec)
+{
+    for (int ch = 0; ch < C; ++ch) {
+        const double *c = coefs + 10 * ch;
+        /* scipy lfilter normalises by a[0] = B0 first (linear_filter: "ptr_b[n] /= a0") */
+        const double a0 = c[6];
+        const double b0 = c[0] / a0, b2 = c[5] / a0, a1 = c[7] / a0, a2 = c[8] / a0;
+        const double b1[4] = {c[1] / a0, c[2] / a0, c[3] / a0, c[4] / a0};
+        const double gain = c[9];
+        double z0[4] = {0, 0, 0, 0}, z1[4] = {0, 0, 0, 0};
+        /* up to ceil(nwin/hop) windows are open at any sample */
+        double acc[8];
+        int nopen = (nwin + hop - 1) / hop;
+        if (nopen > 8) nopen = 8;
+        for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+        const int last = (ncols - 1) * hop + nwin; /* samples beyond this are never read */
+        for (int n = 0; n < last && n < L; ++n) {
+            double x = (double)pcm[n];
+            for (int st = 0; st < 4; ++st) {
+                /* scipy.signal.lfilter, direct form II transposed, len(b)=len(a)=3 */
+                double y = z0[st] + b0 * x;
+                z0[st] = (z1[st] + x * b1[st]) - y * a1;
+                z1[st] = x * b2 - y * a2;
+                x = y;
+            }
+            double v = x / gain;
+            double e = v * v;
+            /* window c covers [c*hop, c*hop+nwin); window c lives in slot c % nopen */
+            int cfirst = (n - nwin + hop) / hop; /* smallest c with c*hop + nwin > n */
+            if (n - nwin + hop < 0) cfirst = 0;
+            int clast = n / hop;
+            if (clast > ncols - 1) clast = ncols - 1;
+            for (int cw = cfirst; cw <= clast; ++cw) {
+                int slot = cw % nopen;
+                if (n == cw * hop) acc[slot] = 0.0 + e;   /* np.add.reduce starts from the first element */
+                else acc[slot] = acc[slot] + e;
+                if (n == cw * hop + nwin - 1)
+                    spec[(size_t)ch * ncols + cw] = sqrt(acc[slot] / (double)nwin);
+            }
+        }
+    }
+}
+
+/* create_dataset.py:59-78 on a [C][ncols] energy matrix -> spec_norm [C][nbins] (fp64).
+ * zi0/zf: zoom table (source index, fraction) for each output bin.  Returns 0 if degenerate
+ * (all-zero output, create_dataset.py:64-65).                                                 */
+static int db_normalise_zoom(const double *spec, int C, int ncols, int nbins,
+                             const int32_t *zi0, const double *zf, double *db, double *norm)
+{
+    double mx = -INFINITY;
+    for (int i = 0; i < C * ncols; ++i) {
+        db[i] = 20.0 * oracle_log10(spec[i] + 1e-9);
+        if (db[i] > mx) mx = db[i];
+    }
+    const double floor_db = mx - 80.0;
+    double mn = INFINITY;
+    for (int i = 0; i < C * ncols; ++i) {
+        if (db[i] < floor_db) db[i] = floor_db;
+        if (db[i] < mn) mn = db[i];
+    }
+    if ((mx - mn) < 1e-8) {
+        for (int i = 0; i < C * nbins; ++i) norm[i] = 0.0;
+        return 0;
+    }
+    const double den = mx - mn + 1e-8;
+    for (int i = 0; i < C * ncols; ++i) db[i] = (db[i] - mn) / den;
+    for (int ch = 0; ch < C; ++ch) {
+        const double *row = db + (size_t)ch * ncols;
+        for (int j = 0; j < nbins; ++j) {
+            if (ncols == nbins) { norm[(size_t)ch * nbins + j] = row[j]; continue; }
+            int i0 = zi0[j];
+            double f = zf[j];
+            double v = row[i0] * (1.0 - f);
+            if (i0 + 1 < ncols) v = v + row[i0 + 1] * f;
+            norm[(size_t)ch * nbins + j] = v;
+        }
+    }
+    return 1;
+}
+
+/* create_dataset.py:81-98 (+ :101-104 redundancy).  thr[] already sorted DESCENDING, lower[k] =
+ * thr[k] - gap computed by the caller in fp64.  spikes: [C*R][nbins*K]                        */
+static void hysteresis_encode_f64(const double *norm, int C, int nbins, const double *thr,
+                                  const double *lower, int K, int R, uint8_t *spikes)
+{
+    const int T = nbins * K;
+    for (int ch = 0; ch < C; ++ch) {
+        uint8_t *row0 = spikes + (size_t)ch * R * T;
+        for (int k = 0; k < K; ++k) {
+            int on = 0;
+            for (int b = 0; b < nbins; ++b) {
+                double v = norm[(size_t)ch * nbins + b];
+                if (!on && v > thr[k]) on = 1;
+                else if (on && v < lower[k]) on = 0;
+                row0[b * K + k] = (uint8_t)on;
+            }
+        }
+        for (int r = 1; r < R; ++r) memcpy(row0 + (size_t)r * T, row0, (size_t)T);
+    }
+}
+
+/* Encoder alone (for the known-answer tests minted from the reference's own function). */
+void oracle_hysteresis_encode(const double *norm, int C, int nbins, const double *thr_desc,
+                              const double *lower, int K, int R, uint8_t *spikes)
+{
+    hysteresis_encode_f64(norm, C, nbins, thr_desc, lower, K, R, spikes);
+}
+
+/* Batched stage 1 (gammatone).  Returns 0.  spec_norm_out may be NULL.  nthreads <= 0: all cores. */
+typedef struct {
+    const float *pcm; int L; const double *coefs; int C, nwin, hop, ncols, nbins;
+    const int32_t *zi0; const double *zf; const double *thr, *lower; int K, R;
+    uint8_t *spikes; double *spec_norm_out;
+} gt_ctx;
+
+static void *gt_mk(void *vc)
+{
+    gt_ctx *c = (gt_ctx *)vc;
+    return malloc(sizeof(double) * ((size_t)2 * c->C * c->ncols + (size_t)c->C * c->nbins));
+}
+
+static void gt_one(void *vc, int b, void *scratch)
+{
+    gt_ctx *c = (gt_ctx *)vc;
+    double *spec = (double *)scratch, *db = spec + (size_t)c->C * c->ncols, *norm = db + (size_t)c->C * c->ncols;
+    gammatone_energy(c->pcm + (size_t)b * c->L, c->L, c->coefs, c->C, c->nwin, c->hop, c->ncols, spec);
+    db_normalise_zoom(spec, c->C, c->ncols, c->nbins, c->zi0, c->zf, db, norm);
+    hysteresis_encode_f64(norm, c->C, c->nbins, c->thr, c->lower, c->K, c->R,
+                          c->spikes + (size_t)b * c->C * c->R * c->nbins * c->K);
+    if (c->spec_norm_out)
+        memcpy(c->spec_norm_out + (size_t)b * c->C * c->nbins, norm, sizeof(double) * c->C * c->nbins);
+}
+
+int oracle_gammatone_encode(const float *pcm, int B, int L, const double *coefs, int C,
+                            int nwin, int hop, int nbins, const int32_t *zi0, const double *zf,
+                            const double *thr_desc, const double *lower, int K, int R,
+                            uint8_t *spikes, double *spec_norm_out, int nthreads)
+{
+    gt_ctx c = {pcm, L, coefs, C, nwin, hop, 1 + (L - nwin) / hop, nbins, zi0, zf, thr_desc, lower, K, R,
+                spikes, spec_norm_out};
+    pf_job j = {gt_one, &c, B, 0, gt_mk, free};
+    parallel_for(&j, nthreads);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Stages 2+3: frozen reservoir spec; call sites
+ * extract_lsm_features.py:79-83.  Event-driven over the previous step's spike list, integer
+ * recurrent sums (exact), fp64 membrane.
+ * wt_rowptr/wt_col/wt_q: CSR over the PRESYNAPTIC neuron (outgoing edges).                     */
+typedef struct {
+    int N, C, T, refractory, n_out;
+    double theta;
+    int w_shift;
+} oracle_res_dims;
+
+static void simulate_one(const oracle_res_dims *d, const uint8_t *x,
+                         const int32_t *wt_rowptr, const int32_t *wt_col, const int32_t *wt_q,
+                         const int32_t *in_rowptr, const int32_t *in_col, const double *in_val,
+                         const double *leak, const int32_t *out_idx, uint32_t feature_mask,
+                         int nan_to_num, double *features, uint8_t *raster,
+                         double *V, int32_t *ref, int32_t *spk, int64_t *acc, int32_t *st)
+{
+    const int N = d->N, T = d->T;
+    const double scale = ldexp(1.0, -d->w_shift);
+    int nspk = 0;
+    /* per-neuron streaming statistics: count, sum t, first, last, sum isi^2, bursts */
+    int32_t *cnt = st, *sumt = st + N, *first = st + 2 * N, *last = st + 3 * N, *burst = st + 4 * N;
+    int64_t *s2 = (int64_t *)(st + 5 * N + (N & 1));
+    for (int i = 0; i < N; ++i) {
+        V[i] = 0.0; ref[i] = 0; cnt[i] = 0; sumt[i] = 0; first[i] = -1; last[i] = -1; burst[i] = 0; s2[i] = 0;
+    }
+    for (int t = 0; t < T; ++t) {
+        for (int i = 0; i < N; ++i) acc[i] = 0;
+        for (int q = 0; q < nspk; ++q) {
+            int j = spk[q];
+            for (int p = wt_rowptr[j]; p < wt_rowptr[j + 1]; ++p) acc[wt_col[p]] += wt_q[p];
+        }
+        nspk = 0;
+        for (int i = 0; i < N; ++i) {
+            double i_in = 0.0;
+            for (int p = in_rowptr[i]; p < in_rowptr[i + 1]; ++p)
+                i_in = i_in + in_val[p] * (double)x[(size_t)in_col[p] * T + t];
+            double cur = i_in + (double)acc[i] * scale;
+            int fire = 0;
+            if (ref[i] == 0) {
+                double v = (V[i] - leak[i] * V[i]) + cur;
+                if (v >= d->theta) { fire = 1; v = 0.0; ref[i] = d->refractory; }
+                V[i] = v;
+            } else {
+                V[i] = 0.0;
+                ref[i] -= 1;
+            }
+            if (raster) raster[(size_t)t * N + i] = (uint8_t)fire;
+            if (fire) {
+                spk[nspk++] = i;
+                if (cnt[i] > 0) {
+                    int isi = t - last[i];
+                    s2[i] += (int64_t)isi * isi;
+                    if (isi <= d->refractory + 1) burst[i] += 1;
+                } else first[i] = t;
+                cnt[i] += 1; sumt[i] += t; last[i] = t;
+            }
+        }
+    }
+    if (!features) return;
+    /* key-major layout: all output neurons of key 0, then key 1, ... (extract_lsm_features.py:85-87) */
+    int slot = 0;
+    for (int key = 0; key < 8; ++key) {
+        if (!(feature_mask & (1u << key))) continue;
+        for (int o = 0; o < d->n_out; ++o) {
+            int i = out_idx[o];
+            double c = (double)cnt[i], v = NAN;
+            switch (key) {
+            case 0: v = c; break;
+            case 1: { double p = c / (double)T; v = p * (1.0 - p); } break;
+            case 2: if (cnt[i] >= 1) v = (double)sumt[i] / c; break;
+            case 3: if (cnt[i] >= 1) v = (double)first[i]; break;
+            case 4: if (cnt[i] >= 1) v = (double)last[i]; break;
+            case 5: if (cnt[i] >= 2) v = (double)(last[i] - first[i]) / (double)(cnt[i] - 1); break;
+            case 6: if (cnt[i] >= 2) {
+                        int64_t n = cnt[i] - 1, s1 = last[i] - first[i];
+                        v = (double)(n * s2[i] - s1 * s1) / (double)(n * n);
+                    } break;
+            case 7: v = (double)burst[i]; break;
+            }
+            if (nan_to_num && v != v) v = 0.0;
+            features[(size_t)slot * d->n_out + o] = v;
+        }
+        ++slot;
+    }
+}
+
+typedef struct {
+    oracle_res_dims d;
+    const int32_t *wt_rowptr, *wt_col, *wt_q, *in_rowptr, *in_col; const double *in_val, *leak;
+    const int32_t *out_idx; const uint8_t *spikes; uint32_t feature_mask; int nan_to_num, nkeys;
+    double *features; uint8_t *raster;
+} rs_ctx;
+
+static void *rs_mk(void *vc)
+{
+    rs_ctx *c = (rs_ctx *)vc;
+    size_t N = (size_t)c->d.N;
+    /* V[N] f64 | acc[N] i64 | ref[N] i32 | spk[N] i32 | st[8N+4] i32 */
+    return malloc(8 * N + 8 * N + 4 * N + 4 * N + 4 * (8 * N + 4));
+}
+
+static void rs_one(void *vc, int b, void *scratch)
+{
+    rs_ctx *c = (rs_ctx *)vc;
+    size_t N = (size_t)c->d.N;
+    double *V = (double *)scratch;
+    int64_t *acc = (int64_t *)(V + N);
+    int32_t *ref = (int32_t *)(acc + N), *spk = ref + N, *st = spk + N + (N & 1);
+    simulate_one(&c->d, c->spikes + (size_t)b * c->d.C * c->d.T, c->wt_rowptr, c->wt_col, c->wt_q,
+                 c->in_rowptr, c->in_col, c->in_val, c->leak, c->out_idx, c->feature_mask, c->nan_to_num,
+                 c->features ? c->features + (size_t)b * c->nkeys * c->d.n_out : NULL,
+                 c->raster ? c->raster + (size_t)b * c->d.T * N : NULL, V, ref, spk, acc, st);
+}
+
+int oracle_reservoir_run(int N, int C, int T, double theta, int refractory, int w_shift,
+                         const int32_t *wt_rowptr, const int32_t *wt_col, const int32_t *wt_q,
+                         const int32_t *in_rowptr, const int32_t *in_col, const double *in_val,
+                         const double *leak, const int32_t *out_idx, int n_out,
+                         const uint8_t *spikes, int B, uint32_t feature_mask, int nan_to_num,
+                         double *features, uint8_t *raster, int nthreads)
+{
+    rs_ctx c = {{N, C, T, refractory, n_out, theta, w_shift}, wt_rowptr, wt_col, wt_q, in_rowptr, in_col,
+                in_val, leak, out_idx, spikes, feature_mask, nan_to_num, 0, features, raster};
+    for (int k = 0; k < 8; ++k) c.nkeys += (feature_mask >> k) & 1;
+    pf_job j = {rs_one, &c, B, 0, rs_mk, free};
+    parallel_for(&j, nthreads);
+    return 0;
+}
+
+int oracle_num_threads(void) { return (int)sysconf(_SC_NPROCESSORS_ONLN); }

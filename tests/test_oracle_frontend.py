@@ -1,0 +1,127 @@
+"""CPU: the oracle against the golden vectors minted from the reference's own functions
+(tests/golden/make_golden.py) and against the installed scipy/numpy (the reference's deps)."""
+import numpy as np
+import pytest
+
+from lsm_speech_classifier_b200 import filterbank
+from oracle import coracle, pyref
+
+THR = [0.70, 0.80, 0.90, 0.95]
+GAP = 0.1
+
+
+def test_encoder_kats_from_reference(golden):
+    g = golden("encoder_kats.npz")
+    assert list(g["thresholds"]) == THR and float(g["gap"]) == GAP
+    assert np.array_equal(pyref.hysteresis_encode(g["spec64"], THR, GAP), g["spikes64"])
+    assert np.array_equal(pyref.hysteresis_encode(g["spec32"], THR, GAP), g["spikes32"])
+    assert np.array_equal(coracle.hysteresis_encode(g["spec64"], THR, GAP), g["spikes64"])
+    assert np.array_equal(coracle.hysteresis_encode(g["spec64"][:5], THR, GAP, redundancy=3), g["redundancy3"])
+    assert np.array_equal(pyref.redundancy(g["spikes64"][:5], 3), g["redundancy3"])
+
+
+def test_encoder_hand_derived():
+    # ramp 0 -> 1 over 100 bins: trigger k turns on at the first bin strictly above its threshold
+    ramp = np.linspace(0.0, 1.0, 100)[None, :]
+    s = coracle.hysteresis_encode(ramp, THR, GAP)[0].reshape(100, 4)
+    for k, thr in enumerate(sorted(THR, reverse=True)):
+        first = int(np.argmax(ramp[0] > thr))
+        assert s[:first, k].sum() == 0 and s[first:, k].all()
+    assert coracle.hysteresis_encode(np.zeros((3, 100)), THR, GAP).sum() == 0
+    assert coracle.hysteresis_encode(np.ones((3, 100)), THR, GAP).all()
+    # level exactly on a threshold never switches on (strict >), exactly on the lower bound never off (strict <)
+    assert coracle.hysteresis_encode(np.full((1, 100), 0.95), THR, GAP)[0].reshape(100, 4)[:, 0].sum() == 0
+
+
+def test_strides_and_zoom_kats():
+    assert filterbank.gtgram_strides(16000, 0.025, 0.01, 16000) == (400, 160, 98)
+    from scipy.ndimage import zoom
+    rng = np.random.default_rng(1)
+    for ncol, dt in ((98, np.float64), (101, np.float32)):
+        v = rng.random((16, ncol)).astype(dt)
+        i0, f = filterbank.zoom_table(ncol, 100)
+        want = zoom(v, (1, 100 / ncol), order=1)
+        vd = v.astype(np.float64)
+        nxt = np.where(i0 + 1 < ncol, i0 + 1, i0)
+        got = vd[:, i0] * (1.0 - f) + np.where(i0 + 1 < ncol, vd[:, nxt] * f, 0.0)
+        got = np.where(i0 + 1 < ncol, got, vd[:, i0] * (1.0 - f)).astype(dt)
+        assert want.shape == (16, 100)
+        assert np.array_equal(got, want)
+        assert np.array_equal(want[:, 0], v[:, 0]) and np.array_equal(want[:, -1], v[:, -1])
+
+
+def test_design_table_close_to_independent_derivation():
+    a = filterbank.gammatone_coefs(16000, 128, 50)
+    b = pyref.gammatone_design(16000, 128, 50)
+    assert a.shape == (128, 10)
+    np.testing.assert_allclose(a, b, rtol=1e-12, atol=0)
+    cf = filterbank.centre_freqs(16000, 128, 50)
+    assert abs(cf[-1] - 50.0) < 1e-9 and np.all(np.diff(cf) < 0)
+    # unit gain at the centre frequency after /gain (4 cascaded biquads)
+    for ch in (0, 31, 64, 127):
+        A0, A11, A12, A13, A14, A2, B0, B1, B2, gain = a[ch]
+        z = np.exp(-2j * np.pi * cf[::-1][ch] / 16000)
+        h = 1.0
+        for A1 in (A11, A12, A13, A14):
+            h *= (A0 + A1 * z + A2 * z * z) / (B0 + B1 * z + B2 * z * z)
+        assert abs(abs(h) / gain - 1.0) < 1e-9
+
+
+def test_c_oracle_gammatone_vs_golden(golden):
+    g = golden("frontend_gammatone.npz")
+    pcm, coefs = g["pcm"], g["coefs"]
+    want = np.unpackbits(g["spikes_packed"], axis=-1)[:, :, :400]
+    i0, f = filterbank.zoom_table(98, 100)
+    got, spec = coracle.gammatone_encode(pcm, coefs, 400, 160, 100, i0, f, THR, GAP, want_spec=True)
+    # spikes: bit-exact against (scipy restatement + the reference's own encoder)
+    assert np.array_equal(got, want)
+    # spectrogram: identical up to log10's last bit (numpy uses the platform libm; the oracle's is fixed)
+    np.testing.assert_allclose(spec[:2], g["spec_norm"], rtol=0, atol=1e-12)
+    assert got[3].sum() == 0 and np.all(spec[3] == 0)          # silent clip (create_dataset.py:64-65)
+    assert got[4].sum() > 0                                     # zero-padded short clip
+    # threads must not change a bit
+    assert np.array_equal(coracle.gammatone_encode(pcm, coefs, 400, 160, 100, i0, f, THR, GAP, nthreads=1), got)
+
+
+def test_pyref_gammatone_pinned_pieces():
+    """lfilter recurrence and window mean, restated scalar-by-scalar, against scipy/numpy."""
+    from scipy.signal import lfilter
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(2000).astype(np.float32)
+    c = filterbank.gammatone_coefs(16000, 8, 50)[5]
+    y = lfilter([c[0], c[2], c[5]], [c[6], c[7], c[8]], x)
+    z0 = z1 = 0.0
+    out = np.empty(len(x))
+    for n, xn in enumerate(x.astype(np.float64)):
+        yn = z0 + c[0] * xn
+        z0 = (z1 + xn * c[2]) - yn * c[7]
+        z1 = xn * c[5] - yn * c[8]
+        out[n] = yn
+    assert np.array_equal(y, out)
+    xe = rng.random((4, 1000))
+    seg = xe[:, 160 + np.arange(400)]
+    m = seg.mean(1)
+    for r in range(4):
+        acc = 0.0
+        for v in xe[r, 160:560]:
+            acc = acc + v
+        assert acc / 400 == m[r]
+
+
+def test_log10_is_a_faithful_libm(golden):
+    xs = np.concatenate([np.random.default_rng(0).uniform(1e-9, 1.0, 3000),
+                         10 ** np.random.default_rng(1).uniform(-9, 3, 3000), [1.0, 1e-9, 10.0, 0.5]])
+    mine = coracle.log10(xs)
+    ref = np.log10(xs)
+    ulp = np.abs(mine - ref) / np.spacing(np.maximum(np.abs(ref), 1e-300))
+    assert ulp.max() <= 2.0
+    assert coracle.log10(np.array([1.0]))[0] == 0.0
+
+
+def test_w_critico_kats(golden):
+    g = golden("w_critico_kats.npz")
+    for i in range(4):
+        assert pyref.w_critico(200, 2.0, 2, list(g[f"d{i}"])) == g["answers"][i]
+    assert g["answers"][3] == (2.0 - 2 * 0.1 * 2) / 100
+    assert pyref.w_critico(0, 2.0, 2, list(g["d0"])) == 0.007
+    assert pyref.w_critico(200, 2.0, 2, []) == 0.007

@@ -1,0 +1,100 @@
+"""CPU: reservoir oracle (C) against the Python restatement's golden rasters, plus the spec's
+sanity band (extract_lsm_features.py:143-151)."""
+import hashlib
+
+import numpy as np
+
+from lsm_speech_classifier_b200 import filterbank
+from lsm_speech_classifier_b200.reservoir import SimulationParams, build_reservoir
+from oracle import coracle, pyref
+
+THR = [0.70, 0.80, 0.90, 0.95]
+
+
+def digest(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h.update(str(a.dtype).encode() + str(a.shape).encode() + a.tobytes())
+    return h.hexdigest()
+
+
+def golden_inputs(golden):
+    g = golden("frontend_gammatone.npz")
+    return np.unpackbits(g["spikes_packed"], axis=-1)[:, :, :400]
+
+
+def build(tag, X, mean_weight):
+    kw = {} if tag == "n1000" else dict(num_neurons=256, small_world_graph_k=50, num_output_neurons=100,
+                                        leak_variance_divisor=4.0)
+    return build_reservoir(SimulationParams(mean_weight=mean_weight, input_spike_times=X[0], **kw))
+
+
+def test_reservoir_builder_is_deterministic_and_oracle_matches_golden(golden):
+    X = golden_inputs(golden)
+    g = golden("reservoir.npz")
+    for tag in ("n1000", "n256_hetero"):
+        r = build(tag, X, float(g[f"{tag}_mean_weight"]))
+        assert digest(r.w_rowptr, r.w_col, r.w_q, r.in_rowptr, r.in_col, r.in_val, r.out_idx, r.leak) == str(g[f"{tag}_digest"])
+        idx = list(g["utt_index"])
+        feats, raster = coracle.reservoir_run(r, X[idx], 0xFF, False, True)
+        want = np.unpackbits(g[f"{tag}_raster_packed"], axis=-1)[:, :, :r.num_neurons]
+        assert np.array_equal(raster, want)
+        assert np.array_equal(feats, g[f"{tag}_features"], equal_nan=True)
+        # silent utterance (index 3 -> position 2): nothing fires, timing features are NaN, counts 0
+        assert raster[2].sum() == 0 and np.isnan(feats[2]).any() and np.all(feats[2][:len(r.out_idx)] == 0)
+
+
+def test_reservoir_structure():
+    X = np.zeros((1, 128, 400), np.uint8)
+    r = build_reservoir(SimulationParams(mean_weight=0.011, input_spike_times=X[0]))
+    n = r.num_neurons
+    deg = np.diff(r.w_rowptr)
+    assert deg.sum() == 200 * n and 150 < deg.min() and deg.max() < 250
+    post = np.repeat(np.arange(n), deg)
+    assert not np.any(post == r.w_col)                                   # no self loops
+    a = set(zip(post.tolist(), r.w_col.tolist()))
+    assert all((j, i) in a for i, j in list(a)[:5000])                   # symmetric pattern
+    assert len(set(r.in_col.tolist())) == 128 and np.all(np.diff(r.in_rowptr) <= 1)
+    assert len(r.out_idx) == 400 and np.all(np.diff(r.out_idx) > 0)
+    w = r.w_q * 2.0 ** -24
+    assert abs(w.mean() - 0.011) < 1e-4 and abs(w.std() - 0.0011) < 1e-4
+
+
+def test_features_match_numpy_definitions(golden):
+    X = golden_inputs(golden)
+    g = golden("reservoir.npz")
+    r = build("n1000", X, float(g["n1000_mean_weight"]))
+    feats, raster = coracle.reservoir_run(r, X[:1], 0xFF, False, True)
+    ras = raster[0]
+    n_out = len(r.out_idx)
+    F = feats[0].reshape(8, n_out)
+    for o in np.argsort(-ras[:, r.out_idx].sum(0).astype(np.int64))[:20]:
+        col = ras[:, r.out_idx[o]].astype(np.float64)
+        t = np.nonzero(col)[0]
+        np.testing.assert_allclose(F[0, o], col.sum())
+        np.testing.assert_allclose(F[1, o], np.var(col), rtol=1e-12)
+        np.testing.assert_allclose(F[2, o], t.mean(), rtol=1e-12)
+        assert F[3, o] == t[0] and F[4, o] == t[-1]
+        if len(t) > 1:
+            np.testing.assert_allclose(F[5, o], np.diff(t).mean(), rtol=1e-12)
+            np.testing.assert_allclose(F[6, o], np.var(np.diff(t)), rtol=1e-9, atol=1e-12)
+            assert F[7, o] == (np.diff(t) <= r.refractory + 1).sum()
+    # feature subsets are key-major slices of the full set, nan_to_num zeroes the NaNs
+    sub, _ = coracle.reservoir_run(r, X[:1], 0b00100111, True, False)
+    want = np.nan_to_num(np.concatenate([F[0], F[1], F[2], F[5]]))
+    assert np.array_equal(sub[0], want)
+
+
+def test_default_multiplier_sits_in_the_reference_health_band(golden):
+    """extract_lsm_features.py:143-151: <40 % participation = sub-critical, >98 % = saturated."""
+    X = golden_inputs(golden)
+    voiced = X[[0, 1, 2]]
+    wc = pyref.w_critico(200, 2.0, 2, list(X))
+    part = {}
+    for mult in (0.4, 0.6, 1.0):
+        r = build_reservoir(SimulationParams(mean_weight=wc * mult, input_spike_times=X[0]))
+        _, raster = coracle.reservoir_run(r, voiced, 0x1, True, True)
+        part[mult] = np.mean([(ras.sum(0) > 0).mean() * 100 for ras in raster])
+    assert part[0.4] < 40 < part[0.6] < 98 < part[1.0] + 1e-9 or part[0.4] < part[0.6] < part[1.0]
+    assert 40 <= part[0.6] <= 98
