@@ -1,0 +1,162 @@
+/*
+ * lsm_b200.h — C ABI of liblsmb200.so: the B200 (sm_100a) implementation of the
+ * audio -> spike train -> liquid-state-machine -> per-neuron feature path of
+ * adelitoo/lsm-speech-classifier.
+ *
+ * The reference has no FFI of its own: it is Python that delegates to three packages.  Each
+ * entry point below therefore names the reference CALL SITE (file:line under /root/reference)
+ * whose work it replaces.  INTEGRATION.md shows the ctypes stubs a maintainer adds.
+ *
+ * Conventions
+ *   - every function returns 0 (LSM_OK) or a negative lsm_status; lsm_last_error(ctx) has the text
+ *   - the caller owns every buffer it passes; the library owns only what lives inside its handles
+ *   - "d_" pointers are device memory on the ctx's device, "h_" pointers are host memory
+ *   - one lsm_ctx per (process, device); a ctx is not thread-safe; work is enqueued on the ctx's
+ *     stream (lsm_set_stream) and is asynchronous unless the name ends in _host or _sync
+ *   - there is NO CPU fallback: without a CUDA device lsm_ctx_create fails
+ */
+#ifndef LSM_B200_H
+#define LSM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lsm_ctx lsm_ctx;
+typedef struct lsm_frontend lsm_frontend;
+typedef struct lsm_reservoir lsm_reservoir;
+
+typedef enum {
+    LSM_OK = 0,
+    LSM_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+    LSM_ERR_CUDA = -2,        /* a CUDA runtime call or kernel failed */
+    LSM_ERR_NOMEM = -3,
+    LSM_ERR_UNSUPPORTED = -4  /* valid request this build cannot serve */
+} lsm_status;
+
+enum { LSM_FILTERBANK_GAMMATONE = 0, LSM_FILTERBANK_MEL = 1 };
+
+/* Feature keys, bit k of feature_mask <-> k-th name of FEATURE_SETS['all']
+ * (extract_lsm_features.py:20-22).  Output layout is key-major: all output neurons of the
+ * lowest selected key, then the next (extract_lsm_features.py:85-87).                      */
+enum {
+    LSM_F_SPIKE_COUNTS = 1u << 0, LSM_F_SPIKE_VARIANCES = 1u << 1, LSM_F_MEAN_SPIKE_TIMES = 1u << 2,
+    LSM_F_FIRST_SPIKE_TIMES = 1u << 3, LSM_F_LAST_SPIKE_TIMES = 1u << 4, LSM_F_MEAN_ISI = 1u << 5,
+    LSM_F_ISI_VARIANCES = 1u << 6, LSM_F_BURST_COUNTS = 1u << 7
+};
+
+/* ---------------------------------------------------------------- context */
+int lsm_ctx_create(lsm_ctx **out, int device_ordinal);
+void lsm_ctx_destroy(lsm_ctx *ctx);
+const char *lsm_last_error(const lsm_ctx *ctx);
+/* Use an existing cudaStream_t (e.g. torch's current stream); NULL = the ctx's own stream. */
+int lsm_set_stream(lsm_ctx *ctx, void *cuda_stream);
+int lsm_sync(lsm_ctx *ctx);
+/* Kernels launched by this ctx since creation (bench.py's gpu_launches). */
+int64_t lsm_launch_count(const lsm_ctx *ctx);
+int lsm_sm_count(const lsm_ctx *ctx);
+
+/* ---------------------------------------------------------------- stage 1: PCM -> spike trains
+ * Replaces, per utterance, create_dataset.py:148-158:
+ *     audio_to_spectrogram (:39-78; gammatone.gtgram.gtgram :51-58 or
+ *                           librosa melspectrogram + power_to_db :45-48,
+ *                           dB floor :59-60, min-max :62-67, scipy zoom :69-78)
+ *     convert_spectrogram_to_spikes_hysteresis (:81-98)
+ *     create_pure_redundancy (:101-104)
+ */
+typedef struct {
+    int32_t kind;            /* LSM_FILTERBANK_* (create_dataset.py:43,49) */
+    int32_t channels;        /* n_filters */
+    int32_t n_samples;       /* 16000 = SAMPLE_RATE*DURATION (create_dataset.py:10-11,28) */
+    int32_t nwin, hop;       /* gammatone: gtgram window/hop in samples (400, 160) */
+    int32_t n_fft, mel_hop;  /* mel: 2048, 160 (librosa defaults + create_dataset.py:44) */
+    int32_t n_bins;          /* TIME_BINS = 100 (create_dataset.py:12) */
+    int32_t n_thresholds;    /* <= 8 */
+    int32_t redundancy;      /* REDUNDANCY_FACTOR (create_dataset.py:17) */
+    double thresholds_desc[8]; /* sorted(thresholds, reverse=True)  (create_dataset.py:87) */
+    double lower_bounds[8];    /* threshold - hysteresis_gap in fp64 (create_dataset.py:89) */
+} lsm_frontend_params;
+
+/* h_table: gammatone -> double[channels][10] rows {A0,A11,A12,A13,A14,A2,B0,B1,B2,gain}, row 0 = the
+ *          lowest centre frequency (gammatone.gtgram.gtgram_xe's flipped make_erb_filters table);
+ *          mel -> float[channels][1 + n_fft/2] (librosa.filters.mel).
+ * h_zoom_i0/h_zoom_f: int32/double[n_bins], scipy.ndimage.zoom(order=1) source index and fraction
+ *          per output bin (ignored when the spectrogram already has n_bins columns).        */
+int lsm_frontend_create(lsm_ctx *ctx, const lsm_frontend_params *p, const void *h_table,
+                        const int32_t *h_zoom_i0, const double *h_zoom_f, lsm_frontend **out);
+void lsm_frontend_destroy(lsm_frontend *fe);
+/* d_pcm: float[B][n_samples].  d_spikes: uint8[B][channels*redundancy][n_bins*n_thresholds] — the
+ * X_spikes layout of speech_spike_dataset_pure_redundancy.npz (create_dataset.py:168).
+ * d_spec_norm_or_null: optional double[B][channels][n_bins] dump of the normalised, resampled
+ * spectrogram (what audio_to_spectrogram returns) for parity tests.                         */
+int lsm_frontend_encode(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int32_t B,
+                        uint8_t *d_spikes, double *d_spec_norm_or_null);
+/* Same through host buffers: H2D, kernel, D2H, synchronous. */
+int lsm_frontend_encode_host(lsm_ctx *ctx, lsm_frontend *fe, const float *h_pcm, int32_t B,
+                             uint8_t *h_spikes);
+
+/* The encoder alone, on spectrograms already in device memory: convert_spectrogram_to_spikes_hysteresis
+ * (create_dataset.py:81-98) + create_pure_redundancy (:101-104).  d_spec: double[B][C][n_bins] or, when
+ * is_f32 != 0, float[B][C][n_bins] compared against float-rounded thresholds as numpy does for a
+ * float32 spectrogram.  thr_desc/lower: host arrays of K values (descending thresholds, threshold - gap). */
+int lsm_hysteresis_encode(lsm_ctx *ctx, const void *d_spec, int32_t is_f32, int32_t B, int32_t C, int32_t n_bins,
+                          const double *h_thr_desc, const double *h_lower, int32_t K, int32_t redundancy,
+                          uint8_t *d_spikes);
+
+/* ---------------------------------------------------------------- stage 2+3: spike trains -> features
+ * Replaces SNN(simulation_params=...) (extract_lsm_features.py:188) and, per utterance,
+ *     lsm.reset(); lsm.set_input_spike_times(sample); lsm.simulate()   (:79-81)
+ *     lsm.extract_features_from_spikes() + key selection + nan_to_num (:83-87)
+ * The reservoir is generated on the HOST (numpy RandomState, see reservoir.py) and uploaded, so the
+ * CPU oracle and the GPU share identical arrays.  Weights are int32 multiples of 2^-w_shift.  */
+typedef struct {
+    int32_t num_neurons;     /* N */
+    int32_t num_inputs;      /* rows of one sample = channels*redundancy */
+    int32_t num_steps;       /* T = columns of one sample (400) */
+    int32_t refractory;      /* refractory_period */
+    int32_t w_shift;         /* 24 */
+    int32_t n_out;           /* num_output_neurons */
+    double theta;            /* membrane_threshold */
+} lsm_reservoir_params;
+
+int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
+                         const int32_t *h_w_rowptr, const int32_t *h_w_col, const int32_t *h_w_q, /* CSR, row = postsynaptic */
+                         const int32_t *h_in_rowptr, const int32_t *h_in_col, const double *h_in_val, /* CSR, row = neuron */
+                         const double *h_leak,            /* double[N] */
+                         const int32_t *h_out_idx,        /* int32[n_out], ascending */
+                         lsm_reservoir **out);
+void lsm_reservoir_destroy(lsm_reservoir *res);
+/* d_spikes: uint8[B][num_inputs][num_steps].  d_features: double[B][popcount(mask)*n_out], RAW
+ * (un-standardised).  nan_to_num != 0 applies extract_lsm_features.py:85's np.nan_to_num on device.
+ * d_raster_or_null: optional uint8[B][num_steps][N] = lsm.spike_matrix (Time x Neurons,
+ * extract_lsm_features.py:113-116) for parity tests and diagnostics.                        */
+int lsm_reservoir_run(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int32_t B,
+                      uint32_t feature_mask, int32_t nan_to_num, double *d_features,
+                      uint8_t *d_raster_or_null);
+int lsm_reservoir_run_host(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *h_spikes, int32_t B,
+                           uint32_t feature_mask, int32_t nan_to_num, double *h_features,
+                           uint8_t *h_raster_or_null);
+
+/* ---------------------------------------------------------------- the whole path, host buffers
+ * audio -> features in one call: the loop bodies of create_dataset.py:143-162 and
+ * extract_lsm_features.py:78-87 for B utterances.  Copies are chunked and overlapped with the
+ * kernels on internal streams.  h_spikes_or_null: optionally also return the spike trains (the
+ * stage-1 file content).  Synchronous.                                                       */
+int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *h_pcm,
+                          int32_t B, uint32_t feature_mask, int32_t nan_to_num, double *h_features,
+                          uint8_t *h_spikes_or_null);
+/* Device-resident variant: d_pcm -> d_features (and d_spikes scratch supplied by the caller). */
+int lsm_pipeline_run(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm,
+                     int32_t B, uint32_t feature_mask, int32_t nan_to_num, uint8_t *d_spikes,
+                     double *d_features);
+
+/* Sum of all spike bytes and their count: the two integers calculate_theoretical_w_critico
+ * reduces over X_train[:500] (extract_lsm_features.py:40-44).  h_out: int64[2].            */
+int lsm_spike_density(lsm_ctx *ctx, const uint8_t *d_spikes, int64_t n_bytes, int64_t *h_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSM_B200_H */

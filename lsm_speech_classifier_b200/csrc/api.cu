@@ -1,0 +1,465 @@
+// liblsmb200.so — C ABI (include/lsm_b200.h): context, handles, host-buffer entry points and the
+// chunked audio -> features pipeline.  No CPU fallback anywhere: every entry point needs a ctx,
+// and a ctx needs a CUDA device.
+#include <new>
+#include <vector>
+
+#include "lsm_common.cuh"
+
+// ------------------------------------------------------------------------------------ context
+extern "C" int lsm_ctx_create(lsm_ctx **out, int device_ordinal)
+{
+    if (!out) return LSM_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device_ordinal < 0 || device_ordinal >= n)
+        return LSM_ERR_CUDA;
+    lsm_ctx *ctx = new (std::nothrow) lsm_ctx();
+    if (!ctx) return LSM_ERR_NOMEM;
+    ctx->device = device_ordinal;
+    if (cudaSetDevice(device_ordinal) != cudaSuccess) { delete ctx; return LSM_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) { delete ctx; return LSM_ERR_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        // built for sm_100a only; fail loudly rather than at the first launch
+        delete ctx;
+        return LSM_ERR_UNSUPPORTED;
+    }
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LSM_ERR_CUDA; }
+    ctx->stream = ctx->own_stream;
+    for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&ctx->copy_stream[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming);
+    *out = ctx;
+    return LSM_OK;
+}
+
+extern "C" void lsm_ctx_destroy(lsm_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 6; ++i) if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
+    for (int i = 0; i < 4; ++i) if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
+    for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 2; ++i) if (ctx->copy_stream[i]) cudaStreamDestroy(ctx->copy_stream[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" const char *lsm_last_error(const lsm_ctx *ctx) { return ctx ? ctx->err : "null ctx"; }
+
+extern "C" int lsm_set_stream(lsm_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return LSM_OK;
+}
+
+extern "C" int lsm_sync(lsm_ctx *ctx)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    LSM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return LSM_OK;
+}
+
+extern "C" int64_t lsm_launch_count(const lsm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int lsm_sm_count(const lsm_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+int lsm_stage_device(lsm_ctx *ctx, int slot, size_t bytes, void **out)
+{
+    if (ctx->d_stage_bytes[slot] < bytes) {
+        if (ctx->d_stage[slot]) { LSM_CUDA(ctx, cudaFree(ctx->d_stage[slot])); ctx->d_stage[slot] = nullptr; ctx->d_stage_bytes[slot] = 0; }
+        if (cudaMalloc(&ctx->d_stage[slot], bytes) != cudaSuccess) LSM_FAIL(ctx, LSM_ERR_NOMEM, "cudaMalloc(%zu) failed", bytes);
+        ctx->d_stage_bytes[slot] = bytes;
+    }
+    *out = ctx->d_stage[slot];
+    return LSM_OK;
+}
+
+int lsm_stage_pinned(lsm_ctx *ctx, int slot, size_t bytes, void **out)
+{
+    if (ctx->h_pin_bytes[slot] < bytes) {
+        if (ctx->h_pin[slot]) { LSM_CUDA(ctx, cudaFreeHost(ctx->h_pin[slot])); ctx->h_pin[slot] = nullptr; ctx->h_pin_bytes[slot] = 0; }
+        if (cudaMallocHost(&ctx->h_pin[slot], bytes) != cudaSuccess) LSM_FAIL(ctx, LSM_ERR_NOMEM, "cudaMallocHost(%zu) failed", bytes);
+        ctx->h_pin_bytes[slot] = bytes;
+    }
+    *out = ctx->h_pin[slot];
+    return LSM_OK;
+}
+
+template <typename T>
+static int upload(lsm_ctx *ctx, T **dst, const T *src, size_t n)
+{
+    *dst = nullptr;
+    if (n == 0) n = 1;  // keep pointers non-null
+    LSM_CUDA(ctx, cudaMalloc((void **)dst, n * sizeof(T)));
+    if (src) LSM_CUDA(ctx, cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return LSM_OK;
+}
+
+// ------------------------------------------------------------------------------------ stage 1
+extern "C" int lsm_frontend_create(lsm_ctx *ctx, const lsm_frontend_params *p, const void *h_table,
+                                   const int32_t *h_zoom_i0, const double *h_zoom_f, lsm_frontend **out)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!p || !h_table || !out) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_frontend_create: null argument");
+    *out = nullptr;
+    if (p->channels <= 0 || p->channels > 1024) LSM_FAIL(ctx, LSM_ERR_INVALID, "channels %d outside 1..1024", p->channels);
+    if (p->n_thresholds <= 0 || p->n_thresholds > 8) LSM_FAIL(ctx, LSM_ERR_INVALID, "n_thresholds %d outside 1..8", p->n_thresholds);
+    if (p->redundancy <= 0 || p->n_bins <= 1 || p->n_samples <= 0) LSM_FAIL(ctx, LSM_ERR_INVALID, "bad redundancy/n_bins/n_samples");
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    lsm_frontend *fe = new (std::nothrow) lsm_frontend();
+    if (!fe) LSM_FAIL(ctx, LSM_ERR_NOMEM, "out of host memory");
+    fe->p = *p;
+    int rc = LSM_OK;
+    if (p->kind == LSM_FILTERBANK_GAMMATONE) {
+        // the kernel keeps exactly three windows open: 2*hop < nwin <= 3*hop (reference: 400 / 160)
+        if (!(p->hop > 0 && 2 * p->hop < p->nwin && p->nwin <= 3 * p->hop && p->nwin <= p->n_samples)) {
+            delete fe;
+            LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "gammatone window/hop %d/%d: need 2*hop < nwin <= 3*hop", p->nwin, p->hop);
+        }
+        if (p->channels > 256) { delete fe; LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "gammatone channels %d > 256", p->channels); }
+        const double *t = (const double *)h_table;
+        for (int c = 0; c < p->channels; ++c)
+            if (t[10 * c + 5] != 0.0) { delete fe; LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "gammatone design with A2 != 0"); }
+        fe->ncols = 1 + (p->n_samples - p->nwin) / p->hop;
+        rc = upload(ctx, &fe->d_coefs, t, (size_t)p->channels * 10);
+        if (rc == LSM_OK) rc = lsm_gammatone_grid(ctx, p, &fe->grid);
+        if (rc == LSM_OK) rc = upload<double>(ctx, &fe->d_scratch, nullptr, (size_t)fe->grid * fe->ncols * p->channels);
+    } else if (p->kind == LSM_FILTERBANK_MEL) {
+        if (p->n_fft <= 0 || (p->n_fft & (p->n_fft - 1)) || p->mel_hop <= 0) { delete fe; LSM_FAIL(ctx, LSM_ERR_INVALID, "mel n_fft must be a power of two"); }
+        fe->ncols = 1 + p->n_samples / p->mel_hop;
+        rc = lsm_mel_create(ctx, fe, (const float *)h_table);
+    } else {
+        delete fe;
+        LSM_FAIL(ctx, LSM_ERR_INVALID, "unknown filterbank kind %d", p->kind);
+    }
+    if (rc == LSM_OK && fe->ncols != p->n_bins) {
+        if (!h_zoom_i0 || !h_zoom_f) { rc = LSM_ERR_INVALID; snprintf(ctx->err, sizeof(ctx->err), "zoom table required: %d columns -> %d bins", fe->ncols, p->n_bins); }
+        else {
+            for (int j = 0; j < p->n_bins && rc == LSM_OK; ++j)
+                if (h_zoom_i0[j] < 0 || h_zoom_i0[j] >= fe->ncols) { rc = LSM_ERR_INVALID; snprintf(ctx->err, sizeof(ctx->err), "zoom index out of range"); }
+            if (rc == LSM_OK) rc = upload(ctx, &fe->d_zoom_i0, h_zoom_i0, (size_t)p->n_bins);
+            if (rc == LSM_OK) rc = upload(ctx, &fe->d_zoom_f, h_zoom_f, (size_t)p->n_bins);
+        }
+    }
+    if (rc != LSM_OK) { lsm_frontend_destroy(fe); return rc; }
+    *out = fe;
+    return LSM_OK;
+}
+
+extern "C" void lsm_frontend_destroy(lsm_frontend *fe)
+{
+    if (!fe) return;
+    cudaFree(fe->d_coefs); cudaFree(fe->d_zoom_i0); cudaFree(fe->d_zoom_f); cudaFree(fe->d_scratch);
+    lsm_mel_destroy(fe);
+    delete fe;
+}
+
+static int frontend_launch(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, uint8_t *d_spikes,
+                           double *d_spec, cudaStream_t st)
+{
+    if (fe->p.kind == LSM_FILTERBANK_GAMMATONE) return lsm_launch_gammatone(ctx, fe, d_pcm, B, d_spikes, d_spec, st);
+    return lsm_launch_mel(ctx, fe, d_pcm, B, d_spikes, d_spec, st);
+}
+
+extern "C" int lsm_frontend_encode(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int32_t B,
+                                   uint8_t *d_spikes, double *d_spec_norm_or_null)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!fe || B < 0 || (B > 0 && (!d_pcm || !d_spikes))) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_frontend_encode: bad argument");
+    if (B == 0) return LSM_OK;   // empty batch: nothing to do (create_dataset.py:164-166 prints and returns)
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    return frontend_launch(ctx, fe, d_pcm, B, d_spikes, d_spec_norm_or_null, ctx->stream);
+}
+
+extern "C" int lsm_frontend_encode_host(lsm_ctx *ctx, lsm_frontend *fe, const float *h_pcm, int32_t B,
+                                        uint8_t *h_spikes)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!fe || B < 0 || (B > 0 && (!h_pcm || !h_spikes))) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_frontend_encode_host: bad argument");
+    if (B == 0) return LSM_OK;
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pcm_bytes = (size_t)B * fe->p.n_samples * sizeof(float);
+    const size_t spk_bytes = (size_t)B * fe->p.channels * fe->p.redundancy * fe->p.n_bins * fe->p.n_thresholds;
+    void *d_pcm, *d_spk;
+    int rc;
+    if ((rc = lsm_stage_device(ctx, 0, pcm_bytes, &d_pcm)) != LSM_OK) return rc;
+    if ((rc = lsm_stage_device(ctx, 1, spk_bytes, &d_spk)) != LSM_OK) return rc;
+    LSM_CUDA(ctx, cudaMemcpyAsync(d_pcm, h_pcm, pcm_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = frontend_launch(ctx, fe, (const float *)d_pcm, B, (uint8_t *)d_spk, nullptr, ctx->stream)) != LSM_OK) return rc;
+    LSM_CUDA(ctx, cudaMemcpyAsync(h_spikes, d_spk, spk_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    LSM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return LSM_OK;
+}
+
+// ------------------------------------------------------------------------------------ encoder alone
+namespace {
+struct EncArgs { double thr[8], lower[8]; float thr32[8], lower32[8]; };
+
+template <typename T>
+__global__ void hysteresis_kernel(const T *__restrict__ spec, int rows, int n_bins, int K, int R, EncArgs e,
+                                  uint8_t *__restrict__ spikes)
+{
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;   // (utterance, channel)
+    if (row >= rows) return;
+    const T *v = spec + (size_t)row * n_bins;
+    uint8_t *out0 = spikes + (size_t)row * R * n_bins * K;
+    unsigned on = 0;
+    for (int j = 0; j < n_bins; ++j) {
+        const T x = v[j];
+        for (int k = 0; k < K; ++k) {
+            const bool is_on = (on >> k) & 1u;
+            bool rise, fall;
+            if (sizeof(T) == 4) { rise = (float)x > e.thr32[k]; fall = (float)x < e.lower32[k]; }
+            else { rise = (double)x > e.thr[k]; fall = (double)x < e.lower[k]; }
+            if (!is_on && rise) on |= 1u << k;
+            else if (is_on && fall) on &= ~(1u << k);
+        }
+        for (int r = 0; r < R; ++r)
+            for (int k = 0; k < K; ++k) out0[(size_t)r * n_bins * K + (size_t)j * K + k] = (on >> k) & 1u;
+    }
+}
+}  // namespace
+
+extern "C" int lsm_hysteresis_encode(lsm_ctx *ctx, const void *d_spec, int32_t is_f32, int32_t B, int32_t C, int32_t n_bins,
+                                     const double *h_thr_desc, const double *h_lower, int32_t K, int32_t redundancy,
+                                     uint8_t *d_spikes)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (B < 0 || C <= 0 || n_bins <= 0 || K <= 0 || K > 8 || redundancy <= 0 || !h_thr_desc || !h_lower ||
+        (B > 0 && (!d_spec || !d_spikes)))
+        LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_hysteresis_encode: bad argument");
+    if (B == 0) return LSM_OK;
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    EncArgs e = {};
+    for (int k = 0; k < K; ++k) {
+        e.thr[k] = h_thr_desc[k]; e.lower[k] = h_lower[k];
+        e.thr32[k] = (float)h_thr_desc[k]; e.lower32[k] = (float)h_lower[k];
+    }
+    const int rows = B * C;
+    const int threads = 128, blocks = (rows + threads - 1) / threads;
+    if (is_f32) hysteresis_kernel<float><<<blocks, threads, 0, ctx->stream>>>((const float *)d_spec, rows, n_bins, K, redundancy, e, d_spikes);
+    else hysteresis_kernel<double><<<blocks, threads, 0, ctx->stream>>>((const double *)d_spec, rows, n_bins, K, redundancy, e, d_spikes);
+    ctx->launches += 1;
+    LSM_CUDA(ctx, cudaGetLastError());
+    return LSM_OK;
+}
+
+// ------------------------------------------------------------------------------------ stage 2+3
+extern "C" int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
+                                    const int32_t *h_w_rowptr, const int32_t *h_w_col, const int32_t *h_w_q,
+                                    const int32_t *h_in_rowptr, const int32_t *h_in_col, const double *h_in_val,
+                                    const double *h_leak, const int32_t *h_out_idx, lsm_reservoir **out)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!p || !h_w_rowptr || !h_in_rowptr || !h_leak || !h_out_idx || !out)
+        LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_create: null argument");
+    *out = nullptr;
+    const int N = p->num_neurons;
+    if (N <= 0 || p->num_inputs <= 0 || p->num_steps <= 0 || p->n_out < 0 || p->n_out > N || p->refractory < 0 ||
+        p->w_shift < 0 || p->w_shift > 52)
+        LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_create: bad dimensions");
+    const int64_t nnz = h_w_rowptr[N];
+    if (nnz > 0 && (!h_w_col || !h_w_q)) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_create: null weights");
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    lsm_reservoir *res = new (std::nothrow) lsm_reservoir();
+    if (!res) LSM_FAIL(ctx, LSM_ERR_NOMEM, "out of host memory");
+    res->p = *p;
+    res->n_pad = ((N + 31) / 32) * 32;
+    // dense presynaptic-major plane: wt[j][i] = weight of j -> i
+    std::vector<int32_t> wt((size_t)N * res->n_pad, 0);
+    std::vector<int64_t> rowabs(N, 0);
+    for (int i = 0; i < N; ++i) {
+        for (int64_t q = h_w_rowptr[i]; q < h_w_rowptr[i + 1]; ++q) {
+            const int j = h_w_col[q];
+            if (j < 0 || j >= N) { delete res; LSM_FAIL(ctx, LSM_ERR_INVALID, "presynaptic index out of range"); }
+            wt[(size_t)j * res->n_pad + i] += h_w_q[q];
+            rowabs[i] += h_w_q[q] < 0 ? -(int64_t)h_w_q[q] : (int64_t)h_w_q[q];
+        }
+        if (rowabs[i] >= (1ll << 31)) { delete res; LSM_FAIL(ctx, LSM_ERR_INVALID, "row %d: sum of |weights| overflows the exact int32 accumulator", i); }
+    }
+    std::vector<int32_t> out_slot(N, -1);
+    for (int o = 0; o < p->n_out; ++o) {
+        if (h_out_idx[o] < 0 || h_out_idx[o] >= N) { delete res; LSM_FAIL(ctx, LSM_ERR_INVALID, "output index out of range"); }
+        out_slot[h_out_idx[o]] = o;
+    }
+    const int64_t nin = h_in_rowptr[N];
+    for (int i = 0; i < N; ++i) {
+        const int d = h_in_rowptr[i + 1] - h_in_rowptr[i];
+        if (d > res->max_in_per_neuron) res->max_in_per_neuron = d;
+    }
+    for (int64_t q = 0; q < nin; ++q)
+        if (h_in_col[q] < 0 || h_in_col[q] >= p->num_inputs) { delete res; LSM_FAIL(ctx, LSM_ERR_INVALID, "input row out of range"); }
+    int rc = upload(ctx, &res->d_wt, wt.data(), wt.size());
+    if (rc == LSM_OK) rc = upload(ctx, &res->d_in_rowptr, h_in_rowptr, (size_t)N + 1);
+    if (rc == LSM_OK) rc = upload(ctx, &res->d_in_col, h_in_col, (size_t)nin);
+    if (rc == LSM_OK) rc = upload(ctx, &res->d_in_val, h_in_val, (size_t)nin);
+    if (rc == LSM_OK) rc = upload(ctx, &res->d_leak, h_leak, (size_t)N);
+    if (rc == LSM_OK) rc = upload(ctx, &res->d_out_slot, out_slot.data(), (size_t)N);
+    if (rc != LSM_OK) { lsm_reservoir_destroy(res); return rc; }
+    *out = res;
+    return LSM_OK;
+}
+
+extern "C" void lsm_reservoir_destroy(lsm_reservoir *res)
+{
+    if (!res) return;
+    cudaFree(res->d_wt); cudaFree(res->d_in_rowptr); cudaFree(res->d_in_col); cudaFree(res->d_in_val);
+    cudaFree(res->d_leak); cudaFree(res->d_out_slot);
+    delete res;
+}
+
+extern "C" int lsm_reservoir_run(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int32_t B,
+                                 uint32_t feature_mask, int32_t nan_to_num, double *d_features,
+                                 uint8_t *d_raster_or_null)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!res || B < 0 || (B > 0 && !d_spikes)) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_run: bad argument");
+    if (B == 0) return LSM_OK;
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    return lsm_launch_reservoir(ctx, res, d_spikes, B, feature_mask, nan_to_num, d_features, d_raster_or_null, ctx->stream);
+}
+
+extern "C" int lsm_reservoir_run_host(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *h_spikes, int32_t B,
+                                      uint32_t feature_mask, int32_t nan_to_num, double *h_features,
+                                      uint8_t *h_raster_or_null)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!res || B < 0 || (B > 0 && !h_spikes)) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_run_host: bad argument");
+    if (B == 0) return LSM_OK;
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const lsm_reservoir_params &p = res->p;
+    const int nkeys = __builtin_popcount(feature_mask & 0xFFu);
+    const size_t spk_bytes = (size_t)B * p.num_inputs * p.num_steps;
+    const size_t feat_bytes = (size_t)B * nkeys * p.n_out * sizeof(double);
+    const size_t ras_bytes = (size_t)B * p.num_steps * p.num_neurons;
+    void *d_spk = nullptr, *d_feat = nullptr, *d_ras = nullptr;
+    int rc;
+    if ((rc = lsm_stage_device(ctx, 1, spk_bytes, &d_spk)) != LSM_OK) return rc;
+    if (h_features && (rc = lsm_stage_device(ctx, 2, feat_bytes, &d_feat)) != LSM_OK) return rc;
+    if (h_raster_or_null && (rc = lsm_stage_device(ctx, 3, ras_bytes, &d_ras)) != LSM_OK) return rc;
+    LSM_CUDA(ctx, cudaMemcpyAsync(d_spk, h_spikes, spk_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = lsm_launch_reservoir(ctx, res, (const uint8_t *)d_spk, B, feature_mask, nan_to_num,
+                                   (double *)d_feat, (uint8_t *)d_ras, ctx->stream)) != LSM_OK) return rc;
+    if (h_features) LSM_CUDA(ctx, cudaMemcpyAsync(h_features, d_feat, feat_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_raster_or_null) LSM_CUDA(ctx, cudaMemcpyAsync(h_raster_or_null, d_ras, ras_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    LSM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return LSM_OK;
+}
+
+// ------------------------------------------------------------------------------------ whole path
+extern "C" int lsm_pipeline_run(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm,
+                                int32_t B, uint32_t feature_mask, int32_t nan_to_num, uint8_t *d_spikes,
+                                double *d_features)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!fe || !res || B < 0 || (B > 0 && (!d_pcm || !d_spikes || !d_features)))
+        LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_pipeline_run: bad argument");
+    if (fe->p.channels * fe->p.redundancy != res->p.num_inputs || fe->p.n_bins * fe->p.n_thresholds != res->p.num_steps)
+        LSM_FAIL(ctx, LSM_ERR_INVALID, "front end emits %dx%d spike trains, reservoir expects %dx%d",
+                 fe->p.channels * fe->p.redundancy, fe->p.n_bins * fe->p.n_thresholds, res->p.num_inputs, res->p.num_steps);
+    if (B == 0) return LSM_OK;
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = frontend_launch(ctx, fe, d_pcm, B, d_spikes, nullptr, ctx->stream);
+    if (rc != LSM_OK) return rc;
+    return lsm_launch_reservoir(ctx, res, d_spikes, B, feature_mask, nan_to_num, d_features, nullptr, ctx->stream);
+}
+
+extern "C" int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *h_pcm,
+                                     int32_t B, uint32_t feature_mask, int32_t nan_to_num, double *h_features,
+                                     uint8_t *h_spikes_or_null)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!fe || !res || B < 0 || (B > 0 && (!h_pcm || !h_features)))
+        LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_pipeline_run_host: bad argument");
+    if (fe->p.channels * fe->p.redundancy != res->p.num_inputs || fe->p.n_bins * fe->p.n_thresholds != res->p.num_steps)
+        LSM_FAIL(ctx, LSM_ERR_INVALID, "front end emits %dx%d spike trains, reservoir expects %dx%d",
+                 fe->p.channels * fe->p.redundancy, fe->p.n_bins * fe->p.n_thresholds, res->p.num_inputs, res->p.num_steps);
+    if (B == 0) return LSM_OK;
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int L = fe->p.n_samples;
+    const size_t spk_per = (size_t)res->p.num_inputs * res->p.num_steps;
+    const int nkeys = __builtin_popcount(feature_mask & 0xFFu);
+    const size_t feat_per = (size_t)nkeys * res->p.n_out;
+    // chunked, three legs on three streams: H2D(c+1) | K1,K2(c) | D2H(c-1).  Chunk = a few waves of K1.
+    int chunk = fe->grid > 0 ? 2 * fe->grid : 1024;
+    if (chunk > B) chunk = B;
+    const int n_chunks = (B + chunk - 1) / chunk;
+    void *d_pcm[2], *d_spk[2], *d_feat[2];
+    int rc;
+    void *base;
+    if ((rc = lsm_stage_device(ctx, 0, 2 * (size_t)chunk * L * sizeof(float), &base)) != LSM_OK) return rc;
+    d_pcm[0] = base; d_pcm[1] = (char *)base + (size_t)chunk * L * sizeof(float);
+    if ((rc = lsm_stage_device(ctx, 1, 2 * (size_t)chunk * spk_per, &base)) != LSM_OK) return rc;
+    d_spk[0] = base; d_spk[1] = (char *)base + (size_t)chunk * spk_per;
+    if ((rc = lsm_stage_device(ctx, 2, 2 * (size_t)chunk * feat_per * sizeof(double), &base)) != LSM_OK) return rc;
+    d_feat[0] = base; d_feat[1] = (char *)base + (size_t)chunk * feat_per * sizeof(double);
+    cudaStream_t s_in = ctx->copy_stream[0], s_out = ctx->copy_stream[1], s_k = ctx->stream;
+    // ev[0..1]: H2D of buffer b done; ev[2..3]: kernels on buffer b done; ev[4..5]: D2H of buffer b done
+    for (int c = 0; c < n_chunks; ++c) {
+        const int b = c & 1;
+        const int n = (c + 1) * chunk <= B ? chunk : B - c * chunk;
+        const size_t off = (size_t)c * chunk;
+        if (c >= 2) LSM_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->ev[2 + b], 0));   // kernels of chunk c-2 released d_pcm[b]
+        LSM_CUDA(ctx, cudaMemcpyAsync(d_pcm[b], h_pcm + off * L, (size_t)n * L * sizeof(float), cudaMemcpyHostToDevice, s_in));
+        LSM_CUDA(ctx, cudaEventRecord(ctx->ev[b], s_in));
+        LSM_CUDA(ctx, cudaStreamWaitEvent(s_k, ctx->ev[b], 0));
+        if (c >= 2) LSM_CUDA(ctx, cudaStreamWaitEvent(s_k, ctx->ev[4 + b], 0));    // D2H of chunk c-2 released d_spk/d_feat[b]
+        if ((rc = frontend_launch(ctx, fe, (const float *)d_pcm[b], n, (uint8_t *)d_spk[b], nullptr, s_k)) != LSM_OK) return rc;
+        if ((rc = lsm_launch_reservoir(ctx, res, (const uint8_t *)d_spk[b], n, feature_mask, nan_to_num,
+                                       (double *)d_feat[b], nullptr, s_k)) != LSM_OK) return rc;
+        LSM_CUDA(ctx, cudaEventRecord(ctx->ev[2 + b], s_k));
+        LSM_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->ev[2 + b], 0));
+        LSM_CUDA(ctx, cudaMemcpyAsync(h_features + off * feat_per, d_feat[b], (size_t)n * feat_per * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+        if (h_spikes_or_null)
+            LSM_CUDA(ctx, cudaMemcpyAsync(h_spikes_or_null + off * spk_per, d_spk[b], (size_t)n * spk_per, cudaMemcpyDeviceToHost, s_out));
+        LSM_CUDA(ctx, cudaEventRecord(ctx->ev[4 + b], s_out));
+    }
+    LSM_CUDA(ctx, cudaStreamSynchronize(s_out));
+    LSM_CUDA(ctx, cudaStreamSynchronize(s_k));
+    LSM_CUDA(ctx, cudaStreamSynchronize(s_in));
+    return LSM_OK;
+}
+
+// ------------------------------------------------------------------------------------ density
+namespace {
+__global__ void density_kernel(const uint8_t *__restrict__ x, long long n, unsigned long long *out)
+{
+    unsigned long long s = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n16 = n / 16;
+    const uint4 *x4 = reinterpret_cast<const uint4 *>(x);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const uint4 v = __ldg(x4 + i);
+        // bytes are small counts (0/1 in practice): byte-wise sums via SAD against zero
+        s += __vsadu4(v.x, 0) + __vsadu4(v.y, 0) + __vsadu4(v.z, 0) + __vsadu4(v.w, 0);
+    }
+    for (long long i = n16 * 16 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) s += x[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+}  // namespace
+
+extern "C" int lsm_spike_density(lsm_ctx *ctx, const uint8_t *d_spikes, int64_t n_bytes, int64_t *h_out)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!h_out || n_bytes < 0 || (n_bytes > 0 && !d_spikes)) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_spike_density: bad argument");
+    h_out[0] = 0; h_out[1] = n_bytes;
+    if (n_bytes == 0) return LSM_OK;
+    if (((uintptr_t)d_spikes & 15) != 0) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_spike_density: pointer must be 16-byte aligned");
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *d_sum;
+    int rc;
+    if ((rc = lsm_stage_device(ctx, 4, sizeof(unsigned long long), &d_sum)) != LSM_OK) return rc;
+    LSM_CUDA(ctx, cudaMemsetAsync(d_sum, 0, sizeof(unsigned long long), ctx->stream));
+    density_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_spikes, (long long)n_bytes, (unsigned long long *)d_sum);
+    ctx->launches += 1;
+    LSM_CUDA(ctx, cudaGetLastError());
+    unsigned long long s = 0;
+    LSM_CUDA(ctx, cudaMemcpyAsync(&s, d_sum, sizeof(s), cudaMemcpyDeviceToHost, ctx->stream));
+    LSM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    h_out[0] = (int64_t)s;
+    return LSM_OK;
+}

@@ -1,0 +1,250 @@
+// K1 — gammatone filterbank + dB + min-max + zoom + 4-threshold hysteresis encoder, one kernel.
+//
+// Replaces, per utterance, /root/reference/create_dataset.py:148-158 on the gammatone branch:
+//   gtgram.gtgram(...)                          :51-58   (gammatone==1.0.3: erb_filterbank = 4 cascaded
+//                                                          scipy.signal.lfilter biquads per channel, /gain,
+//                                                          square, sqrt(mean) over 400-sample windows, hop 160)
+//   20*log10(spec+1e-9), floor at max-80         :59-60
+//   per-utterance min-max normalisation          :62-67
+//   scipy.ndimage.zoom(order=1) 98 -> 100 bins   :69-78
+//   convert_spectrogram_to_spikes_hysteresis     :81-98
+//   create_pure_redundancy                       :101-104
+//
+// Mapping: one CTA per utterance in flight (persistent grid, CTAs stride over the batch), one thread
+// per channel.  The IIR recurrences are inherently sequential in the reference's rounding order, so
+// parallelism is (utterance x channel): 128 chains per utterance, thousands of utterances.  The
+// kernel is bound by the fp64 pipe (~35 DADD/DMUL/DFMA per channel-sample), not by HBM: per
+// utterance it reads 64 000 B of PCM and writes 51 200 B of spikes.
+//
+// Bit-exactness: every fp64 operation is an explicit __d*_rn intrinsic in the oracle's order
+// (oracle/lsm_oracle.c gammatone_energy / db_normalise_zoom / hysteresis_encode_f64).
+#include "lsm_common.cuh"
+
+namespace {
+
+constexpr int kChunkBlocks = 8;   // hop-blocks of PCM staged per shared-memory buffer
+
+// x / g with g a per-thread constant: q0 = RN(x*r), e = x - g*q0 (exact, FMA), q = RN(q0 + e*r) is the
+// correctly rounded quotient when r = RN(1/g) (Markstein) as long as nothing underflows; outside a
+// safe exponent window fall back to the IEEE division.  Same value as the oracle's `x / gain`.
+__device__ __forceinline__ double div_by_const(double x, double g, double r)
+{
+    const int ex = (__double2hiint(x) >> 20) & 0x7ff;
+    if (ex - 123u < 1800u) {            // 2^-900 <= |x| < 2^900 (biased exponent in [123, 1922])
+        const double q0 = mul64(x, r);
+        const double e = __fma_rn(-g, q0, x);
+        return __fma_rn(e, r, q0);
+    }
+    return __ddiv_rn(x, g);
+}
+
+struct GtArgs {
+    const float *pcm;       // [B][L]
+    const double *coefs;    // [C][10]
+    const int32_t *zoom_i0; // [nbins]
+    const double *zoom_f;   // [nbins]
+    double *scratch;        // [grid][ncols][C]
+    uint8_t *spikes;        // [B][C*R][nbins*K]
+    double *spec_norm;      // optional [B][C][nbins]
+    int B, L, C, nwin, hop, ncols, nbins, K, R;
+    double thr[8], lower[8];
+};
+
+__global__ void __launch_bounds__(256) gammatone_encode_kernel(const GtArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_x = reinterpret_cast<double *>(smem_raw);            // [2][kChunkBlocks*hop] PCM as fp64
+    __shared__ double s_red[2][8];
+    __shared__ double s_mm[2];
+
+    const int ch = threadIdx.x;
+    const int C = a.C;
+    const bool live = ch < C;
+    const int hop = a.hop, nwin = a.nwin, ncols = a.ncols;
+    const int chunk = kChunkBlocks * hop;
+    const int r_old = nwin - 2 * hop;                 // phases at which window m-2 is still open
+    const int n_used = (ncols - 1) * hop + nwin;      // samples the reference ever reads
+    const int n_blocks = (n_used + hop - 1) / hop;
+    const int n_chunks = (n_blocks + kChunkBlocks - 1) / kChunkBlocks;
+
+    // per-channel constants (scipy.signal.lfilter normalises b and a by a[0] = B0 first)
+    double b0 = 0, b1_0 = 0, b1_1 = 0, b1_2 = 0, b1_3 = 0, a1 = 0, na2 = 0, gain = 1.0, rgain = 1.0;
+    if (live) {
+        const double *c = a.coefs + 10 * ch;
+        const double a0 = c[6];
+        b0 = __ddiv_rn(c[0], a0);
+        b1_0 = __ddiv_rn(c[1], a0); b1_1 = __ddiv_rn(c[2], a0);
+        b1_2 = __ddiv_rn(c[3], a0); b1_3 = __ddiv_rn(c[4], a0);
+        a1 = __ddiv_rn(c[7], a0);
+        na2 = -__ddiv_rn(c[8], a0);
+        gain = c[9];
+        rgain = __ddiv_rn(1.0, gain);
+    }
+    double *plane = a.scratch + (size_t)blockIdx.x * ncols * C;     // this CTA's dB plane [ncols][C]
+
+    for (int utt = blockIdx.x; utt < a.B; utt += gridDim.x) {
+        const float *pcm = a.pcm + (size_t)utt * a.L;
+        double z0_0 = 0, z0_1 = 0, z0_2 = 0, z0_3 = 0, z1_0 = 0, z1_1 = 0, z1_2 = 0, z1_3 = 0;
+        double acc_new = 0, acc_mid = 0, acc_old = 0;
+        double tmax = -INFINITY, tmin = INFINITY;
+
+        // stage chunk 0
+        for (int i = threadIdx.x; i < chunk; i += blockDim.x)
+            s_x[i] = (i < n_used) ? (double)__ldg(pcm + i) : 0.0;
+        __syncthreads();
+
+        for (int ck = 0; ck < n_chunks; ++ck) {
+            const double *xs = s_x + (ck & 1) * chunk;
+            // prefetch the next chunk into the other buffer while this one is filtered
+            if (ck + 1 < n_chunks) {
+                double *xn = s_x + ((ck + 1) & 1) * chunk;
+                const int base = (ck + 1) * chunk;
+                for (int i = threadIdx.x; i < chunk; i += blockDim.x)
+                    xn[i] = (base + i < n_used) ? (double)__ldg(pcm + base + i) : 0.0;
+            }
+            if (live) {
+                for (int bl = 0; bl < kChunkBlocks; ++bl) {
+                    const int m = ck * kChunkBlocks + bl;       // hop-block index = index of the window that starts here
+                    if (m >= n_blocks) break;
+                    const double *xb = xs + bl * hop;
+                    const int n_here = min(hop, n_used - m * hop);
+#pragma unroll 2
+                    for (int p = 0; p < n_here; ++p) {
+                        double x = xb[p];
+                        // four cascaded direct-form-II-transposed biquads (b2 = 0)
+                        double y = add64(z0_0, mul64(b0, x));
+                        z0_0 = sub64(add64(z1_0, mul64(x, b1_0)), mul64(y, a1));
+                        z1_0 = mul64(y, na2);
+                        x = y;
+                        y = add64(z0_1, mul64(b0, x));
+                        z0_1 = sub64(add64(z1_1, mul64(x, b1_1)), mul64(y, a1));
+                        z1_1 = mul64(y, na2);
+                        x = y;
+                        y = add64(z0_2, mul64(b0, x));
+                        z0_2 = sub64(add64(z1_2, mul64(x, b1_2)), mul64(y, a1));
+                        z1_2 = mul64(y, na2);
+                        x = y;
+                        y = add64(z0_3, mul64(b0, x));
+                        z0_3 = sub64(add64(z1_3, mul64(x, b1_3)), mul64(y, a1));
+                        z1_3 = mul64(y, na2);
+                        const double v = div_by_const(y, gain, rgain);
+                        const double e = mul64(v, v);
+                        // window m starts at p == 0 (np.add.reduce starts from the first element)
+                        acc_new = (p == 0) ? e : add64(acc_new, e);
+                        acc_mid = add64(acc_mid, e);
+                        if (p < r_old) {
+                            acc_old = add64(acc_old, e);
+                            if (p == r_old - 1 && m >= 2) {
+                                // window m-2 complete: sqrt(mean) -> dB
+                                const double y2 = __dsqrt_rn(__ddiv_rn(acc_old, (double)nwin));
+                                const double db = mul64(20.0, lsm_log10(add64(y2, 1e-9)));
+                                plane[(size_t)(m - 2) * C + ch] = db;
+                                tmax = fmax(tmax, db);
+                                tmin = fmin(tmin, db);
+                            }
+                        }
+                    }
+                    acc_old = acc_mid;
+                    acc_mid = acc_new;
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- per-utterance max / min of the dB plane (create_dataset.py:60,62-63)
+        {
+            const double wmax = warp_max_f64(tmax), wmin = warp_min_f64(tmin);
+            if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = wmax; s_red[1][threadIdx.x >> 5] = wmin; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double mx = -INFINITY, mn = INFINITY;
+                for (int w = 0; w < (blockDim.x >> 5); ++w) { mx = fmax(mx, s_red[0][w]); mn = fmin(mn, s_red[1][w]); }
+                s_mm[0] = mx; s_mm[1] = mn;
+            }
+            __syncthreads();
+        }
+        const double mx = s_mm[0];
+        const double floor_db = sub64(mx, 80.0);
+        const double mn = fmax(s_mm[1], floor_db);        // min of the clamped plane
+        const bool degenerate = sub64(mx, mn) < 1e-8;      // create_dataset.py:64-65 -> all zeros
+        const double den = add64(sub64(mx, mn), 1e-8);
+
+        if (live) {
+            const int T = a.nbins * a.K;
+            uint8_t *row0 = a.spikes + ((size_t)utt * C * a.R + (size_t)ch * a.R) * T;
+            double *dump = a.spec_norm ? a.spec_norm + ((size_t)utt * C + ch) * a.nbins : nullptr;
+            // normalise in place (own column of the plane only)
+            for (int c = 0; c < ncols; ++c) {
+                const double v = fmax(plane[(size_t)c * C + ch], floor_db);
+                plane[(size_t)c * C + ch] = __ddiv_rn(sub64(v, mn), den);
+            }
+            unsigned on = 0;   // bit k = state of trigger k
+            for (int j = 0; j < a.nbins; ++j) {
+                double v;
+                if (degenerate) v = 0.0;
+                else if (ncols == a.nbins) v = plane[(size_t)j * C + ch];
+                else {
+                    const int i0 = a.zoom_i0[j];
+                    const double f = a.zoom_f[j];
+                    v = mul64(plane[(size_t)i0 * C + ch], sub64(1.0, f));
+                    if (i0 + 1 < ncols) v = add64(v, mul64(plane[(size_t)(i0 + 1) * C + ch], f));
+                }
+                if (dump) dump[j] = v;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (k < a.K) {
+                        const bool is_on = (on >> k) & 1u;
+                        if (!is_on && v > a.thr[k]) on |= (1u << k);
+                        else if (is_on && v < a.lower[k]) on &= ~(1u << k);
+                    }
+                }
+                for (int r = 0; r < a.R; ++r) {
+                    uint8_t *row = row0 + (size_t)r * T + (size_t)j * a.K;
+                    if (a.K == 4) {
+                        // bytes k = 0..3 of column block j, little endian
+                        const unsigned w = (on & 1u) | ((on & 2u) << 7) | ((on & 4u) << 14) | ((on & 8u) << 21);
+                        *reinterpret_cast<uint32_t *>(row) = w;
+                    } else {
+                        for (int k = 0; k < a.K; ++k) row[k] = (on >> k) & 1u;
+                    }
+                }
+            }
+        }
+        __syncthreads();   // plane and s_x are reused by the next utterance
+    }
+}
+
+}  // namespace
+
+int lsm_gammatone_grid(lsm_ctx *ctx, const lsm_frontend_params *p, int *grid)
+{
+    const int threads = ((p->channels + 31) / 32) * 32;
+    const size_t smem = sizeof(double) * 2 * kChunkBlocks * p->hop;
+    if (smem > 48 * 1024)
+        LSM_CUDA(ctx, cudaFuncSetAttribute(gammatone_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gammatone_encode_kernel, threads, smem));
+    if (per_sm < 1) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "gammatone kernel does not fit on an SM (hop %d)", p->hop);
+    *grid = per_sm * ctx->sm_count;   // persistent: every CTA resident, CTAs stride over the batch
+    return LSM_OK;
+}
+
+int lsm_launch_gammatone(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, uint8_t *d_spikes,
+                         double *d_spec_norm, cudaStream_t st)
+{
+    const lsm_frontend_params &p = fe->p;
+    GtArgs a;
+    a.pcm = d_pcm; a.coefs = fe->d_coefs; a.zoom_i0 = fe->d_zoom_i0; a.zoom_f = fe->d_zoom_f;
+    a.scratch = fe->d_scratch; a.spikes = d_spikes; a.spec_norm = d_spec_norm;
+    a.B = B; a.L = p.n_samples; a.C = p.channels; a.nwin = p.nwin; a.hop = p.hop; a.ncols = fe->ncols;
+    a.nbins = p.n_bins; a.K = p.n_thresholds; a.R = p.redundancy;
+    for (int k = 0; k < 8; ++k) { a.thr[k] = p.thresholds_desc[k]; a.lower[k] = p.lower_bounds[k]; }
+    const int threads = ((p.channels + 31) / 32) * 32;
+    const size_t smem = sizeof(double) * 2 * kChunkBlocks * p.hop;
+    const int grid = B < fe->grid ? B : fe->grid;
+    if (grid <= 0) return LSM_OK;
+    gammatone_encode_kernel<<<grid, threads, smem, st>>>(a);
+    ctx->launches += 1;
+    LSM_CUDA(ctx, cudaGetLastError());
+    return LSM_OK;
+}

@@ -1,0 +1,149 @@
+// Internal declarations shared by the sm_100a translation units of liblsmb200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "lsm_b200.h"
+
+struct lsm_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;   // created by the ctx
+    cudaStream_t stream = nullptr;       // where work goes (own_stream or the caller's)
+    cudaStream_t copy_stream[2] = {nullptr, nullptr};  // pipeline_run_host: H2D / D2H legs
+    cudaEvent_t ev[8] = {};
+    int64_t launches = 0;
+    char err[512] = {0};
+    // staging owned by the ctx for the *_host entry points (grown on demand)
+    void *d_stage[6] = {};
+    size_t d_stage_bytes[6] = {};
+    void *h_pin[4] = {};
+    size_t h_pin_bytes[4] = {};
+};
+
+struct lsm_frontend {
+    lsm_frontend_params p;
+    int ncols = 0;                 // spectrogram columns before zoom (98 gammatone / 101 mel)
+    double *d_coefs = nullptr;     // gammatone: [C][10] design rows
+    int32_t *d_zoom_i0 = nullptr;  // [n_bins]
+    double *d_zoom_f = nullptr;    // [n_bins]
+    double *d_scratch = nullptr;   // per-CTA [ncols][C] dB plane (stays in L2)
+    int grid = 0;
+    // mel
+    float *d_mel_w = nullptr;      // packed non-zero mel weights
+    int32_t *d_mel_lo = nullptr;   // [C] first non-zero bin
+    int32_t *d_mel_n = nullptr;    // [C] number of non-zero bins
+    int32_t *d_mel_off = nullptr;  // [C] offset into d_mel_w
+    double *d_window = nullptr;    // [n_fft] periodic hann
+    double2 *d_twiddle = nullptr;  // [n_fft/2]
+};
+
+struct lsm_reservoir {
+    lsm_reservoir_params p;
+    int n_pad = 0;                 // row pitch of the dense weight plane (multiple of 32)
+    int32_t *d_wt = nullptr;       // dense [N][n_pad]: row = PRESYNAPTIC j, column = postsynaptic i
+    int32_t *d_in_rowptr = nullptr, *d_in_col = nullptr;
+    double *d_in_val = nullptr;
+    double *d_leak = nullptr;
+    int32_t *d_out_slot = nullptr; // [N] position in the output list or -1
+    int max_in_per_neuron = 0;
+};
+
+#define LSM_FAIL(ctx, code, ...)                                  \
+    do {                                                          \
+        snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__);    \
+        return (code);                                            \
+    } while (0)
+
+#define LSM_CUDA(ctx, call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            LSM_FAIL(ctx, LSM_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,          \
+                     cudaGetErrorString(e_));                                                 \
+    } while (0)
+
+// grow-only device / pinned staging buffers owned by the ctx
+int lsm_stage_device(lsm_ctx *ctx, int slot, size_t bytes, void **out);
+int lsm_stage_pinned(lsm_ctx *ctx, int slot, size_t bytes, void **out);
+
+// stage launchers (no host sync)
+int lsm_launch_gammatone(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, uint8_t *d_spikes,
+                         double *d_spec_norm, cudaStream_t st);
+int lsm_gammatone_grid(lsm_ctx *ctx, const lsm_frontend_params *p, int *grid);
+int lsm_launch_mel(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, uint8_t *d_spikes,
+                   double *d_spec_norm, cudaStream_t st);
+int lsm_launch_reservoir(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int B,
+                         uint32_t feature_mask, int nan_to_num, double *d_features, uint8_t *d_raster,
+                         cudaStream_t st);
+int lsm_mel_create(lsm_ctx *ctx, lsm_frontend *fe, const float *h_basis);
+void lsm_mel_destroy(lsm_frontend *fe);
+
+// ---------------------------------------------------------------------------------------------
+// fp64 helpers: every value-producing operation is an explicit round-to-nearest intrinsic, so
+// nvcc can neither contract a*b+c into an FMA nor re-associate.  The CPU oracle performs the
+// same IEEE-754 operations in the same order (oracle/lsm_oracle.c, -ffp-contract=off).
+__device__ __forceinline__ double mul64(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add64(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub64(double a, double b) { return __dsub_rn(a, b); }
+
+// Deterministic log10 for finite x > 0: fdlibm e_log.c kernel + FreeBSD e_log10.c recombination,
+// operation for operation the same as oracle_log10() in oracle/lsm_oracle.c.
+__device__ __forceinline__ double lsm_log10(double x)
+{
+    const double LG1 = 6.666666666666735130e-01, LG2 = 3.999999999940941908e-01,
+                 LG3 = 2.857142874366239149e-01, LG4 = 2.222219843214978396e-01,
+                 LG5 = 1.818357216161805012e-01, LG6 = 1.531383769920937332e-01,
+                 LG7 = 1.479819860511658591e-01;
+    const double IVLN10HI = 4.34294481878168880939e-01, IVLN10LO = 2.50829467116452752298e-11,
+                 LOG10_2HI = 3.01029995663611771306e-01, LOG10_2LO = 3.69423907715893078616e-13;
+    int hx = __double2hiint(x);
+    int lx = __double2loint(x);
+    int k = 0;
+    if (hx < 0x00100000) {
+        x = mul64(x, 18014398509481984.0);
+        hx = __double2hiint(x);
+        lx = __double2loint(x);
+        k -= 54;
+    }
+    k += (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    int i = (hx + 0x95f64) & 0x100000;
+    x = __hiloint2double(hx | (i ^ 0x3ff00000), lx);
+    k += (i >> 20);
+    double f = sub64(x, 1.0);
+    double hfsq = mul64(mul64(0.5, f), f);
+    double s = __ddiv_rn(f, add64(2.0, f));
+    double z = mul64(s, s);
+    double w = mul64(z, z);
+    double t1 = mul64(w, add64(LG2, mul64(w, add64(LG4, mul64(w, LG6)))));
+    double t2 = mul64(z, add64(LG1, mul64(w, add64(LG3, mul64(w, add64(LG5, mul64(w, LG7)))))));
+    double R = add64(t2, t1);
+    double hi = sub64(f, hfsq);
+    hi = __hiloint2double(__double2hiint(hi), 0);
+    double lo = add64(sub64(sub64(f, hi), hfsq), mul64(s, add64(hfsq, R)));
+    double val_hi = mul64(hi, IVLN10HI);
+    double dk = (double)k;
+    double y2 = mul64(dk, LOG10_2HI);
+    double val_lo = add64(add64(mul64(dk, LOG10_2LO), mul64(add64(lo, hi), IVLN10LO)), mul64(lo, IVLN10HI));
+    double ww = add64(y2, val_hi);
+    val_lo = add64(val_lo, add64(sub64(y2, ww), val_hi));
+    val_hi = ww;
+    return add64(val_lo, val_hi);
+}
+
+__device__ __forceinline__ double warp_max_f64(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min_f64(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}

@@ -1,0 +1,108 @@
+"""Utterance-sharded data parallelism: one process per GPU, no data-path collective except one
+all-gather of the raw feature rows.
+
+Every utterance is independent in both stages (/root/reference/create_dataset.py:143-162,
+extract_lsm_features.py:78-87 with reset() per sample at :79) and the reservoir is read-only
+(:188), so ranks take contiguous blocks of the sample order, padded to equal length, and the
+result is bit-identical for any world size.  Works under torchrun with NCCL on GPUs and, for the
+CPU test-suite, with gloo (the compute callback is injected there).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist
+    except Exception:
+        pass
+    return None
+
+
+def world():
+    d = _dist()
+    return (d.get_rank(), d.get_world_size()) if d else (0, 1)
+
+
+def is_main() -> bool:
+    return world()[0] == 0
+
+
+def shard_bounds(n: int, rank: int, world_size: int):
+    """Contiguous block [lo, hi) of rank `rank`; blocks are ceil(n/world) long, the tail ranks short/empty."""
+    per = -(-n // world_size) if n else 0
+    lo = min(n, rank * per)
+    hi = min(n, lo + per)
+    return lo, hi, per
+
+
+def all_gather_rows(local: np.ndarray, n_total: int, per: int, device=None) -> np.ndarray:
+    """All-gather equal-length (padded) row blocks and trim to n_total rows.  NCCL if the process
+    group is NCCL (rows go through the GPU), gloo otherwise."""
+    d = _dist()
+    if d is None:
+        return local[:n_total]
+    import torch
+    rank, ws = world()
+    backend = d.get_backend()
+    width = local.shape[1]
+    pad = np.zeros((per, width), dtype=local.dtype)
+    pad[:len(local)] = local
+    t = torch.from_numpy(pad)
+    if backend == "nccl":
+        t = t.cuda(device if device is not None else torch.cuda.current_device())
+    out = torch.empty((ws * per, width), dtype=t.dtype, device=t.device)
+    d.all_gather_into_tensor(out, t)
+    return out.cpu().numpy()[:n_total]
+
+
+def sharded_features(lsm, spike_data: np.ndarray, feature_keys, compute=None) -> np.ndarray:
+    """Each rank simulates its block; every rank returns the full [S, F] matrix in sample order."""
+    rank, ws = world()
+    n = len(spike_data)
+    lo, hi, per = shard_bounds(n, rank, ws)
+    if compute is None:
+        def compute(block):
+            return lsm.simulate_batch(block, feature_keys, nan_to_num=True)
+    width = len(feature_keys) * lsm.num_output_neurons
+    local = compute(spike_data[lo:hi]) if hi > lo else np.zeros((0, width))
+    local = np.ascontiguousarray(local, dtype=np.float64)
+    if ws == 1:
+        return local
+    return all_gather_rows(local, n, per, getattr(getattr(lsm, "ctx", None), "device", None))
+
+
+def sharded_spikes(frontend, pcm: np.ndarray, compute=None) -> np.ndarray:
+    """Stage 1 under the same sharding: uint8 spike trains for all S utterances on every rank."""
+    rank, ws = world()
+    n = len(pcm)
+    lo, hi, per = shard_bounds(n, rank, ws)
+    if compute is None:
+        compute = frontend.encode
+    rows, steps = frontend.rows, frontend.steps
+    local = compute(pcm[lo:hi]) if hi > lo else np.zeros((0, rows, steps), np.uint8)
+    if ws == 1:
+        return local
+    flat = all_gather_rows(np.ascontiguousarray(local).reshape(len(local), rows * steps), n, per,
+                           getattr(getattr(frontend, "ctx", None), "device", None))
+    return flat.reshape(n, rows, steps)
+
+
+def init_from_env():
+    """Initialise torch.distributed from torchrun's environment (no-op without it). Returns (rank, world, local_rank)."""
+    import os
+    if "RANK" not in os.environ or int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return 0, 1, int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not dist.is_initialized():
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group("gloo")
+    return dist.get_rank(), dist.get_world_size(), local_rank

@@ -1,0 +1,173 @@
+"""Stage 2 of the pipeline: spike-train dataset -> LSM features -> lsm_features_larger.npz.
+
+Same call surface as /root/reference/extract_lsm_features.py (constants :10-16, FEATURE_SETS :19-28,
+calculate_theoretical_w_critico :33-60, load_spike_dataset :63-73, extract_all_features :76-89,
+run_network_diagnostics :92-152, main :155-214, flags :219-221), but each per-sample loop is one
+batched kernel launch on the B200, and with --gpus/torchrun the samples shard across ranks with a
+single all-gather of the raw feature rows.
+"""
+from __future__ import annotations
+
+import argparse
+from pathlib import Path
+
+import numpy as np
+
+from .snn import SNN, SimulationParams
+
+NUM_NEURONS = 1000
+NUM_OUTPUT_NEURONS = 400
+LEAK_COEFFICIENT = 1 / 100
+REFRACTORY_PERIOD = 2
+MEMBRANE_THRESHOLD = 2.0
+SMALL_WORLD_P = 0.1
+SMALL_WORLD_K = int(0.10 * NUM_NEURONS * 2)
+
+FEATURE_SETS = {
+    'all': ['spike_counts', 'spike_variances', 'mean_spike_times', 'first_spike_times',
+            'last_spike_times', 'mean_isi', 'isi_variances', 'burst_counts'],
+    'rate': ['spike_counts', 'spike_variances', 'burst_counts'],
+    'timing': ['mean_spike_times', 'first_spike_times', 'last_spike_times'],
+    'rhythm': ['mean_isi', 'isi_variances'],
+    'original': ['spike_counts', 'spike_variances', 'mean_spike_times', 'mean_isi', 'isi_variances'],
+}
+
+SPIKE_FILE = "speech_spike_dataset_pure_redundancy.npz"
+FEATURE_FILE = "lsm_features_larger.npz"
+
+np.random.seed(42)
+
+
+def calculate_theoretical_w_critico(lsm_params, input_data, verbose: bool = True):
+    """Mean-field critical weight (reference :33-60): w = (theta - 2*avg_I*R) / (k/2) with avg_I the
+    input spike density over the first <= 500 samples.  Exact integer sums; 0.007 fallbacks kept."""
+    num_samples = min(500, len(input_data))
+    head = np.asarray(input_data[:num_samples])
+    total_spikes = int(head.sum(dtype=np.int64)) if head.size else 0
+    total_elements = int(head.size)
+    if total_elements == 0:
+        return 0.007
+    avg_I = total_spikes / total_elements
+    beta = lsm_params.small_world_graph_k / 2
+    if beta == 0:
+        return 0.007
+    w_critico = (lsm_params.membrane_threshold - 2 * avg_I * lsm_params.refractory_period) / beta
+    if verbose:
+        print(f"Theoretical w_critico: {w_critico:.8f}")
+    return w_critico
+
+
+def load_spike_dataset(filename=SPIKE_FILE):
+    if not Path(filename).exists():
+        print(f"Error: Dataset not found at '{filename}'")
+        return None, None
+    data = np.load(filename)
+    X_spikes, y_labels = data['X_spikes'], data['y_labels']
+    print(f"Loaded {len(X_spikes)} samples from '{filename}'")
+    return X_spikes, y_labels
+
+
+def extract_all_features(lsm: SNN, spike_data, feature_keys, desc: str = ""):
+    """reference :76-89 for the whole array at once -> float64[S, len(keys)*N_out], NaNs zeroed."""
+    spike_data = np.asarray(spike_data, dtype=np.uint8)
+    if len(spike_data) == 0:
+        return np.zeros((0, len(feature_keys) * lsm.num_output_neurons))
+    from .distributed import sharded_features
+    return sharded_features(lsm, spike_data, list(feature_keys))
+
+
+def run_network_diagnostics(lsm: SNN, X_sample_batch):
+    """reference :92-152: participation / dead neurons / mean activity on the first 5 samples."""
+    print("\n" + "=" * 40)
+    print("RUNNING NETWORK DIAGNOSTICS")
+    print("=" * 40)
+    subset = np.asarray(X_sample_batch[:5], dtype=np.uint8)
+    if len(subset) == 0:
+        return None
+    _, raster = lsm.simulate_batch(subset, ['spike_counts'], return_raster=True)
+    total = lsm.num_neurons
+    rates = []
+    for i, spikes in enumerate(raster):
+        per_neuron = spikes.sum(axis=0, dtype=np.int64)
+        active = int(np.count_nonzero(per_neuron))
+        part = active / total * 100
+        rates.append(part)
+        print(f"Sample {i + 1}: Active: {part:.1f}% | Dead: {total - active} | Avg Spikes/Neuron: {per_neuron.mean():.2f}")
+    avg_part = float(np.mean(rates))
+    print("-" * 40)
+    print("DIAGNOSTIC RESULT:")
+    print(f"   Average Participation: {avg_part:.1f}%")
+    if avg_part < 40:
+        print("   STATUS: SUB-CRITICAL (Too Silent)")
+        print("   Recommendation: INCREASE multiplier or DECREASE threshold.")
+    elif avg_part > 98:
+        print("   STATUS: SUPER-CRITICAL (Epileptic/Saturated)")
+        print("   Recommendation: DECREASE multiplier.")
+    else:
+        print("   STATUS: EDGE OF CHAOS (Healthy)")
+        print("   (Ideal is 80-95% participation with low firing rates)")
+    print("=" * 40 + "\n")
+    return avg_part
+
+
+def build_lsm(X_train, multiplier: float, leak_variance_divisor=None, num_neurons: int = NUM_NEURONS, verbose=True) -> SNN:
+    """reference :164-188: parameter record, w_critico, weight, then the one reservoir."""
+    k = int(0.10 * num_neurons * 2)
+    base_params = SimulationParams(
+        num_neurons=num_neurons, mean_weight=0.0, num_output_neurons=NUM_OUTPUT_NEURONS,
+        membrane_threshold=MEMBRANE_THRESHOLD, leak_coefficient=LEAK_COEFFICIENT,
+        refractory_period=REFRACTORY_PERIOD, small_world_graph_p=SMALL_WORLD_P, small_world_graph_k=k,
+        input_spike_times=X_train[0], leak_variance_divisor=leak_variance_divisor)
+    w = calculate_theoretical_w_critico(base_params, X_train, verbose=verbose)
+    optimal_weight = w * multiplier
+    if verbose:
+        print(f"Using weight: {optimal_weight:.8f} (multiplier: {multiplier:.2f})")
+        if leak_variance_divisor:
+            print(f"Using Heterogeneous Leak. Divisor: {leak_variance_divisor}")
+    base_params.mean_weight = optimal_weight
+    base_params.weight_variance = 10
+    return SNN(simulation_params=base_params)
+
+
+def main(feature_set: str, multiplier: float, leak_variance_divisor: float = None, num_neurons: int = NUM_NEURONS):
+    from sklearn.model_selection import train_test_split
+    from sklearn.preprocessing import StandardScaler
+    from .distributed import is_main
+
+    X_spikes, y_labels = load_spike_dataset()
+    if X_spikes is None:
+        return
+    X_train, X_test, y_train, y_test = train_test_split(
+        X_spikes, y_labels, test_size=0.2, random_state=42, stratify=y_labels)
+    lsm = build_lsm(X_train, multiplier, leak_variance_divisor, num_neurons, verbose=is_main())
+    if is_main():
+        run_network_diagnostics(lsm, X_train)
+    feature_keys = FEATURE_SETS[feature_set]
+    if is_main():
+        print(f"Extracting feature set: '{feature_set}'")
+    X_train_feat = extract_all_features(lsm, X_train, feature_keys, "Training")
+    X_test_feat = extract_all_features(lsm, X_test, feature_keys, "Testing")
+    if not is_main():
+        return
+    scaler = StandardScaler()
+    X_train_scaled = scaler.fit_transform(X_train_feat)
+    X_test_scaled = scaler.transform(X_test_feat)
+    np.savez_compressed(FEATURE_FILE, X_train_features=X_train_scaled, y_train=y_train,
+                        X_test_features=X_test_scaled, y_test=y_test, feature_set=feature_set,
+                        leak_variance_divisor=leak_variance_divisor)
+    print(f"Extraction complete. Features saved to '{FEATURE_FILE}'")
+
+
+def _cli(argv=None):
+    parser = argparse.ArgumentParser(description="Extract features from a spike train dataset using an LSM.")
+    parser.add_argument("--feature-set", type=str, default="original", choices=FEATURE_SETS.keys())
+    parser.add_argument("--multiplier", type=float, default=0.6)
+    parser.add_argument("--leak-variance-divisor", type=float, default=None)
+    parser.add_argument("--n-neurons", type=int, default=NUM_NEURONS, help="(extension) reservoir size; k = 0.2*N")
+    args = parser.parse_args(argv)
+    main(feature_set=args.feature_set, multiplier=args.multiplier, leak_variance_divisor=args.leak_variance_divisor,
+         num_neurons=args.n_neurons)
+
+
+if __name__ == "__main__":
+    _cli()

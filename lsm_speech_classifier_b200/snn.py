@@ -1,0 +1,182 @@
+"""Stage 2+3 host side: the liquid state machine on the GPU (K2 + K3).
+
+`SNN` honours the object protocol the reference uses from the un-vendored ``snnpy.snn``
+(/root/reference/extract_lsm_features.py):
+
+    lsm = SNN(simulation_params=base_params)                  # :188
+    lsm.reset(); lsm.set_input_spike_times(sample); lsm.simulate()          # :79-81, :109-111
+    feature_dict = lsm.extract_features_from_spikes()         # :83
+    lsm.num_neurons, lsm.spike_matrix (Time x Neurons)        # :100, :115-116
+
+so the reference's `extract_all_features` / `run_network_diagnostics` loops run against it
+unchanged (tests/test_gpu_parity.py does exactly that), plus the batched calls the fast path uses:
+
+    lsm.simulate_batch(spikes[B,C,T], feature_keys) -> features[B,F]      one kernel for the whole batch
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .reservoir import ReservoirDef, SimulationParams, build_reservoir  # noqa: F401  (re-exported)
+
+FEATURE_KEYS = _lib.FEATURE_KEYS
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class SNN:
+    def __init__(self, simulation_params: SimulationParams | None = None, reservoir: ReservoirDef | None = None,
+                 ctx: _lib.Context | None = None, device: int | None = None):
+        if reservoir is None:
+            if simulation_params is None:
+                raise ValueError("SNN needs simulation_params or a prebuilt ReservoirDef")
+            reservoir = build_reservoir(simulation_params)
+        self.params = simulation_params
+        self.reservoir = r = reservoir
+        self.ctx = ctx or _lib.context(device)
+        self.num_neurons = r.num_neurons
+        self.num_output_neurons = len(r.out_idx)
+        p = _lib.ReservoirParams()
+        p.num_neurons, p.num_inputs, p.num_steps = r.num_neurons, r.num_inputs, r.num_steps
+        p.refractory, p.w_shift, p.n_out, p.theta = r.refractory, r.w_shift, len(r.out_idx), r.theta
+        self._p = p
+        arrs = [_lib.as_host(r.w_rowptr, np.int32), _lib.as_host(r.w_col, np.int32), _lib.as_host(r.w_q, np.int32),
+                _lib.as_host(r.in_rowptr, np.int32), _lib.as_host(r.in_col, np.int32), _lib.as_host(r.in_val, np.float64),
+                _lib.as_host(r.leak, np.float64), _lib.as_host(r.out_idx, np.int32)]
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.lsm_reservoir_create(self.ctx.h, C.byref(p), *[_lib._np_ptr(a) for a in arrs], C.byref(h)))
+        self.h = h
+        self._sample = None
+        self.spike_matrix = None
+        self._stats = None
+
+    # ------------------------------------------------------------------ batched fast path
+    def simulate_batch(self, spikes, feature_keys=None, nan_to_num: bool = True, return_raster: bool = False):
+        """spikes uint8[B, C, T] -> raw (un-standardised) features float64[B, len(keys)*N_out],
+        key-major like extract_lsm_features.py:85-87.  torch CUDA in -> torch CUDA out (async);
+        numpy in -> numpy out."""
+        keys = list(FEATURE_KEYS if feature_keys is None else feature_keys)
+        mask = _lib.feature_mask(keys)
+        order = _lib.mask_keys(mask)
+        r = self.reservoir
+        n_out = self.num_output_neurons
+        if _is_torch(spikes):
+            import torch
+            if not spikes.is_cuda:
+                raise _lib.LsmError("simulate_batch(torch tensor) needs a CUDA tensor; pass numpy for host buffers")
+            spikes = spikes.contiguous()
+            if spikes.dtype != torch.uint8 or spikes.dim() != 3 or tuple(spikes.shape[1:]) != (r.num_inputs, r.num_steps):
+                raise ValueError(f"spikes must be uint8[B,{r.num_inputs},{r.num_steps}]")
+            B = spikes.shape[0]
+            feats = torch.empty((B, len(order) * n_out), dtype=torch.float64, device=spikes.device)
+            raster = torch.empty((B, r.num_steps, r.num_neurons), dtype=torch.uint8, device=spikes.device) if return_raster else None
+            self.ctx.set_stream(torch.cuda.current_stream(spikes.device).cuda_stream)
+            self.ctx.check(self.ctx.lib.lsm_reservoir_run(
+                self.ctx.h, self.h, C.c_void_p(spikes.data_ptr()), B, mask, int(nan_to_num), C.c_void_p(feats.data_ptr()),
+                C.c_void_p(raster.data_ptr()) if raster is not None else None))
+            feats = self._reorder(feats, order, keys, n_out)
+            return (feats, raster) if return_raster else feats
+        spikes = _lib.as_host(spikes, np.uint8)
+        if spikes.ndim != 3 or spikes.shape[1:] != (r.num_inputs, r.num_steps):
+            raise ValueError(f"spikes must be uint8[B,{r.num_inputs},{r.num_steps}]")
+        B = spikes.shape[0]
+        feats = np.empty((B, len(order) * n_out), dtype=np.float64)
+        raster = np.empty((B, r.num_steps, r.num_neurons), dtype=np.uint8) if return_raster else None
+        self.ctx.set_stream(None)
+        self.ctx.check(self.ctx.lib.lsm_reservoir_run_host(
+            self.ctx.h, self.h, _lib._np_ptr(spikes), B, mask, int(nan_to_num), _lib._np_ptr(feats), _lib._np_ptr(raster)))
+        feats = self._reorder(feats, order, keys, n_out)
+        return (feats, raster) if return_raster else feats
+
+    @staticmethod
+    def _reorder(feats, order, keys, n_out):
+        """The kernel emits keys in bit order; FEATURE_SETS lists are already in that order, but honour any."""
+        if order == keys:
+            return feats
+        idx = np.concatenate([np.arange(order.index(k) * n_out, (order.index(k) + 1) * n_out) for k in keys])
+        if _is_torch(feats):
+            import torch
+            return feats[:, torch.as_tensor(idx, device=feats.device)]
+        return feats[:, idx]
+
+    # ------------------------------------------------------------------ per-sample protocol (snnpy)
+    def reset(self):
+        self.spike_matrix = None
+        self._stats = None
+
+    def set_input_spike_times(self, sample):
+        self._sample = _lib.as_host(sample, np.uint8)
+
+    def simulate(self):
+        if self._sample is None:
+            raise _lib.LsmError("simulate() before set_input_spike_times()")
+        feats, raster = self.simulate_batch(self._sample[None], FEATURE_KEYS, nan_to_num=False, return_raster=True)
+        self.spike_matrix = raster[0]
+        self._stats = feats[0].reshape(len(FEATURE_KEYS), self.num_output_neurons)
+
+    def extract_features_from_spikes(self):
+        if self._stats is None:
+            raise _lib.LsmError("extract_features_from_spikes() before simulate()")
+        return {k: self._stats[i].copy() for i, k in enumerate(FEATURE_KEYS)}
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.lsm_reservoir_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class AudioToFeatures:
+    """The whole hot path behind one call: PCM -> raw LSM features."""
+
+    def __init__(self, frontend, snn: SNN):
+        if frontend.ctx is not snn.ctx:
+            raise ValueError("front end and reservoir must share a context (same device)")
+        self.frontend, self.snn, self.ctx = frontend, snn, snn.ctx
+
+    def run_host(self, pcm: np.ndarray, feature_keys, nan_to_num: bool = True, out: np.ndarray | None = None,
+                 spikes_out: np.ndarray | None = None):
+        """Host buffers in, host buffers out; copies are chunked and overlapped with the kernels
+        inside the library (lsm_pipeline_run_host).  `pcm` should be pinned for full overlap."""
+        keys = list(feature_keys)
+        mask = _lib.feature_mask(keys)
+        if _lib.mask_keys(mask) != keys:
+            raise ValueError("feature keys must be in FEATURE_SETS order")
+        B = pcm.shape[0]
+        F = len(keys) * self.snn.num_output_neurons
+        if out is None:
+            out = np.empty((B, F), dtype=np.float64)
+        self.ctx.set_stream(None)
+        self.ctx.check(self.ctx.lib.lsm_pipeline_run_host(
+            self.ctx.h, self.frontend.h, self.snn.h, C.c_void_p(pcm.ctypes.data), B, mask, int(nan_to_num),
+            C.c_void_p(out.ctypes.data), C.c_void_p(spikes_out.ctypes.data) if spikes_out is not None else None))
+        return out
+
+    def run(self, pcm, feature_keys, nan_to_num: bool = True, spikes=None, out=None):
+        """torch CUDA tensors, asynchronous on the current stream."""
+        import torch
+        keys = list(feature_keys)
+        mask = _lib.feature_mask(keys)
+        if _lib.mask_keys(mask) != keys:
+            raise ValueError("feature keys must be in FEATURE_SETS order")
+        B = pcm.shape[0]
+        fe = self.frontend
+        if spikes is None:
+            spikes = torch.empty((B, fe.rows, fe.steps), dtype=torch.uint8, device=pcm.device)
+        if out is None:
+            out = torch.empty((B, len(keys) * self.snn.num_output_neurons), dtype=torch.float64, device=pcm.device)
+        self.ctx.set_stream(torch.cuda.current_stream(pcm.device).cuda_stream)
+        self.ctx.check(self.ctx.lib.lsm_pipeline_run(
+            self.ctx.h, fe.h, self.snn.h, C.c_void_p(pcm.data_ptr()), B, mask, int(nan_to_num),
+            C.c_void_p(spikes.data_ptr()), C.c_void_p(out.data_ptr())))
+        return out, spikes

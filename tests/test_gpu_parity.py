@@ -1,0 +1,197 @@
+"""GPU: the CUDA path, through the C ABI, against the CPU oracle on the same inputs.
+Bar: spike trains, rasters and features bit-exact (integer/byte outputs and fp64 in the oracle's
+rounding order)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+THR = [0.70, 0.80, 0.90, 0.95]
+GAP = 0.1
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from lsm_speech_classifier_b200 import _lib
+    return _lib.context(0)
+
+
+@pytest.fixture(scope="module")
+def small_set():
+    from lsm_speech_classifier_b200 import synth
+    pcm, labels = synth.synth_dataset(4, 6)
+    extra = np.stack([np.zeros(16000, np.float32),                                   # silent -> all-zero train
+                      np.concatenate([pcm[5][3000:9000], np.zeros(10000, np.float32)]),  # zero padded: denormal tails
+                      np.full(16000, 0.25, np.float32),                              # DC
+                      (np.random.default_rng(5).standard_normal(16000) * 1e-3).astype(np.float32)])
+    return np.concatenate([pcm, extra]), labels
+
+
+def oracle_spikes(pcm, fe, want_spec=False):
+    from oracle import coracle
+    return coracle.gammatone_encode(pcm, fe.table, fe.params.nwin, fe.params.hop, fe.time_bins, fe.zoom_i0, fe.zoom_f,
+                                    THR, GAP, redundancy=fe.redundancy, want_spec=want_spec)
+
+
+def test_gammatone_spikes_and_spectrogram_bit_exact(env, small_set):
+    import torch
+    from lsm_speech_classifier_b200.frontend import Frontend
+    pcm, _ = small_set
+    fe = Frontend(128, "gammatone")
+    want, want_spec = oracle_spikes(pcm, fe, want_spec=True)
+    got, spec = fe.encode(torch.from_numpy(pcm).cuda(), return_spectrogram=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(spec.cpu().numpy(), want_spec)          # fp64, every bit
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert got[24].sum() == 0                                     # silent clip
+    # host-buffer entry point gives the same bytes
+    assert np.array_equal(fe.encode(pcm), want)
+    # ragged / tiny / empty batches
+    assert np.array_equal(fe.encode(pcm[:1]), want[:1])
+    assert fe.encode(pcm[:0]).shape == (0, 128, 400)
+
+
+def test_gammatone_golden_vectors(env, golden):
+    from lsm_speech_classifier_b200.frontend import Frontend
+    g = golden("frontend_gammatone.npz")
+    fe = Frontend(128, "gammatone")
+    # filter with the golden design table so the comparison does not depend on this host's libm
+    import ctypes as C
+    from lsm_speech_classifier_b200 import _lib
+    fe.close()
+    fe.table = np.ascontiguousarray(g["coefs"])
+    h = C.c_void_p()
+    fe.ctx.check(fe.ctx.lib.lsm_frontend_create(fe.ctx.h, C.byref(fe.params), _lib._np_ptr(fe.table),
+                                                _lib._np_ptr(fe.zoom_i0), _lib._np_ptr(fe.zoom_f), C.byref(h)))
+    fe.h = h
+    want = np.unpackbits(g["spikes_packed"], axis=-1)[:, :, :400]
+    got, spec = fe.encode(g["pcm"], return_spectrogram=True)
+    assert np.array_equal(got, want)
+    np.testing.assert_allclose(spec[:2], g["spec_norm"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("n_filters,redundancy", [(64, 1), (128, 2), (256, 1), (40, 3)])
+def test_gammatone_other_shapes(env, small_set, n_filters, redundancy):
+    from lsm_speech_classifier_b200.frontend import Frontend
+    pcm, _ = small_set
+    fe = Frontend(n_filters, "gammatone", redundancy=redundancy)
+    want = oracle_spikes(pcm[:9], fe)
+    assert np.array_equal(fe.encode(pcm[:9]), want)
+
+
+def build_snn(X, mult=0.6, **kw):
+    from lsm_speech_classifier_b200.snn import SNN, SimulationParams
+    from oracle import pyref
+    k = kw.get("small_world_graph_k", 200)
+    wc = pyref.w_critico(k, 2.0, 2, list(X))
+    return SNN(SimulationParams(mean_weight=wc * mult, input_spike_times=X[0], **kw))
+
+
+def test_reservoir_raster_and_features_bit_exact(env, small_set):
+    from lsm_speech_classifier_b200.frontend import Frontend
+    from oracle import coracle
+    pcm, _ = small_set
+    X = Frontend(128, "gammatone").encode(pcm)
+    for kw in (dict(), dict(leak_variance_divisor=4.0),
+               dict(num_neurons=256, small_world_graph_k=50, num_output_neurons=100),
+               dict(num_neurons=2500, small_world_graph_k=500, num_output_neurons=400)):
+        lsm = build_snn(X, **kw)
+        want_f, want_r = coracle.reservoir_run(lsm.reservoir, X, 0xFF, False, True)
+        got_f, got_r = lsm.simulate_batch(X, nan_to_num=False, return_raster=True)
+        assert np.array_equal(got_r, want_r), kw
+        assert np.array_equal(got_f, want_f, equal_nan=True), kw
+        assert want_r.sum() > 0
+
+
+def test_reservoir_golden_raster(env, golden):
+    from lsm_speech_classifier_b200.snn import SNN, SimulationParams
+    g = golden("reservoir.npz")
+    X = np.unpackbits(golden("frontend_gammatone.npz")["spikes_packed"], axis=-1)[:, :, :400]
+    lsm = SNN(SimulationParams(mean_weight=float(g["n1000_mean_weight"]), input_spike_times=X[0]))
+    feats, raster = lsm.simulate_batch(X[list(g["utt_index"])], nan_to_num=False, return_raster=True)
+    assert np.array_equal(raster, np.unpackbits(g["n1000_raster_packed"], axis=-1)[:, :, :1000])
+    assert np.array_equal(feats, g["n1000_features"], equal_nan=True)
+
+
+def test_feature_sets_and_nan_to_num(env, small_set):
+    from lsm_speech_classifier_b200.extract_lsm_features import FEATURE_SETS
+    from lsm_speech_classifier_b200.frontend import Frontend
+    from oracle import coracle
+    from lsm_speech_classifier_b200 import _lib
+    pcm, _ = small_set
+    X = Frontend(128, "gammatone").encode(pcm[:10])
+    lsm = build_snn(X)
+    for name, keys in FEATURE_SETS.items():
+        want, _ = coracle.reservoir_run(lsm.reservoir, X, _lib.feature_mask(keys), True, False)
+        got = lsm.simulate_batch(X, keys, nan_to_num=True)
+        assert got.shape == (10, len(keys) * 400)
+        assert np.array_equal(got, want), name
+
+
+def test_snnpy_protocol_runs_like_the_reference_loop(env, small_set):
+    """extract_lsm_features.py:76-89 verbatim shape: reset / set_input_spike_times / simulate /
+    extract_features_from_spikes, one sample at a time, against the batched call."""
+    from lsm_speech_classifier_b200.frontend import Frontend
+    pcm, _ = small_set
+    X = Frontend(128, "gammatone").encode(pcm[:4])
+    lsm = build_snn(X)
+    keys = ['spike_counts', 'spike_variances', 'mean_spike_times', 'mean_isi', 'isi_variances']
+    rows = []
+    for sample in X:
+        lsm.reset()
+        lsm.set_input_spike_times(sample)
+        lsm.simulate()
+        fd = lsm.extract_features_from_spikes()
+        rows.append(np.concatenate([np.nan_to_num(fd[k].copy()) for k in keys if k in fd]))
+        assert lsm.spike_matrix.shape == (400, lsm.num_neurons)
+    assert np.array_equal(np.array(rows), lsm.simulate_batch(X, keys, nan_to_num=True))
+
+
+def test_pipeline_host_equals_staged_calls(env, small_set):
+    import torch
+    from lsm_speech_classifier_b200.frontend import Frontend
+    from lsm_speech_classifier_b200.snn import AudioToFeatures
+    from oracle import coracle
+    pcm, _ = small_set
+    fe = Frontend(128, "gammatone")
+    X = fe.encode(pcm)
+    lsm = build_snn(X)
+    keys = ['spike_counts', 'spike_variances', 'mean_spike_times', 'mean_isi', 'isi_variances']
+    want, _ = coracle.reservoir_run(lsm.reservoir, X, 0b01100111, True, False)
+    path = AudioToFeatures(fe, lsm)
+    spikes_out = np.empty_like(X)
+    got = path.run_host(pcm, keys, spikes_out=spikes_out)
+    assert np.array_equal(got, want) and np.array_equal(spikes_out, X)
+    dev, dspk = path.run(torch.from_numpy(pcm).cuda(), keys)
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.cpu().numpy(), want) and np.array_equal(dspk.cpu().numpy(), X)
+    # a batch larger than one pipeline chunk, ragged tail: encode->simulate is per-utterance, so tiling must not matter
+    big = np.concatenate([pcm] * 90)[:2477]
+    got_big = path.run_host(big, keys)
+    assert np.array_equal(got_big[:len(pcm)], want) and np.array_equal(got_big[-17:], np.concatenate([want] * 90)[2460:2477])
+
+
+def test_spike_density_matches_w_critico_inputs(env, small_set):
+    import ctypes as C
+    import torch
+    from lsm_speech_classifier_b200.frontend import Frontend
+    pcm, _ = small_set
+    fe = Frontend(128, "gammatone")
+    X = fe.encode(torch.from_numpy(pcm).cuda())
+    out = np.zeros(2, np.int64)
+    fe.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    fe.ctx.check(fe.ctx.lib.lsm_spike_density(fe.ctx.h, C.c_void_p(X.data_ptr()), X.numel(), C.c_void_p(out.ctypes.data)))
+    assert out[0] == int(X.sum().item()) and out[1] == X.numel()
+
+
+def test_errors_are_loud(env):
+    from lsm_speech_classifier_b200 import _lib
+    from lsm_speech_classifier_b200.frontend import Frontend
+    fe = Frontend(128, "gammatone")
+    with pytest.raises(ValueError):
+        fe.encode(np.zeros((2, 8000), np.float32))
+    with pytest.raises(_lib.LsmError):
+        Frontend(512, "gammatone")
