@@ -186,6 +186,9 @@ def main():
         reference_arm(args, rank, world)
         return
 
+    # synthesise the inputs first: the generator forks worker processes, which must happen before CUDA is initialised
+    pcm_np, _ = make_inputs(rank)
+
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -200,7 +203,6 @@ def main():
     from lsm_speech_classifier_b200.snn import AudioToFeatures
 
     keys = FEATURE_SETS[FEATURE_SET]
-    pcm_np, _ = make_inputs(rank)
     B = len(pcm_np)
     h_pcm = torch.from_numpy(pcm_np).pin_memory()
     d_pcm = h_pcm.cuda(non_blocking=True)

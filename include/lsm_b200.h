@@ -51,8 +51,10 @@ enum {
 int lsm_ctx_create(lsm_ctx **out, int device_ordinal);
 void lsm_ctx_destroy(lsm_ctx *ctx);
 const char *lsm_last_error(const lsm_ctx *ctx);
-/* Use an existing cudaStream_t (e.g. torch's current stream); NULL = the ctx's own stream. */
+/* Enqueue on an existing cudaStream_t (e.g. torch's current stream; NULL = CUDA's default stream). */
 int lsm_set_stream(lsm_ctx *ctx, void *cuda_stream);
+/* Go back to the non-blocking stream the ctx created for itself (the initial state). */
+int lsm_reset_stream(lsm_ctx *ctx);
 int lsm_sync(lsm_ctx *ctx);
 /* Kernels launched by this ctx since creation (bench.py's gpu_launches). */
 int64_t lsm_launch_count(const lsm_ctx *ctx);

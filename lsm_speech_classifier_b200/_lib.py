@@ -18,7 +18,7 @@ FEATURE_KEYS = ['spike_counts', 'spike_variances', 'mean_spike_times', 'first_sp
                 'last_spike_times', 'mean_isi', 'isi_variances', 'burst_counts']
 
 EXPORTS = [
-    "lsm_ctx_create", "lsm_ctx_destroy", "lsm_last_error", "lsm_set_stream", "lsm_sync", "lsm_launch_count",
+    "lsm_ctx_create", "lsm_ctx_destroy", "lsm_last_error", "lsm_set_stream", "lsm_reset_stream", "lsm_sync", "lsm_launch_count",
     "lsm_sm_count", "lsm_frontend_create", "lsm_frontend_destroy", "lsm_frontend_encode",
     "lsm_frontend_encode_host", "lsm_reservoir_create", "lsm_reservoir_destroy", "lsm_reservoir_run",
     "lsm_reservoir_run_host", "lsm_pipeline_run_host", "lsm_pipeline_run", "lsm_spike_density",
@@ -62,6 +62,7 @@ def load():
     lib.lsm_last_error.argtypes = [vp]
     lib.lsm_last_error.restype = C.c_char_p
     lib.lsm_set_stream.argtypes = [vp, vp]
+    lib.lsm_reset_stream.argtypes = [vp]
     lib.lsm_sync.argtypes = [vp]
     lib.lsm_launch_count.argtypes = [vp]
     lib.lsm_launch_count.restype = i64
@@ -117,7 +118,12 @@ class Context:
             raise LsmError(f"status {rc}: {self.lib.lsm_last_error(self.h).decode(errors='replace')}")
 
     def set_stream(self, cuda_stream_handle: int | None):
-        self.check(self.lib.lsm_set_stream(self.h, C.c_void_p(cuda_stream_handle or 0)))
+        """An int (0 = CUDA's default stream, what torch uses unless told otherwise) enqueues there;
+        None goes back to the ctx's own stream (used by the synchronous *_host calls)."""
+        if cuda_stream_handle is None:
+            self.check(self.lib.lsm_reset_stream(self.h))
+        else:
+            self.check(self.lib.lsm_set_stream(self.h, C.c_void_p(int(cuda_stream_handle))))
 
     def sync(self):
         self.check(self.lib.lsm_sync(self.h))

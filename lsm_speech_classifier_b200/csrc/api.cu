@@ -52,7 +52,14 @@ extern "C" const char *lsm_last_error(const lsm_ctx *ctx) { return ctx ? ctx->er
 extern "C" int lsm_set_stream(lsm_ctx *ctx, void *cuda_stream)
 {
     if (!ctx) return LSM_ERR_INVALID;
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return LSM_OK;
+}
+
+extern "C" int lsm_reset_stream(lsm_ctx *ctx)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    ctx->stream = ctx->own_stream;
     return LSM_OK;
 }
 
