@@ -134,6 +134,7 @@ extern "C" int lsm_frontend_create(lsm_ctx *ctx, const lsm_frontend_params *p, c
         rc = upload(ctx, &fe->d_coefs, t, (size_t)p->channels * 10);
         if (rc == LSM_OK) rc = lsm_gammatone_grid(ctx, p, &fe->grid);
         if (rc == LSM_OK) rc = upload<double>(ctx, &fe->d_scratch, nullptr, (size_t)fe->grid * fe->ncols * p->channels);
+        if (rc == LSM_OK) rc = upload<int>(ctx, &fe->d_counters, nullptr, 64);
     } else if (p->kind == LSM_FILTERBANK_MEL) {
         if (p->n_fft <= 0 || (p->n_fft & (p->n_fft - 1)) || p->mel_hop <= 0) { delete fe; LSM_FAIL(ctx, LSM_ERR_INVALID, "mel n_fft must be a power of two"); }
         fe->ncols = 1 + p->n_samples / p->mel_hop;
@@ -159,7 +160,7 @@ extern "C" int lsm_frontend_create(lsm_ctx *ctx, const lsm_frontend_params *p, c
 extern "C" void lsm_frontend_destroy(lsm_frontend *fe)
 {
     if (!fe) return;
-    cudaFree(fe->d_coefs); cudaFree(fe->d_zoom_i0); cudaFree(fe->d_zoom_f); cudaFree(fe->d_scratch);
+    cudaFree(fe->d_coefs); cudaFree(fe->d_zoom_i0); cudaFree(fe->d_zoom_f); cudaFree(fe->d_scratch); cudaFree(fe->d_counters);
     lsm_mel_destroy(fe);
     delete fe;
 }
@@ -293,10 +294,17 @@ extern "C" int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
         out_slot[h_out_idx[o]] = o;
     }
     const int64_t nin = h_in_rowptr[N];
+    std::vector<int32_t> in_row(N, -1);
     for (int i = 0; i < N; ++i) {
         const int d = h_in_rowptr[i + 1] - h_in_rowptr[i];
         if (d > res->max_in_per_neuron) res->max_in_per_neuron = d;
+        if (d == 1) in_row[i] = h_in_col[h_in_rowptr[i]];
+        else if (d > 1) in_row[i] = -2;
     }
+    res->leak_uniform = 1;
+    res->leak0 = h_leak[0];
+    for (int i = 1; i < N; ++i)
+        if (memcmp(&h_leak[i], &h_leak[0], sizeof(double)) != 0) { res->leak_uniform = 0; break; }
     for (int64_t q = 0; q < nin; ++q)
         if (h_in_col[q] < 0 || h_in_col[q] >= p->num_inputs) { delete res; LSM_FAIL(ctx, LSM_ERR_INVALID, "input row out of range"); }
     int rc = upload(ctx, &res->d_wt, wt.data(), wt.size());
@@ -305,6 +313,7 @@ extern "C" int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
     if (rc == LSM_OK) rc = upload(ctx, &res->d_in_val, h_in_val, (size_t)nin);
     if (rc == LSM_OK) rc = upload(ctx, &res->d_leak, h_leak, (size_t)N);
     if (rc == LSM_OK) rc = upload(ctx, &res->d_out_slot, out_slot.data(), (size_t)N);
+    if (rc == LSM_OK) rc = upload(ctx, &res->d_in_row, in_row.data(), (size_t)N);
     if (rc != LSM_OK) { lsm_reservoir_destroy(res); return rc; }
     *out = res;
     return LSM_OK;
@@ -314,7 +323,7 @@ extern "C" void lsm_reservoir_destroy(lsm_reservoir *res)
 {
     if (!res) return;
     cudaFree(res->d_wt); cudaFree(res->d_in_rowptr); cudaFree(res->d_in_col); cudaFree(res->d_in_val);
-    cudaFree(res->d_leak); cudaFree(res->d_out_slot);
+    cudaFree(res->d_leak); cudaFree(res->d_out_slot); cudaFree(res->d_in_row);
     delete res;
 }
 

@@ -50,12 +50,28 @@ struct GtArgs {
     double thr[8], lower[8];
 };
 
-__global__ void __launch_bounds__(256) gammatone_encode_kernel(const GtArgs a)
+// One biquad step (scipy.signal.lfilter direct form II transposed, b2 = 0): y = z0 + b0*x;
+// z0' = (z1 + x*b1) - y*a1; z1' = -(y*a2).
+#define LSM_BIQUAD(y, x, z0, z1, b1)                           \
+    {                                                          \
+        y = add64(z0, mul64(b0, x));                           \
+        z0 = sub64(add64(z1, mul64(x, b1)), mul64(y, a1));     \
+        z1 = mul64(y, na2);                                    \
+    }
+
+__global__ void __launch_bounds__(256) gammatone_encode_kernel(const GtArgs a, int *next_utt)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_x = reinterpret_cast<double *>(smem_raw);            // [2][kChunkBlocks*hop] PCM as fp64
+    double *s_x = reinterpret_cast<double *>(smem_raw);            // [2][kChunkBlocks*hop] PCM as fp64, shifted by kSkew
     __shared__ double s_red[2][8];
     __shared__ double s_mm[2];
+    __shared__ int s_utt;
+
+    // The four cascaded stages are software-skewed: in one loop iteration stage k works on sample
+    // s + (3 - k), so the four recurrences are independent instruction chains (ILP 4) while every
+    // stage still performs exactly the reference's operations in the reference's order.  The stage-4
+    // output of iteration s is the cascade output for sample s.
+    constexpr int kSkew = 3;
 
     const int ch = threadIdx.x;
     const int C = a.C;
@@ -82,15 +98,34 @@ __global__ void __launch_bounds__(256) gammatone_encode_kernel(const GtArgs a)
     }
     double *plane = a.scratch + (size_t)blockIdx.x * ncols * C;     // this CTA's dB plane [ncols][C]
 
-    for (int utt = blockIdx.x; utt < a.B; utt += gridDim.x) {
+    for (;;) {
+        // dynamic work distribution: utterances are handed out one at a time, so every SM stays busy to the end
+        if (threadIdx.x == 0) s_utt = atomicAdd(next_utt, 1);
+        __syncthreads();
+        const int utt = s_utt;
+        if (utt >= a.B) break;
         const float *pcm = a.pcm + (size_t)utt * a.L;
         double z0_0 = 0, z0_1 = 0, z0_2 = 0, z0_3 = 0, z1_0 = 0, z1_1 = 0, z1_2 = 0, z1_3 = 0;
+        double y1 = 0, y2 = 0, y3 = 0, y4 = 0;
         double acc_new = 0, acc_mid = 0, acc_old = 0;
         double tmax = -INFINITY, tmin = INFINITY;
 
-        // stage chunk 0
+        // stage chunk 0; buffer element i of chunk k holds sample k*chunk + i + kSkew
         for (int i = threadIdx.x; i < chunk; i += blockDim.x)
-            s_x[i] = (i < n_used) ? (double)__ldg(pcm + i) : 0.0;
+            s_x[i] = (i + kSkew < a.L) ? (double)__ldg(pcm + i + kSkew) : 0.0;
+        if (live) {
+            // prologue: iterations s = -3, -2, -1 fill the skewed pipeline (outputs belong to no sample)
+#pragma unroll
+            for (int s = 0; s < kSkew; ++s) {
+                const double x = (double)__ldg(pcm + s);
+                double t1, t2, t3;
+                LSM_BIQUAD(t1, x, z0_0, z1_0, b1_0);
+                LSM_BIQUAD(t2, y1, z0_1, z1_1, b1_1);
+                LSM_BIQUAD(t3, y2, z0_2, z1_2, b1_2);
+                LSM_BIQUAD(y4, y3, z0_3, z1_3, b1_3);
+                y1 = t1; y2 = t2; y3 = t3;
+            }
+        }
         __syncthreads();
 
         for (int ck = 0; ck < n_chunks; ++ck) {
@@ -98,9 +133,9 @@ __global__ void __launch_bounds__(256) gammatone_encode_kernel(const GtArgs a)
             // prefetch the next chunk into the other buffer while this one is filtered
             if (ck + 1 < n_chunks) {
                 double *xn = s_x + ((ck + 1) & 1) * chunk;
-                const int base = (ck + 1) * chunk;
+                const int base = (ck + 1) * chunk + kSkew;
                 for (int i = threadIdx.x; i < chunk; i += blockDim.x)
-                    xn[i] = (base + i < n_used) ? (double)__ldg(pcm + base + i) : 0.0;
+                    xn[i] = (base + i < a.L) ? (double)__ldg(pcm + base + i) : 0.0;
             }
             if (live) {
                 for (int bl = 0; bl < kChunkBlocks; ++bl) {
@@ -108,26 +143,16 @@ __global__ void __launch_bounds__(256) gammatone_encode_kernel(const GtArgs a)
                     if (m >= n_blocks) break;
                     const double *xb = xs + bl * hop;
                     const int n_here = min(hop, n_used - m * hop);
-#pragma unroll 2
+#pragma unroll 4
                     for (int p = 0; p < n_here; ++p) {
-                        double x = xb[p];
-                        // four cascaded direct-form-II-transposed biquads (b2 = 0)
-                        double y = add64(z0_0, mul64(b0, x));
-                        z0_0 = sub64(add64(z1_0, mul64(x, b1_0)), mul64(y, a1));
-                        z1_0 = mul64(y, na2);
-                        x = y;
-                        y = add64(z0_1, mul64(b0, x));
-                        z0_1 = sub64(add64(z1_1, mul64(x, b1_1)), mul64(y, a1));
-                        z1_1 = mul64(y, na2);
-                        x = y;
-                        y = add64(z0_2, mul64(b0, x));
-                        z0_2 = sub64(add64(z1_2, mul64(x, b1_2)), mul64(y, a1));
-                        z1_2 = mul64(y, na2);
-                        x = y;
-                        y = add64(z0_3, mul64(b0, x));
-                        z0_3 = sub64(add64(z1_3, mul64(x, b1_3)), mul64(y, a1));
-                        z1_3 = mul64(y, na2);
-                        const double v = div_by_const(y, gain, rgain);
+                        const double x = xb[p];                 // sample m*hop + p + 3
+                        double t1, t2, t3;
+                        LSM_BIQUAD(t1, x, z0_0, z1_0, b1_0);    // stage 1 on sample s+3
+                        LSM_BIQUAD(t2, y1, z0_1, z1_1, b1_1);   // stage 2 on sample s+2
+                        LSM_BIQUAD(t3, y2, z0_2, z1_2, b1_2);   // stage 3 on sample s+1
+                        LSM_BIQUAD(y4, y3, z0_3, z1_3, b1_3);   // stage 4 on sample s = m*hop + p
+                        y1 = t1; y2 = t2; y3 = t3;
+                        const double v = div_by_const(y4, gain, rgain);
                         const double e = mul64(v, v);
                         // window m starts at p == 0 (np.add.reduce starts from the first element)
                         acc_new = (p == 0) ? e : add64(acc_new, e);
@@ -136,8 +161,8 @@ __global__ void __launch_bounds__(256) gammatone_encode_kernel(const GtArgs a)
                             acc_old = add64(acc_old, e);
                             if (p == r_old - 1 && m >= 2) {
                                 // window m-2 complete: sqrt(mean) -> dB
-                                const double y2 = __dsqrt_rn(__ddiv_rn(acc_old, (double)nwin));
-                                const double db = mul64(20.0, lsm_log10(add64(y2, 1e-9)));
+                                const double y2w = __dsqrt_rn(__ddiv_rn(acc_old, (double)nwin));
+                                const double db = mul64(20.0, lsm_log10(add64(y2w, 1e-9)));
                                 plane[(size_t)(m - 2) * C + ch] = db;
                                 tmax = fmax(tmax, db);
                                 tmin = fmin(tmin, db);
@@ -210,7 +235,7 @@ __global__ void __launch_bounds__(256) gammatone_encode_kernel(const GtArgs a)
                 }
             }
         }
-        __syncthreads();   // plane and s_x are reused by the next utterance
+        __syncthreads();   // plane, s_x and s_utt are reused by the next utterance
     }
 }
 
@@ -243,7 +268,10 @@ int lsm_launch_gammatone(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int
     const size_t smem = sizeof(double) * 2 * kChunkBlocks * p.hop;
     const int grid = B < fe->grid ? B : fe->grid;
     if (grid <= 0) return LSM_OK;
-    gammatone_encode_kernel<<<grid, threads, smem, st>>>(a);
+    // work counter: one int per launch out of a small ring, so back-to-back launches on different streams do not share it
+    int *counter = fe->d_counters + (fe->counter_next++ % 64);
+    LSM_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), st));
+    gammatone_encode_kernel<<<grid, threads, smem, st>>>(a, counter);
     ctx->launches += 1;
     LSM_CUDA(ctx, cudaGetLastError());
     return LSM_OK;

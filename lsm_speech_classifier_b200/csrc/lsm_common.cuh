@@ -32,6 +32,8 @@ struct lsm_frontend {
     double *d_zoom_f = nullptr;    // [n_bins]
     double *d_scratch = nullptr;   // per-CTA [ncols][C] dB plane (stays in L2)
     int grid = 0;
+    int *d_counters = nullptr;     // [64] dynamic work counters, one per in-flight launch
+    unsigned counter_next = 0;
     // mel
     float *d_mel_w = nullptr;      // packed non-zero mel weights
     int32_t *d_mel_lo = nullptr;   // [C] first non-zero bin
@@ -49,7 +51,10 @@ struct lsm_reservoir {
     double *d_in_val = nullptr;
     double *d_leak = nullptr;
     int32_t *d_out_slot = nullptr; // [N] position in the output list or -1
+    int32_t *d_in_row = nullptr;   // [N] single input row, -1 none, -2 several
     int max_in_per_neuron = 0;
+    int leak_uniform = 0;
+    double leak0 = 0.0;
 };
 
 #define LSM_FAIL(ctx, code, ...)                                  \

@@ -305,7 +305,7 @@ static void simulate_one(const oracle_res_dims *d, const uint8_t *x,
         for (int i = 0; i < N; ++i) {
             double i_in = 0.0;
             for (int p = in_rowptr[i]; p < in_rowptr[i + 1]; ++p)
-                i_in = i_in + in_val[p] * (double)x[(size_t)in_col[p] * T + t];
+                i_in = i_in + in_val[p] * (x[(size_t)in_col[p] * T + t] ? 1.0 : 0.0);  /* level signal: non-zero = on */
             double cur = i_in + (double)acc[i] * scale;
             int fire = 0;
             if (ref[i] == 0) {

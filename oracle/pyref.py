@@ -242,7 +242,7 @@ def simulate(x, w_rows, w_cols, w_q, w_shift, in_rowptr, in_col, in_val, leak, t
         for i in range(N):
             acc = 0.0
             for p in range(in_rowptr[i], in_rowptr[i + 1]):
-                acc = acc + in_val[p] * float(x[in_col[p], t])
+                acc = acc + in_val[p] * (1.0 if x[in_col[p], t] else 0.0)   # level signal: non-zero = on
             i_in[i] = acc
         cur = i_in + i_rec
         active = ref == 0

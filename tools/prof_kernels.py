@@ -1,0 +1,28 @@
+"""Small driver for ncu: K1 and K2 on one 2400-utterance batch, three launches each.
+    python tools/prof_kernels.py [B]"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lsm_speech_classifier_b200 import synth  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 2400
+base, _ = synth.synth_dataset(12, 20, workers=os.cpu_count() or 1)
+pcm = np.concatenate([base] * (B // len(base) + 1))[:B]
+
+import torch  # noqa: E402
+from lsm_speech_classifier_b200.extract_lsm_features import FEATURE_SETS, build_lsm  # noqa: E402
+from lsm_speech_classifier_b200.frontend import Frontend  # noqa: E402
+
+d_pcm = torch.from_numpy(pcm).cuda()
+fe = Frontend(128, "gammatone")
+spikes = fe.encode(d_pcm)
+lsm = build_lsm(spikes[:500].cpu().numpy(), 0.6, verbose=False)
+keys = FEATURE_SETS["original"]
+for _ in range(3):
+    spikes = fe.encode(d_pcm)
+    feats = lsm.simulate_batch(spikes, keys)
+torch.cuda.synchronize()
+print("ok", spikes.float().mean().item(), feats.shape)
