@@ -275,9 +275,11 @@ extern "C" int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
     lsm_reservoir *res = new (std::nothrow) lsm_reservoir();
     if (!res) LSM_FAIL(ctx, LSM_ERR_NOMEM, "out of host memory");
     res->p = *p;
-    res->n_pad = ((N + 31) / 32) * 32;
-    // dense presynaptic-major plane: wt[j][i] = weight of j -> i
-    std::vector<int32_t> wt((size_t)N * res->n_pad, 0);
+    int npt, threads;
+    lsm_reservoir_geometry(N, &npt, &threads, &res->n_pad);
+    if (threads > 1024) { delete res; LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "num_neurons %d > 16384 not supported by the event-driven kernel", N); }
+    // dense presynaptic-major plane: wt[j][i] = weight of j -> i; one extra all-zero row (index N) pads spike lists
+    std::vector<int32_t> wt((size_t)(N + 1) * res->n_pad, 0);
     std::vector<int64_t> rowabs(N, 0);
     for (int i = 0; i < N; ++i) {
         for (int64_t q = h_w_rowptr[i]; q < h_w_rowptr[i + 1]; ++q) {
@@ -294,17 +296,21 @@ extern "C" int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
         out_slot[h_out_idx[o]] = o;
     }
     const int64_t nin = h_in_rowptr[N];
-    std::vector<int32_t> in_row(N, -1);
+    std::vector<int32_t> in_row(res->n_pad, -1);
     for (int i = 0; i < N; ++i) {
         const int d = h_in_rowptr[i + 1] - h_in_rowptr[i];
         if (d > res->max_in_per_neuron) res->max_in_per_neuron = d;
         if (d == 1) in_row[i] = h_in_col[h_in_rowptr[i]];
         else if (d > 1) in_row[i] = -2;
     }
-    res->leak_uniform = 1;
+    // lean kernel variant: uniform leak, uniform input gain (and no -0.0), at most one input row per neuron
+    res->lean = res->max_in_per_neuron <= 1;
     res->leak0 = h_leak[0];
-    for (int i = 1; i < N; ++i)
-        if (memcmp(&h_leak[i], &h_leak[0], sizeof(double)) != 0) { res->leak_uniform = 0; break; }
+    res->gain0 = nin > 0 ? h_in_val[0] + 0.0 : 0.0;
+    for (int i = 1; i < N && res->lean; ++i)
+        if (memcmp(&h_leak[i], &h_leak[0], sizeof(double)) != 0) res->lean = 0;
+    for (int64_t q = 0; q < nin && res->lean; ++q)
+        if (memcmp(&h_in_val[q], &h_in_val[0], sizeof(double)) != 0) res->lean = 0;
     for (int64_t q = 0; q < nin; ++q)
         if (h_in_col[q] < 0 || h_in_col[q] >= p->num_inputs) { delete res; LSM_FAIL(ctx, LSM_ERR_INVALID, "input row out of range"); }
     int rc = upload(ctx, &res->d_wt, wt.data(), wt.size());
@@ -313,7 +319,7 @@ extern "C" int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
     if (rc == LSM_OK) rc = upload(ctx, &res->d_in_val, h_in_val, (size_t)nin);
     if (rc == LSM_OK) rc = upload(ctx, &res->d_leak, h_leak, (size_t)N);
     if (rc == LSM_OK) rc = upload(ctx, &res->d_out_slot, out_slot.data(), (size_t)N);
-    if (rc == LSM_OK) rc = upload(ctx, &res->d_in_row, in_row.data(), (size_t)N);
+    if (rc == LSM_OK) rc = upload(ctx, &res->d_in_row, in_row.data(), in_row.size());
     if (rc != LSM_OK) { lsm_reservoir_destroy(res); return rc; }
     *out = res;
     return LSM_OK;

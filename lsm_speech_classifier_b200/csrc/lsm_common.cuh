@@ -53,8 +53,8 @@ struct lsm_reservoir {
     int32_t *d_out_slot = nullptr; // [N] position in the output list or -1
     int32_t *d_in_row = nullptr;   // [N] single input row, -1 none, -2 several
     int max_in_per_neuron = 0;
-    int leak_uniform = 0;
-    double leak0 = 0.0;
+    int lean = 0;                  // uniform leak and gain, <= 1 input row per neuron
+    double leak0 = 0.0, gain0 = 0.0;
 };
 
 #define LSM_FAIL(ctx, code, ...)                                  \
@@ -84,6 +84,7 @@ int lsm_launch_mel(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, ui
 int lsm_launch_reservoir(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int B,
                          uint32_t feature_mask, int nan_to_num, double *d_features, uint8_t *d_raster,
                          cudaStream_t st);
+void lsm_reservoir_geometry(int N, int *npt, int *threads, int *n_pad);
 int lsm_mel_create(lsm_ctx *ctx, lsm_frontend *fe, const float *h_basis);
 void lsm_mel_destroy(lsm_frontend *fe);
 
