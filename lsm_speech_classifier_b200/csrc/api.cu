@@ -132,6 +132,7 @@ extern "C" int lsm_frontend_create(lsm_ctx *ctx, const lsm_frontend_params *p, c
             if (t[10 * c + 5] != 0.0) { delete fe; LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "gammatone design with A2 != 0"); }
         fe->ncols = 1 + (p->n_samples - p->nwin) / p->hop;
         rc = upload(ctx, &fe->d_coefs, t, (size_t)p->channels * 10);
+        fe->minb = lsm_gammatone_minb();
         if (rc == LSM_OK) rc = lsm_gammatone_grid(ctx, p, &fe->grid);
         if (rc == LSM_OK) rc = upload<double>(ctx, &fe->d_scratch, nullptr, (size_t)fe->grid * fe->ncols * p->channels);
         if (rc == LSM_OK) rc = upload<int>(ctx, &fe->d_counters, nullptr, 64);

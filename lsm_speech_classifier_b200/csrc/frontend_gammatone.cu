@@ -18,6 +18,8 @@
 //
 // Bit-exactness: every fp64 operation is an explicit __d*_rn intrinsic in the oracle's order
 // (oracle/lsm_oracle.c gammatone_energy / db_normalise_zoom / hysteresis_encode_f64).
+#include <stdlib.h>
+
 #include "lsm_common.cuh"
 
 namespace {
@@ -25,17 +27,16 @@ namespace {
 constexpr int kChunkBlocks = 8;   // hop-blocks of PCM staged per shared-memory buffer
 
 // x / g with g a per-thread constant: q0 = RN(x*r), e = x - g*q0 (exact, FMA), q = RN(q0 + e*r) is the
-// correctly rounded quotient when r = RN(1/g) (Markstein) as long as nothing underflows; outside a
-// safe exponent window fall back to the IEEE division.  Same value as the oracle's `x / gain`.
+// correctly rounded quotient when r = RN(1/g) (Markstein's theorem) as long as the residual does not
+// underflow, i.e. for |x| >= 2^-900 (tests/test_oracle_frontend.py checks it against IEEE division).
+// No guard is needed for smaller |x|: the only consumer is the square v*v, and with |x| < 2^-900 and
+// |1/g| < 2^60 both the exact quotient and this one are far below 2^-538, so the square is exactly +0
+// either way.  |x| >= 2^900 cannot occur for float32 PCM.
 __device__ __forceinline__ double div_by_const(double x, double g, double r)
 {
-    const int ex = (__double2hiint(x) >> 20) & 0x7ff;
-    if (ex - 123u < 1800u) {            // 2^-900 <= |x| < 2^900 (biased exponent in [123, 1922])
-        const double q0 = mul64(x, r);
-        const double e = __fma_rn(-g, q0, x);
-        return __fma_rn(e, r, q0);
-    }
-    return __ddiv_rn(x, g);
+    const double q0 = mul64(x, r);
+    const double e = __fma_rn(-g, q0, x);
+    return __fma_rn(e, r, q0);
 }
 
 struct GtArgs {
@@ -59,7 +60,8 @@ struct GtArgs {
         z1 = mul64(y, na2);                                    \
     }
 
-__global__ void __launch_bounds__(256) gammatone_encode_kernel(const GtArgs a, int *next_utt)
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) gammatone_encode_kernel(const GtArgs a, int *next_utt)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_x = reinterpret_cast<double *>(smem_raw);            // [2][kChunkBlocks*hop] PCM as fp64, shifted by kSkew
@@ -143,32 +145,44 @@ __global__ void __launch_bounds__(256) gammatone_encode_kernel(const GtArgs a, i
                     if (m >= n_blocks) break;
                     const double *xb = xs + bl * hop;
                     const int n_here = min(hop, n_used - m * hop);
+                    const int n_a = min(n_here, r_old);      // phases where windows m, m-1 and m-2 are all open
+                    // window m starts here: np.add.reduce begins with the first element, and 0.0 + e == e
+                    acc_new = 0.0;
+#define LSM_SAMPLE(xin)                                                                   \
+                    {                                                                     \
+                        double t1, t2, t3;                                                \
+                        LSM_BIQUAD(t1, xin, z0_0, z1_0, b1_0);  /* stage 1, sample s+3 */ \
+                        LSM_BIQUAD(t2, y1, z0_1, z1_1, b1_1);   /* stage 2, sample s+2 */ \
+                        LSM_BIQUAD(t3, y2, z0_2, z1_2, b1_2);   /* stage 3, sample s+1 */ \
+                        LSM_BIQUAD(y4, y3, z0_3, z1_3, b1_3);   /* stage 4, sample s   */ \
+                        y1 = t1; y2 = t2; y3 = t3;                                        \
+                    }
 #pragma unroll 4
-                    for (int p = 0; p < n_here; ++p) {
-                        const double x = xb[p];                 // sample m*hop + p + 3
-                        double t1, t2, t3;
-                        LSM_BIQUAD(t1, x, z0_0, z1_0, b1_0);    // stage 1 on sample s+3
-                        LSM_BIQUAD(t2, y1, z0_1, z1_1, b1_1);   // stage 2 on sample s+2
-                        LSM_BIQUAD(t3, y2, z0_2, z1_2, b1_2);   // stage 3 on sample s+1
-                        LSM_BIQUAD(y4, y3, z0_3, z1_3, b1_3);   // stage 4 on sample s = m*hop + p
-                        y1 = t1; y2 = t2; y3 = t3;
+                    for (int p = 0; p < n_a; ++p) {
+                        LSM_SAMPLE(xb[p]);
                         const double v = div_by_const(y4, gain, rgain);
                         const double e = mul64(v, v);
-                        // window m starts at p == 0 (np.add.reduce starts from the first element)
-                        acc_new = (p == 0) ? e : add64(acc_new, e);
+                        acc_new = add64(acc_new, e);
                         acc_mid = add64(acc_mid, e);
-                        if (p < r_old) {
-                            acc_old = add64(acc_old, e);
-                            if (p == r_old - 1 && m >= 2) {
-                                // window m-2 complete: sqrt(mean) -> dB
-                                const double y2w = __dsqrt_rn(__ddiv_rn(acc_old, (double)nwin));
-                                const double db = mul64(20.0, lsm_log10(add64(y2w, 1e-9)));
-                                plane[(size_t)(m - 2) * C + ch] = db;
-                                tmax = fmax(tmax, db);
-                                tmin = fmin(tmin, db);
-                            }
-                        }
+                        acc_old = add64(acc_old, e);
                     }
+                    if (n_a == r_old && m >= 2) {
+                        // window m-2 complete: sqrt(mean) -> dB
+                        const double y2w = __dsqrt_rn(__ddiv_rn(acc_old, (double)nwin));
+                        const double db = mul64(20.0, lsm_log10(add64(y2w, 1e-9)));
+                        plane[(size_t)(m - 2) * C + ch] = db;
+                        tmax = fmax(tmax, db);
+                        tmin = fmin(tmin, db);
+                    }
+#pragma unroll 4
+                    for (int p = n_a; p < n_here; ++p) {
+                        LSM_SAMPLE(xb[p]);
+                        const double v = div_by_const(y4, gain, rgain);
+                        const double e = mul64(v, v);
+                        acc_new = add64(acc_new, e);
+                        acc_mid = add64(acc_mid, e);
+                    }
+#undef LSM_SAMPLE
                     acc_old = acc_mid;
                     acc_mid = acc_new;
                 }
@@ -241,16 +255,35 @@ __global__ void __launch_bounds__(256) gammatone_encode_kernel(const GtArgs a, i
 
 }  // namespace
 
+// occupancy target: CTAs per SM the register allocation is bounded for (4, 5 or 6 at <= 128 channels)
+static int k1_minb()
+{
+    const char *e = getenv("LSM_K1_MINB");
+    const int v = e ? atoi(e) : 5;
+    return v < 4 ? 4 : (v > 6 ? 6 : v);
+}
+
+template <int MAXT, int MINB>
+static int k1_grid(lsm_ctx *ctx, int threads, size_t smem, int *per_sm)
+{
+    if (smem > 48 * 1024)
+        LSM_CUDA(ctx, cudaFuncSetAttribute(gammatone_encode_kernel<MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, gammatone_encode_kernel<MAXT, MINB>, threads, smem));
+    return LSM_OK;
+}
+
 int lsm_gammatone_grid(lsm_ctx *ctx, const lsm_frontend_params *p, int *grid)
 {
     const int threads = ((p->channels + 31) / 32) * 32;
     const size_t smem = sizeof(double) * 2 * kChunkBlocks * p->hop;
-    if (smem > 48 * 1024)
-        LSM_CUDA(ctx, cudaFuncSetAttribute(gammatone_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gammatone_encode_kernel, threads, smem));
+    int per_sm = 0, rc;
+    if (threads > 128) rc = k1_grid<256, 2>(ctx, threads, smem, &per_sm);
+    else if (k1_minb() == 4) rc = k1_grid<128, 4>(ctx, threads, smem, &per_sm);
+    else if (k1_minb() == 5) rc = k1_grid<128, 5>(ctx, threads, smem, &per_sm);
+    else rc = k1_grid<128, 6>(ctx, threads, smem, &per_sm);
+    if (rc != LSM_OK) return rc;
     if (per_sm < 1) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "gammatone kernel does not fit on an SM (hop %d)", p->hop);
-    *grid = per_sm * ctx->sm_count;   // persistent: every CTA resident, CTAs stride over the batch
+    *grid = per_sm * ctx->sm_count;   // persistent: every CTA resident, utterances handed out dynamically
     return LSM_OK;
 }
 
@@ -271,8 +304,13 @@ int lsm_launch_gammatone(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int
     // work counter: one int per launch out of a small ring, so back-to-back launches on different streams do not share it
     int *counter = fe->d_counters + (fe->counter_next++ % 64);
     LSM_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), st));
-    gammatone_encode_kernel<<<grid, threads, smem, st>>>(a, counter);
+    if (threads > 128) gammatone_encode_kernel<256, 2><<<grid, threads, smem, st>>>(a, counter);
+    else if (fe->minb == 4) gammatone_encode_kernel<128, 4><<<grid, threads, smem, st>>>(a, counter);
+    else if (fe->minb == 5) gammatone_encode_kernel<128, 5><<<grid, threads, smem, st>>>(a, counter);
+    else gammatone_encode_kernel<128, 6><<<grid, threads, smem, st>>>(a, counter);
     ctx->launches += 1;
     LSM_CUDA(ctx, cudaGetLastError());
     return LSM_OK;
 }
+
+int lsm_gammatone_minb(void) { return k1_minb(); }

@@ -34,6 +34,7 @@ struct lsm_frontend {
     int grid = 0;
     int *d_counters = nullptr;     // [64] dynamic work counters, one per in-flight launch
     unsigned counter_next = 0;
+    int minb = 5;                  // K1 occupancy target the kernel was instantiated for
     // mel
     float *d_mel_w = nullptr;      // packed non-zero mel weights
     int32_t *d_mel_lo = nullptr;   // [C] first non-zero bin
@@ -79,6 +80,7 @@ int lsm_stage_pinned(lsm_ctx *ctx, int slot, size_t bytes, void **out);
 int lsm_launch_gammatone(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, uint8_t *d_spikes,
                          double *d_spec_norm, cudaStream_t st);
 int lsm_gammatone_grid(lsm_ctx *ctx, const lsm_frontend_params *p, int *grid);
+int lsm_gammatone_minb(void);
 int lsm_launch_mel(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, uint8_t *d_spikes,
                    double *d_spec_norm, cudaStream_t st);
 int lsm_launch_reservoir(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int B,

@@ -46,6 +46,13 @@ def encoder_tables(thresholds, gap):
     return thr, lower
 
 
+def check_const_division(x, g):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    f = lib().oracle_check_const_division
+    f.restype = C.c_int64
+    return int(f(_p(x, C.c_double), C.c_int64(len(x)), C.c_double(float(g))))
+
+
 def hysteresis_encode(norm, thresholds, gap, redundancy=1):
     norm = np.ascontiguousarray(norm, dtype=np.float64)
     Cc, nb = norm.shape

@@ -224,6 +224,22 @@ static void hysteresis_encode_f64(const double *norm, int C, int nbins, const do
     }
 }
 
+/* Checker for the GPU's constant-divisor division (csrc/frontend_gammatone.cu div_by_const):
+ * counts how many of the n quotients q = fma(fma(-g, x*r, x), r, x*r), r = 1/g, differ from x/g. */
+int64_t oracle_check_const_division(const double *x, int64_t n, double g)
+{
+    const double r = 1.0 / g;
+    int64_t bad = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const double q0 = x[i] * r;
+        const double e = fma(-g, q0, x[i]);
+        const double q = fma(e, r, q0);
+        const double want = x[i] / g;
+        if (memcmp(&q, &want, 8) != 0) ++bad;
+    }
+    return bad;
+}
+
 /* Encoder alone (for the known-answer tests minted from the reference's own function). */
 void oracle_hysteresis_encode(const double *norm, int C, int nbins, const double *thr_desc,
                               const double *lower, int K, int R, uint8_t *spikes)

@@ -125,3 +125,21 @@ def test_w_critico_kats(golden):
     assert g["answers"][3] == (2.0 - 2 * 0.1 * 2) / 100
     assert pyref.w_critico(0, 2.0, 2, list(g["d0"])) == 0.007
     assert pyref.w_critico(200, 2.0, 2, []) == 0.007
+
+
+def test_constant_divisor_division_is_ieee_exact():
+    """K1 divides by the per-channel gain with q0 = x*r, e = fma(-g,q0,x), q = fma(e,r,q0) (r = 1/g).
+    Markstein: correctly rounded when r = RN(1/g) and the residual cannot underflow (|x| >= 2^-900).
+    Checked here against IEEE division for every design gain over random mantissas and exponents."""
+    gains = filterbank.gammatone_coefs(16000, 128, 50)[:, 9]
+    rng = np.random.default_rng(7)
+    for g in list(gains[::9]) + [gains[0], gains[-1], 3.0, 1.0 / 3.0, 0.1]:
+        mant = rng.uniform(1.0, 2.0, 200000)
+        expo = rng.integers(-890, 300, 200000)
+        x = np.ldexp(mant, expo) * rng.choice([-1.0, 1.0], 200000)
+        x[:1000] = np.ldexp(1.0 + np.arange(1000) * 2.0 ** -52, -3)         # neighbouring mantissas
+        x[1000:1003] = [0.0, -0.0, 1.0]
+        assert coracle.check_const_division(x, g) <= 1                        # only -0.0 may differ (sign of zero)
+    # below the window the quotient need not be exact, but its square is exactly 0 either way
+    tiny = np.ldexp(rng.uniform(1.0, 2.0, 1000), -901 - rng.integers(0, 120, 1000))
+    assert np.all((tiny / gains.min()) ** 2 == 0.0)

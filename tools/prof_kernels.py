@@ -25,4 +25,13 @@ for _ in range(3):
     spikes = fe.encode(d_pcm)
     feats = lsm.simulate_batch(spikes, keys)
 torch.cuda.synchronize()
+if os.environ.get("LSM_TIME"):
+    def tm(fn, reps=5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    print("K1 ms", tm(lambda: fe.encode(d_pcm)), "K2 ms", tm(lambda: lsm.simulate_batch(spikes, keys)), "minb", os.environ.get("LSM_K1_MINB"))
 print("ok", spikes.float().mean().item(), feats.shape)
