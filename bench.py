@@ -288,6 +288,8 @@ def main():
             dist.destroy_process_group()
         return
 
+    ctx.set_stream(None)
+    fp64_peak = ctx.fp64_peak_gops()
     peaks, peak_kind = measured_peaks()
     hbm_peak = float(peaks["hbm_gbs"])
     k1_gbs = K1_BYTES_PER_UTT * B / (k1_ms / 1e3) / 1e9
@@ -301,10 +303,13 @@ def main():
         "clocks": clocks,
         "roofline": {"kernel": "gammatone_encode_kernel (K1)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak,
                      "unit": "GB/s", "frac": k1_gbs / hbm_peak, "traffic": None, "peak_source": f"{peak_kind} MEASURED_PEAKS.json hbm_gbs",
-                     "note": "K1 is bound by the fp64 pipe and dependent-chain latency, not HBM (SURVEY.md 8d); see fp64_pipe"},
-        "fp64_pipe": {"kernel": "gammatone_encode_kernel (K1)", "achieved_gops": K1_FP64_OPS_PER_UTT * B / (k1_ms / 1e3) / 1e9,
-                      "nominal_peak_gops": 148 * 64 * 1.965, "unit": "G fp64 instr-lanes/s (DADD/DMUL/DFMA each 1)",
-                      "note": "nominal = 148 SMs x 64 lanes/clk x 1.965 GHz"},
+                     "note": "K1 is bound by the fp64 pipe, not HBM (SURVEY.md 8d): see roofline_fp64"},
+        "roofline_fp64": {"kernel": "gammatone_encode_kernel (K1)", "bound": "fp64 pipe",
+                          "achieved": K1_FP64_OPS_PER_UTT * B / (k1_ms / 1e3) / 1e9, "peak": fp64_peak,
+                          "unit": "G fp64 lane-ops/s (DADD, DMUL, DFMA each count 1)",
+                          "frac": K1_FP64_OPS_PER_UTT * B / (k1_ms / 1e3) / 1e9 / fp64_peak,
+                          "peak_source": "measured live by lsm_fp64_peak_gops (independent DADD/DMUL register chains); "
+                                         "nominal 148 SMs x 64 lanes x 1.965 GHz = 18612"},
         "kernel_ms": {"K1_gammatone_encode": k1_ms, "K2_reservoir_features": k2_ms},
     }
     if not args.no_cpu_baseline and world == 1:

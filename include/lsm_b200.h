@@ -158,6 +158,10 @@ int lsm_pipeline_run(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const f
  * reduces over X_train[:500] (extract_lsm_features.py:40-44).  h_out: int64[2].            */
 int lsm_spike_density(lsm_ctx *ctx, const uint8_t *d_spikes, int64_t n_bytes, int64_t *h_out);
 
+/* Diagnostic: measured ceiling of the fp64 pipe on this device, in 1e9 DADD/DMUL lane-operations per
+ * second (independent register chains, 8 warps per scheduler).  K1's roofline denominator in bench.py. */
+int lsm_fp64_peak_gops(lsm_ctx *ctx, double *h_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,7 @@ EXPORTS = [
     "lsm_sm_count", "lsm_frontend_create", "lsm_frontend_destroy", "lsm_frontend_encode",
     "lsm_frontend_encode_host", "lsm_reservoir_create", "lsm_reservoir_destroy", "lsm_reservoir_run",
     "lsm_reservoir_run_host", "lsm_pipeline_run_host", "lsm_pipeline_run", "lsm_spike_density",
-    "lsm_hysteresis_encode",
+    "lsm_hysteresis_encode", "lsm_fp64_peak_gops",
 ]
 
 
@@ -81,6 +81,7 @@ def load():
     lib.lsm_pipeline_run.argtypes = [vp, vp, vp, vp, i32, u32, i32, vp, vp]
     lib.lsm_spike_density.argtypes = [vp, vp, i64, vp]
     lib.lsm_hysteresis_encode.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, i32, i32, vp]
+    lib.lsm_fp64_peak_gops.argtypes = [vp, vp]
     _lib = lib
     return lib
 
@@ -135,6 +136,11 @@ class Context:
     @property
     def sm_count(self) -> int:
         return int(self.lib.lsm_sm_count(self.h))
+
+    def fp64_peak_gops(self) -> float:
+        out = C.c_double(0.0)
+        self.check(self.lib.lsm_fp64_peak_gops(self.h, C.byref(out)))
+        return float(out.value)
 
     def close(self):
         if getattr(self, "h", None):

@@ -486,3 +486,51 @@ extern "C" int lsm_spike_density(lsm_ctx *ctx, const uint8_t *d_spikes, int64_t 
     h_out[0] = (int64_t)s;
     return LSM_OK;
 }
+
+// ------------------------------------------------------------------------------------ fp64 ceiling
+namespace {
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = a + threadIdx.x * 1e-9 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[i] = __dmul_rn(v[i], b); v[i] = __dadd_rn(v[i], a); }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+extern "C" int lsm_fp64_peak_gops(lsm_ctx *ctx, double *h_out)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!h_out) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_fp64_peak_gops: null argument");
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int threads = 256, blocks = ctx->sm_count * 4, iters = 20000;   // 8 warps per scheduler
+    void *d_out;
+    int rc;
+    if ((rc = lsm_stage_device(ctx, 5, sizeof(double) * threads * blocks, &d_out)) != LSM_OK) return rc;
+    cudaEvent_t e0, e1;
+    LSM_CUDA(ctx, cudaEventCreate(&e0));
+    LSM_CUDA(ctx, cudaEventCreate(&e1));
+    fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((double *)d_out, 200, 1.0, 0.999999);
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        LSM_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((double *)d_out, iters, 1.0, 0.999999);
+        LSM_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        LSM_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0;
+        LSM_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        const double gops = (double)blocks * threads * iters * 16.0 / (ms * 1e6);
+        if (gops > best) best = gops;
+    }
+    ctx->launches += 4;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *h_out = best;
+    return LSM_OK;
+}
