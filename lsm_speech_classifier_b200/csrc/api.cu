@@ -378,13 +378,17 @@ extern "C" int lsm_pipeline_run(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *r
                                 double *d_features)
 {
     if (!ctx) return LSM_ERR_INVALID;
-    if (!fe || !res || B < 0 || (B > 0 && (!d_pcm || !d_spikes || !d_features)))
+    if (!fe || !res || B < 0 || (B > 0 && (!d_pcm || !d_features)))
         LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_pipeline_run: bad argument");
     if (fe->p.channels * fe->p.redundancy != res->p.num_inputs || fe->p.n_bins * fe->p.n_thresholds != res->p.num_steps)
         LSM_FAIL(ctx, LSM_ERR_INVALID, "front end emits %dx%d spike trains, reservoir expects %dx%d",
                  fe->p.channels * fe->p.redundancy, fe->p.n_bins * fe->p.n_thresholds, res->p.num_inputs, res->p.num_steps);
     if (B == 0) return LSM_OK;
     LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    // one fused kernel when the pair allows it (spikes handed over in shared memory; d_spikes optional)
+    if (lsm_fused_npt(fe, res))
+        return lsm_launch_fused(ctx, fe, res, d_pcm, B, d_spikes, feature_mask, nan_to_num, d_features, ctx->stream);
+    if (!d_spikes) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_pipeline_run: this configuration runs as two kernels and needs a d_spikes buffer");
     int rc = frontend_launch(ctx, fe, d_pcm, B, d_spikes, nullptr, ctx->stream);
     if (rc != LSM_OK) return rc;
     return lsm_launch_reservoir(ctx, res, d_spikes, B, feature_mask, nan_to_num, d_features, nullptr, ctx->stream);
@@ -420,6 +424,7 @@ extern "C" int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservo
     if ((rc = lsm_stage_device(ctx, 2, 2 * (size_t)chunk * feat_per * sizeof(double), &base)) != LSM_OK) return rc;
     d_feat[0] = base; d_feat[1] = (char *)base + (size_t)chunk * feat_per * sizeof(double);
     cudaStream_t s_in = ctx->copy_stream[0], s_out = ctx->copy_stream[1], s_k = ctx->stream;
+    const bool fused = lsm_fused_npt(fe, res) != 0;
     // ev[0..1]: H2D of buffer b done; ev[2..3]: kernels on buffer b done; ev[4..5]: D2H of buffer b done
     for (int c = 0; c < n_chunks; ++c) {
         const int b = c & 1;
@@ -430,9 +435,14 @@ extern "C" int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservo
         LSM_CUDA(ctx, cudaEventRecord(ctx->ev[b], s_in));
         LSM_CUDA(ctx, cudaStreamWaitEvent(s_k, ctx->ev[b], 0));
         if (c >= 2) LSM_CUDA(ctx, cudaStreamWaitEvent(s_k, ctx->ev[4 + b], 0));    // D2H of chunk c-2 released d_spk/d_feat[b]
-        if ((rc = frontend_launch(ctx, fe, (const float *)d_pcm[b], n, (uint8_t *)d_spk[b], nullptr, s_k)) != LSM_OK) return rc;
-        if ((rc = lsm_launch_reservoir(ctx, res, (const uint8_t *)d_spk[b], n, feature_mask, nan_to_num,
-                                       (double *)d_feat[b], nullptr, s_k)) != LSM_OK) return rc;
+        if (fused) {
+            if ((rc = lsm_launch_fused(ctx, fe, res, (const float *)d_pcm[b], n, h_spikes_or_null ? (uint8_t *)d_spk[b] : nullptr,
+                                       feature_mask, nan_to_num, (double *)d_feat[b], s_k)) != LSM_OK) return rc;
+        } else {
+            if ((rc = frontend_launch(ctx, fe, (const float *)d_pcm[b], n, (uint8_t *)d_spk[b], nullptr, s_k)) != LSM_OK) return rc;
+            if ((rc = lsm_launch_reservoir(ctx, res, (const uint8_t *)d_spk[b], n, feature_mask, nan_to_num,
+                                           (double *)d_feat[b], nullptr, s_k)) != LSM_OK) return rc;
+        }
         LSM_CUDA(ctx, cudaEventRecord(ctx->ev[2 + b], s_k));
         LSM_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->ev[2 + b], 0));
         LSM_CUDA(ctx, cudaMemcpyAsync(h_features + off * feat_per, d_feat[b], (size_t)n * feat_per * sizeof(double), cudaMemcpyDeviceToHost, s_out));

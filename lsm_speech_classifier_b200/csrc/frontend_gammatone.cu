@@ -20,7 +20,7 @@
 // (oracle/lsm_oracle.c gammatone_energy / db_normalise_zoom / hysteresis_encode_f64).
 #include <stdlib.h>
 
-#include "lsm_common.cuh"
+#include "reservoir_core.cuh"
 
 namespace {
 
@@ -49,6 +49,7 @@ struct GtArgs {
     double *spec_norm;      // optional [B][C][nbins]
     int B, L, C, nwin, hop, ncols, nbins, K, R;
     double thr[8], lower[8];
+    ResArgs res;            // fused mode only: the reservoir this utterance's spikes feed
 };
 
 // One biquad step (scipy.signal.lfilter direct form II transposed, b2 = 0): y = z0 + b0*x;
@@ -60,7 +61,11 @@ struct GtArgs {
         z1 = mul64(y, na2);                                    \
     }
 
-template <int MAXT, int MINB>
+// FNPT = 0: front end only (spike trains to global memory).  FNPT > 0: fused audio -> features: after
+// encoding an utterance the same CTA simulates its reservoir (FNPT neurons per thread, blockDim == C) with
+// the spikes handed over as bits in shared memory; the reservoir phase is latency/issue bound and uses
+// almost no fp64, so it hides under the filter phases of the other CTAs resident on the SM.
+template <int MAXT, int MINB, int FNPT, bool LEAN>
 __global__ void __launch_bounds__(MAXT, MINB) gammatone_encode_kernel(const GtArgs a, int *next_utt)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -68,6 +73,7 @@ __global__ void __launch_bounds__(MAXT, MINB) gammatone_encode_kernel(const GtAr
     __shared__ double s_red[2][8];
     __shared__ double s_mm[2];
     __shared__ int s_utt;
+    __shared__ int s_cnt3[3];
 
     // The four cascaded stages are software-skewed: in one loop iteration stage k works on sample
     // s + (3 - k), so the four recurrences are independent instruction chains (ILP 4) while every
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(MAXT, MINB) gammatone_encode_kernel(const GtAr
 
         if (live) {
             const int T = a.nbins * a.K;
-            uint8_t *row0 = a.spikes + ((size_t)utt * C * a.R + (size_t)ch * a.R) * T;
+            uint8_t *row0 = a.spikes ? a.spikes + ((size_t)utt * C * a.R + (size_t)ch * a.R) * T : nullptr;
             double *dump = a.spec_norm ? a.spec_norm + ((size_t)utt * C + ch) * a.nbins : nullptr;
             // normalise in place (own column of the plane only)
             for (int c = 0; c < ncols; ++c) {
@@ -237,7 +243,16 @@ __global__ void __launch_bounds__(MAXT, MINB) gammatone_encode_kernel(const GtAr
                         else if (is_on && v < a.lower[k]) on &= ~(1u << k);
                     }
                 }
-                for (int r = 0; r < a.R; ++r) {
+                if (FNPT > 0) {
+                    // hand the spikes to the reservoir phase: word (t, warp) = ballot over this warp's 32 channels
+                    unsigned *s_bits = reinterpret_cast<unsigned *>(smem_raw);
+                    const int CW = C >> 5;
+                    for (int k = 0; k < a.K; ++k) {
+                        const unsigned word = __ballot_sync(0xffffffffu, (on >> k) & 1u);
+                        if ((threadIdx.x & 31) == 0) s_bits[(j * a.K + k) * CW + (threadIdx.x >> 5)] = word;
+                    }
+                }
+                for (int r = 0; row0 && r < a.R; ++r) {
                     uint8_t *row = row0 + (size_t)r * T + (size_t)j * a.K;
                     if (a.K == 4) {
                         // bytes k = 0..3 of column block j, little endian
@@ -249,7 +264,11 @@ __global__ void __launch_bounds__(MAXT, MINB) gammatone_encode_kernel(const GtAr
                 }
             }
         }
-        __syncthreads();   // plane, s_x and s_utt are reused by the next utterance
+        if (FNPT > 0) {
+            __syncthreads();   // bits complete and visible
+            reservoir_simulate<(FNPT > 0 ? FNPT : 4), LEAN>(a.res, utt, smem_raw, s_cnt3);
+        }
+        __syncthreads();   // plane, shared memory and s_utt are reused by the next utterance
     }
 }
 
@@ -263,12 +282,12 @@ static int k1_minb()
     return v < 4 ? 4 : (v > 6 ? 6 : v);
 }
 
-template <int MAXT, int MINB>
+template <int MAXT, int MINB, int FNPT, bool LEAN>
 static int k1_grid(lsm_ctx *ctx, int threads, size_t smem, int *per_sm)
 {
     if (smem > 48 * 1024)
-        LSM_CUDA(ctx, cudaFuncSetAttribute(gammatone_encode_kernel<MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, gammatone_encode_kernel<MAXT, MINB>, threads, smem));
+        LSM_CUDA(ctx, cudaFuncSetAttribute(gammatone_encode_kernel<MAXT, MINB, FNPT, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, gammatone_encode_kernel<MAXT, MINB, FNPT, LEAN>, threads, smem));
     return LSM_OK;
 }
 
@@ -277,13 +296,32 @@ int lsm_gammatone_grid(lsm_ctx *ctx, const lsm_frontend_params *p, int *grid)
     const int threads = ((p->channels + 31) / 32) * 32;
     const size_t smem = sizeof(double) * 2 * kChunkBlocks * p->hop;
     int per_sm = 0, rc;
-    if (threads > 128) rc = k1_grid<256, 2>(ctx, threads, smem, &per_sm);
-    else if (k1_minb() == 4) rc = k1_grid<128, 4>(ctx, threads, smem, &per_sm);
-    else if (k1_minb() == 5) rc = k1_grid<128, 5>(ctx, threads, smem, &per_sm);
-    else rc = k1_grid<128, 6>(ctx, threads, smem, &per_sm);
+    if (threads > 128) rc = k1_grid<256, 2, 0, true>(ctx, threads, smem, &per_sm);
+    else if (k1_minb() == 4) rc = k1_grid<128, 4, 0, true>(ctx, threads, smem, &per_sm);
+    else if (k1_minb() == 5) rc = k1_grid<128, 5, 0, true>(ctx, threads, smem, &per_sm);
+    else rc = k1_grid<128, 6, 0, true>(ctx, threads, smem, &per_sm);
     if (rc != LSM_OK) return rc;
     if (per_sm < 1) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "gammatone kernel does not fit on an SM (hop %d)", p->hop);
     *grid = per_sm * ctx->sm_count;   // persistent: every CTA resident, utterances handed out dynamically
+    return LSM_OK;
+}
+
+static void fill_args(const lsm_frontend *fe, const float *d_pcm, int B, uint8_t *d_spikes, double *d_spec_norm, GtArgs *out)
+{
+    const lsm_frontend_params &p = fe->p;
+    GtArgs &a = *out;
+    a.pcm = d_pcm; a.coefs = fe->d_coefs; a.zoom_i0 = fe->d_zoom_i0; a.zoom_f = fe->d_zoom_f;
+    a.scratch = fe->d_scratch; a.spikes = d_spikes; a.spec_norm = d_spec_norm;
+    a.B = B; a.L = p.n_samples; a.C = p.channels; a.nwin = p.nwin; a.hop = p.hop; a.ncols = fe->ncols;
+    a.nbins = p.n_bins; a.K = p.n_thresholds; a.R = p.redundancy;
+    for (int k = 0; k < 8; ++k) { a.thr[k] = p.thresholds_desc[k]; a.lower[k] = p.lower_bounds[k]; }
+}
+
+static int next_counter(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st, int **counter)
+{
+    // work counter: one int per launch out of a small ring, so back-to-back launches on different streams do not share it
+    *counter = fe->d_counters + (fe->counter_next++ % 64);
+    LSM_CUDA(ctx, cudaMemsetAsync(*counter, 0, sizeof(int), st));
     return LSM_OK;
 }
 
@@ -292,25 +330,75 @@ int lsm_launch_gammatone(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int
 {
     const lsm_frontend_params &p = fe->p;
     GtArgs a;
-    a.pcm = d_pcm; a.coefs = fe->d_coefs; a.zoom_i0 = fe->d_zoom_i0; a.zoom_f = fe->d_zoom_f;
-    a.scratch = fe->d_scratch; a.spikes = d_spikes; a.spec_norm = d_spec_norm;
-    a.B = B; a.L = p.n_samples; a.C = p.channels; a.nwin = p.nwin; a.hop = p.hop; a.ncols = fe->ncols;
-    a.nbins = p.n_bins; a.K = p.n_thresholds; a.R = p.redundancy;
-    for (int k = 0; k < 8; ++k) { a.thr[k] = p.thresholds_desc[k]; a.lower[k] = p.lower_bounds[k]; }
+    fill_args(fe, d_pcm, B, d_spikes, d_spec_norm, &a);
+    memset(&a.res, 0, sizeof(a.res));
     const int threads = ((p.channels + 31) / 32) * 32;
     const size_t smem = sizeof(double) * 2 * kChunkBlocks * p.hop;
     const int grid = B < fe->grid ? B : fe->grid;
     if (grid <= 0) return LSM_OK;
-    // work counter: one int per launch out of a small ring, so back-to-back launches on different streams do not share it
-    int *counter = fe->d_counters + (fe->counter_next++ % 64);
-    LSM_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), st));
-    if (threads > 128) gammatone_encode_kernel<256, 2><<<grid, threads, smem, st>>>(a, counter);
-    else if (fe->minb == 4) gammatone_encode_kernel<128, 4><<<grid, threads, smem, st>>>(a, counter);
-    else if (fe->minb == 5) gammatone_encode_kernel<128, 5><<<grid, threads, smem, st>>>(a, counter);
-    else gammatone_encode_kernel<128, 6><<<grid, threads, smem, st>>>(a, counter);
+    int *counter, rc;
+    if ((rc = next_counter(ctx, fe, st, &counter)) != LSM_OK) return rc;
+    if (threads > 128) gammatone_encode_kernel<256, 2, 0, true><<<grid, threads, smem, st>>>(a, counter);
+    else if (fe->minb == 4) gammatone_encode_kernel<128, 4, 0, true><<<grid, threads, smem, st>>>(a, counter);
+    else if (fe->minb == 5) gammatone_encode_kernel<128, 5, 0, true><<<grid, threads, smem, st>>>(a, counter);
+    else gammatone_encode_kernel<128, 6, 0, true><<<grid, threads, smem, st>>>(a, counter);
     ctx->launches += 1;
     LSM_CUDA(ctx, cudaGetLastError());
     return LSM_OK;
+}
+
+// Can this (front end, reservoir) pair run as one fused kernel?  Gammatone, no redundancy, one thread
+// per channel with whole warps, and a reservoir whose padded width is channels x {4, 8, 16} neurons per thread.
+int lsm_fused_npt(const lsm_frontend *fe, const lsm_reservoir *res)
+{
+    const lsm_frontend_params &p = fe->p;
+    if (getenv("LSM_NO_FUSE")) return 0;
+    if (p.kind != LSM_FILTERBANK_GAMMATONE || p.redundancy != 1 || (p.channels & 31) || p.channels > 256) return 0;
+    if (res->p.num_inputs != p.channels || res->p.num_steps != p.n_bins * p.n_thresholds) return 0;
+    if (res->n_pad % p.channels) return 0;
+    const int npt = res->n_pad / p.channels;
+    if (p.channels == 256) return npt == 4 ? 4 : 0;
+    return (npt == 8 || npt == 16) ? npt : 0;
+}
+
+template <int MAXT, int MINB, int FNPT>
+static int launch_fused_t(lsm_ctx *ctx, lsm_frontend *fe, const lsm_reservoir *res, const GtArgs &a, int threads, size_t smem,
+                          cudaStream_t st)
+{
+    int per_sm = 0, rc;
+    if (res->lean) rc = k1_grid<MAXT, MINB, FNPT, true>(ctx, threads, smem, &per_sm);
+    else rc = k1_grid<MAXT, MINB, FNPT, false>(ctx, threads, smem, &per_sm);
+    if (rc != LSM_OK) return rc;
+    if (per_sm < 1) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "fused kernel does not fit on an SM (%zu B shared memory)", smem);
+    int grid = per_sm * ctx->sm_count;
+    if (grid > fe->grid) grid = fe->grid;      // the dB scratch plane is sized for fe->grid CTAs
+    if (grid > a.B) grid = a.B;
+    int *counter;
+    if ((rc = next_counter(ctx, fe, st, &counter)) != LSM_OK) return rc;
+    if (res->lean) gammatone_encode_kernel<MAXT, MINB, FNPT, true><<<grid, threads, smem, st>>>(a, counter);
+    else gammatone_encode_kernel<MAXT, MINB, FNPT, false><<<grid, threads, smem, st>>>(a, counter);
+    ctx->launches += 1;
+    LSM_CUDA(ctx, cudaGetLastError());
+    return LSM_OK;
+}
+
+int lsm_launch_fused(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B,
+                     uint8_t *d_spikes_or_null, uint32_t feature_mask, int nan_to_num, double *d_features, cudaStream_t st)
+{
+    const int npt = lsm_fused_npt(fe, res);
+    if (!npt) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "this front end / reservoir pair cannot run fused");
+    if (B <= 0) return LSM_OK;
+    const lsm_frontend_params &p = fe->p;
+    GtArgs a;
+    fill_args(fe, d_pcm, B, d_spikes_or_null, nullptr, &a);
+    lsm_reservoir_fill_args(res, nullptr, B, feature_mask, nan_to_num, d_features, nullptr, &a.res);
+    const int threads = p.channels;
+    size_t smem = sizeof(double) * 2 * kChunkBlocks * p.hop;
+    const size_t smem_res = lsm_res_smem_bytes(a.res.T, a.res.CW, threads * npt, a.res.N);
+    if (smem_res > smem) smem = smem_res;
+    if (threads == 256) return launch_fused_t<256, 2, 4>(ctx, fe, res, a, threads, smem, st);
+    if (npt == 8) return launch_fused_t<128, 4, 8>(ctx, fe, res, a, threads, smem, st);
+    return launch_fused_t<128, 4, 16>(ctx, fe, res, a, threads, smem, st);
 }
 
 int lsm_gammatone_minb(void) { return k1_minb(); }

@@ -81,6 +81,12 @@ int lsm_launch_gammatone(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int
                          double *d_spec_norm, cudaStream_t st);
 int lsm_gammatone_grid(lsm_ctx *ctx, const lsm_frontend_params *p, int *grid);
 int lsm_gammatone_minb(void);
+int lsm_fused_npt(const lsm_frontend *fe, const lsm_reservoir *res);
+int lsm_launch_fused(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B,
+                     uint8_t *d_spikes_or_null, uint32_t feature_mask, int nan_to_num, double *d_features, cudaStream_t st);
+struct ResArgs;
+void lsm_reservoir_fill_args(const lsm_reservoir *res, const uint8_t *d_spikes, int B, uint32_t feature_mask,
+                             int nan_to_num, double *d_features, uint8_t *d_raster, ResArgs *out);
 int lsm_launch_mel(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, uint8_t *d_spikes,
                    double *d_spec_norm, cudaStream_t st);
 int lsm_launch_reservoir(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int B,

@@ -1,0 +1,209 @@
+// Reservoir step loop + feature readout shared by the stand-alone kernel (reservoir.cu) and the fused
+// audio -> features kernel (frontend_gammatone.cu).  Semantics: DESIGN.md reservoir spec R6, R8-R10;
+// oracle/lsm_oracle.c simulate_one.  Replaces /root/reference/extract_lsm_features.py:79-87 per utterance.
+#pragma once
+
+#include "lsm_common.cuh"
+
+struct ResArgs {
+    const uint8_t *spikes;    // [B][C][T]  level signal: any non-zero byte is "on"
+    const int32_t *wt;        // [N+1][n_pad]  row = presynaptic neuron, row N = zeros (list padding)
+    const int32_t *in_rowptr; // [N+1]
+    const int32_t *in_col;
+    const double *in_val;
+    const int32_t *in_row;    // [n_pad] the single input row of a neuron, -1 none, -2 several (generic CSR walk)
+    const double *leak;       // [N]
+    const int32_t *out_slot;  // [N]
+    double *features;         // [B][nkeys][n_out]
+    uint8_t *raster;          // optional [B][T][N]
+    int B, N, n_pad, C, CW, T, refractory, n_out, nkeys, nan_to_num;
+    unsigned feature_mask;
+    double theta, scale, leak0, gain0;
+};
+
+
+// Shared-memory plan (per CTA = per utterance), S = blockDim.x * NPT neuron slots:
+//   bits  uint32[T][CW]     input spikes, time-major, one bit per input row (filled by the caller)
+//   stat  int32[6][S]       per-neuron count, sum t, first, last, sum isi^2, bursts
+//   list  uint16[2][NL]     neurons that fired in the previous / current step (read 4 at a time; slots past
+//                           the end select the all-zero weight row)
+__host__ __device__ inline size_t lsm_res_smem_bytes(int T, int CW, int slots, int N)
+{
+    return sizeof(unsigned) * (size_t)T * CW + sizeof(int) * 6 * (size_t)slots + sizeof(unsigned short) * 2 * (size_t)((N + 7) & ~3);
+}
+
+// Caller contract: s_bits holds the utterance's input and a __syncthreads() has made it visible.
+// LEAN = uniform leak, uniform input gain, at most one input row per neuron (the reference's setup).
+template <int NPT, bool LEAN>
+__device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int utt, unsigned char *smem_raw, int *s_cnt)
+{
+    const int tid = threadIdx.x;
+    const int nthr = blockDim.x;
+    const int lane = tid & 31;
+    const int N = a.N, T = a.T, CW = a.CW;
+    const int S = nthr * NPT;
+    const int NL = (N + 7) & ~3;                       // list capacity, multiple of 4
+    unsigned *s_bits = reinterpret_cast<unsigned *>(smem_raw);
+    int *s_stat = reinterpret_cast<int *>(s_bits + (size_t)T * CW);
+    unsigned short *s_list = reinterpret_cast<unsigned short *>(s_stat + 6 * (size_t)S);
+
+    for (int i = tid; i < S; i += nthr) {
+        s_stat[i] = 0; s_stat[S + i] = 0; s_stat[2 * S + i] = -1; s_stat[3 * S + i] = -1; s_stat[4 * S + i] = 0; s_stat[5 * S + i] = 0;
+    }
+    if (tid < 3) s_cnt[tid] = 0;
+
+    // per-neuron state in registers: thread tid owns the NPT consecutive neurons tid*NPT ...
+    const int i0 = tid * NPT;
+    double V[NPT], lk[NPT];
+    int ref[NPT], in_word[NPT];
+    unsigned in_mask[NPT];
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+        const int i = i0 + k;
+        V[k] = 0.0; ref[k] = 0;
+        const int r = __ldg(a.in_row + i);            // padded to n_pad with -1
+        in_word[k] = r >= 0 ? (r >> 5) : (r == -2 ? -2 : 0);
+        in_mask[k] = r >= 0 ? (1u << (r & 31)) : 0u;
+        lk[k] = (LEAN || i >= N) ? a.leak0 : __ldg(a.leak + i);
+    }
+    const int32_t *wrow = a.wt + i0;
+    __syncthreads();
+
+    int c_cur = 0, c_nxt = 1, c_zero = 2;
+    for (int t = 0; t < T; ++t) {
+        const unsigned short *list = s_list + (t & 1) * NL;
+        unsigned short *list_next = s_list + ((t + 1) & 1) * NL;
+        const int n_prev = s_cnt[c_cur];
+        if (tid == 0) s_cnt[c_zero] = 0;
+
+        // ---- recurrent current: exact integer sum over the neurons that fired at t-1; one 16-byte
+        //      load per (presynaptic row, 4 consecutive postsynaptic neurons)
+        int acc[NPT];
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) acc[k] = 0;
+        for (int q = 0; q < n_prev; q += 4) {
+            const uint2 jj = *reinterpret_cast<const uint2 *>(list + q);
+            // entries past the end of the list select the all-zero weight row (index N)
+            const int j0 = jj.x & 0xffff;
+            const int j1 = (q + 1 < n_prev) ? (int)(jj.x >> 16) : N;
+            const int j2 = (q + 2 < n_prev) ? (int)(jj.y & 0xffff) : N;
+            const int j3 = (q + 3 < n_prev) ? (int)(jj.y >> 16) : N;
+            const int32_t *r0 = wrow + j0 * a.n_pad, *r1 = wrow + j1 * a.n_pad;
+            const int32_t *r2 = wrow + j2 * a.n_pad, *r3 = wrow + j3 * a.n_pad;
+#pragma unroll
+            for (int u = 0; u < NPT / 4; ++u) {
+                const int4 w0 = __ldg(reinterpret_cast<const int4 *>(r0) + u);
+                const int4 w1 = __ldg(reinterpret_cast<const int4 *>(r1) + u);
+                const int4 w2 = __ldg(reinterpret_cast<const int4 *>(r2) + u);
+                const int4 w3 = __ldg(reinterpret_cast<const int4 *>(r3) + u);
+                acc[4 * u + 0] += (w0.x + w1.x) + (w2.x + w3.x);
+                acc[4 * u + 1] += (w0.y + w1.y) + (w2.y + w3.y);
+                acc[4 * u + 2] += (w0.z + w1.z) + (w2.z + w3.z);
+                acc[4 * u + 3] += (w0.w + w1.w) + (w2.w + w3.w);
+            }
+        }
+
+        // ---- membrane update, threshold, reset, refractory (spec R6), branch-free
+        const unsigned *bits_t = s_bits + t * CW;
+        unsigned fired = 0;                            // bit k: neuron i0+k fired
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) {
+            const int i = i0 + k;
+            double i_in;
+            if (LEAN) {
+                const bool on = (bits_t[in_word[k]] & in_mask[k]) != 0u;
+                i_in = on ? a.gain0 : 0.0;
+            } else {
+                i_in = 0.0;
+                if (in_word[k] >= 0) {
+                    if (bits_t[in_word[k]] & in_mask[k]) i_in = add64(0.0, __ldg(a.in_val + __ldg(a.in_rowptr + i)));
+                } else {
+                    for (int p = __ldg(a.in_rowptr + i); p < __ldg(a.in_rowptr + i + 1); ++p) {
+                        const int rr = __ldg(a.in_col + p);
+                        const double on = ((bits_t[rr >> 5] >> (rr & 31)) & 1u) ? 1.0 : 0.0;
+                        i_in = add64(i_in, mul64(__ldg(a.in_val + p), on));
+                    }
+                }
+            }
+            const double cur = add64(i_in, mul64((double)acc[k], a.scale));
+            const double v = add64(sub64(V[k], mul64(lk[k], V[k])), cur);
+            const bool active = ref[k] == 0;
+            const bool fire = active && (v >= a.theta) && (i < N);
+            V[k] = (active && !fire) ? v : 0.0;
+            ref[k] = fire ? a.refractory : (active ? 0 : ref[k] - 1);
+            fired |= fire ? (1u << k) : 0u;
+        }
+        if (a.raster) {
+#pragma unroll
+            for (int k = 0; k < NPT; ++k)
+                if (i0 + k < N) a.raster[((size_t)utt * T + t) * N + i0 + k] = (fired >> k) & 1u;
+        }
+        // ---- spikes are rare: statistics (spec R9) and list compaction only for warps that have one
+        if (__any_sync(0xffffffffu, fired != 0u)) {
+#pragma unroll
+            for (int k = 0; k < NPT; ++k) {
+                const bool fire = (fired >> k) & 1u;
+                if (fire) {
+                    const int sl = k * nthr + tid;
+                    const int c = s_stat[sl];
+                    if (c > 0) {
+                        const int isi = t - s_stat[3 * S + sl];
+                        s_stat[4 * S + sl] += isi * isi;
+                        if (isi <= a.refractory + 1) s_stat[5 * S + sl] += 1;
+                    } else s_stat[2 * S + sl] = t;
+                    s_stat[sl] = c + 1;
+                    s_stat[S + sl] += t;
+                    s_stat[3 * S + sl] = t;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, fire);
+                if (m) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_cnt[c_nxt], __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (fire) list_next[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(i0 + k);
+                }
+            }
+        }
+        __syncthreads();
+        const int tmp = c_cur; c_cur = c_nxt; c_nxt = c_zero; c_zero = tmp;
+    }
+
+    // ---- K3: feature readout, key-major [nkeys][n_out] (extract_lsm_features.py:85-87)
+    if (a.features) {
+        double *f = a.features + (size_t)utt * a.nkeys * a.n_out;
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) {
+            const int i = i0 + k;
+            if (i >= N) continue;
+            const int o = __ldg(a.out_slot + i);
+            if (o < 0) continue;
+            const int sl = k * nthr + tid;
+            const int cnt = s_stat[sl], sumt = s_stat[S + sl], first = s_stat[2 * S + sl], last = s_stat[3 * S + sl];
+            const int s2 = s_stat[4 * S + sl], burst = s_stat[5 * S + sl];
+            const double c = (double)cnt;
+            int slot = 0;
+#pragma unroll
+            for (int key = 0; key < 8; ++key) {
+                if (!(a.feature_mask & (1u << key))) continue;
+                double v = nan;
+                switch (key) {
+                case 0: v = c; break;
+                case 1: { const double p = __ddiv_rn(c, (double)T); v = mul64(p, sub64(1.0, p)); } break;
+                case 2: if (cnt >= 1) v = __ddiv_rn((double)sumt, c); break;
+                case 3: if (cnt >= 1) v = (double)first; break;
+                case 4: if (cnt >= 1) v = (double)last; break;
+                case 5: if (cnt >= 2) v = __ddiv_rn((double)(last - first), (double)(cnt - 1)); break;
+                case 6: if (cnt >= 2) {
+                            const long long n = cnt - 1, s1 = last - first;
+                            v = __ddiv_rn((double)(n * (long long)s2 - s1 * s1), (double)(n * n));
+                        } break;
+                case 7: v = (double)burst; break;
+                }
+                if (a.nan_to_num && v != v) v = 0.0;
+                f[(size_t)slot * a.n_out + o] = v;
+                ++slot;
+            }
+        }
+    }
+}

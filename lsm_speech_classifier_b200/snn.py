@@ -162,8 +162,9 @@ class AudioToFeatures:
             C.c_void_p(out.ctypes.data), C.c_void_p(spikes_out.ctypes.data) if spikes_out is not None else None))
         return out
 
-    def run(self, pcm, feature_keys, nan_to_num: bool = True, spikes=None, out=None):
-        """torch CUDA tensors, asynchronous on the current stream."""
+    def run(self, pcm, feature_keys, nan_to_num: bool = True, spikes=None, out=None, want_spikes: bool = True):
+        """torch CUDA tensors, asynchronous on the current stream.  One fused kernel when the pair allows it;
+        with want_spikes=False the spike trains then never leave the SM."""
         import torch
         keys = list(feature_keys)
         mask = _lib.feature_mask(keys)
@@ -171,12 +172,12 @@ class AudioToFeatures:
             raise ValueError("feature keys must be in FEATURE_SETS order")
         B = pcm.shape[0]
         fe = self.frontend
-        if spikes is None:
+        if spikes is None and want_spikes:
             spikes = torch.empty((B, fe.rows, fe.steps), dtype=torch.uint8, device=pcm.device)
         if out is None:
             out = torch.empty((B, len(keys) * self.snn.num_output_neurons), dtype=torch.float64, device=pcm.device)
         self.ctx.set_stream(torch.cuda.current_stream(pcm.device).cuda_stream)
         self.ctx.check(self.ctx.lib.lsm_pipeline_run(
             self.ctx.h, fe.h, self.snn.h, C.c_void_p(pcm.data_ptr()), B, mask, int(nan_to_num),
-            C.c_void_p(spikes.data_ptr()), C.c_void_p(out.data_ptr())))
+            C.c_void_p(spikes.data_ptr()) if spikes is not None else None, C.c_void_p(out.data_ptr())))
         return out, spikes

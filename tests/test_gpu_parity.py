@@ -174,6 +174,41 @@ def test_pipeline_host_equals_staged_calls(env, small_set):
     assert np.array_equal(got_big[:len(pcm)], want) and np.array_equal(got_big[-17:], np.concatenate([want] * 90)[2460:2477])
 
 
+@pytest.mark.parametrize("n_filters,kw", [(128, {}), (128, dict(leak_variance_divisor=4.0)), (64, {}), (256, {}),
+                                          (128, dict(num_neurons=700, small_world_graph_k=140, num_output_neurons=300))])
+def test_fused_kernel_equals_two_kernel_path_and_oracle(env, small_set, n_filters, kw, monkeypatch):
+    """audio -> features as ONE kernel (spikes handed over in shared memory) vs K1 then K2 vs the oracle."""
+    import torch
+    from lsm_speech_classifier_b200.frontend import Frontend
+    from lsm_speech_classifier_b200.snn import AudioToFeatures
+    from oracle import coracle
+    pcm, _ = small_set
+    fe = Frontend(n_filters, "gammatone")
+    X = oracle_spikes(pcm, fe)
+    lsm = build_snn(X, **kw)
+    want, _ = coracle.reservoir_run(lsm.reservoir, X, 0xFF, True, False)
+    keys = list(lsm_keys())
+    path = AudioToFeatures(fe, lsm)
+    d_pcm = torch.from_numpy(pcm).cuda()
+    fused, spk = path.run(d_pcm, keys)
+    fused_nospk, none = path.run(d_pcm, keys, want_spikes=False)
+    torch.cuda.synchronize()
+    assert none is None
+    monkeypatch.setenv("LSM_NO_FUSE", "1")
+    unfused, spk2 = path.run(d_pcm, keys)
+    torch.cuda.synchronize()
+    monkeypatch.delenv("LSM_NO_FUSE")
+    assert np.array_equal(spk.cpu().numpy(), X) and np.array_equal(spk2.cpu().numpy(), X)
+    for got in (fused, fused_nospk, unfused):
+        assert np.array_equal(got.cpu().numpy(), want)
+    assert np.array_equal(path.run_host(pcm, keys), want)
+
+
+def lsm_keys():
+    from lsm_speech_classifier_b200 import _lib
+    return _lib.FEATURE_KEYS
+
+
 def test_spike_density_matches_w_critico_inputs(env, small_set):
     import ctypes as C
     import torch
