@@ -89,6 +89,11 @@ typedef struct {
 int lsm_frontend_create(lsm_ctx *ctx, const lsm_frontend_params *p, const void *h_table,
                         const int32_t *h_zoom_i0, const double *h_zoom_f, lsm_frontend **out);
 void lsm_frontend_destroy(lsm_frontend *fe);
+/* Mel only, optional: replace the library's own (host libm) STFT tables with the caller's, so that another
+ * implementation filtering with the same tables is reproduced bit for bit.  h_window: double[n_fft] periodic hann;
+ * h_tw: double[n_fft/4][2] = exp(-2*pi*i*q/(n_fft/2)); h_tw2: double[n_fft/2+1][2] = exp(-2*pi*i*k/n_fft).   */
+int lsm_frontend_mel_tables(lsm_ctx *ctx, lsm_frontend *fe, const double *h_window, const double *h_tw,
+                            const double *h_tw2);
 /* d_pcm: float[B][n_samples].  d_spikes: uint8[B][channels*redundancy][n_bins*n_thresholds] — the
  * X_spikes layout of speech_spike_dataset_pure_redundancy.npz (create_dataset.py:168).
  * d_spec_norm_or_null: optional double[B][channels][n_bins] dump of the normalised, resampled
@@ -155,6 +160,9 @@ int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, co
 int lsm_pipeline_run(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm,
                      int32_t B, uint32_t feature_mask, int32_t nan_to_num, uint8_t *d_spikes_or_null,
                      double *d_features);
+
+/* 1 if lsm_pipeline_run / lsm_pipeline_run_host execute this pair as one fused kernel, else 0. */
+int lsm_pipeline_is_fused(const lsm_frontend *fe, const lsm_reservoir *res);
 
 /* Sum of all spike bytes and their count: the two integers calculate_theoretical_w_critico
  * reduces over X_train[:500] (extract_lsm_features.py:40-44).  h_out: int64[2].            */

@@ -22,7 +22,7 @@ EXPORTS = [
     "lsm_sm_count", "lsm_frontend_create", "lsm_frontend_destroy", "lsm_frontend_encode",
     "lsm_frontend_encode_host", "lsm_reservoir_create", "lsm_reservoir_destroy", "lsm_reservoir_run",
     "lsm_reservoir_run_host", "lsm_pipeline_run_host", "lsm_pipeline_run", "lsm_spike_density",
-    "lsm_hysteresis_encode", "lsm_fp64_peak_gops",
+    "lsm_hysteresis_encode", "lsm_fp64_peak_gops", "lsm_pipeline_is_fused", "lsm_frontend_mel_tables",
 ]
 
 
@@ -82,6 +82,8 @@ def load():
     lib.lsm_spike_density.argtypes = [vp, vp, i64, vp]
     lib.lsm_hysteresis_encode.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, i32, i32, vp]
     lib.lsm_fp64_peak_gops.argtypes = [vp, vp]
+    lib.lsm_pipeline_is_fused.argtypes = [vp, vp]
+    lib.lsm_frontend_mel_tables.argtypes = [vp, vp, vp, vp, vp]
     _lib = lib
     return lib
 

@@ -166,6 +166,16 @@ extern "C" void lsm_frontend_destroy(lsm_frontend *fe)
     delete fe;
 }
 
+extern "C" int lsm_frontend_mel_tables(lsm_ctx *ctx, lsm_frontend *fe, const double *h_window, const double *h_tw,
+                                       const double *h_tw2)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!fe || !h_window || !h_tw || !h_tw2) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_frontend_mel_tables: null argument");
+    if (fe->p.kind != LSM_FILTERBANK_MEL) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_frontend_mel_tables: not a mel front end");
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    return lsm_mel_set_tables(ctx, fe, h_window, h_tw, h_tw2);
+}
+
 static int frontend_launch(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, uint8_t *d_spikes,
                            double *d_spec, cudaStream_t st)
 {
@@ -394,6 +404,11 @@ extern "C" int lsm_pipeline_run(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *r
     return lsm_launch_reservoir(ctx, res, d_spikes, B, feature_mask, nan_to_num, d_features, nullptr, ctx->stream);
 }
 
+extern "C" int lsm_pipeline_is_fused(const lsm_frontend *fe, const lsm_reservoir *res)
+{
+    return (fe && res && lsm_fused_npt(fe, res)) ? 1 : 0;
+}
+
 extern "C" int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *h_pcm,
                                      int32_t B, uint32_t feature_mask, int32_t nan_to_num, double *h_features,
                                      uint8_t *h_spikes_or_null)
@@ -410,25 +425,32 @@ extern "C" int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservo
     const size_t spk_per = (size_t)res->p.num_inputs * res->p.num_steps;
     const int nkeys = __builtin_popcount(feature_mask & 0xFFu);
     const size_t feat_per = (size_t)nkeys * res->p.n_out;
-    // chunked, three legs on three streams: H2D(c+1) | K1,K2(c) | D2H(c-1).  Chunk = a few waves of K1.
-    int chunk = fe->grid > 0 ? 2 * fe->grid : 1024;
-    if (chunk > B) chunk = B;
-    const int n_chunks = (B + chunk - 1) / chunk;
+    // chunked, three legs on three streams: H2D(c+1) | kernels(c) | D2H(c-1).  A chunk is one full wave of the
+    // persistent front-end grid (every CTA gets exactly one utterance, so a chunk has no drain tail); a short
+    // remainder is folded into the last chunk.  The first chunk's H2D and the last chunk's D2H are the only
+    // copies that are not hidden.
+    const bool fused = lsm_fused_npt(fe, res) != 0;
+    int wave = fe->grid > 0 ? fe->grid : 1024;
+    if (fused) { const int w = lsm_fused_wave(ctx, fe, res); if (w > 0) wave = w; }
+    int n_chunks = B / wave;
+    if (n_chunks < 1) n_chunks = 1;
+    const int chunk = wave < B ? wave : B;                       // all chunks but the last
+    const int last = B - (n_chunks - 1) * chunk;                 // chunk + remainder (< 2*chunk)
+    const int cap = last > chunk ? last : chunk;
     void *d_pcm[2], *d_spk[2], *d_feat[2];
     int rc;
     void *base;
-    if ((rc = lsm_stage_device(ctx, 0, 2 * (size_t)chunk * L * sizeof(float), &base)) != LSM_OK) return rc;
-    d_pcm[0] = base; d_pcm[1] = (char *)base + (size_t)chunk * L * sizeof(float);
-    if ((rc = lsm_stage_device(ctx, 1, 2 * (size_t)chunk * spk_per, &base)) != LSM_OK) return rc;
-    d_spk[0] = base; d_spk[1] = (char *)base + (size_t)chunk * spk_per;
-    if ((rc = lsm_stage_device(ctx, 2, 2 * (size_t)chunk * feat_per * sizeof(double), &base)) != LSM_OK) return rc;
-    d_feat[0] = base; d_feat[1] = (char *)base + (size_t)chunk * feat_per * sizeof(double);
+    if ((rc = lsm_stage_device(ctx, 0, 2 * (size_t)cap * L * sizeof(float), &base)) != LSM_OK) return rc;
+    d_pcm[0] = base; d_pcm[1] = (char *)base + (size_t)cap * L * sizeof(float);
+    if ((rc = lsm_stage_device(ctx, 1, 2 * (size_t)cap * spk_per, &base)) != LSM_OK) return rc;
+    d_spk[0] = base; d_spk[1] = (char *)base + (size_t)cap * spk_per;
+    if ((rc = lsm_stage_device(ctx, 2, 2 * (size_t)cap * feat_per * sizeof(double), &base)) != LSM_OK) return rc;
+    d_feat[0] = base; d_feat[1] = (char *)base + (size_t)cap * feat_per * sizeof(double);
     cudaStream_t s_in = ctx->copy_stream[0], s_out = ctx->copy_stream[1], s_k = ctx->stream;
-    const bool fused = lsm_fused_npt(fe, res) != 0;
     // ev[0..1]: H2D of buffer b done; ev[2..3]: kernels on buffer b done; ev[4..5]: D2H of buffer b done
     for (int c = 0; c < n_chunks; ++c) {
         const int b = c & 1;
-        const int n = (c + 1) * chunk <= B ? chunk : B - c * chunk;
+        const int n = (c + 1 < n_chunks) ? chunk : last;
         const size_t off = (size_t)c * chunk;
         if (c >= 2) LSM_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->ev[2 + b], 0));   // kernels of chunk c-2 released d_pcm[b]
         LSM_CUDA(ctx, cudaMemcpyAsync(d_pcm[b], h_pcm + off * L, (size_t)n * L * sizeof(float), cudaMemcpyHostToDevice, s_in));

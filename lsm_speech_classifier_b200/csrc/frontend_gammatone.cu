@@ -361,9 +361,10 @@ int lsm_fused_npt(const lsm_frontend *fe, const lsm_reservoir *res)
     return (npt == 8 || npt == 16) ? npt : 0;
 }
 
+// launch == false: only report the resident grid (one wave) of this variant through *wave
 template <int MAXT, int MINB, int FNPT>
 static int launch_fused_t(lsm_ctx *ctx, lsm_frontend *fe, const lsm_reservoir *res, const GtArgs &a, int threads, size_t smem,
-                          cudaStream_t st)
+                          cudaStream_t st, bool launch = true, int *wave = nullptr)
 {
     int per_sm = 0, rc;
     if (res->lean) rc = k1_grid<MAXT, MINB, FNPT, true>(ctx, threads, smem, &per_sm);
@@ -372,6 +373,8 @@ static int launch_fused_t(lsm_ctx *ctx, lsm_frontend *fe, const lsm_reservoir *r
     if (per_sm < 1) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "fused kernel does not fit on an SM (%zu B shared memory)", smem);
     int grid = per_sm * ctx->sm_count;
     if (grid > fe->grid) grid = fe->grid;      // the dB scratch plane is sized for fe->grid CTAs
+    if (wave) *wave = grid;
+    if (!launch) return LSM_OK;
     if (grid > a.B) grid = a.B;
     int *counter;
     if ((rc = next_counter(ctx, fe, st, &counter)) != LSM_OK) return rc;
@@ -382,12 +385,32 @@ static int launch_fused_t(lsm_ctx *ctx, lsm_frontend *fe, const lsm_reservoir *r
     return LSM_OK;
 }
 
+static int fused_dispatch(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B,
+                          uint8_t *d_spikes_or_null, uint32_t feature_mask, int nan_to_num, double *d_features, cudaStream_t st,
+                          bool launch, int *wave);
+
 int lsm_launch_fused(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B,
                      uint8_t *d_spikes_or_null, uint32_t feature_mask, int nan_to_num, double *d_features, cudaStream_t st)
 {
+    if (B <= 0) return LSM_OK;
+    return fused_dispatch(ctx, fe, res, d_pcm, B, d_spikes_or_null, feature_mask, nan_to_num, d_features, st, true, nullptr);
+}
+
+// CTAs resident at once for the fused kernel of this pair = utterances per wave (0 if not fusable)
+int lsm_fused_wave(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res)
+{
+    int wave = 0;
+    if (!lsm_fused_npt(fe, res)) return 0;
+    if (fused_dispatch(ctx, fe, res, nullptr, 1, nullptr, 1u, 0, nullptr, nullptr, false, &wave) != LSM_OK) return 0;
+    return wave;
+}
+
+static int fused_dispatch(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B,
+                          uint8_t *d_spikes_or_null, uint32_t feature_mask, int nan_to_num, double *d_features, cudaStream_t st,
+                          bool launch, int *wave)
+{
     const int npt = lsm_fused_npt(fe, res);
     if (!npt) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "this front end / reservoir pair cannot run fused");
-    if (B <= 0) return LSM_OK;
     const lsm_frontend_params &p = fe->p;
     GtArgs a;
     fill_args(fe, d_pcm, B, d_spikes_or_null, nullptr, &a);
@@ -396,9 +419,12 @@ int lsm_launch_fused(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const f
     size_t smem = sizeof(double) * 2 * kChunkBlocks * p.hop;
     const size_t smem_res = lsm_res_smem_bytes(a.res.T, a.res.CW, threads * npt, a.res.N);
     if (smem_res > smem) smem = smem_res;
-    if (threads == 256) return launch_fused_t<256, 2, 4>(ctx, fe, res, a, threads, smem, st);
-    if (npt == 8) return launch_fused_t<128, 4, 8>(ctx, fe, res, a, threads, smem, st);
-    return launch_fused_t<128, 4, 16>(ctx, fe, res, a, threads, smem, st);
+    if (threads == 256) return launch_fused_t<256, 2, 4>(ctx, fe, res, a, threads, smem, st, launch, wave);
+    if (npt == 8) {
+        if (fe->minb >= 5) return launch_fused_t<128, 5, 8>(ctx, fe, res, a, threads, smem, st, launch, wave);
+        return launch_fused_t<128, 4, 8>(ctx, fe, res, a, threads, smem, st, launch, wave);
+    }
+    return launch_fused_t<128, 4, 16>(ctx, fe, res, a, threads, smem, st, launch, wave);
 }
 
 int lsm_gammatone_minb(void) { return k1_minb(); }

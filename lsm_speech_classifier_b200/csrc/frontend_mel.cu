@@ -1,12 +1,281 @@
-// K1m — mel front end (placeholder until the STFT kernel lands; fails loudly, never falls back).
+// K1m — mel front end: STFT power -> mel projection -> power_to_db -> min-max -> zoom -> hysteresis encoder.
+//
+// Replaces, per utterance, /root/reference/create_dataset.py:148-158 on the mel branch:
+//   librosa.feature.melspectrogram(y, sr=16000, n_mels=n, hop_length=160)   :45-47  (librosa==0.11.0: n_fft 2048,
+//        periodic hann, centre zero padding, |STFT|^2 in float32 from a complex64 STFT, Slaney mel basis)
+//   librosa.power_to_db(spec, ref=np.max)                                     :48     (amin 1e-10, top_db 80)
+//   min-max normalisation :62-67, scipy zoom 101 -> 100 :69-78, encoder :81-98, redundancy :101-104
+//
+// Mapping: one CTA (256 threads) per utterance in flight, persistent grid with dynamic hand-out.  Per frame: the
+// 2048 real samples (fp64 window x float32 PCM) are packed as 1024 complex numbers, transformed by a shared-
+// memory radix-2 FFT in fp64 and untangled to the 1025 real-input bins; power in float32; each thread owns one
+// mel band and sums its (short) triangle in ascending-bin order.  The per-utterance epilogue (dB, floor,
+// normalise, zoom, Schmitt triggers) is the float32 twin of K1's.
+//
+// Bit-exactness: every operation and its order equals oracle/lsm_oracle.c (fft1024 / frame_power / mel_one);
+// explicit *_rn intrinsics, no FMA contraction.  librosa's own FFT (pocketfft) has a different internal order;
+// the oracle documents that and is itself compared with scipy.fft.
+#include <math.h>
+#include <vector>
+
 #include "lsm_common.cuh"
 
-int lsm_mel_create(lsm_ctx *ctx, lsm_frontend *, const float *)
+namespace {
+
+constexpr int kFft = 2048, kHalf = 1024, kThreads = 256;
+
+struct MelArgs {
+    const float *pcm;        // [B][L]
+    const double *win;       // [2048]
+    const double2 *tw;       // [512]
+    const double2 *tw2;      // [1025]
+    const float *mel_w;      // packed
+    const int32_t *mel_lo, *mel_n, *mel_off;
+    const int32_t *zoom_i0;
+    const double *zoom_f;
+    float *scratch;          // [grid][ncols][C]
+    uint8_t *spikes;
+    double *spec_norm;       // optional [B][C][nbins]
+    int B, L, C, hop, ncols, nbins, K, R;
+    double thr[8], lower[8];
+};
+
+__device__ __forceinline__ float block_reduce_f32(float v, bool want_max, float *s_red)
 {
-    LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "mel front end not built yet");
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = want_max ? fmaxf(v, other) : fminf(v, other);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = s_red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = want_max ? fmaxf(r, s_red[w]) : fminf(r, s_red[w]);
+    return r;
 }
-void lsm_mel_destroy(lsm_frontend *) {}
-int lsm_launch_mel(lsm_ctx *ctx, lsm_frontend *, const float *, int, uint8_t *, double *, cudaStream_t)
+
+__global__ void __launch_bounds__(kThreads) mel_encode_kernel(const MelArgs a, int *next_utt)
 {
-    LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "mel front end not built yet");
+    __shared__ double s_re[kHalf], s_im[kHalf];
+    __shared__ float s_S[kHalf + 8];
+    __shared__ float s_red[kThreads / 32];
+    __shared__ int s_utt;
+
+    const int tid = threadIdx.x;
+    const int C = a.C, ncols = a.ncols;
+    float *plane = a.scratch + (size_t)blockIdx.x * ncols * C;     // mel power / dB plane [ncols][C]
+
+    for (;;) {
+        if (tid == 0) s_utt = atomicAdd(next_utt, 1);
+        __syncthreads();
+        const int utt = s_utt;
+        if (utt >= a.B) break;
+        const float *pcm = a.pcm + (size_t)utt * a.L;
+
+        for (int t = 0; t < ncols; ++t) {
+            const int start = t * a.hop - kHalf;                   // centre padding: n_fft/2 zeros each side
+            // ---- windowed frame, packed z[j] = x[2j] + i x[2j+1], stored bit-reversed for the DIT FFT
+            for (int j = tid; j < kHalf; j += kThreads) {
+                const int i0 = start + 2 * j, i1 = i0 + 1;
+                const double x0 = (i0 >= 0 && i0 < a.L) ? __dmul_rn(__ldg(a.win + 2 * j), (double)__ldg(pcm + i0)) : 0.0;
+                const double x1 = (i1 >= 0 && i1 < a.L) ? __dmul_rn(__ldg(a.win + 2 * j + 1), (double)__ldg(pcm + i1)) : 0.0;
+                const int r = (int)(__brev((unsigned)j) >> 22);
+                s_re[r] = x0; s_im[r] = x1;
+            }
+            __syncthreads();
+            // ---- 10 radix-2 stages, 512 butterflies each
+#pragma unroll 1
+            for (int s = 1; s <= 10; ++s) {
+                const int half = 1 << (s - 1), stride = kHalf >> s;
+                for (int idx = tid; idx < kHalf / 2; idx += kThreads) {
+                    const int j = idx & (half - 1);
+                    const int p = ((idx >> (s - 1)) << s) + j, q = p + half;
+                    const double2 w = __ldg(a.tw + j * stride);
+                    const double qr = s_re[q], qi = s_im[q];
+                    const double tr = __dsub_rn(__dmul_rn(w.x, qr), __dmul_rn(w.y, qi));
+                    const double ti = __dadd_rn(__dmul_rn(w.x, qi), __dmul_rn(w.y, qr));
+                    const double ur = s_re[p], ui = s_im[p];
+                    s_re[p] = __dadd_rn(ur, tr); s_im[p] = __dadd_rn(ui, ti);
+                    s_re[q] = __dsub_rn(ur, tr); s_im[q] = __dsub_rn(ui, ti);
+                }
+                __syncthreads();
+            }
+            // ---- real-input untangle, complex64 rounding, |.|^2 in float32
+            for (int k = tid; k <= kHalf; k += kThreads) {
+                const int k1 = k & (kHalf - 1), k2 = (kHalf - k) & (kHalf - 1);
+                const double zr = s_re[k1], zi = s_im[k1], cr = s_re[k2], ci = -s_im[k2];
+                const double ar = __dmul_rn(0.5, __dadd_rn(zr, cr)), ai = __dmul_rn(0.5, __dadd_rn(zi, ci));
+                const double br = __dmul_rn(0.5, __dsub_rn(zr, cr)), bi = __dmul_rn(0.5, __dsub_rn(zi, ci));
+                const double2 w = __ldg(a.tw2 + k);
+                const double c_re = w.y, c_im = -w.x;                                   // -i * W
+                const double xr = __dadd_rn(ar, __dsub_rn(__dmul_rn(c_re, br), __dmul_rn(c_im, bi)));
+                const double xi = __dadd_rn(ai, __dadd_rn(__dmul_rn(c_re, bi), __dmul_rn(c_im, br)));
+                const float r32 = (float)xr, i32 = (float)xi;
+                const double r64 = (double)r32, i64 = (double)i32;
+                const float mag = (float)__dsqrt_rn(__dadd_rn(__dmul_rn(r64, r64), __dmul_rn(i64, i64)));
+                s_S[k] = __fmul_rn(mag, mag);
+            }
+            __syncthreads();
+            // ---- mel projection: one band per thread, ascending bins, float32 multiply then add
+            for (int m = tid; m < C; m += kThreads) {
+                const float *w = a.mel_w + __ldg(a.mel_off + m);
+                const int lo = __ldg(a.mel_lo + m), n = __ldg(a.mel_n + m);
+                float acc = 0.0f;
+                for (int q = 0; q < n; ++q) acc = __fadd_rn(acc, __fmul_rn(__ldg(w + q), s_S[lo + q]));
+                plane[(size_t)t * C + m] = acc;
+            }
+            // the next frame's loads touch s_re/s_im only, and ten barriers separate this read of s_S from its next write
+        }
+
+        // ---- power_to_db(ref=np.max, amin=1e-10, top_db=80), create_dataset.py:48
+        float tmax = -INFINITY;
+        for (int m = tid; m < C; m += kThreads)
+            for (int t = 0; t < ncols; ++t) tmax = fmaxf(tmax, plane[(size_t)t * C + m]);
+        const float ref = block_reduce_f32(tmax, true, s_red);
+        const double refd = ((double)ref > 1e-10) ? (double)ref : 1e-10;               // scalar path is float64 (numpy 1.26)
+        const float ref_db = (float)__dmul_rn(10.0, lsm_log10(refd));
+        float dmax = -INFINITY, dmin = INFINITY;
+        for (int m = tid; m < C; m += kThreads)
+            for (int t = 0; t < ncols; ++t) {
+                const float v = fmaxf(plane[(size_t)t * C + m], 1e-10f);
+                const float d = __fsub_rn(__fmul_rn(10.0f, (float)lsm_log10((double)v)), ref_db);
+                plane[(size_t)t * C + m] = d;
+                dmax = fmaxf(dmax, d); dmin = fminf(dmin, d);
+            }
+        const float mx = block_reduce_f32(dmax, true, s_red);
+        const float rawmin = block_reduce_f32(dmin, false, s_red);
+        const float floor_db = (float)__dsub_rn((double)mx, 80.0);
+        const float mn = fmaxf(rawmin, floor_db);                                       // min of the clamped plane
+        const float diff = __fsub_rn(mx, mn);
+        const bool degenerate = (double)diff < 1e-8;                                    // create_dataset.py:64-65
+        const float den = (float)__dadd_rn((double)diff, 1e-8);
+
+        for (int m = tid; m < C; m += kThreads) {
+            const int T = a.nbins * a.K;
+            uint8_t *row0 = a.spikes + ((size_t)utt * C * a.R + (size_t)m * a.R) * T;
+            double *dump = a.spec_norm ? a.spec_norm + ((size_t)utt * C + m) * a.nbins : nullptr;
+            for (int c = 0; c < ncols; ++c) {
+                const float v = fmaxf(plane[(size_t)c * C + m], floor_db);
+                plane[(size_t)c * C + m] = __fdiv_rn(__fsub_rn(v, mn), den);
+            }
+            unsigned on = 0;
+            for (int j = 0; j < a.nbins; ++j) {
+                float v;
+                if (degenerate) v = 0.0f;
+                else if (ncols == a.nbins) v = plane[(size_t)j * C + m];
+                else {
+                    const int i0 = a.zoom_i0[j];
+                    const double f = a.zoom_f[j];
+                    double vd = __dmul_rn((double)plane[(size_t)i0 * C + m], __dsub_rn(1.0, f));
+                    if (i0 + 1 < ncols) vd = __dadd_rn(vd, __dmul_rn((double)plane[(size_t)(i0 + 1) * C + m], f));
+                    v = (float)vd;
+                }
+                if (dump) dump[j] = (double)v;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (k < a.K) {
+                        const bool is_on = (on >> k) & 1u;
+                        if (!is_on && v > (float)a.thr[k]) on |= (1u << k);
+                        else if (is_on && v < (float)a.lower[k]) on &= ~(1u << k);
+                    }
+                }
+                for (int r = 0; r < a.R; ++r) {
+                    uint8_t *row = row0 + (size_t)r * T + (size_t)j * a.K;
+                    if (a.K == 4) {
+                        const unsigned w = (on & 1u) | ((on & 2u) << 7) | ((on & 4u) << 14) | ((on & 8u) << 21);
+                        *reinterpret_cast<uint32_t *>(row) = w;
+                    } else {
+                        for (int k = 0; k < a.K; ++k) row[k] = (on >> k) & 1u;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+int up(lsm_ctx *ctx, T **dst, const T *src, size_t n)
+{
+    *dst = nullptr;
+    LSM_CUDA(ctx, cudaMalloc((void **)dst, (n ? n : 1) * sizeof(T)));
+    if (src && n) LSM_CUDA(ctx, cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return LSM_OK;
+}
+
+}  // namespace
+
+int lsm_mel_set_tables(lsm_ctx *ctx, lsm_frontend *fe, const double *h_win, const double *h_tw, const double *h_tw2)
+{
+    LSM_CUDA(ctx, cudaMemcpy(fe->d_window, h_win, sizeof(double) * kFft, cudaMemcpyHostToDevice));
+    LSM_CUDA(ctx, cudaMemcpy(fe->d_twiddle, h_tw, sizeof(double) * 2 * (kHalf / 2), cudaMemcpyHostToDevice));
+    LSM_CUDA(ctx, cudaMemcpy(fe->d_twiddle2, h_tw2, sizeof(double) * 2 * (kHalf + 1), cudaMemcpyHostToDevice));
+    return LSM_OK;
+}
+
+int lsm_mel_create(lsm_ctx *ctx, lsm_frontend *fe, const float *h_basis)
+{
+    const lsm_frontend_params &p = fe->p;
+    if (p.n_fft != kFft) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "mel n_fft %d: only 2048 (librosa's default) is built", p.n_fft);
+    const int C = p.channels, nb = 1 + p.n_fft / 2;
+    // pack the non-zero run of every triangle (zeros add exactly nothing)
+    std::vector<float> w;
+    std::vector<int32_t> lo(C, 0), n(C, 0), off(C, 0);
+    for (int m = 0; m < C; ++m) {
+        int a = -1, b = -1;
+        for (int f = 0; f < nb; ++f)
+            if (h_basis[(size_t)m * nb + f] != 0.0f) { if (a < 0) a = f; b = f + 1; }
+        off[m] = (int32_t)w.size();
+        if (a >= 0) { lo[m] = a; n[m] = b - a; w.insert(w.end(), h_basis + (size_t)m * nb + a, h_basis + (size_t)m * nb + b); }
+    }
+    int rc = up(ctx, &fe->d_mel_w, w.data(), w.size());
+    if (rc == LSM_OK) rc = up(ctx, &fe->d_mel_lo, lo.data(), (size_t)C);
+    if (rc == LSM_OK) rc = up(ctx, &fe->d_mel_n, n.data(), (size_t)C);
+    if (rc == LSM_OK) rc = up(ctx, &fe->d_mel_off, off.data(), (size_t)C);
+    // default tables from the host libm; callers that need bit parity with another implementation override them
+    std::vector<double> win(kFft), tw(kHalf), tw2(2 * (kHalf + 1));
+    const double pi = 3.14159265358979323846;
+    for (int i = 0; i < kFft; ++i) win[i] = 0.5 - 0.5 * cos(2 * pi * i / kFft);
+    for (int q = 0; q < kHalf / 2; ++q) { tw[2 * q] = cos(2 * pi * q / kHalf); tw[2 * q + 1] = -sin(2 * pi * q / kHalf); }
+    for (int k = 0; k <= kHalf; ++k) { tw2[2 * k] = cos(2 * pi * k / kFft); tw2[2 * k + 1] = -sin(2 * pi * k / kFft); }
+    if (rc == LSM_OK) rc = up(ctx, &fe->d_window, win.data(), win.size());
+    if (rc == LSM_OK) rc = up(ctx, (double **)&fe->d_twiddle, tw.data(), tw.size());
+    if (rc == LSM_OK) rc = up(ctx, (double **)&fe->d_twiddle2, tw2.data(), tw2.size());
+    if (rc != LSM_OK) return rc;
+    int per_sm = 0;
+    LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_encode_kernel, kThreads, 0));
+    if (per_sm < 1) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "mel kernel does not fit on an SM");
+    fe->grid = per_sm * ctx->sm_count;
+    rc = up<float>(ctx, &fe->d_mel_scratch, nullptr, (size_t)fe->grid * fe->ncols * C);
+    if (rc == LSM_OK) rc = up<int>(ctx, &fe->d_counters, nullptr, 64);
+    return rc;
+}
+
+void lsm_mel_destroy(lsm_frontend *fe)
+{
+    cudaFree(fe->d_mel_w); cudaFree(fe->d_mel_lo); cudaFree(fe->d_mel_n); cudaFree(fe->d_mel_off);
+    cudaFree(fe->d_window); cudaFree(fe->d_twiddle); cudaFree(fe->d_twiddle2); cudaFree(fe->d_mel_scratch);
+}
+
+int lsm_launch_mel(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, uint8_t *d_spikes, double *d_spec_norm,
+                   cudaStream_t st)
+{
+    const lsm_frontend_params &p = fe->p;
+    if (B <= 0) return LSM_OK;
+    MelArgs a;
+    a.pcm = d_pcm; a.win = fe->d_window; a.tw = fe->d_twiddle; a.tw2 = fe->d_twiddle2;
+    a.mel_w = fe->d_mel_w; a.mel_lo = fe->d_mel_lo; a.mel_n = fe->d_mel_n; a.mel_off = fe->d_mel_off;
+    a.zoom_i0 = fe->d_zoom_i0; a.zoom_f = fe->d_zoom_f; a.scratch = fe->d_mel_scratch;
+    a.spikes = d_spikes; a.spec_norm = d_spec_norm;
+    a.B = B; a.L = p.n_samples; a.C = p.channels; a.hop = p.mel_hop; a.ncols = fe->ncols; a.nbins = p.n_bins;
+    a.K = p.n_thresholds; a.R = p.redundancy;
+    for (int k = 0; k < 8; ++k) { a.thr[k] = p.thresholds_desc[k]; a.lower[k] = p.lower_bounds[k]; }
+    int *counter = fe->d_counters + (fe->counter_next++ % 64);
+    LSM_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), st));
+    const int grid = B < fe->grid ? B : fe->grid;
+    mel_encode_kernel<<<grid, kThreads, 0, st>>>(a, counter);
+    ctx->launches += 1;
+    LSM_CUDA(ctx, cudaGetLastError());
+    return LSM_OK;
 }

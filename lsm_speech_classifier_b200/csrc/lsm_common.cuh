@@ -41,7 +41,9 @@ struct lsm_frontend {
     int32_t *d_mel_n = nullptr;    // [C] number of non-zero bins
     int32_t *d_mel_off = nullptr;  // [C] offset into d_mel_w
     double *d_window = nullptr;    // [n_fft] periodic hann
-    double2 *d_twiddle = nullptr;  // [n_fft/2]
+    double2 *d_twiddle = nullptr;  // [n_fft/4]  exp(-2 pi i q / (n_fft/2))
+    double2 *d_twiddle2 = nullptr; // [n_fft/2 + 1]  exp(-2 pi i k / n_fft)
+    float *d_mel_scratch = nullptr; // per-CTA [ncols][C] mel power / dB plane
 };
 
 struct lsm_reservoir {
@@ -84,6 +86,7 @@ int lsm_gammatone_minb(void);
 int lsm_fused_npt(const lsm_frontend *fe, const lsm_reservoir *res);
 int lsm_launch_fused(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B,
                      uint8_t *d_spikes_or_null, uint32_t feature_mask, int nan_to_num, double *d_features, cudaStream_t st);
+int lsm_fused_wave(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res);
 struct ResArgs;
 void lsm_reservoir_fill_args(const lsm_reservoir *res, const uint8_t *d_spikes, int B, uint32_t feature_mask,
                              int nan_to_num, double *d_features, uint8_t *d_raster, ResArgs *out);
@@ -95,6 +98,7 @@ int lsm_launch_reservoir(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spik
 void lsm_reservoir_geometry(int N, int *npt, int *threads, int *n_pad);
 int lsm_mel_create(lsm_ctx *ctx, lsm_frontend *fe, const float *h_basis);
 void lsm_mel_destroy(lsm_frontend *fe);
+int lsm_mel_set_tables(lsm_ctx *ctx, lsm_frontend *fe, const double *h_win, const double *h_tw, const double *h_tw2);
 
 // ---------------------------------------------------------------------------------------------
 // fp64 helpers: every value-producing operation is an explicit round-to-nearest intrinsic, so

@@ -149,3 +149,34 @@ def mel_basis(sr: int, n_fft: int, n_mels: int, fmin: float = 0.0, fmax: float |
 def hann_periodic(n: int) -> np.ndarray:
     """scipy.signal.get_window('hann', n, fftbins=True) as float64."""
     return 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(n) / n)
+
+
+def fft_tables(n_fft: int = 2048):
+    """Twiddle tables for the 1024-point complex FFT of a packed real 2048-point frame:
+    tw[q] = exp(-2*pi*i*q/(n_fft/2)), q < n_fft/4;  tw2[k] = exp(-2*pi*i*k/n_fft), k <= n_fft/2.
+    float64[..., 2] (re, im), built once on the host and handed to both the CUDA kernel and the oracle."""
+    half = n_fft // 2
+    q = np.arange(half // 2, dtype=np.float64)
+    k = np.arange(half + 1, dtype=np.float64)
+    tw = np.stack([np.cos(2 * np.pi * q / half), -np.sin(2 * np.pi * q / half)], axis=1)
+    tw2 = np.stack([np.cos(2 * np.pi * k / n_fft), -np.sin(2 * np.pi * k / n_fft)], axis=1)
+    return np.ascontiguousarray(tw), np.ascontiguousarray(tw2)
+
+
+def pack_mel_basis(basis: np.ndarray):
+    """Non-zero run of every mel triangle: (weights float32[total], lo int32[C], n int32[C], off int32[C]).
+    Zeros add exactly nothing in the projection, so skipping them is exact."""
+    basis = np.asarray(basis, dtype=np.float32)
+    lo, n, off, w = [], [], [], []
+    total = 0
+    for row in basis:
+        nz = np.nonzero(row)[0]
+        if len(nz) == 0:
+            lo.append(0); n.append(0); off.append(total)
+            continue
+        a, b = int(nz[0]), int(nz[-1]) + 1
+        lo.append(a); n.append(b - a); off.append(total)
+        w.append(row[a:b])
+        total += b - a
+    wcat = np.concatenate(w) if w else np.zeros(1, np.float32)
+    return (np.ascontiguousarray(wcat, dtype=np.float32), np.array(lo, np.int32), np.array(n, np.int32), np.array(off, np.int32))

@@ -70,6 +70,12 @@ class Frontend:
         self.ctx.check(self.ctx.lib.lsm_frontend_create(
             self.ctx.h, C.byref(p), _lib._np_ptr(self.table), _lib._np_ptr(self.zoom_i0), _lib._np_ptr(self.zoom_f), C.byref(h)))
         self.h = h
+        if filterbank == "mel":
+            # hand the STFT tables over as data too, so the CPU oracle and the GPU transform with identical bits
+            self.window = fb.hann_periodic(2048)
+            self.tw, self.tw2 = fb.fft_tables(2048)
+            self.ctx.check(self.ctx.lib.lsm_frontend_mel_tables(self.ctx.h, self.h, _lib._np_ptr(self.window),
+                                                                _lib._np_ptr(self.tw), _lib._np_ptr(self.tw2)))
 
     @property
     def rows(self) -> int:

@@ -144,6 +144,11 @@ class AudioToFeatures:
             raise ValueError("front end and reservoir must share a context (same device)")
         self.frontend, self.snn, self.ctx = frontend, snn, snn.ctx
 
+    @property
+    def fused(self) -> bool:
+        """True when the pair runs as one kernel (spikes handed over in shared memory)."""
+        return bool(self.ctx.lib.lsm_pipeline_is_fused(self.frontend.h, self.snn.h))
+
     def run_host(self, pcm: np.ndarray, feature_keys, nan_to_num: bool = True, out: np.ndarray | None = None,
                  spikes_out: np.ndarray | None = None):
         """Host buffers in, host buffers out; copies are chunked and overlapped with the kernels
@@ -172,7 +177,7 @@ class AudioToFeatures:
             raise ValueError("feature keys must be in FEATURE_SETS order")
         B = pcm.shape[0]
         fe = self.frontend
-        if spikes is None and want_spikes:
+        if spikes is None and (want_spikes or not self.fused):
             spikes = torch.empty((B, fe.rows, fe.steps), dtype=torch.uint8, device=pcm.device)
         if out is None:
             out = torch.empty((B, len(keys) * self.snn.num_output_neurons), dtype=torch.float64, device=pcm.device)

@@ -83,6 +83,30 @@ def gammatone_encode(pcm, coefs, nwin, hop, nbins, zi0, zf, thresholds, gap, red
     return (spikes, spec) if want_spec else spikes
 
 
+def mel_encode(pcm, basis, win, tw, tw2, packed, hop, nbins, zi0, zf, thresholds, gap, redundancy=1,
+               want_spec=False, nthreads=0):
+    """packed = (weights f32, lo, n, off) from filterbank.pack_mel_basis(basis)."""
+    pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+    B, L = pcm.shape
+    Cc = basis.shape[0]
+    thr, lower = encoder_tables(thresholds, gap)
+    K = len(thr)
+    w, lo, n, off = packed
+    zi0 = np.ascontiguousarray(zi0, dtype=np.int32)
+    zf = np.ascontiguousarray(zf, dtype=np.float64)
+    spikes = np.zeros((B, Cc * redundancy, nbins * K), dtype=np.uint8)
+    spec = np.zeros((B, Cc, nbins), dtype=np.float32) if want_spec else None
+    f = lib().oracle_mel_encode
+    f.argtypes = None
+    rc = f(_p(pcm, C.c_float), C.c_int(B), C.c_int(L), C.c_int(2048), C.c_int(hop), C.c_int(Cc), C.c_int(nbins),
+           _p(win, C.c_double), _p(tw, C.c_double), _p(tw2, C.c_double), _p(w, C.c_float), _p(lo, C.c_int32),
+           _p(n, C.c_int32), _p(off, C.c_int32), _p(zi0, C.c_int32), _p(zf, C.c_double), _p(thr, C.c_double),
+           _p(lower, C.c_double), C.c_int(K), C.c_int(redundancy), _p(spikes, C.c_uint8), _p(spec, C.c_float),
+           C.c_int(int(nthreads)))
+    assert rc == 0
+    return (spikes, spec) if want_spec else spikes
+
+
 def transpose_csr(rowptr, col, val, n):
     """CSR over postsynaptic rows -> CSR over presynaptic neuron (outgoing edges)."""
     post = np.repeat(np.arange(n, dtype=np.int32), np.diff(rowptr))

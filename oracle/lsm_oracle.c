@@ -284,6 +284,205 @@ int oracle_gammatone_encode(const float *pcm, int B, int L, const double *coefs,
     return 0;
 }
 
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 1, mel branch: create_dataset.py:43-48 + :62-78 (librosa==0.11.0 melspectrogram + power_to_db,
+ * SURVEY Appendix B.2), with numpy 1.26 (the reference's pin) scalar-promotion semantics where they matter.
+ *
+ * STFT: n_fft = 2048, hop 160, centre zero padding, periodic hann in fp64 times float32 samples => fp64
+ * frame; fp64 FFT; result stored as complex64 (librosa's dtype for float32 input).  librosa's FFT is
+ * pocketfft, whose internal operation order is not reproducible here; this oracle fixes ONE order
+ * (radix-2 decimation in time on the 1024-point complex packing of the real frame, then the real-input
+ * untangle, twiddles from a table) that the CUDA kernel repeats operation for operation.  The two differ
+ * from pocketfft at the 1e-16 level before the rounding to float32 (tests compare against scipy.fft).
+ * tw:  double[512][2]  exp(-2*pi*i*q/1024), q = 0..511
+ * tw2: double[1025][2] exp(-2*pi*i*k/2048), k = 0..1024
+ * win: double[2048]    periodic hann                                                              */
+static void fft1024(double *re, double *im, const double *tw)
+{
+    /* in: bit-reversed order already applied by the caller; 10 radix-2 DIT stages */
+    for (int s = 1; s <= 10; ++s) {
+        const int m = 1 << s, half = m >> 1, stride = 1024 >> s;
+        for (int base = 0; base < 1024; base += m)
+            for (int j = 0; j < half; ++j) {
+                const double wr = tw[2 * (j * stride)], wi = tw[2 * (j * stride) + 1];
+                const int p = base + j, q = p + half;
+                const double tr = wr * re[q] - wi * im[q];
+                const double ti = wr * im[q] + wi * re[q];
+                const double ur = re[p], ui = im[p];
+                re[p] = ur + tr; im[p] = ui + ti;
+                re[q] = ur - tr; im[q] = ui - ti;
+            }
+    }
+}
+
+static inline int bitrev10(int x)
+{
+    int r = 0;
+    for (int b = 0; b < 10; ++b) r |= ((x >> b) & 1) << (9 - b);
+    return r;
+}
+
+/* power spectrum of one frame -> S[1025] float32 */
+static void frame_power(const float *pcm, int L, int start, const double *win, const double *tw, const double *tw2,
+                        double *re, double *im, float *S)
+{
+    for (int j = 0; j < 1024; ++j) {
+        const int n0 = 2 * j, n1 = 2 * j + 1;
+        const int i0 = start + n0, i1 = start + n1;
+        const double x0 = (i0 >= 0 && i0 < L) ? win[n0] * (double)pcm[i0] : 0.0;
+        const double x1 = (i1 >= 0 && i1 < L) ? win[n1] * (double)pcm[i1] : 0.0;
+        const int r = bitrev10(j);
+        re[r] = x0; im[r] = x1;
+    }
+    fft1024(re, im, tw);
+    for (int k = 0; k <= 1024; ++k) {
+        const int k1 = k & 1023, k2 = (1024 - k) & 1023;
+        const double zr = re[k1], zi = im[k1], cr = re[k2], ci = -im[k2];   /* Z[k], conj(Z[N-k]) */
+        const double ar = 0.5 * (zr + cr), ai = 0.5 * (zi + ci);
+        const double br = 0.5 * (zr - cr), bi = 0.5 * (zi - ci);
+        const double wr = tw2[2 * k], wi = tw2[2 * k + 1];
+        const double c_re = wi, c_im = -wr;                                 /* -i * W */
+        const double xr = ar + (c_re * br - c_im * bi);
+        const double xi = ai + (c_re * bi + c_im * br);
+        const float r32 = (float)xr, i32 = (float)xi;                       /* complex64 STFT */
+        const float mag = (float)sqrt((double)r32 * (double)r32 + (double)i32 * (double)i32);  /* np.abs = hypotf */
+        S[k] = mag * mag;                                                   /* ** 2.0 in float32 */
+    }
+}
+
+static float oracle_log10f(float x) { return (float)oracle_log10((double)x); }
+
+/* One utterance.  mel_w/lo/n/off: packed non-zero mel weights (float32), ascending bins.
+ * norm: out float32[C][nbins].  Returns 0 if degenerate.                                          */
+static int mel_one(const float *pcm, int L, int n_fft, int hop, int C, int ncols, int nbins,
+                   const double *win, const double *tw, const double *tw2,
+                   const float *mel_w, const int32_t *mel_lo, const int32_t *mel_n, const int32_t *mel_off,
+                   const int32_t *zi0, const double *zf, double *re, double *im, float *S, float *M, float *norm)
+{
+    (void)n_fft;
+    for (int t = 0; t < ncols; ++t) {
+        frame_power(pcm, L, t * hop - 1024, win, tw, tw2, re, im, S);
+        for (int m = 0; m < C; ++m) {
+            float acc = 0.0f;
+            const float *w = mel_w + mel_off[m];
+            for (int q = 0; q < mel_n[m]; ++q) {
+                const float prod = w[q] * S[mel_lo[m] + q];
+                acc = acc + prod;
+            }
+            M[(size_t)m * ncols + t] = acc;
+        }
+    }
+    /* power_to_db(ref=np.max, amin=1e-10, top_db=80) */
+    float ref = M[0];
+    for (int i = 1; i < C * ncols; ++i) if (M[i] > ref) ref = M[i];
+    const float amin = 1e-10f;
+    const double refd = ((double)ref > 1e-10) ? (double)ref : 1e-10;          /* scalar path: float64 in numpy 1.26 */
+    const float ref_db = (float)(10.0 * oracle_log10(refd));
+    float mx = -INFINITY;
+    for (int i = 0; i < C * ncols; ++i) {
+        const float v = M[i] > amin ? M[i] : amin;
+        float d = 10.0f * oracle_log10f(v);
+        d = d - ref_db;
+        M[i] = d;
+        if (d > mx) mx = d;
+    }
+    const float floor_db = (float)((double)mx - 80.0);
+    float mn = INFINITY;
+    for (int i = 0; i < C * ncols; ++i) {
+        if (M[i] < floor_db) M[i] = floor_db;
+        if (M[i] < mn) mn = M[i];
+    }
+    /* create_dataset.py:62-67 */
+    const float diff = mx - mn;
+    if ((double)diff < 1e-8) {
+        for (int i = 0; i < C * nbins; ++i) norm[i] = 0.0f;
+        return 0;
+    }
+    const float den = (float)((double)diff + 1e-8);
+    for (int i = 0; i < C * ncols; ++i) M[i] = (M[i] - mn) / den;
+    /* zoom (create_dataset.py:69-78): float64 arithmetic, float32 result */
+    for (int ch = 0; ch < C; ++ch) {
+        const float *row = M + (size_t)ch * ncols;
+        for (int j = 0; j < nbins; ++j) {
+            if (ncols == nbins) { norm[(size_t)ch * nbins + j] = row[j]; continue; }
+            const int i0 = zi0[j];
+            const double f = zf[j];
+            double v = (double)row[i0] * (1.0 - f);
+            if (i0 + 1 < ncols) v = v + (double)row[i0 + 1] * f;
+            norm[(size_t)ch * nbins + j] = (float)v;
+        }
+    }
+    return 1;
+}
+
+/* create_dataset.py:81-98 on a float32 spectrogram: comparisons in float32 against float32-rounded bounds */
+static void hysteresis_encode_f32(const float *norm, int C, int nbins, const double *thr,
+                                  const double *lower, int K, int R, uint8_t *spikes)
+{
+    const int T = nbins * K;
+    for (int ch = 0; ch < C; ++ch) {
+        uint8_t *row0 = spikes + (size_t)ch * R * T;
+        for (int k = 0; k < K; ++k) {
+            const float th = (float)thr[k], lo = (float)lower[k];
+            int on = 0;
+            for (int b = 0; b < nbins; ++b) {
+                const float v = norm[(size_t)ch * nbins + b];
+                if (!on && v > th) on = 1;
+                else if (on && v < lo) on = 0;
+                row0[b * K + k] = (uint8_t)on;
+            }
+        }
+        for (int r = 1; r < R; ++r) memcpy(row0 + (size_t)r * T, row0, (size_t)T);
+    }
+}
+
+void oracle_hysteresis_encode_f32(const float *norm, int C, int nbins, const double *thr_desc,
+                                  const double *lower, int K, int R, uint8_t *spikes)
+{
+    hysteresis_encode_f32(norm, C, nbins, thr_desc, lower, K, R, spikes);
+}
+
+typedef struct {
+    const float *pcm; int L, n_fft, hop, C, ncols, nbins;
+    const double *win, *tw, *tw2; const float *mel_w; const int32_t *mel_lo, *mel_n, *mel_off;
+    const int32_t *zi0; const double *zf; const double *thr, *lower; int K, R;
+    uint8_t *spikes; float *spec_norm_out;
+} mel_ctx;
+
+static void *mel_mk(void *vc)
+{
+    mel_ctx *c = (mel_ctx *)vc;
+    return malloc(sizeof(double) * 2048 + sizeof(float) * (1025 + 8 + (size_t)c->C * c->ncols + (size_t)c->C * c->nbins));
+}
+
+static void mel_run_one(void *vc, int b, void *scratch)
+{
+    mel_ctx *c = (mel_ctx *)vc;
+    double *re = (double *)scratch, *im = re + 1024;
+    float *S = (float *)(im + 1024), *M = S + 1032, *norm = M + (size_t)c->C * c->ncols;
+    mel_one(c->pcm + (size_t)b * c->L, c->L, c->n_fft, c->hop, c->C, c->ncols, c->nbins, c->win, c->tw, c->tw2,
+            c->mel_w, c->mel_lo, c->mel_n, c->mel_off, c->zi0, c->zf, re, im, S, M, norm);
+    hysteresis_encode_f32(norm, c->C, c->nbins, c->thr, c->lower, c->K, c->R,
+                          c->spikes + (size_t)b * c->C * c->R * c->nbins * c->K);
+    if (c->spec_norm_out)
+        memcpy(c->spec_norm_out + (size_t)b * c->C * c->nbins, norm, sizeof(float) * c->C * c->nbins);
+}
+
+int oracle_mel_encode(const float *pcm, int B, int L, int n_fft, int hop, int C, int nbins,
+                      const double *win, const double *tw, const double *tw2,
+                      const float *mel_w, const int32_t *mel_lo, const int32_t *mel_n, const int32_t *mel_off,
+                      const int32_t *zi0, const double *zf, const double *thr_desc, const double *lower, int K, int R,
+                      uint8_t *spikes, float *spec_norm_out, int nthreads)
+{
+    if (n_fft != 2048) return -1;
+    mel_ctx c = {pcm, L, n_fft, hop, C, 1 + L / hop, nbins, win, tw, tw2, mel_w, mel_lo, mel_n, mel_off, zi0, zf,
+                 thr_desc, lower, K, R, spikes, spec_norm_out};
+    pf_job j = {mel_run_one, &c, B, 0, mel_mk, free};
+    parallel_for(&j, nthreads);
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Stages 2+3: frozen reservoir spec; call sites
  * extract_lsm_features.py:79-83.  Event-driven over the previous step's spike list, integer

@@ -143,11 +143,14 @@ def mel_power_db(audio, n_mels, sr=SAMPLE_RATE, n_fft=2048, hop=160, basis=None)
         for f in nz:  # ascending bin order, float32 multiply then float32 add
             acc = (acc + (basis[m, f] * S[f]).astype(np.float32)).astype(np.float32)
         M[m] = acc
+    # power_to_db under numpy 1.26 (the reference's pin): array ops stay float32, scalar-only expressions
+    # (the reference level) are float64 and are rounded to float32 when they meet the array
     amin = np.float32(1e-10)
     ref = np.max(M)
     log_spec = (np.float32(10.0) * np.log10(np.maximum(amin, M))).astype(np.float32)
-    log_spec = log_spec - np.float32(10.0) * np.log10(np.maximum(amin, ref)).astype(np.float32)
-    return np.maximum(log_spec, log_spec.max() - np.float32(80.0))
+    ref_db = np.float32(10.0 * np.log10(max(1e-10, float(ref))))
+    log_spec = (log_spec - ref_db).astype(np.float32)
+    return np.maximum(log_spec, np.float32(float(log_spec.max()) - 80.0))
 
 
 # --------------------------------------------------------------------------- stage 1 glue
@@ -163,9 +166,10 @@ def audio_to_spectrogram(audio, n_filters, filterbank, coefs=None):
         spec_db = np.maximum(spec_db, spec_db.max() - 80.0)          # :60
     lo = spec_db.min()                                               # :62
     hi = spec_db.max()                                               # :63
-    if (hi - lo) < 1e-8:                                             # :64-65
+    if float(hi - lo) < 1e-8:                                        # :64-65
         return np.zeros((n_filters, TIME_BINS), dtype=np.float32)
-    spec_norm = (spec_db - lo) / (hi - lo + 1e-8)                    # :67
+    # :67 - the denominator is a scalar-only expression (float64 under numpy 1.26), then meets the array's dtype
+    spec_norm = (spec_db - lo) / spec_db.dtype.type(float(hi - lo) + 1e-8)
     if spec_norm.shape[1] != TIME_BINS:                              # :69-72
         spec_norm = zoom(spec_norm, (1, TIME_BINS / spec_norm.shape[1]), order=1)
     return spec_norm[:, :TIME_BINS]                                  # :78

@@ -193,7 +193,8 @@ def test_fused_kernel_equals_two_kernel_path_and_oracle(env, small_set, n_filter
     fused, spk = path.run(d_pcm, keys)
     fused_nospk, none = path.run(d_pcm, keys, want_spikes=False)
     torch.cuda.synchronize()
-    assert none is None
+    assert path.fused == (kw.get("num_neurons", 1000) == 1000)
+    assert (none is None) == path.fused
     monkeypatch.setenv("LSM_NO_FUSE", "1")
     unfused, spk2 = path.run(d_pcm, keys)
     torch.cuda.synchronize()
@@ -230,3 +231,39 @@ def test_errors_are_loud(env):
         fe.encode(np.zeros((2, 8000), np.float32))
     with pytest.raises(_lib.LsmError):
         Frontend(512, "gammatone")
+
+
+def oracle_mel(pcm, fe, want_spec=False):
+    from lsm_speech_classifier_b200 import filterbank as fb
+    from oracle import coracle
+    return coracle.mel_encode(pcm, fe.table, fe.window, fe.tw, fe.tw2, fb.pack_mel_basis(fe.table), fe.params.mel_hop,
+                              fe.time_bins, fe.zoom_i0, fe.zoom_f, THR, GAP, redundancy=fe.redundancy, want_spec=want_spec)
+
+
+@pytest.mark.parametrize("n_filters,redundancy", [(128, 1), (64, 2), (256, 1), (40, 1)])
+def test_mel_spikes_and_spectrogram_bit_exact(env, small_set, n_filters, redundancy):
+    """Mel front end (config 3): GPU vs the C oracle, which fixes the FFT operation order (bit-exact), and vs the
+    scipy.fft restatement on the goldens (float32 tolerance)."""
+    import torch
+    from lsm_speech_classifier_b200.frontend import Frontend
+    pcm, _ = small_set
+    fe = Frontend(n_filters, "mel", redundancy=redundancy)
+    want, want_spec = oracle_mel(pcm, fe, want_spec=True)
+    got, spec = fe.encode(torch.from_numpy(pcm).cuda(), return_spectrogram=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(spec.cpu().numpy().astype(np.float32), want_spec)
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert np.array_equal(fe.encode(pcm), want)
+    assert got[24].sum() == 0      # silent clip
+
+
+def test_mel_golden_vectors(env, golden):
+    from lsm_speech_classifier_b200.frontend import Frontend
+    g = golden("frontend_mel64.npz")
+    pcm = golden("frontend_gammatone.npz")["pcm"][:3]
+    fe = Frontend(64, "mel")
+    got, spec = fe.encode(pcm, return_spectrogram=True)
+    want = np.unpackbits(g["spikes_packed"], axis=-1)[:, :, :400]
+    # the goldens come from scipy.fft (pocketfft order) + np.log10; ours is a fixed order: >= 99.9 % of bytes must agree
+    assert (got == want).mean() >= 0.999
+    np.testing.assert_allclose(spec[:1].astype(np.float32), g["spec_norm"], rtol=0, atol=2e-6)

@@ -143,3 +143,26 @@ def test_constant_divisor_division_is_ieee_exact():
     # below the window the quotient need not be exact, but its square is exactly 0 either way
     tiny = np.ldexp(rng.uniform(1.0, 2.0, 1000), -901 - rng.integers(0, 120, 1000))
     assert np.all((tiny / gains.min()) ** 2 == 0.0)
+
+
+def test_c_oracle_mel_vs_scipy_restatement(golden):
+    """Mel branch: the C oracle (fixed radix-2 FFT order, deterministic log10, numpy-1.26 scalar semantics) against
+    the goldens minted by the scipy.fft restatement + the reference's own encoder."""
+    g = golden("frontend_mel64.npz")
+    pcm = golden("frontend_gammatone.npz")["pcm"][:3]
+    basis = filterbank.mel_basis(16000, 2048, 64)
+    tw, tw2 = filterbank.fft_tables(2048)
+    i0, f = filterbank.zoom_table(101, 100)
+    got, spec = coracle.mel_encode(pcm, basis, filterbank.hann_periodic(2048), tw, tw2, filterbank.pack_mel_basis(basis),
+                                   160, 100, i0, f, THR, GAP, want_spec=True)
+    want = np.unpackbits(g["spikes_packed"], axis=-1)[:, :, :400]
+    assert (got == want).mean() >= 0.999            # pocketfft vs our FFT order, np.log10 vs fixed log10: near-ties only
+    assert np.array_equal(got, want)                # ... and on these clips there are none
+    np.testing.assert_allclose(spec[:1], g["spec_norm"], rtol=0, atol=2e-6)
+    # the mel basis restated scalar-by-scalar equals the vectorised product table
+    assert np.array_equal(basis, pyref.mel_filters(16000, 2048, 64))
+    # 256 bands: narrow low-frequency triangles may be empty -> silent rows, never NaN
+    b256 = filterbank.mel_basis(16000, 2048, 256)
+    s256 = coracle.mel_encode(pcm[:1], b256, filterbank.hann_periodic(2048), tw, tw2, filterbank.pack_mel_basis(b256),
+                              160, 100, i0, f, THR, GAP)
+    assert s256.shape == (1, 256, 400)

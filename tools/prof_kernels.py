@@ -35,3 +35,10 @@ if os.environ.get("LSM_TIME"):
         return a.elapsed_time(b) / reps
     print("K1 ms", tm(lambda: fe.encode(d_pcm)), "K2 ms", tm(lambda: lsm.simulate_batch(spikes, keys)), "minb", os.environ.get("LSM_K1_MINB"))
 print("ok", spikes.float().mean().item(), feats.shape)
+if os.environ.get("LSM_TIME"):
+    from lsm_speech_classifier_b200.snn import AudioToFeatures
+    path = AudioToFeatures(fe, lsm)
+    out, spk = path.run(d_pcm, keys)
+    torch.cuda.synchronize()
+    print("fused" if path.fused else "two-kernel", "pipeline ms", tm(lambda: path.run(d_pcm, keys, spikes=spk, out=out)),
+          "no-spikes ms", tm(lambda: path.run(d_pcm, keys, out=out, want_spikes=False)))
