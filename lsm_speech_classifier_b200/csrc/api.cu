@@ -1,6 +1,8 @@
 // liblsmb200.so — C ABI (include/lsm_b200.h): context, handles, host-buffer entry points and the
 // chunked audio -> features pipeline.  No CPU fallback anywhere: every entry point needs a ctx,
 // and a ctx needs a CUDA device.
+#include <stdlib.h>
+
 #include <new>
 #include <vector>
 
@@ -404,6 +406,15 @@ extern "C" int lsm_pipeline_run(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *r
     return lsm_launch_reservoir(ctx, res, d_spikes, B, feature_mask, nan_to_num, d_features, nullptr, ctx->stream);
 }
 
+// Is this host pointer pinned/registered memory the device can address directly (UVA)?  Returns its device alias.
+static bool device_visible(const void *h, void **d)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (at.type == cudaMemoryTypeHost && at.devicePointer) { *d = at.devicePointer; return true; }
+    return false;
+}
+
 extern "C" int lsm_pipeline_is_fused(const lsm_frontend *fe, const lsm_reservoir *res)
 {
     return (fe && res && lsm_fused_npt(fe, res)) ? 1 : 0;
@@ -425,6 +436,24 @@ extern "C" int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservo
     const size_t spk_per = (size_t)res->p.num_inputs * res->p.num_steps;
     const int nkeys = __builtin_popcount(feature_mask & 0xFFu);
     const size_t feat_per = (size_t)nkeys * res->p.n_out;
+    // Zero-copy path: with pinned host buffers the one fused persistent kernel reads each PCM sample exactly once
+    // straight over PCIe as it consumes it (~15 GB/s at full speed) and writes the feature rows straight back, so
+    // there is no staging copy, no chunking and no per-chunk drain tail.  Pageable buffers take the staged path below.
+    {
+        void *dv_pcm = nullptr, *dv_feat = nullptr;
+        if (lsm_fused_npt(fe, res) && !getenv("LSM_NO_ZEROCOPY") && device_visible(h_pcm, &dv_pcm) &&
+            device_visible(h_features, &dv_feat)) {
+            void *d_spk = nullptr;
+            int rc0;
+            if (h_spikes_or_null && (rc0 = lsm_stage_device(ctx, 1, (size_t)B * spk_per, &d_spk)) != LSM_OK) return rc0;
+            if ((rc0 = lsm_launch_fused(ctx, fe, res, (const float *)dv_pcm, B, (uint8_t *)d_spk, feature_mask, nan_to_num,
+                                        (double *)dv_feat, ctx->stream)) != LSM_OK) return rc0;
+            if (h_spikes_or_null)
+                LSM_CUDA(ctx, cudaMemcpyAsync(h_spikes_or_null, d_spk, (size_t)B * spk_per, cudaMemcpyDeviceToHost, ctx->stream));
+            LSM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            return LSM_OK;
+        }
+    }
     // chunked, three legs on three streams: H2D(c+1) | kernels(c) | D2H(c-1).  A chunk is one full wave of the
     // persistent front-end grid (every CTA gets exactly one utterance, so a chunk has no drain tail); a short
     // remainder is folded into the last chunk.  The first chunk's H2D and the last chunk's D2H are the only

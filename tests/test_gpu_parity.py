@@ -203,6 +203,12 @@ def test_fused_kernel_equals_two_kernel_path_and_oracle(env, small_set, n_filter
     for got in (fused, fused_nospk, unfused):
         assert np.array_equal(got.cpu().numpy(), want)
     assert np.array_equal(path.run_host(pcm, keys), want)
+    # pinned host buffers: the fused kernel reads PCM and writes features straight over PCIe (zero-copy path)
+    h_pcm = torch.from_numpy(pcm).pin_memory()
+    h_out = torch.empty((len(pcm), want.shape[1]), dtype=torch.float64).pin_memory()
+    h_spk = np.empty_like(X)
+    path.run_host(h_pcm.numpy(), keys, out=h_out.numpy(), spikes_out=h_spk)
+    assert np.array_equal(h_out.numpy(), want) and np.array_equal(h_spk, X)
 
 
 def lsm_keys():
