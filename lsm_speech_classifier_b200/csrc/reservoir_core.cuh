@@ -168,42 +168,52 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
         const int tmp = c_cur; c_cur = c_nxt; c_nxt = c_zero; c_zero = tmp;
     }
 
-    // ---- K3: feature readout, key-major [nkeys][n_out] (extract_lsm_features.py:85-87)
+    // ---- K3: feature readout, key-major [nkeys][n_out] (extract_lsm_features.py:85-87).  Each key's values are
+    //      gathered in shared memory (the input-bit plane is free now) and written as one contiguous, coalesced
+    //      run: full 128-byte lines whether the destination is HBM or pinned host memory across PCIe.
     if (a.features) {
         double *f = a.features + (size_t)utt * a.nkeys * a.n_out;
+        double *s_buf = reinterpret_cast<double *>(smem_raw);
+        const int cap = (T * CW * (int)sizeof(unsigned)) / (int)sizeof(double);   // doubles that fit in the bit plane
         const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        int o_k[NPT];
 #pragma unroll
-        for (int k = 0; k < NPT; ++k) {
-            const int i = i0 + k;
-            if (i >= N) continue;
-            const int o = __ldg(a.out_slot + i);
-            if (o < 0) continue;
-            const int sl = k * nthr + tid;
-            const int cnt = s_stat[sl], sumt = s_stat[S + sl], first = s_stat[2 * S + sl], last = s_stat[3 * S + sl];
-            const int s2 = s_stat[4 * S + sl], burst = s_stat[5 * S + sl];
-            const double c = (double)cnt;
-            int slot = 0;
+        for (int k = 0; k < NPT; ++k) o_k[k] = (i0 + k < N) ? __ldg(a.out_slot + i0 + k) : -1;
+        int slot = 0;
+        for (int key = 0; key < 8; ++key) {
+            if (!(a.feature_mask & (1u << key))) continue;
+            for (int tile = 0; tile < a.n_out; tile += cap) {
 #pragma unroll
-            for (int key = 0; key < 8; ++key) {
-                if (!(a.feature_mask & (1u << key))) continue;
-                double v = nan;
-                switch (key) {
-                case 0: v = c; break;
-                case 1: { const double p = __ddiv_rn(c, (double)T); v = mul64(p, sub64(1.0, p)); } break;
-                case 2: if (cnt >= 1) v = __ddiv_rn((double)sumt, c); break;
-                case 3: if (cnt >= 1) v = (double)first; break;
-                case 4: if (cnt >= 1) v = (double)last; break;
-                case 5: if (cnt >= 2) v = __ddiv_rn((double)(last - first), (double)(cnt - 1)); break;
-                case 6: if (cnt >= 2) {
-                            const long long n = cnt - 1, s1 = last - first;
-                            v = __ddiv_rn((double)(n * (long long)s2 - s1 * s1), (double)(n * n));
-                        } break;
-                case 7: v = (double)burst; break;
+                for (int k = 0; k < NPT; ++k) {
+                    const int o = o_k[k];
+                    if (o < tile || o >= tile + cap) continue;
+                    const int sl = k * nthr + tid;
+                    const int cnt = s_stat[sl], sumt = s_stat[S + sl], first = s_stat[2 * S + sl], last = s_stat[3 * S + sl];
+                    const int s2 = s_stat[4 * S + sl], burst = s_stat[5 * S + sl];
+                    const double c = (double)cnt;
+                    double v = nan;
+                    switch (key) {
+                    case 0: v = c; break;
+                    case 1: { const double p = __ddiv_rn(c, (double)T); v = mul64(p, sub64(1.0, p)); } break;
+                    case 2: if (cnt >= 1) v = __ddiv_rn((double)sumt, c); break;
+                    case 3: if (cnt >= 1) v = (double)first; break;
+                    case 4: if (cnt >= 1) v = (double)last; break;
+                    case 5: if (cnt >= 2) v = __ddiv_rn((double)(last - first), (double)(cnt - 1)); break;
+                    case 6: if (cnt >= 2) {
+                                const long long n = cnt - 1, s1 = last - first;
+                                v = __ddiv_rn((double)(n * (long long)s2 - s1 * s1), (double)(n * n));
+                            } break;
+                    default: v = (double)burst; break;
+                    }
+                    if (a.nan_to_num && v != v) v = 0.0;
+                    s_buf[o - tile] = v;
                 }
-                if (a.nan_to_num && v != v) v = 0.0;
-                f[(size_t)slot * a.n_out + o] = v;
-                ++slot;
+                __syncthreads();
+                const int n_here = min(cap, a.n_out - tile);
+                for (int idx = tid; idx < n_here; idx += nthr) f[(size_t)slot * a.n_out + tile + idx] = s_buf[idx];
+                __syncthreads();
             }
+            ++slot;
         }
     }
 }
