@@ -56,7 +56,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -245,7 +245,6 @@ def main():
     fence()
     ms_total = e0.elapsed_time(e1)
     gpu_launches = ctx.launches - launches0 + (args.steps if world > 1 else 0)
-    clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -281,6 +280,7 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * B * args.steps / float(te.item())
+    clocks = sampler.stop() if sampler else None
     assert np.array_equal(h_feat.numpy(), d_feat.cpu().numpy()), "host-buffer path and device path disagree"
 
     if rank != 0:

@@ -1,0 +1,28 @@
+"""ncu driver: the fused audio -> features kernel on one 2400-utterance batch (3 launches after warm-up)."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lsm_speech_classifier_b200 import synth  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 2400
+base, _ = synth.synth_dataset(12, 20, workers=os.cpu_count() or 1)
+pcm = np.concatenate([base] * (B // len(base) + 1))[:B]
+
+import torch  # noqa: E402
+from lsm_speech_classifier_b200.extract_lsm_features import FEATURE_SETS, build_lsm  # noqa: E402
+from lsm_speech_classifier_b200.frontend import Frontend  # noqa: E402
+from lsm_speech_classifier_b200.snn import AudioToFeatures  # noqa: E402
+
+d_pcm = torch.from_numpy(pcm).cuda()
+fe = Frontend(128, "gammatone")
+lsm = build_lsm(fe.encode(d_pcm[:500]).cpu().numpy(), 0.6, verbose=False)
+path = AudioToFeatures(fe, lsm)
+keys = FEATURE_SETS["original"]
+out, spk = path.run(d_pcm, keys)
+for _ in range(3):
+    path.run(d_pcm, keys, spikes=spk, out=out)
+torch.cuda.synchronize()
+print("ok fused" if path.fused else "ok two-kernel", float(out.sum()))
