@@ -149,7 +149,7 @@ def reference_arm(args, rank, world):
     dt = time.perf_counter() - t0
     val = len(pcm) * args.steps / dt
     sample = f"{len(pcm)} utterances per step (bounded sample of the {N_CLASSES * PER_CLASS}-utterance workload), all host threads"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "utterances/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -157,7 +157,7 @@ def reference_arm(args, rank, world):
         "cpu_baseline": {"value": val, "unit": "utterances/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "neuron_steps_per_s": val * N_NEURONS * T_STEPS,
-    }), flush=True)
+    })
 
 
 def workload_config():
@@ -169,7 +169,26 @@ def workload_config():
             "parallelism": "utterance-sharded, one process per GPU"}
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Libraries (NCCL's version banner, for one) write to fd 1; the contract is ONE JSON line on stdout.
+    Point fd 1 at stderr for the whole run and keep the real stdout for that line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+
+
+def emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -330,7 +349,7 @@ def main():
         out["cpu_baseline"] = {"value": len(sample) / dt, "unit": "utterances/s", "cores": cores, "kind": "port",
                                "sample": f"{len(sample)} of the step's {B} utterances, oracle C port, {cores} threads",
                                "value_1core": 16 / dt1, "gpu_matches_cpu_bit_exact": bool(np.array_equal(got, ref))}
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
