@@ -41,7 +41,7 @@ extern "C" void lsm_ctx_destroy(lsm_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 6; ++i) if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
+    for (int i = 0; i < 8; ++i) if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
     for (int i = 0; i < 4; ++i) if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
     for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 2; ++i) if (ctx->copy_stream[i]) cudaStreamDestroy(ctx->copy_stream[i]);

@@ -18,8 +18,8 @@ struct lsm_ctx {
     int64_t launches = 0;
     char err[512] = {0};
     // staging owned by the ctx for the *_host entry points (grown on demand)
-    void *d_stage[6] = {};
-    size_t d_stage_bytes[6] = {};
+    void *d_stage[8] = {};
+    size_t d_stage_bytes[8] = {};
     void *h_pin[4] = {};
     size_t h_pin_bytes[4] = {};
 };

@@ -76,7 +76,7 @@ void lsm_reservoir_fill_args(const lsm_reservoir *res, const uint8_t *d_spikes, 
     ResArgs &a = *out;
     a.spikes = d_spikes; a.wt = res->d_wt; a.in_rowptr = res->d_in_rowptr; a.in_col = res->d_in_col;
     a.in_val = res->d_in_val; a.in_row = res->d_in_row; a.leak = res->d_leak; a.out_slot = res->d_out_slot;
-    a.features = d_features; a.raster = d_raster;
+    a.features = d_features; a.raster = d_raster; a.stat_global = nullptr;
     a.B = B; a.N = p.num_neurons; a.n_pad = res->n_pad; a.C = p.num_inputs; a.CW = (p.num_inputs + 31) / 32; a.T = p.num_steps;
     a.refractory = p.refractory; a.n_out = p.n_out; a.nan_to_num = nan_to_num;
     a.leak0 = res->leak0; a.gain0 = res->gain0;
@@ -98,8 +98,16 @@ int lsm_launch_reservoir(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spik
     int npt, threads, n_pad;
     lsm_reservoir_geometry(N, &npt, &threads, &n_pad);
     if (threads > 1024) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "num_neurons %d > 16384 not supported by the event-driven kernel", N);
-    const size_t smem = lsm_res_smem_bytes(a.T, a.CW, threads * npt, N);
-    if (smem > 227 * 1024) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "reservoir needs %zu bytes of shared memory per utterance", smem);
+    size_t smem = lsm_res_smem_bytes(a.T, a.CW, threads * npt, N);
+    if (smem > 200 * 1024) {
+        // large reservoirs: the per-neuron statistics (touched only on a spike) move to a global scratch, one slab per CTA
+        smem = lsm_res_smem_bytes(a.T, a.CW, threads * npt, N, false);
+        if (smem > 227 * 1024) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "reservoir needs %zu bytes of shared memory per utterance", smem);
+        void *slab;
+        int rc = lsm_stage_device(ctx, 6, sizeof(int) * 6 * (size_t)threads * npt * B, &slab);
+        if (rc != LSM_OK) return rc;
+        a.stat_global = (int *)slab;
+    }
 
 #define LSM_RES_LAUNCH(NPT, LEAN)                                                                    \
     do {                                                                                             \

@@ -16,6 +16,7 @@ struct ResArgs {
     const int32_t *out_slot;  // [N]
     double *features;         // [B][nkeys][n_out]
     uint8_t *raster;          // optional [B][T][N]
+    int *stat_global;         // per-CTA [6][slots] statistics when they do not fit in shared memory (large N), else null
     int B, N, n_pad, C, CW, T, refractory, n_out, nkeys, nan_to_num;
     unsigned feature_mask;
     double theta, scale, leak0, gain0;
@@ -27,9 +28,10 @@ struct ResArgs {
 //   stat  int32[6][S]       per-neuron count, sum t, first, last, sum isi^2, bursts
 //   list  uint16[2][NL]     neurons that fired in the previous / current step (read 4 at a time; slots past
 //                           the end select the all-zero weight row)
-__host__ __device__ inline size_t lsm_res_smem_bytes(int T, int CW, int slots, int N)
+__host__ __device__ inline size_t lsm_res_smem_bytes(int T, int CW, int slots, int N, bool stat_in_smem = true)
 {
-    return sizeof(unsigned) * (size_t)T * CW + sizeof(int) * 6 * (size_t)slots + sizeof(unsigned short) * 2 * (size_t)((N + 7) & ~3);
+    return sizeof(unsigned) * (size_t)T * CW + (stat_in_smem ? sizeof(int) * 6 * (size_t)slots : 0) +
+           sizeof(unsigned short) * 2 * (size_t)((N + 7) & ~3);
 }
 
 // Caller contract: s_bits holds the utterance's input and a __syncthreads() has made it visible.
@@ -44,8 +46,9 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
     const int S = nthr * NPT;
     const int NL = (N + 7) & ~3;                       // list capacity, multiple of 4
     unsigned *s_bits = reinterpret_cast<unsigned *>(smem_raw);
-    int *s_stat = reinterpret_cast<int *>(s_bits + (size_t)T * CW);
-    unsigned short *s_list = reinterpret_cast<unsigned short *>(s_stat + 6 * (size_t)S);
+    int *s_stat = a.stat_global ? a.stat_global + (size_t)blockIdx.x * 6 * S : reinterpret_cast<int *>(s_bits + (size_t)T * CW);
+    unsigned short *s_list = reinterpret_cast<unsigned short *>(reinterpret_cast<int *>(s_bits + (size_t)T * CW) +
+                                                                (a.stat_global ? 0 : 6 * (size_t)S));
 
     for (int i = tid; i < S; i += nthr) {
         s_stat[i] = 0; s_stat[S + i] = 0; s_stat[2 * S + i] = -1; s_stat[3 * S + i] = -1; s_stat[4 * S + i] = 0; s_stat[5 * S + i] = 0;
