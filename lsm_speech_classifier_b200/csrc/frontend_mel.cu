@@ -55,9 +55,23 @@ __device__ __forceinline__ float block_reduce_f32(float v, bool want_max, float 
     return r;
 }
 
+// shared-memory index with one pad double every 16: breaks the power-of-two strides of the FFT passes
+__device__ __forceinline__ int phys(int i) { return i + (i >> 4); }
+
+// one radix-2 DIT butterfly, the oracle's operation order: t = w*a[q]; a[p] = u + t; a[q] = u - t
+__device__ __forceinline__ void bfly(double &pr, double &pi, double &qr, double &qi, const double2 w)
+{
+    const double tr = __dsub_rn(__dmul_rn(w.x, qr), __dmul_rn(w.y, qi));
+    const double ti = __dadd_rn(__dmul_rn(w.x, qi), __dmul_rn(w.y, qr));
+    const double ur = pr, ui = pi;
+    pr = __dadd_rn(ur, tr); pi = __dadd_rn(ui, ti);
+    qr = __dsub_rn(ur, tr); qi = __dsub_rn(ui, ti);
+}
+
 __global__ void __launch_bounds__(kThreads) mel_encode_kernel(const MelArgs a, int *next_utt)
 {
-    __shared__ double s_re[kHalf], s_im[kHalf];
+    __shared__ double s_re[kHalf + kHalf / 16], s_im[kHalf + kHalf / 16];
+    __shared__ double2 s_tw[kHalf / 2];
     __shared__ float s_S[kHalf + 8];
     __shared__ float s_red[kThreads / 32];
     __shared__ int s_utt;
@@ -65,6 +79,7 @@ __global__ void __launch_bounds__(kThreads) mel_encode_kernel(const MelArgs a, i
     const int tid = threadIdx.x;
     const int C = a.C, ncols = a.ncols;
     float *plane = a.scratch + (size_t)blockIdx.x * ncols * C;     // mel power / dB plane [ncols][C]
+    for (int q = tid; q < kHalf / 2; q += kThreads) s_tw[q] = __ldg(a.tw + q);
 
     for (;;) {
         if (tid == 0) s_utt = atomicAdd(next_utt, 1);
@@ -80,31 +95,35 @@ __global__ void __launch_bounds__(kThreads) mel_encode_kernel(const MelArgs a, i
                 const int i0 = start + 2 * j, i1 = i0 + 1;
                 const double x0 = (i0 >= 0 && i0 < a.L) ? __dmul_rn(__ldg(a.win + 2 * j), (double)__ldg(pcm + i0)) : 0.0;
                 const double x1 = (i1 >= 0 && i1 < a.L) ? __dmul_rn(__ldg(a.win + 2 * j + 1), (double)__ldg(pcm + i1)) : 0.0;
-                const int r = (int)(__brev((unsigned)j) >> 22);
+                const int r = phys((int)(__brev((unsigned)j) >> 22));
                 s_re[r] = x0; s_im[r] = x1;
             }
             __syncthreads();
-            // ---- 10 radix-2 stages, 512 butterflies each
-#pragma unroll 1
-            for (int s = 1; s <= 10; ++s) {
-                const int half = 1 << (s - 1), stride = kHalf >> s;
-                for (int idx = tid; idx < kHalf / 2; idx += kThreads) {
-                    const int j = idx & (half - 1);
-                    const int p = ((idx >> (s - 1)) << s) + j, q = p + half;
-                    const double2 w = __ldg(a.tw + j * stride);
-                    const double qr = s_re[q], qi = s_im[q];
-                    const double tr = __dsub_rn(__dmul_rn(w.x, qr), __dmul_rn(w.y, qi));
-                    const double ti = __dadd_rn(__dmul_rn(w.x, qi), __dmul_rn(w.y, qr));
-                    const double ur = s_re[p], ui = s_im[p];
-                    s_re[p] = __dadd_rn(ur, tr); s_im[p] = __dadd_rn(ui, ti);
-                    s_re[q] = __dsub_rn(ur, tr); s_im[q] = __dsub_rn(ui, ti);
-                }
+            // ---- 10 radix-2 stages as 5 passes of two stages each: a thread owns the 4 points p, p+h, p+2h, p+3h
+            //      and runs stage s on (p,p+h), (p+2h,p+3h) then stage s+1 on (p,p+2h), (p+h,p+3h) in registers.
+            //      Exactly the radix-2 operations of the oracle, with half the barriers and shared-memory traffic.
+#pragma unroll
+            for (int s = 1; s <= 9; s += 2) {
+                const int h = 1 << (s - 1);
+                const int j = tid & (h - 1);
+                const int p = ((tid >> (s - 1)) << (s + 1)) + j;
+                const int i0 = phys(p), i1 = phys(p + h), i2 = phys(p + 2 * h), i3 = phys(p + 3 * h);
+                double r0 = s_re[i0], m0 = s_im[i0], r1 = s_re[i1], m1 = s_im[i1];
+                double r2 = s_re[i2], m2 = s_im[i2], r3 = s_re[i3], m3 = s_im[i3];
+                const double2 ws = s_tw[j * (kHalf >> s)];
+                bfly(r0, m0, r1, m1, ws);
+                bfly(r2, m2, r3, m3, ws);
+                const double2 wa = s_tw[j * (kHalf >> (s + 1))], wb = s_tw[(j + h) * (kHalf >> (s + 1))];
+                bfly(r0, m0, r2, m2, wa);
+                bfly(r1, m1, r3, m3, wb);
+                s_re[i0] = r0; s_im[i0] = m0; s_re[i1] = r1; s_im[i1] = m1;
+                s_re[i2] = r2; s_im[i2] = m2; s_re[i3] = r3; s_im[i3] = m3;
                 __syncthreads();
             }
             // ---- real-input untangle, complex64 rounding, |.|^2 in float32
             for (int k = tid; k <= kHalf; k += kThreads) {
                 const int k1 = k & (kHalf - 1), k2 = (kHalf - k) & (kHalf - 1);
-                const double zr = s_re[k1], zi = s_im[k1], cr = s_re[k2], ci = -s_im[k2];
+                const double zr = s_re[phys(k1)], zi = s_im[phys(k1)], cr = s_re[phys(k2)], ci = -s_im[phys(k2)];
                 const double ar = __dmul_rn(0.5, __dadd_rn(zr, cr)), ai = __dmul_rn(0.5, __dadd_rn(zi, ci));
                 const double br = __dmul_rn(0.5, __dsub_rn(zr, cr)), bi = __dmul_rn(0.5, __dsub_rn(zi, ci));
                 const double2 w = __ldg(a.tw2 + k);
