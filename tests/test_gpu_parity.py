@@ -273,3 +273,43 @@ def test_mel_golden_vectors(env, golden):
     # the goldens come from scipy.fft (pocketfft order) + np.log10; ours is a fixed order: >= 99.9 % of bytes must agree
     assert (got == want).mean() >= 0.999
     np.testing.assert_allclose(spec[:1].astype(np.float32), g["spec_norm"], rtol=0, atol=2e-6)
+
+
+def test_encoder_entry_point_matches_reference_kats(env, golden):
+    """lsm_hysteresis_encode (the reference's convert_spectrogram_to_spikes_hysteresis on the GPU) on the KATs minted from
+    the reference's own function, float64 and float32 spectrograms, other threshold sets."""
+    from lsm_speech_classifier_b200.create_dataset import convert_spectrogram_to_spikes_hysteresis, create_pure_redundancy
+    from oracle import pyref
+    g = golden("encoder_kats.npz")
+    assert np.array_equal(convert_spectrogram_to_spikes_hysteresis(g["spec64"], THR, GAP), g["spikes64"])
+    assert np.array_equal(convert_spectrogram_to_spikes_hysteresis(g["spec32"], THR, GAP), g["spikes32"])
+    assert np.array_equal(create_pure_redundancy(g["spikes64"][:5], 3), g["redundancy3"])
+    for thr, gap in (([0.5], 0.05), ([0.2, 0.4, 0.6, 0.8, 0.9, 0.95], 0.15), ([0.9, 0.3], 0.05)):
+        assert np.array_equal(convert_spectrogram_to_spikes_hysteresis(g["spec64"], thr, gap), pyref.hysteresis_encode(g["spec64"], thr, gap))
+
+
+def test_audio_to_spectrogram_wrapper(env, small_set):
+    from lsm_speech_classifier_b200.create_dataset import audio_to_spectrogram
+    pcm, _ = small_set
+    s = audio_to_spectrogram(pcm[0], 128, "gammatone")
+    assert s.shape == (128, 100) and s.dtype == np.float64 and 0.0 <= s.min() and s.max() < 1.0
+    m = audio_to_spectrogram(pcm[0], 64, "mel")
+    assert m.shape == (64, 100) and m.dtype == np.float32
+    z = audio_to_spectrogram(np.zeros(16000, np.float32), 128, "gammatone")
+    assert z.dtype == np.float32 and not z.any()                       # create_dataset.py:64-65
+
+
+def test_other_threshold_counts_and_empty_batches(env, small_set):
+    from lsm_speech_classifier_b200.frontend import Frontend
+    from oracle import coracle
+    pcm, _ = small_set
+    fe = Frontend(128, "gammatone", thresholds=[0.6, 0.8, 0.9], hysteresis_gap=0.05)
+    want = coracle.gammatone_encode(pcm[:6], fe.table, fe.params.nwin, fe.params.hop, fe.time_bins, fe.zoom_i0, fe.zoom_f,
+                                    [0.6, 0.8, 0.9], 0.05)
+    got = fe.encode(pcm[:6])
+    assert got.shape == (6, 128, 300) and np.array_equal(got, want)
+    X = Frontend(128, "gammatone").encode(pcm[:2])
+    lsm = build_snn(X)
+    assert lsm.simulate_batch(X[:0]).shape == (0, 8 * 400)
+    with pytest.raises(ValueError):
+        lsm.simulate_batch(np.zeros((1, 64, 400), np.uint8))
