@@ -28,8 +28,10 @@ sys.path.insert(0, ROOT)
 N_CLASSES, PER_CLASS = 12, 200          # configs[1]: 2400 utterances
 N_FILTERS, FILTERBANK, FEATURE_SET, MULTIPLIER = 128, "gammatone", "original", 0.6
 N_NEURONS, T_STEPS, L = 1000, 400, 16000
-# algorithmic bytes per utterance of the dominant kernel K1: 64 000 B PCM in + 51 200 B spikes out
+# algorithmic bytes per utterance: K1 = 64 000 B PCM in + 51 200 B spikes out; the fused
+# audio -> features kernel adds the 16 000 B feature row (2000 x fp64)
 K1_BYTES_PER_UTT = 64000 + 51200
+FUSED_BYTES_PER_UTT = 64000 + 51200 + 16000
 # fp64-pipe operations per utterance in K1: 128 ch x 15920 samples x 35 (28 biquad + 3 divide + 1 square + 3 window adds)
 K1_FP64_OPS_PER_UTT = 128 * 15920 * 35
 METRIC = "utterances/sec audio->LSM features"
@@ -311,22 +313,41 @@ def main():
     fp64_peak = ctx.fp64_peak_gops()
     peaks, peak_kind = measured_peaks()
     hbm_peak = float(peaks["hbm_gbs"])
-    k1_gbs = K1_BYTES_PER_UTT * B / (k1_ms / 1e3) / 1e9
+    step_ms = ms_total / args.steps
+    fused = bool(path.fused)
+    # dominant kernel: the fused audio->features kernel (one launch per step) when the pair fuses, else K1
+    dom_ms = step_ms if (fused and world == 1) else k1_ms
+    dom_bytes = (FUSED_BYTES_PER_UTT if fused else K1_BYTES_PER_UTT) * B
+    dom_gbs = dom_bytes / (dom_ms / 1e3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tj = json.load(f)
+        if fused and tj.get("utterances_per_launch") == B:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        pass
+    k1_gops = K1_FP64_OPS_PER_UTT * B / (k1_ms / 1e3) / 1e9
     out = {
         "metric": METRIC, "value": value, "unit": "utterances/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(),
         "neuron_steps_per_s": value * N_NEURONS * T_STEPS,
         "e2e": {"value": e2e_val, "unit": "utterances/s", "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * F * 8},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
-        "roofline": {"kernel": "gammatone_encode_kernel (K1)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": k1_gbs / hbm_peak, "traffic": None, "peak_source": f"{peak_kind} MEASURED_PEAKS.json hbm_gbs",
-                     "note": "K1 is bound by the fp64 pipe, not HBM (SURVEY.md 8d): see roofline_fp64"},
-        "roofline_fp64": {"kernel": "gammatone_encode_kernel (K1)", "bound": "fp64 pipe",
-                          "achieved": K1_FP64_OPS_PER_UTT * B / (k1_ms / 1e3) / 1e9, "peak": fp64_peak,
-                          "unit": "G fp64 lane-ops/s (DADD, DMUL, DFMA each count 1)",
-                          "frac": K1_FP64_OPS_PER_UTT * B / (k1_ms / 1e3) / 1e9 / fp64_peak,
+        "roofline": {"kernel": "gammatone_encode_kernel fused audio->features (K1+K2+K3)" if fused else "gammatone_encode_kernel (K1)",
+                     "bound": "hbm", "achieved": dom_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": dom_gbs / hbm_peak,
+                     "traffic": traffic, "algorithmic_bytes_per_launch": dom_bytes,
+                     "peak_source": f"{peak_kind} MEASURED_PEAKS.json hbm_gbs",
+                     "note": "this kernel is bound by the fp64 pipe / instruction issue, not HBM (SURVEY.md 8d): see roofline_fp64; "
+                             "traffic = dram read+write bytes per launch from ncu (profiles/r1_traffic.json)"},
+        "roofline_fp64": {"kernel": "gammatone_encode_kernel (K1, stand-alone launch)", "bound": "fp64 pipe",
+                          "achieved": k1_gops, "peak": fp64_peak,
+                          "unit": "G fp64 lane-ops/s (DADD, DMUL, DFMA each count 1)", "frac": k1_gops / fp64_peak,
+                          "in_fused_kernel": {"achieved": K1_FP64_OPS_PER_UTT * B / (step_ms / 1e3) / 1e9,
+                                              "frac": K1_FP64_OPS_PER_UTT * B / (step_ms / 1e3) / 1e9 / fp64_peak,
+                                              "note": "filter-bank lane-ops only, over the whole fused step (reservoir and readout included in the time)"},
                           "peak_source": "measured live by lsm_fp64_peak_gops (independent DADD/DMUL register chains); "
                                          "nominal 148 SMs x 64 lanes x 1.965 GHz = 18612"},
         "kernel_ms": {"K1_gammatone_encode": k1_ms, "K2_reservoir_features": k2_ms},

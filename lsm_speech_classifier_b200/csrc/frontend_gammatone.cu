@@ -291,10 +291,16 @@ static int k1_grid(lsm_ctx *ctx, int threads, size_t smem, int *per_sm)
     return LSM_OK;
 }
 
+static size_t k1_pad_smem()
+{
+    const char *e = getenv("LSM_K1_PAD_SMEM");      // experiment knob: extra dynamic smem to force lower occupancy
+    return e ? (size_t)atoi(e) : 0;
+}
+
 int lsm_gammatone_grid(lsm_ctx *ctx, const lsm_frontend_params *p, int *grid)
 {
     const int threads = ((p->channels + 31) / 32) * 32;
-    const size_t smem = sizeof(double) * 2 * kChunkBlocks * p->hop;
+    const size_t smem = sizeof(double) * 2 * kChunkBlocks * p->hop + k1_pad_smem();
     int per_sm = 0, rc;
     if (threads > 128) rc = k1_grid<256, 2, 0, true>(ctx, threads, smem, &per_sm);
     else if (k1_minb() == 4) rc = k1_grid<128, 4, 0, true>(ctx, threads, smem, &per_sm);
@@ -317,8 +323,40 @@ static void fill_args(const lsm_frontend *fe, const float *d_pcm, int B, uint8_t
     for (int k = 0; k < 8; ++k) { a.thr[k] = p.thresholds_desc[k]; a.lower[k] = p.lower_bounds[k]; }
 }
 
+// The per-CTA dB planes (grid x ~100 KB) are written and re-read by the same CTA for every utterance.  Mark that
+// region L2-persisting on the launch stream so it is not evicted to HBM by the PCM / spike streams passing through.
+static void pin_scratch_in_l2(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st)
+{
+    if (getenv("LSM_NO_L2_PIN")) return;
+    const size_t bytes = sizeof(double) * (size_t)fe->grid * fe->ncols * fe->p.channels;
+    if (!fe->l2_window_ready) {
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+        fe->l2_window_bytes = 0;
+        if (max_persist > 0 && max_window > 0) {
+            size_t want = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+                fe->l2_window_bytes = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+            fe->l2_hit_ratio = bytes <= want ? 1.0f : (float)want / (float)bytes;
+        }
+        cudaGetLastError();
+        fe->l2_window_ready = 1;
+    }
+    if (!fe->l2_window_bytes) return;
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof(v));
+    v.accessPolicyWindow.base_ptr = fe->d_scratch;
+    v.accessPolicyWindow.num_bytes = fe->l2_window_bytes;
+    v.accessPolicyWindow.hitRatio = fe->l2_hit_ratio;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+}
+
 static int next_counter(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st, int **counter)
 {
+    pin_scratch_in_l2(ctx, fe, st);
     // work counter: one int per launch out of a small ring, so back-to-back launches on different streams do not share it
     *counter = fe->d_counters + (fe->counter_next++ % 64);
     LSM_CUDA(ctx, cudaMemsetAsync(*counter, 0, sizeof(int), st));
@@ -333,7 +371,7 @@ int lsm_launch_gammatone(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int
     fill_args(fe, d_pcm, B, d_spikes, d_spec_norm, &a);
     memset(&a.res, 0, sizeof(a.res));
     const int threads = ((p.channels + 31) / 32) * 32;
-    const size_t smem = sizeof(double) * 2 * kChunkBlocks * p.hop;
+    const size_t smem = sizeof(double) * 2 * kChunkBlocks * p.hop + k1_pad_smem();
     const int grid = B < fe->grid ? B : fe->grid;
     if (grid <= 0) return LSM_OK;
     int *counter, rc;

@@ -35,6 +35,9 @@ struct lsm_frontend {
     int *d_counters = nullptr;     // [64] dynamic work counters, one per in-flight launch
     unsigned counter_next = 0;
     int minb = 5;                  // K1 occupancy target the kernel was instantiated for
+    int l2_window_ready = 0;       // L2 persisting window for the scratch planes
+    size_t l2_window_bytes = 0;
+    float l2_hit_ratio = 1.0f;
     // mel
     float *d_mel_w = nullptr;      // packed non-zero mel weights
     int32_t *d_mel_lo = nullptr;   // [C] first non-zero bin
