@@ -17,7 +17,7 @@
 
 namespace {
 
-template <int NPT, bool LEAN>
+template <int NPT, bool LEAN, bool STAT_GLOBAL>
 __global__ void __launch_bounds__(1024) reservoir_kernel(const ResArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(1024) reservoir_kernel(const ResArgs a)
         }
     }
     __syncthreads();
-    reservoir_simulate<NPT, LEAN>(a, utt, smem_raw, s_cnt);
+    reservoir_simulate<NPT, LEAN, STAT_GLOBAL>(a, utt, smem_raw, s_cnt);
 }
 
 }  // namespace
@@ -102,6 +102,7 @@ int lsm_launch_reservoir(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spik
     if (smem > 200 * 1024) {
         // large reservoirs: the per-neuron statistics (touched only on a spike) move to a global scratch, one slab per CTA
         smem = lsm_res_smem_bytes(a.T, a.CW, threads * npt, N, false);
+        if (npt != 16) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "reservoir with %d neurons per thread does not fit in shared memory", npt);
         if (smem > 227 * 1024) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "reservoir needs %zu bytes of shared memory per utterance", smem);
         void *slab;
         int rc = lsm_stage_device(ctx, 6, sizeof(int) * 6 * (size_t)threads * npt * B, &slab);
@@ -109,21 +110,24 @@ int lsm_launch_reservoir(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spik
         a.stat_global = (int *)slab;
     }
 
-#define LSM_RES_LAUNCH(NPT, LEAN)                                                                    \
+#define LSM_RES_LAUNCH(NPT, LEAN, SG)                                                                \
     do {                                                                                             \
         if (smem > 48 * 1024)                                                                        \
-            LSM_CUDA(ctx, cudaFuncSetAttribute(reservoir_kernel<NPT, LEAN>,                          \
+            LSM_CUDA(ctx, cudaFuncSetAttribute(reservoir_kernel<NPT, LEAN, SG>,                      \
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        reservoir_kernel<NPT, LEAN><<<B, threads, smem, st>>>(a);                                    \
+        reservoir_kernel<NPT, LEAN, SG><<<B, threads, smem, st>>>(a);                                \
     } while (0)
-    if (res->lean) {
-        if (npt == 4) LSM_RES_LAUNCH(4, true);
-        else if (npt == 8) LSM_RES_LAUNCH(8, true);
-        else LSM_RES_LAUNCH(16, true);
+    if (a.stat_global) {            // only the 16-neurons-per-thread shapes are large enough to need the slab
+        if (res->lean) LSM_RES_LAUNCH(16, true, true);
+        else LSM_RES_LAUNCH(16, false, true);
+    } else if (res->lean) {
+        if (npt == 4) LSM_RES_LAUNCH(4, true, false);
+        else if (npt == 8) LSM_RES_LAUNCH(8, true, false);
+        else LSM_RES_LAUNCH(16, true, false);
     } else {
-        if (npt == 4) LSM_RES_LAUNCH(4, false);
-        else if (npt == 8) LSM_RES_LAUNCH(8, false);
-        else LSM_RES_LAUNCH(16, false);
+        if (npt == 4) LSM_RES_LAUNCH(4, false, false);
+        else if (npt == 8) LSM_RES_LAUNCH(8, false, false);
+        else LSM_RES_LAUNCH(16, false, false);
     }
 #undef LSM_RES_LAUNCH
     ctx->launches += 1;

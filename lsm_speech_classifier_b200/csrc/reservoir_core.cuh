@@ -36,7 +36,8 @@ __host__ __device__ inline size_t lsm_res_smem_bytes(int T, int CW, int slots, i
 
 // Caller contract: s_bits holds the utterance's input and a __syncthreads() has made it visible.
 // LEAN = uniform leak, uniform input gain, at most one input row per neuron (the reference's setup).
-template <int NPT, bool LEAN>
+// STAT_GLOBAL = per-neuron statistics in a.stat_global instead of shared memory (reservoirs too large for it).
+template <int NPT, bool LEAN, bool STAT_GLOBAL = false>
 __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int utt, unsigned char *smem_raw, int *s_cnt)
 {
     const int tid = threadIdx.x;
@@ -46,9 +47,9 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
     const int S = nthr * NPT;
     const int NL = (N + 7) & ~3;                       // list capacity, multiple of 4
     unsigned *s_bits = reinterpret_cast<unsigned *>(smem_raw);
-    int *s_stat = a.stat_global ? a.stat_global + (size_t)blockIdx.x * 6 * S : reinterpret_cast<int *>(s_bits + (size_t)T * CW);
+    int *s_stat = STAT_GLOBAL ? a.stat_global + (size_t)blockIdx.x * 6 * S : reinterpret_cast<int *>(s_bits + (size_t)T * CW);
     unsigned short *s_list = reinterpret_cast<unsigned short *>(reinterpret_cast<int *>(s_bits + (size_t)T * CW) +
-                                                                (a.stat_global ? 0 : 6 * (size_t)S));
+                                                                (STAT_GLOBAL ? 0 : 6 * (size_t)S));
 
     for (int i = tid; i < S; i += nthr) {
         s_stat[i] = 0; s_stat[S + i] = 0; s_stat[2 * S + i] = -1; s_stat[3 * S + i] = -1; s_stat[4 * S + i] = 0; s_stat[5 * S + i] = 0;
