@@ -150,7 +150,8 @@ int lsm_reservoir_run_host(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *h_sp
  * audio -> features in one call: the loop bodies of create_dataset.py:143-162 and
  * extract_lsm_features.py:78-87 for B utterances.  Copies are chunked and overlapped with the
  * kernels on internal streams.  h_spikes_or_null: optionally also return the spike trains (the
- * stage-1 file content).  Synchronous.                                                       */
+ * stage-1 file content).  Synchronous.  When h_pcm and h_features are pinned host memory (or device memory) the
+ * fused kernel addresses them directly: PCM is read across PCIe as it is consumed and no staging copy is made.                                                       */
 int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *h_pcm,
                           int32_t B, uint32_t feature_mask, int32_t nan_to_num, double *h_features,
                           uint8_t *h_spikes_or_null);

@@ -406,12 +406,15 @@ extern "C" int lsm_pipeline_run(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *r
     return lsm_launch_reservoir(ctx, res, d_spikes, B, feature_mask, nan_to_num, d_features, nullptr, ctx->stream);
 }
 
-// Is this host pointer pinned/registered memory the device can address directly (UVA)?  Returns its device alias.
+// Can the device address this buffer directly?  Pinned/registered host memory (UVA alias) or device/managed memory.
 static bool device_visible(const void *h, void **d)
 {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return false; }
-    if (at.type == cudaMemoryTypeHost && at.devicePointer) { *d = at.devicePointer; return true; }
+    if ((at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) && at.devicePointer) {
+        *d = at.devicePointer;
+        return true;
+    }
     return false;
 }
 

@@ -149,10 +149,11 @@ class AudioToFeatures:
         """True when the pair runs as one kernel (spikes handed over in shared memory)."""
         return bool(self.ctx.lib.lsm_pipeline_is_fused(self.frontend.h, self.snn.h))
 
-    def run_host(self, pcm: np.ndarray, feature_keys, nan_to_num: bool = True, out: np.ndarray | None = None,
-                 spikes_out: np.ndarray | None = None):
-        """Host buffers in, host buffers out; copies are chunked and overlapped with the kernels
-        inside the library (lsm_pipeline_run_host).  `pcm` should be pinned for full overlap."""
+    def run_host(self, pcm, feature_keys, nan_to_num: bool = True, out=None, spikes_out: np.ndarray | None = None):
+        """Host buffers in, host buffers out (lsm_pipeline_run_host), synchronous.  With pinned buffers (e.g.
+        `torch.Tensor.pin_memory().numpy()`) the fused kernel reads the PCM and writes the feature rows directly
+        across PCIe; pageable buffers go through a chunked copy/compute pipeline.  `out` may also be a CUDA tensor
+        (features stay on the device, e.g. for an all-gather)."""
         keys = list(feature_keys)
         mask = _lib.feature_mask(keys)
         if _lib.mask_keys(mask) != keys:
@@ -161,10 +162,11 @@ class AudioToFeatures:
         F = len(keys) * self.snn.num_output_neurons
         if out is None:
             out = np.empty((B, F), dtype=np.float64)
+        ptr = (lambda a: a.data_ptr() if _is_torch(a) else a.ctypes.data)
         self.ctx.set_stream(None)
         self.ctx.check(self.ctx.lib.lsm_pipeline_run_host(
-            self.ctx.h, self.frontend.h, self.snn.h, C.c_void_p(pcm.ctypes.data), B, mask, int(nan_to_num),
-            C.c_void_p(out.ctypes.data), C.c_void_p(spikes_out.ctypes.data) if spikes_out is not None else None))
+            self.ctx.h, self.frontend.h, self.snn.h, C.c_void_p(ptr(pcm)), B, mask, int(nan_to_num),
+            C.c_void_p(ptr(out)), C.c_void_p(spikes_out.ctypes.data) if spikes_out is not None else None))
         return out
 
     def run(self, pcm, feature_keys, nan_to_num: bool = True, spikes=None, out=None, want_spikes: bool = True):
