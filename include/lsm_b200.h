@@ -146,6 +146,11 @@ int lsm_reservoir_run_host(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *h_sp
                            uint32_t feature_mask, int32_t nan_to_num, double *h_features,
                            uint8_t *h_raster_or_null);
 
+/* Network diagnostics of run_network_diagnostics (extract_lsm_features.py:92-152) reduced on the device instead of
+ * shipping the raster: for each utterance, d_diag[2*b] = neurons (of all N) that fired at least once,
+ * d_diag[2*b+1] = total spikes.  Participation % = 100*d_diag[2b]/N, average spikes per neuron = d_diag[2b+1]/N. */
+int lsm_reservoir_diagnostics(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int32_t B, int32_t *d_diag);
+
 /* ---------------------------------------------------------------- the whole path, host buffers
  * audio -> features in one call: the loop bodies of create_dataset.py:143-162 and
  * extract_lsm_features.py:78-87 for B utterances.  Copies are chunked and overlapped with the

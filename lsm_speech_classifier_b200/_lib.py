@@ -22,7 +22,7 @@ EXPORTS = [
     "lsm_sm_count", "lsm_frontend_create", "lsm_frontend_destroy", "lsm_frontend_encode",
     "lsm_frontend_encode_host", "lsm_reservoir_create", "lsm_reservoir_destroy", "lsm_reservoir_run",
     "lsm_reservoir_run_host", "lsm_pipeline_run_host", "lsm_pipeline_run", "lsm_spike_density",
-    "lsm_hysteresis_encode", "lsm_fp64_peak_gops", "lsm_pipeline_is_fused", "lsm_frontend_mel_tables",
+    "lsm_hysteresis_encode", "lsm_fp64_peak_gops", "lsm_pipeline_is_fused", "lsm_frontend_mel_tables", "lsm_reservoir_diagnostics",
 ]
 
 
@@ -84,6 +84,7 @@ def load():
     lib.lsm_fp64_peak_gops.argtypes = [vp, vp]
     lib.lsm_pipeline_is_fused.argtypes = [vp, vp]
     lib.lsm_frontend_mel_tables.argtypes = [vp, vp, vp, vp, vp]
+    lib.lsm_reservoir_diagnostics.argtypes = [vp, vp, vp, i32, vp]
     _lib = lib
     return lib
 

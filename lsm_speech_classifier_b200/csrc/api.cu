@@ -357,6 +357,15 @@ extern "C" int lsm_reservoir_run(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t
     return lsm_launch_reservoir(ctx, res, d_spikes, B, feature_mask, nan_to_num, d_features, d_raster_or_null, ctx->stream);
 }
 
+extern "C" int lsm_reservoir_diagnostics(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int32_t B, int32_t *d_diag)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!res || B < 0 || (B > 0 && (!d_spikes || !d_diag))) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_diagnostics: bad argument");
+    if (B == 0) return LSM_OK;
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    return lsm_launch_reservoir(ctx, res, d_spikes, B, 0u, 0, nullptr, nullptr, ctx->stream, d_diag);
+}
+
 extern "C" int lsm_reservoir_run_host(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *h_spikes, int32_t B,
                                       uint32_t feature_mask, int32_t nan_to_num, double *h_features,
                                       uint8_t *h_raster_or_null)

@@ -97,7 +97,7 @@ int lsm_launch_mel(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, ui
                    double *d_spec_norm, cudaStream_t st);
 int lsm_launch_reservoir(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int B,
                          uint32_t feature_mask, int nan_to_num, double *d_features, uint8_t *d_raster,
-                         cudaStream_t st);
+                         cudaStream_t st, int *d_diag = nullptr);
 void lsm_reservoir_geometry(int N, int *npt, int *threads, int *n_pad);
 int lsm_mel_create(lsm_ctx *ctx, lsm_frontend *fe, const float *h_basis);
 void lsm_mel_destroy(lsm_frontend *fe);

@@ -76,7 +76,7 @@ void lsm_reservoir_fill_args(const lsm_reservoir *res, const uint8_t *d_spikes, 
     ResArgs &a = *out;
     a.spikes = d_spikes; a.wt = res->d_wt; a.in_rowptr = res->d_in_rowptr; a.in_col = res->d_in_col;
     a.in_val = res->d_in_val; a.in_row = res->d_in_row; a.leak = res->d_leak; a.out_slot = res->d_out_slot;
-    a.features = d_features; a.raster = d_raster; a.stat_global = nullptr;
+    a.features = d_features; a.raster = d_raster; a.stat_global = nullptr; a.diag = nullptr;
     a.B = B; a.N = p.num_neurons; a.n_pad = res->n_pad; a.C = p.num_inputs; a.CW = (p.num_inputs + 31) / 32; a.T = p.num_steps;
     a.refractory = p.refractory; a.n_out = p.n_out; a.nan_to_num = nan_to_num;
     a.leak0 = res->leak0; a.gain0 = res->gain0;
@@ -88,12 +88,13 @@ void lsm_reservoir_fill_args(const lsm_reservoir *res, const uint8_t *d_spikes, 
 
 int lsm_launch_reservoir(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int B,
                          uint32_t feature_mask, int nan_to_num, double *d_features, uint8_t *d_raster,
-                         cudaStream_t st)
+                         cudaStream_t st, int *d_diag)
 {
     const lsm_reservoir_params &p = res->p;
     if (B <= 0) return LSM_OK;
     ResArgs a;
     lsm_reservoir_fill_args(res, d_spikes, B, feature_mask, nan_to_num, d_features, d_raster, &a);
+    a.diag = d_diag;
     const int N = p.num_neurons;
     int npt, threads, n_pad;
     lsm_reservoir_geometry(N, &npt, &threads, &n_pad);

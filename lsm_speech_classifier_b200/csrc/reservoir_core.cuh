@@ -17,6 +17,7 @@ struct ResArgs {
     double *features;         // [B][nkeys][n_out]
     uint8_t *raster;          // optional [B][T][N]
     int *stat_global;         // per-CTA [6][slots] statistics when they do not fit in shared memory (large N), else null
+    int *diag;                // optional [B][2]: neurons that fired at least once, total spikes (run_network_diagnostics)
     int B, N, n_pad, C, CW, T, refractory, n_out, nkeys, nan_to_num;
     unsigned feature_mask;
     double theta, scale, leak0, gain0;
@@ -170,6 +171,22 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
         }
         __syncthreads();
         const int tmp = c_cur; c_cur = c_nxt; c_nxt = c_zero; c_zero = tmp;
+    }
+
+    // ---- network diagnostics (extract_lsm_features.py:117-131) over ALL neurons: participation and activity
+    if (a.diag) {
+        int active = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) {
+            if (i0 + k < N) { const int c = s_stat[k * nthr + tid]; active += c > 0 ? 1 : 0; total += c; }
+        }
+        active = __reduce_add_sync(0xffffffffu, active);
+        total = __reduce_add_sync(0xffffffffu, total);
+        if (tid < 2) s_cnt[tid] = 0;
+        __syncthreads();
+        if (lane == 0) { atomicAdd(&s_cnt[0], active); atomicAdd(&s_cnt[1], total); }
+        __syncthreads();
+        if (tid < 2) a.diag[(size_t)utt * 2 + tid] = s_cnt[tid];
     }
 
     // ---- K3: feature readout, key-major [nkeys][n_out] (extract_lsm_features.py:85-87).  Each key's values are

@@ -84,15 +84,12 @@ def run_network_diagnostics(lsm: SNN, X_sample_batch):
     subset = np.asarray(X_sample_batch[:5], dtype=np.uint8)
     if len(subset) == 0:
         return None
-    _, raster = lsm.simulate_batch(subset, ['spike_counts'], return_raster=True)
-    total = lsm.num_neurons
+    # reduced in the kernel epilogue; no raster leaves the device
+    participation, dead, avg_spikes = lsm.diagnostics(subset)
     rates = []
-    for i, spikes in enumerate(raster):
-        per_neuron = spikes.sum(axis=0, dtype=np.int64)
-        active = int(np.count_nonzero(per_neuron))
-        part = active / total * 100
-        rates.append(part)
-        print(f"Sample {i + 1}: Active: {part:.1f}% | Dead: {total - active} | Avg Spikes/Neuron: {per_neuron.mean():.2f}")
+    for i in range(len(subset)):
+        rates.append(float(participation[i]))
+        print(f"Sample {i + 1}: Active: {participation[i]:.1f}% | Dead: {int(dead[i])} | Avg Spikes/Neuron: {avg_spikes[i]:.2f}")
     avg_part = float(np.mean(rates))
     print("-" * 40)
     print("DIAGNOSTIC RESULT:")

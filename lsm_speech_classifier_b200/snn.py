@@ -93,6 +93,25 @@ class SNN:
         feats = self._reorder(feats, order, keys, n_out)
         return (feats, raster) if return_raster else feats
 
+    def diagnostics(self, spikes):
+        """Per utterance (participation %, dead neurons, average spikes per neuron) over all N neurons, reduced
+        on the device (lsm_reservoir_diagnostics) - what run_network_diagnostics derives from spike_matrix."""
+        import torch
+        r = self.reservoir
+        if not _is_torch(spikes):
+            spikes = torch.from_numpy(_lib.as_host(spikes, np.uint8)).cuda(self.ctx.device)
+        spikes = spikes.contiguous()
+        if spikes.dtype != torch.uint8 or spikes.dim() != 3 or tuple(spikes.shape[1:]) != (r.num_inputs, r.num_steps):
+            raise ValueError(f"spikes must be uint8[B,{r.num_inputs},{r.num_steps}]")
+        B = spikes.shape[0]
+        diag = torch.zeros((B, 2), dtype=torch.int32, device=spikes.device)
+        self.ctx.set_stream(torch.cuda.current_stream(spikes.device).cuda_stream)
+        self.ctx.check(self.ctx.lib.lsm_reservoir_diagnostics(self.ctx.h, self.h, C.c_void_p(spikes.data_ptr()), B,
+                                                              C.c_void_p(diag.data_ptr())))
+        d = diag.cpu().numpy().astype(np.int64)
+        n = self.num_neurons
+        return d[:, 0] / n * 100.0, n - d[:, 0], d[:, 1] / n
+
     @staticmethod
     def _reorder(feats, order, keys, n_out):
         """The kernel emits keys in bit order; FEATURE_SETS lists are already in that order, but honour any."""

@@ -313,3 +313,19 @@ def test_other_threshold_counts_and_empty_batches(env, small_set):
     assert lsm.simulate_batch(X[:0]).shape == (0, 8 * 400)
     with pytest.raises(ValueError):
         lsm.simulate_batch(np.zeros((1, 64, 400), np.uint8))
+
+
+def test_device_diagnostics_match_the_raster(env, small_set):
+    """run_network_diagnostics' numbers (extract_lsm_features.py:117-131) reduced on the device vs the raster."""
+    from lsm_speech_classifier_b200.frontend import Frontend
+    pcm, _ = small_set
+    X = Frontend(128, "gammatone").encode(pcm[:10])
+    for kw in (dict(), dict(num_neurons=2500, small_world_graph_k=500)):
+        lsm = build_snn(X, **kw)
+        part, dead, avg = lsm.diagnostics(X)
+        _, raster = lsm.simulate_batch(X, ['spike_counts'], return_raster=True)
+        per_neuron = raster.sum(axis=1, dtype=np.int64)                      # [B, N]
+        active = (per_neuron > 0).sum(axis=1)
+        assert np.array_equal(dead, lsm.num_neurons - active)
+        np.testing.assert_allclose(part, active / lsm.num_neurons * 100)
+        np.testing.assert_allclose(avg, per_neuron.mean(axis=1))
