@@ -104,6 +104,13 @@ int lsm_frontend_encode(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int3
 int lsm_frontend_encode_host(lsm_ctx *ctx, lsm_frontend *fe, const float *h_pcm, int32_t B,
                              uint8_t *h_spikes);
 
+/* Host-side design helpers for callers without numpy (plain libm; no device work).
+ * lsm_gammatone_design: the table gammatone.gtgram.gtgram_xe filters with - make_erb_filters(fs, centre_freqs(fs,
+ *   channels, f_min)) flipped so row 0 is the lowest centre frequency; h_out: double[channels][10].
+ * lsm_zoom_table: scipy.ndimage.zoom(order=1) source index / fraction for n_in -> n_out columns.           */
+int lsm_gammatone_design(double fs, int32_t channels, double f_min, double *h_out);
+int lsm_zoom_table(int32_t n_in, int32_t n_out, int32_t *h_i0, double *h_f);
+
 /* The encoder alone, on spectrograms already in device memory: convert_spectrogram_to_spikes_hysteresis
  * (create_dataset.py:81-98) + create_pure_redundancy (:101-104).  d_spec: double[B][C][n_bins] or, when
  * is_f32 != 0, float[B][C][n_bins] compared against float-rounded thresholds as numpy does for a

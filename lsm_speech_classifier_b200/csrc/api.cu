@@ -1,8 +1,10 @@
 // liblsmb200.so — C ABI (include/lsm_b200.h): context, handles, host-buffer entry points and the
 // chunked audio -> features pipeline.  No CPU fallback anywhere: every entry point needs a ctx,
 // and a ctx needs a CUDA device.
+#include <math.h>
 #include <stdlib.h>
 
+#include <complex>
 #include <new>
 #include <vector>
 
@@ -212,6 +214,48 @@ extern "C" int lsm_frontend_encode_host(lsm_ctx *ctx, lsm_frontend *fe, const fl
     if ((rc = frontend_launch(ctx, fe, (const float *)d_pcm, B, (uint8_t *)d_spk, nullptr, ctx->stream)) != LSM_OK) return rc;
     LSM_CUDA(ctx, cudaMemcpyAsync(h_spikes, d_spk, spk_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     LSM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return LSM_OK;
+}
+
+// ------------------------------------------------------------------------------------ host design helpers
+// Slaney's ERBSpace / MakeERBFilters as published in gammatone==1.0.3 (call site create_dataset.py:51-58); the same
+// formulas as lsm_speech_classifier_b200/filterbank.py, for C callers.  Transcendentals come from the host libm, so
+// the last bit may differ from numpy's: pass the same table to every implementation you want to agree bit for bit.
+extern "C" int lsm_gammatone_design(double fs, int32_t channels, double f_min, double *h_out)
+{
+    if (!h_out || channels <= 0 || fs <= 0 || f_min <= 0 || f_min >= fs / 2) return LSM_ERR_INVALID;
+    const double ear_q = 9.26449, min_bw = 24.7, pi = 3.14159265358979323846;
+    const double c = ear_q * min_bw, hi = fs / 2, T = 1 / fs;
+    const double rt_pos = sqrt(3 + pow(2.0, 1.5)), rt_neg = sqrt(3 - pow(2.0, 1.5));
+    for (int i = 1; i <= channels; ++i) {
+        const double cf = -c + exp(((double)i / channels) * (-log(hi + c) + log(f_min + c))) * (hi + c);
+        const double erb = cf / ear_q + min_bw;
+        const double B = 1.019 * 2 * pi * erb;
+        const double arg = 2 * cf * pi * T;
+        const std::complex<double> vec = std::exp(std::complex<double>(0, 2 * arg));
+        const double B1 = -2 * cos(arg) / exp(B * T), B2 = exp(-2 * B * T);
+        const double common = -T * exp(-(B * T));
+        const double k[4] = {cos(arg) + rt_pos * sin(arg), cos(arg) - rt_pos * sin(arg),
+                             cos(arg) + rt_neg * sin(arg), cos(arg) - rt_neg * sin(arg)};
+        const std::complex<double> g = std::exp(std::complex<double>(-B * T, arg));
+        const std::complex<double> q = T * exp(B * T) / (-1 / exp(B * T) + 1.0 + vec * (1 - exp(B * T)));
+        const double gain = std::abs((vec - g * k[0]) * (vec - g * k[1]) * (vec - g * k[2]) * (vec - g * k[3]) * q * q * q * q);
+        double *row = h_out + 10 * (size_t)(channels - i);      // flipud: row 0 = lowest centre frequency
+        row[0] = T; row[1] = common * k[0]; row[2] = common * k[1]; row[3] = common * k[2]; row[4] = common * k[3];
+        row[5] = 0.0; row[6] = 1.0; row[7] = B1; row[8] = B2; row[9] = gain;
+    }
+    return LSM_OK;
+}
+
+extern "C" int lsm_zoom_table(int32_t n_in, int32_t n_out, int32_t *h_i0, double *h_f)
+{
+    if (!h_i0 || !h_f || n_in < 2 || n_out < 2) return LSM_ERR_INVALID;
+    const double zz = (double)(n_in - 1) / (double)(n_out - 1);
+    for (int j = 0; j < n_out; ++j) {
+        const double cc = (double)j * zz, fl = floor(cc);
+        h_i0[j] = (int32_t)fl;
+        h_f[j] = cc - fl;
+    }
     return LSM_OK;
 }
 

@@ -51,3 +51,21 @@ def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(_lib.FrontendParams) == 10 * 4 + 16 * 8
     assert C.sizeof(_lib.ReservoirParams) == 6 * 4 + 8
+
+
+def test_host_design_helpers_agree_with_numpy():
+    """lsm_gammatone_design / lsm_zoom_table are plain host code (no device work): check them here."""
+    import ctypes as C
+    import numpy as np
+    from lsm_speech_classifier_b200 import filterbank as fb
+    lib = _lib.load()
+    for ch in (40, 64, 128, 256):
+        out = np.zeros((ch, 10))
+        assert lib.lsm_gammatone_design(16000.0, ch, 50.0, C.c_void_p(out.ctypes.data)) == 0
+        np.testing.assert_allclose(out, fb.gammatone_coefs(16000, ch, 50), rtol=1e-12, atol=0)
+    for n_in in (98, 101):
+        i0, f = np.zeros(100, np.int32), np.zeros(100)
+        assert lib.lsm_zoom_table(n_in, 100, C.c_void_p(i0.ctypes.data), C.c_void_p(f.ctypes.data)) == 0
+        a, b = fb.zoom_table(n_in, 100)
+        assert np.array_equal(i0, a) and np.array_equal(f, b)
+    assert lib.lsm_gammatone_design(16000.0, 0, 50.0, None) != 0
