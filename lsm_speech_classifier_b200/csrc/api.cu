@@ -165,6 +165,8 @@ extern "C" int lsm_frontend_create(lsm_ctx *ctx, const lsm_frontend_params *p, c
 extern "C" void lsm_frontend_destroy(lsm_frontend *fe)
 {
     if (!fe) return;
+    if (fe->ev_valid) cudaEventSynchronize(fe->ev_last);
+    if (fe->ev_last) cudaEventDestroy(fe->ev_last);
     cudaFree(fe->d_coefs); cudaFree(fe->d_zoom_i0); cudaFree(fe->d_zoom_f); cudaFree(fe->d_scratch); cudaFree(fe->d_counters);
     lsm_mel_destroy(fe);
     delete fe;
@@ -178,6 +180,24 @@ extern "C" int lsm_frontend_mel_tables(lsm_ctx *ctx, lsm_frontend *fe, const dou
     if (fe->p.kind != LSM_FILTERBANK_MEL) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_frontend_mel_tables: not a mel front end");
     LSM_CUDA(ctx, cudaSetDevice(ctx->device));
     return lsm_mel_set_tables(ctx, fe, h_window, h_tw, h_tw2);
+}
+
+// The per-CTA scratch planes (and the work-counter ring) of a front end are shared by all its launches.  Launches on one
+// stream are ordered by the stream; when the stream changes (torch's stream for the device-pointer calls, the ctx's
+// own stream for the *_host calls) the new launch first waits for the previous one.
+int lsm_frontend_order_before(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st)
+{
+    if (fe->ev_valid && fe->last_stream != st) LSM_CUDA(ctx, cudaStreamWaitEvent(st, fe->ev_last, 0));
+    return LSM_OK;
+}
+
+int lsm_frontend_order_after(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st)
+{
+    if (!fe->ev_last) LSM_CUDA(ctx, cudaEventCreateWithFlags(&fe->ev_last, cudaEventDisableTiming));
+    LSM_CUDA(ctx, cudaEventRecord(fe->ev_last, st));
+    fe->last_stream = st;
+    fe->ev_valid = 1;
+    return LSM_OK;
 }
 
 static int frontend_launch(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, uint8_t *d_spikes,

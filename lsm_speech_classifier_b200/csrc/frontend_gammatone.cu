@@ -356,6 +356,8 @@ static void pin_scratch_in_l2(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st)
 
 static int next_counter(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st, int **counter)
 {
+    int rc = lsm_frontend_order_before(ctx, fe, st);
+    if (rc != LSM_OK) return rc;
     pin_scratch_in_l2(ctx, fe, st);
     // work counter: one int per launch out of a small ring, so back-to-back launches on different streams do not share it
     *counter = fe->d_counters + (fe->counter_next++ % 64);
@@ -382,7 +384,7 @@ int lsm_launch_gammatone(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int
     else gammatone_encode_kernel<128, 6, 0, true><<<grid, threads, smem, st>>>(a, counter);
     ctx->launches += 1;
     LSM_CUDA(ctx, cudaGetLastError());
-    return LSM_OK;
+    return lsm_frontend_order_after(ctx, fe, st);
 }
 
 // Can this (front end, reservoir) pair run as one fused kernel?  Gammatone, no redundancy, one thread
@@ -420,7 +422,7 @@ static int launch_fused_t(lsm_ctx *ctx, lsm_frontend *fe, const lsm_reservoir *r
     else gammatone_encode_kernel<MAXT, MINB, FNPT, false><<<grid, threads, smem, st>>>(a, counter);
     ctx->launches += 1;
     LSM_CUDA(ctx, cudaGetLastError());
-    return LSM_OK;
+    return lsm_frontend_order_after(ctx, fe, st);
 }
 
 static int fused_dispatch(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B,

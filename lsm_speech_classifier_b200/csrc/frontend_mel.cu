@@ -290,11 +290,13 @@ int lsm_launch_mel(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, ui
     a.B = B; a.L = p.n_samples; a.C = p.channels; a.hop = p.mel_hop; a.ncols = fe->ncols; a.nbins = p.n_bins;
     a.K = p.n_thresholds; a.R = p.redundancy;
     for (int k = 0; k < 8; ++k) { a.thr[k] = p.thresholds_desc[k]; a.lower[k] = p.lower_bounds[k]; }
+    int rc = lsm_frontend_order_before(ctx, fe, st);
+    if (rc != LSM_OK) return rc;
     int *counter = fe->d_counters + (fe->counter_next++ % 64);
     LSM_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), st));
     const int grid = B < fe->grid ? B : fe->grid;
     mel_encode_kernel<<<grid, kThreads, 0, st>>>(a, counter);
     ctx->launches += 1;
     LSM_CUDA(ctx, cudaGetLastError());
-    return LSM_OK;
+    return lsm_frontend_order_after(ctx, fe, st);
 }

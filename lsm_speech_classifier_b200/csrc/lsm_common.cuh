@@ -35,6 +35,10 @@ struct lsm_frontend {
     int *d_counters = nullptr;     // [64] dynamic work counters, one per in-flight launch
     unsigned counter_next = 0;
     int minb = 5;                  // K1 occupancy target the kernel was instantiated for
+    // launches on different streams share the scratch planes: each launch waits for the previous one's event
+    cudaEvent_t ev_last = nullptr;
+    cudaStream_t last_stream = nullptr;
+    int ev_valid = 0;
     int l2_window_ready = 0;       // L2 persisting window for the scratch planes
     size_t l2_window_bytes = 0;
     float l2_hit_ratio = 1.0f;
@@ -86,6 +90,8 @@ int lsm_launch_gammatone(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int
                          double *d_spec_norm, cudaStream_t st);
 int lsm_gammatone_grid(lsm_ctx *ctx, const lsm_frontend_params *p, int *grid);
 int lsm_gammatone_minb(void);
+int lsm_frontend_order_before(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st);   // call before a launch that uses fe's scratch
+int lsm_frontend_order_after(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st);    // ... and right after it
 int lsm_fused_npt(const lsm_frontend *fe, const lsm_reservoir *res);
 int lsm_launch_fused(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B,
                      uint8_t *d_spikes_or_null, uint32_t feature_mask, int nan_to_num, double *d_features, cudaStream_t st);

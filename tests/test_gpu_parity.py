@@ -329,3 +329,33 @@ def test_device_diagnostics_match_the_raster(env, small_set):
         assert np.array_equal(dead, lsm.num_neurons - active)
         np.testing.assert_allclose(part, active / lsm.num_neurons * 100)
         np.testing.assert_allclose(avg, per_neuron.mean(axis=1))
+
+
+def test_back_to_back_calls_on_different_streams_do_not_race(env, small_set):
+    """A device-pointer call (torch's stream, asynchronous) followed at once by a host-buffer call (the ctx's own stream)
+    share the front end's scratch planes: the library must order them.  No synchronize() in between on purpose."""
+    import torch
+    from lsm_speech_classifier_b200.frontend import Frontend
+    from lsm_speech_classifier_b200.snn import AudioToFeatures
+    from oracle import coracle
+    pcm, _ = small_set
+    big = np.concatenate([pcm] * 30)                 # long enough that the first kernel is still running
+    fe = Frontend(128, "gammatone")
+    X = oracle_spikes(pcm, fe)
+    lsm = build_snn(X)
+    keys = list(lsm_keys())
+    want, _ = coracle.reservoir_run(lsm.reservoir, X, 0xFF, True, False)
+    want_big = np.concatenate([want] * 30)
+    path = AudioToFeatures(fe, lsm)
+    d_big = torch.from_numpy(big).cuda()
+    side = torch.cuda.Stream()
+    for _ in range(3):
+        out, _ = path.run(d_big, keys, want_spikes=False)            # async, torch's current stream
+        host = path.run_host(pcm, keys)                              # synchronous, ctx's own stream
+        with torch.cuda.stream(side):
+            out2 = fe.encode(d_big)                                  # a third stream
+        spikes_host = fe.encode(pcm)
+        torch.cuda.synchronize()
+        assert np.array_equal(host, want) and np.array_equal(spikes_host, X)
+        assert np.array_equal(out.cpu().numpy(), want_big)
+        assert np.array_equal(out2.cpu().numpy(), np.concatenate([X] * 30))

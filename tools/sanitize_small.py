@@ -32,7 +32,9 @@ for C, fb, R in ((128, "gammatone", 1), (64, "gammatone", 1), (256, "gammatone",
         ho = torch.empty((len(pcm), h.shape[1]), dtype=torch.float64).pin_memory()
         path.run_host(hp.numpy(), keys, out=ho.numpy())
         torch.cuda.synchronize()
-        assert np.array_equal(h, f) and np.array_equal(ho.numpy(), f) and np.array_equal(out.cpu().numpy(), f), (C, fb, kw)
+        for name, got in (("run_host pageable", h), ("run_host pinned", ho.numpy()), ("fused device", out.cpu().numpy())):
+            bad = np.argwhere(got != f)
+            assert len(bad) == 0, (C, fb, kw, name, len(bad), bad[:4].tolist(), [(float(got[tuple(b)]), float(f[tuple(b)])) for b in bad[:4]])
         lsm.close()
     fe.close()
 print("sanitize run ok")
