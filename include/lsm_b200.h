@@ -181,6 +181,14 @@ int lsm_pipeline_is_fused(const lsm_frontend *fe, const lsm_reservoir *res);
  * reduces over X_train[:500] (extract_lsm_features.py:40-44).  h_out: int64[2].            */
 int lsm_spike_density(lsm_ctx *ctx, const uint8_t *d_spikes, int64_t n_bytes, int64_t *h_out);
 
+/* ---------------------------------------------------------------- downstream of the path
+ * sklearn.preprocessing.StandardScaler on the device, bit-exact with scikit-learn's dense float64 path
+ * (extract_lsm_features.py:199-201).  d_X: double[n][F] row-major; d_mean/d_var/d_scale: double[F].
+ * transform may run in place (d_out == d_X).                                                                  */
+int lsm_standardize_fit(lsm_ctx *ctx, const double *d_X, int32_t n, int32_t F, double *d_mean, double *d_var, double *d_scale);
+int lsm_standardize_transform(lsm_ctx *ctx, const double *d_X, int32_t n, int32_t F, const double *d_mean,
+                              const double *d_scale, double *d_out);
+
 /* Diagnostic: measured ceiling of the fp64 pipe on this device, in 1e9 DADD/DMUL lane-operations per
  * second (independent register chains, 8 warps per scheduler).  K1's roofline denominator in bench.py. */
 int lsm_fp64_peak_gops(lsm_ctx *ctx, double *h_out);
