@@ -94,6 +94,21 @@ void lsm_frontend_destroy(lsm_frontend *fe);
  * h_tw: double[n_fft/4][2] = exp(-2*pi*i*q/(n_fft/2)); h_tw2: double[n_fft/2+1][2] = exp(-2*pi*i*k/n_fft).   */
 int lsm_frontend_mel_tables(lsm_ctx *ctx, lsm_frontend *fe, const double *h_window, const double *h_tw,
                             const double *h_tw2);
+/* Gammatone only: how the filter bank is evaluated.  Either way the spike trains that leave the library are those of
+ * the reference's operation order (scipy.signal.lfilter x 4, /gain, square, window mean: create_dataset.py:51-58 via
+ * gammatone.gtgram), byte for byte.
+ *   LSM_FILTER_EXACT        every fp64 operation in the reference's order (35 separate roundings per channel-sample).
+ *   LSM_FILTER_SPECULATIVE  (default) a mathematically equivalent arrangement of the same cascade in 13 fused
+ *                           multiply-adds; an utterance in which any normalised value comes within delta_db decibels of an
+ *                           encoder threshold / hysteresis bound / the silent-clip test is filtered again in exact mode
+ *                           inside the same kernel.  delta_db = 0 keeps the current margin (1e-7 dB by default; the two
+ *                           arrangements differ by < 1e-10 dB).  The optional d_spec_norm dump always uses the exact path.
+ * lsm_frontend_reruns: number of utterances that were filtered twice since creation / the last reset (waits for the
+ * front end's last launch).                                                                                          */
+#define LSM_FILTER_EXACT 0
+#define LSM_FILTER_SPECULATIVE 1
+int lsm_frontend_set_mode(lsm_ctx *ctx, lsm_frontend *fe, int mode, double delta_db);
+int lsm_frontend_reruns(lsm_ctx *ctx, lsm_frontend *fe, int64_t *h_out, int reset);
 /* d_pcm: float[B][n_samples].  d_spikes: uint8[B][channels*redundancy][n_bins*n_thresholds] — the
  * X_spikes layout of speech_spike_dataset_pure_redundancy.npz (create_dataset.py:168).
  * d_spec_norm_or_null: optional double[B][channels][n_bins] dump of the normalised, resampled

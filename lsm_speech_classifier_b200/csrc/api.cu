@@ -139,7 +139,9 @@ extern "C" int lsm_frontend_create(lsm_ctx *ctx, const lsm_frontend_params *p, c
         fe->minb = lsm_gammatone_minb();
         if (rc == LSM_OK) rc = lsm_gammatone_grid(ctx, p, &fe->grid);
         if (rc == LSM_OK) rc = upload<double>(ctx, &fe->d_scratch, nullptr, (size_t)fe->grid * fe->ncols * p->channels);
-        if (rc == LSM_OK) rc = upload<int>(ctx, &fe->d_counters, nullptr, 64);
+        if (rc == LSM_OK) rc = upload<int>(ctx, &fe->d_counters, nullptr, 72);
+        if (rc == LSM_OK && cudaMemset(fe->d_counters, 0, 72 * sizeof(int)) != cudaSuccess) rc = LSM_ERR_CUDA;
+        fe->mode = getenv("LSM_EXACT_FILTER") ? LSM_FILTER_EXACT : LSM_FILTER_SPECULATIVE;
     } else if (p->kind == LSM_FILTERBANK_MEL) {
         if (p->n_fft <= 0 || (p->n_fft & (p->n_fft - 1)) || p->mel_hop <= 0) { delete fe; LSM_FAIL(ctx, LSM_ERR_INVALID, "mel n_fft must be a power of two"); }
         fe->ncols = 1 + p->n_samples / p->mel_hop;
@@ -170,6 +172,31 @@ extern "C" void lsm_frontend_destroy(lsm_frontend *fe)
     cudaFree(fe->d_coefs); cudaFree(fe->d_zoom_i0); cudaFree(fe->d_zoom_f); cudaFree(fe->d_scratch); cudaFree(fe->d_counters);
     lsm_mel_destroy(fe);
     delete fe;
+}
+
+extern "C" int lsm_frontend_set_mode(lsm_ctx *ctx, lsm_frontend *fe, int mode, double delta_db)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!fe || (mode != LSM_FILTER_EXACT && mode != LSM_FILTER_SPECULATIVE) || !(delta_db >= 0.0))
+        LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_frontend_set_mode: mode must be 0 or 1 and delta_db >= 0");
+    fe->mode = mode;
+    if (delta_db > 0.0) fe->spec_delta = delta_db;
+    return LSM_OK;
+}
+
+extern "C" int lsm_frontend_reruns(lsm_ctx *ctx, lsm_frontend *fe, int64_t *h_out, int reset)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!fe || !h_out) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_frontend_reruns: null argument");
+    *h_out = 0;
+    if (fe->p.kind != LSM_FILTERBANK_GAMMATONE) return LSM_OK;
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (fe->ev_valid) LSM_CUDA(ctx, cudaEventSynchronize(fe->ev_last));
+    int v = 0;
+    LSM_CUDA(ctx, cudaMemcpy(&v, fe->d_counters + 64, sizeof(int), cudaMemcpyDeviceToHost));
+    if (reset) LSM_CUDA(ctx, cudaMemset(fe->d_counters + 64, 0, sizeof(int)));
+    *h_out = v;
+    return LSM_OK;
 }
 
 extern "C" int lsm_frontend_mel_tables(lsm_ctx *ctx, lsm_frontend *fe, const double *h_window, const double *h_tw,

@@ -48,6 +48,9 @@ struct GtArgs {
     uint8_t *spikes;        // [B][C*R][nbins*K]
     double *spec_norm;      // optional [B][C][nbins]
     int B, L, C, nwin, hop, ncols, nbins, K, R;
+    int mode;               // 0 = exact filter only; 1 = speculative filter, exact re-execution of near-ties
+    double spec_delta;      // dB margin of the near-tie test
+    int *reruns;            // number of utterances filtered twice (speculative mode)
     double thr[8], lower[8];
     ResArgs res;            // fused mode only: the reservoir this utterance's spikes feed
 };
@@ -61,26 +64,32 @@ struct GtArgs {
         z1 = mul64(y, na2);                                    \
     }
 
-// FNPT = 0: front end only (spike trains to global memory).  FNPT > 0: fused audio -> features: after
-// encoding an utterance the same CTA simulates its reservoir (FNPT neurons per thread, blockDim == C) with
-// the spikes handed over as bits in shared memory; the reservoir phase is latency/issue bound and uses
-// almost no fp64, so it hides under the filter phases of the other CTAs resident on the SM.
-template <int MAXT, int MINB, int FNPT, bool LEAN>
-__global__ void __launch_bounds__(MAXT, MINB) gammatone_encode_kernel(const GtArgs a, int *next_utt)
+// The four cascaded stages are software-skewed: in one loop iteration stage k works on sample
+// s + (3 - k), so the four recurrences are independent instruction chains (ILP 4) while every
+// stage still performs exactly the reference's operations in the reference's order.  The stage-4
+// output of iteration s is the cascade output for sample s.
+constexpr int kSkew = 3;
+
+// PCM -> fp64 in shared memory; buffer element i of chunk k holds sample k*chunk + i + kSkew
+__device__ __forceinline__ void stage_pcm(double *dst, const float *pcm, int base, int chunk, int L)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_x = reinterpret_cast<double *>(smem_raw);            // [2][kChunkBlocks*hop] PCM as fp64, shifted by kSkew
-    __shared__ double s_red[2][8];
-    __shared__ double s_mm[2];
-    __shared__ int s_utt;
-    __shared__ int s_cnt3[3];
+    for (int i = threadIdx.x; i < chunk; i += blockDim.x) dst[i] = (base + i < L) ? (double)__ldg(pcm + base + i) : 0.0;
+}
 
-    // The four cascaded stages are software-skewed: in one loop iteration stage k works on sample
-    // s + (3 - k), so the four recurrences are independent instruction chains (ILP 4) while every
-    // stage still performs exactly the reference's operations in the reference's order.  The stage-4
-    // output of iteration s is the cascade output for sample s.
-    constexpr int kSkew = 3;
+// sqrt(mean) -> dB of one finished window (create_dataset.py:59) into the CTA's plane
+__device__ __forceinline__ void emit_db(double y2w, double *plane, int col, int C, int ch, double &tmax, double &tmin)
+{
+    const double db = mul64(20.0, lsm_log10(add64(y2w, 1e-9)));
+    plane[(size_t)col * C + ch] = db;
+    tmax = fmax(tmax, db);
+    tmin = fmin(tmin, db);
+}
 
+// ---- EXACT filter: the reference's operations in the reference's order (scipy lfilter x4, /gain, square,
+//      left-to-right window sums).  35 fp64 operations per channel-sample, none of them fused.
+__device__ __forceinline__ void gt_filter_exact(const GtArgs &a, const float *pcm, double *s_x, double *plane, double &tmax,
+                                                double &tmin)
+{
     const int ch = threadIdx.x;
     const int C = a.C;
     const bool live = ch < C;
@@ -104,6 +113,177 @@ __global__ void __launch_bounds__(MAXT, MINB) gammatone_encode_kernel(const GtAr
         gain = c[9];
         rgain = __ddiv_rn(1.0, gain);
     }
+    double z0_0 = 0, z0_1 = 0, z0_2 = 0, z0_3 = 0, z1_0 = 0, z1_1 = 0, z1_2 = 0, z1_3 = 0;
+    double y1 = 0, y2 = 0, y3 = 0, y4 = 0;
+    double acc_new = 0, acc_mid = 0, acc_old = 0;
+
+    stage_pcm(s_x, pcm, kSkew, chunk, a.L);
+    if (live) {
+        // prologue: iterations s = -3, -2, -1 fill the skewed pipeline (outputs belong to no sample)
+#pragma unroll
+        for (int s = 0; s < kSkew; ++s) {
+            const double x = (double)__ldg(pcm + s);
+            double t1, t2, t3;
+            LSM_BIQUAD(t1, x, z0_0, z1_0, b1_0);
+            LSM_BIQUAD(t2, y1, z0_1, z1_1, b1_1);
+            LSM_BIQUAD(t3, y2, z0_2, z1_2, b1_2);
+            LSM_BIQUAD(y4, y3, z0_3, z1_3, b1_3);
+            y1 = t1; y2 = t2; y3 = t3;
+        }
+    }
+    __syncthreads();
+
+    for (int ck = 0; ck < n_chunks; ++ck) {
+        const double *xs = s_x + (ck & 1) * chunk;
+        // prefetch the next chunk into the other buffer while this one is filtered
+        if (ck + 1 < n_chunks) stage_pcm(s_x + ((ck + 1) & 1) * chunk, pcm, (ck + 1) * chunk + kSkew, chunk, a.L);
+        if (live) {
+            for (int bl = 0; bl < kChunkBlocks; ++bl) {
+                const int m = ck * kChunkBlocks + bl;       // hop-block index = index of the window that starts here
+                if (m >= n_blocks) break;
+                const double *xb = xs + bl * hop;
+                const int n_here = min(hop, n_used - m * hop);
+                const int n_a = min(n_here, r_old);      // phases where windows m, m-1 and m-2 are all open
+                // window m starts here: np.add.reduce begins with the first element, and 0.0 + e == e
+                acc_new = 0.0;
+#define LSM_SAMPLE(xin)                                                                   \
+                {                                                                         \
+                    double t1, t2, t3;                                                    \
+                    LSM_BIQUAD(t1, xin, z0_0, z1_0, b1_0);  /* stage 1, sample s+3 */     \
+                    LSM_BIQUAD(t2, y1, z0_1, z1_1, b1_1);   /* stage 2, sample s+2 */     \
+                    LSM_BIQUAD(t3, y2, z0_2, z1_2, b1_2);   /* stage 3, sample s+1 */     \
+                    LSM_BIQUAD(y4, y3, z0_3, z1_3, b1_3);   /* stage 4, sample s   */     \
+                    y1 = t1; y2 = t2; y3 = t3;                                            \
+                }
+#pragma unroll 4
+                for (int p = 0; p < n_a; ++p) {
+                    LSM_SAMPLE(xb[p]);
+                    const double v = div_by_const(y4, gain, rgain);
+                    const double e = mul64(v, v);
+                    acc_new = add64(acc_new, e);
+                    acc_mid = add64(acc_mid, e);
+                    acc_old = add64(acc_old, e);
+                }
+                // window m-2 complete: sqrt(mean) -> dB
+                if (n_a == r_old && m >= 2) emit_db(__dsqrt_rn(__ddiv_rn(acc_old, (double)nwin)), plane, m - 2, C, ch, tmax, tmin);
+#pragma unroll 4
+                for (int p = n_a; p < n_here; ++p) {
+                    LSM_SAMPLE(xb[p]);
+                    const double v = div_by_const(y4, gain, rgain);
+                    const double e = mul64(v, v);
+                    acc_new = add64(acc_new, e);
+                    acc_mid = add64(acc_mid, e);
+                }
+#undef LSM_SAMPLE
+                acc_old = acc_mid;
+                acc_mid = acc_new;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- SPECULATIVE filter: the same cascade in a cheaper, mathematically equivalent arrangement - 13 fused
+//      multiply-adds per channel-sample instead of 35 separate operations:
+//        * every numerator is normalised to (1 + c_k z^-1); the common factor A0^4 / gain moves to the window level;
+//        * direct form, y[n] = (x[n] + c_k x[n-1] - a2 y[n-2]) - a1 y[n-1]: three FMAs, one on the loop-carried path;
+//        * one running energy sum; window m-2 = full(m-2) + full(m-1) + head(m) of hop-block sums.
+//      Its dB plane differs from the exact one by rounding noise only (measured <= 6e-11 dB on pathological clips,
+//      ~2e-12 dB on speech-like ones).  The encoder epilogue flags every utterance in which some normalised value
+//      comes within a.spec_delta dB (default 1e-7) of an encoder threshold, of a hysteresis bound or of the
+//      degenerate-clip test, and those utterances are filtered again by gt_filter_exact: the spike trains that leave the
+//      kernel are the exact path's, byte for byte, as long as the two planes agree to a third of that margin.
+__device__ __forceinline__ void gt_filter_fast(const GtArgs &a, const float *pcm, double *s_x, double *plane, double &tmax,
+                                               double &tmin)
+{
+    const int ch = threadIdx.x;
+    const int C = a.C;
+    const bool live = ch < C;
+    const int hop = a.hop, nwin = a.nwin, ncols = a.ncols;
+    const int chunk = kChunkBlocks * hop;
+    const int r_old = nwin - 2 * hop;
+    const int n_used = (ncols - 1) * hop + nwin;
+    const int n_blocks = (n_used + hop - 1) / hop;
+    const int n_chunks = (n_blocks + kChunkBlocks - 1) / kChunkBlocks;
+
+    double c1 = 0, c2 = 0, c3 = 0, c4 = 0, na1 = 0, na2 = 0, g2n = 0;
+    if (live) {
+        const double *c = a.coefs + 10 * ch;
+        const double a0 = c[6], A0 = c[0];
+        c1 = c[1] / A0; c2 = c[2] / A0; c3 = c[3] / A0; c4 = c[4] / A0;
+        na1 = -(c[7] / a0);
+        na2 = -(c[8] / a0);
+        const double s = A0 / a0;
+        const double G = (s * s) * (s * s) / c[9];
+        g2n = G * G / (double)nwin;
+    }
+    // stage k at iteration s works on sample s + 4 - k: p_k = its previous output, q_k = the one before
+    double xp = 0, p1 = 0, q1 = 0, p2 = 0, q2 = 0, p3 = 0, q3 = 0, p4 = 0, q4 = 0;
+    double acc = 0, full1 = 0, full2 = 0;
+
+#define LSM_FAST_SAMPLE(xin)                                                       \
+    {                                                                              \
+        const double x_ = (xin);                                                   \
+        const double n1 = fma(na1, p1, fma(na2, q1, fma(c1, xp, x_)));             \
+        const double n2 = fma(na1, p2, fma(na2, q2, fma(c2, q1, p1)));             \
+        const double n3 = fma(na1, p3, fma(na2, q3, fma(c3, q2, p2)));             \
+        const double n4 = fma(na1, p4, fma(na2, q4, fma(c4, q3, p3)));             \
+        xp = x_;                                                                   \
+        q1 = p1; p1 = n1; q2 = p2; p2 = n2; q3 = p3; p3 = n3; q4 = p4; p4 = n4;    \
+        acc = fma(n4, n4, acc);                                                    \
+    }
+
+    stage_pcm(s_x, pcm, kSkew, chunk, a.L);
+    if (live) {
+#pragma unroll
+        for (int s = 0; s < kSkew; ++s) LSM_FAST_SAMPLE((double)__ldg(pcm + s));
+        acc = 0.0;   // (already zero: stage 4 has seen no sample yet)
+    }
+    __syncthreads();
+
+    for (int ck = 0; ck < n_chunks; ++ck) {
+        const double *xs = s_x + (ck & 1) * chunk;
+        if (ck + 1 < n_chunks) stage_pcm(s_x + ((ck + 1) & 1) * chunk, pcm, (ck + 1) * chunk + kSkew, chunk, a.L);
+        if (live) {
+            for (int bl = 0; bl < kChunkBlocks; ++bl) {
+                const int m = ck * kChunkBlocks + bl;
+                if (m >= n_blocks) break;
+                const double *xb = xs + bl * hop;
+                const int n_here = min(hop, n_used - m * hop);
+                const int n_a = min(n_here, r_old);
+                acc = 0.0;
+#pragma unroll 8
+                for (int p = 0; p < n_a; ++p) LSM_FAST_SAMPLE(xb[p]);
+                if (n_a == r_old && m >= 2) emit_db(sqrt(((full2 + full1) + acc) * g2n), plane, m - 2, C, ch, tmax, tmin);
+#pragma unroll 8
+                for (int p = n_a; p < n_here; ++p) LSM_FAST_SAMPLE(xb[p]);
+                full2 = full1;
+                full1 = acc;
+            }
+        }
+        __syncthreads();
+    }
+#undef LSM_FAST_SAMPLE
+}
+
+// FNPT = 0: front end only (spike trains to global memory).  FNPT > 0: fused audio -> features: after
+// encoding an utterance the same CTA simulates its reservoir (FNPT neurons per thread, blockDim == C) with
+// the spikes handed over as bits in shared memory; the reservoir phase is latency/issue bound and uses
+// almost no fp64, so it hides under the filter phases of the other CTAs resident on the SM.
+template <int MAXT, int MINB, int FNPT, bool LEAN>
+__global__ void __launch_bounds__(MAXT, MINB) gammatone_encode_kernel(const GtArgs a, int *next_utt)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_x = reinterpret_cast<double *>(smem_raw);            // [2][kChunkBlocks*hop] PCM as fp64, shifted by kSkew
+    __shared__ double s_red[2][8];
+    __shared__ double s_mm[2];
+    __shared__ int s_utt;
+    __shared__ int s_cnt3[3];
+
+    const int ch = threadIdx.x;
+    const int C = a.C;
+    const bool live = ch < C;
+    const int ncols = a.ncols;
     double *plane = a.scratch + (size_t)blockIdx.x * ncols * C;     // this CTA's dB plane [ncols][C]
 
     for (;;) {
@@ -113,156 +293,90 @@ __global__ void __launch_bounds__(MAXT, MINB) gammatone_encode_kernel(const GtAr
         const int utt = s_utt;
         if (utt >= a.B) break;
         const float *pcm = a.pcm + (size_t)utt * a.L;
-        double z0_0 = 0, z0_1 = 0, z0_2 = 0, z0_3 = 0, z1_0 = 0, z1_1 = 0, z1_2 = 0, z1_3 = 0;
-        double y1 = 0, y2 = 0, y3 = 0, y4 = 0;
-        double acc_new = 0, acc_mid = 0, acc_old = 0;
-        double tmax = -INFINITY, tmin = INFINITY;
+        bool exact = a.mode == 0;
+        for (;;) {
+            double tmax = -INFINITY, tmin = INFINITY;
+            if (exact) gt_filter_exact(a, pcm, s_x, plane, tmax, tmin);
+            else gt_filter_fast(a, pcm, s_x, plane, tmax, tmin);
 
-        // stage chunk 0; buffer element i of chunk k holds sample k*chunk + i + kSkew
-        for (int i = threadIdx.x; i < chunk; i += blockDim.x)
-            s_x[i] = (i + kSkew < a.L) ? (double)__ldg(pcm + i + kSkew) : 0.0;
-        if (live) {
-            // prologue: iterations s = -3, -2, -1 fill the skewed pipeline (outputs belong to no sample)
-#pragma unroll
-            for (int s = 0; s < kSkew; ++s) {
-                const double x = (double)__ldg(pcm + s);
-                double t1, t2, t3;
-                LSM_BIQUAD(t1, x, z0_0, z1_0, b1_0);
-                LSM_BIQUAD(t2, y1, z0_1, z1_1, b1_1);
-                LSM_BIQUAD(t3, y2, z0_2, z1_2, b1_2);
-                LSM_BIQUAD(y4, y3, z0_3, z1_3, b1_3);
-                y1 = t1; y2 = t2; y3 = t3;
+            // ---- per-utterance max / min of the dB plane (create_dataset.py:60,62-63)
+            {
+                const double wmax = warp_max_f64(tmax), wmin = warp_min_f64(tmin);
+                if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = wmax; s_red[1][threadIdx.x >> 5] = wmin; }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    double mx = -INFINITY, mn = INFINITY;
+                    for (int w = 0; w < (blockDim.x >> 5); ++w) { mx = fmax(mx, s_red[0][w]); mn = fmin(mn, s_red[1][w]); }
+                    s_mm[0] = mx; s_mm[1] = mn;
+                }
+                __syncthreads();
             }
-        }
-        __syncthreads();
+            const double mx = s_mm[0];
+            const double floor_db = sub64(mx, 80.0);
+            const double mn = fmax(s_mm[1], floor_db);        // min of the clamped plane
+            const double range = sub64(mx, mn);
+            const bool degenerate = range < 1e-8;              // create_dataset.py:64-65 -> all zeros
+            const double den = add64(range, 1e-8);
+            // speculative pass: margin (in normalised units) inside which a comparison could come out differently
+            const double margin = exact ? 0.0 : a.spec_delta / den;
+            bool near = !exact && fabs(range - 1e-8) < a.spec_delta;
 
-        for (int ck = 0; ck < n_chunks; ++ck) {
-            const double *xs = s_x + (ck & 1) * chunk;
-            // prefetch the next chunk into the other buffer while this one is filtered
-            if (ck + 1 < n_chunks) {
-                double *xn = s_x + ((ck + 1) & 1) * chunk;
-                const int base = (ck + 1) * chunk + kSkew;
-                for (int i = threadIdx.x; i < chunk; i += blockDim.x)
-                    xn[i] = (base + i < a.L) ? (double)__ldg(pcm + base + i) : 0.0;
-            }
             if (live) {
-                for (int bl = 0; bl < kChunkBlocks; ++bl) {
-                    const int m = ck * kChunkBlocks + bl;       // hop-block index = index of the window that starts here
-                    if (m >= n_blocks) break;
-                    const double *xb = xs + bl * hop;
-                    const int n_here = min(hop, n_used - m * hop);
-                    const int n_a = min(n_here, r_old);      // phases where windows m, m-1 and m-2 are all open
-                    // window m starts here: np.add.reduce begins with the first element, and 0.0 + e == e
-                    acc_new = 0.0;
-#define LSM_SAMPLE(xin)                                                                   \
-                    {                                                                     \
-                        double t1, t2, t3;                                                \
-                        LSM_BIQUAD(t1, xin, z0_0, z1_0, b1_0);  /* stage 1, sample s+3 */ \
-                        LSM_BIQUAD(t2, y1, z0_1, z1_1, b1_1);   /* stage 2, sample s+2 */ \
-                        LSM_BIQUAD(t3, y2, z0_2, z1_2, b1_2);   /* stage 3, sample s+1 */ \
-                        LSM_BIQUAD(y4, y3, z0_3, z1_3, b1_3);   /* stage 4, sample s   */ \
-                        y1 = t1; y2 = t2; y3 = t3;                                        \
-                    }
-#pragma unroll 4
-                    for (int p = 0; p < n_a; ++p) {
-                        LSM_SAMPLE(xb[p]);
-                        const double v = div_by_const(y4, gain, rgain);
-                        const double e = mul64(v, v);
-                        acc_new = add64(acc_new, e);
-                        acc_mid = add64(acc_mid, e);
-                        acc_old = add64(acc_old, e);
-                    }
-                    if (n_a == r_old && m >= 2) {
-                        // window m-2 complete: sqrt(mean) -> dB
-                        const double y2w = __dsqrt_rn(__ddiv_rn(acc_old, (double)nwin));
-                        const double db = mul64(20.0, lsm_log10(add64(y2w, 1e-9)));
-                        plane[(size_t)(m - 2) * C + ch] = db;
-                        tmax = fmax(tmax, db);
-                        tmin = fmin(tmin, db);
-                    }
-#pragma unroll 4
-                    for (int p = n_a; p < n_here; ++p) {
-                        LSM_SAMPLE(xb[p]);
-                        const double v = div_by_const(y4, gain, rgain);
-                        const double e = mul64(v, v);
-                        acc_new = add64(acc_new, e);
-                        acc_mid = add64(acc_mid, e);
-                    }
-#undef LSM_SAMPLE
-                    acc_old = acc_mid;
-                    acc_mid = acc_new;
+                const int T = a.nbins * a.K;
+                uint8_t *row0 = a.spikes ? a.spikes + ((size_t)utt * C * a.R + (size_t)ch * a.R) * T : nullptr;
+                double *dump = a.spec_norm ? a.spec_norm + ((size_t)utt * C + ch) * a.nbins : nullptr;
+                // normalise in place (own column of the plane only)
+                for (int c = 0; c < ncols; ++c) {
+                    const double v = fmax(plane[(size_t)c * C + ch], floor_db);
+                    plane[(size_t)c * C + ch] = __ddiv_rn(sub64(v, mn), den);
                 }
-            }
-            __syncthreads();
-        }
-
-        // ---- per-utterance max / min of the dB plane (create_dataset.py:60,62-63)
-        {
-            const double wmax = warp_max_f64(tmax), wmin = warp_min_f64(tmin);
-            if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = wmax; s_red[1][threadIdx.x >> 5] = wmin; }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double mx = -INFINITY, mn = INFINITY;
-                for (int w = 0; w < (blockDim.x >> 5); ++w) { mx = fmax(mx, s_red[0][w]); mn = fmin(mn, s_red[1][w]); }
-                s_mm[0] = mx; s_mm[1] = mn;
-            }
-            __syncthreads();
-        }
-        const double mx = s_mm[0];
-        const double floor_db = sub64(mx, 80.0);
-        const double mn = fmax(s_mm[1], floor_db);        // min of the clamped plane
-        const bool degenerate = sub64(mx, mn) < 1e-8;      // create_dataset.py:64-65 -> all zeros
-        const double den = add64(sub64(mx, mn), 1e-8);
-
-        if (live) {
-            const int T = a.nbins * a.K;
-            uint8_t *row0 = a.spikes ? a.spikes + ((size_t)utt * C * a.R + (size_t)ch * a.R) * T : nullptr;
-            double *dump = a.spec_norm ? a.spec_norm + ((size_t)utt * C + ch) * a.nbins : nullptr;
-            // normalise in place (own column of the plane only)
-            for (int c = 0; c < ncols; ++c) {
-                const double v = fmax(plane[(size_t)c * C + ch], floor_db);
-                plane[(size_t)c * C + ch] = __ddiv_rn(sub64(v, mn), den);
-            }
-            unsigned on = 0;   // bit k = state of trigger k
-            for (int j = 0; j < a.nbins; ++j) {
-                double v;
-                if (degenerate) v = 0.0;
-                else if (ncols == a.nbins) v = plane[(size_t)j * C + ch];
-                else {
-                    const int i0 = a.zoom_i0[j];
-                    const double f = a.zoom_f[j];
-                    v = mul64(plane[(size_t)i0 * C + ch], sub64(1.0, f));
-                    if (i0 + 1 < ncols) v = add64(v, mul64(plane[(size_t)(i0 + 1) * C + ch], f));
-                }
-                if (dump) dump[j] = v;
+                unsigned on = 0;   // bit k = state of trigger k
+                for (int j = 0; j < a.nbins; ++j) {
+                    double v;
+                    if (degenerate) v = 0.0;
+                    else if (ncols == a.nbins) v = plane[(size_t)j * C + ch];
+                    else {
+                        const int i0 = a.zoom_i0[j];
+                        const double f = a.zoom_f[j];
+                        v = mul64(plane[(size_t)i0 * C + ch], sub64(1.0, f));
+                        if (i0 + 1 < ncols) v = add64(v, mul64(plane[(size_t)(i0 + 1) * C + ch], f));
+                    }
+                    if (dump) dump[j] = v;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if (k < a.K) {
-                        const bool is_on = (on >> k) & 1u;
-                        if (!is_on && v > a.thr[k]) on |= (1u << k);
-                        else if (is_on && v < a.lower[k]) on &= ~(1u << k);
+                    for (int k = 0; k < 8; ++k) {
+                        if (k < a.K) {
+                            const bool is_on = (on >> k) & 1u;
+                            if (!is_on && v > a.thr[k]) on |= (1u << k);
+                            else if (is_on && v < a.lower[k]) on &= ~(1u << k);
+                            if (!exact) near |= (fabs(v - a.thr[k]) < margin) | (fabs(v - a.lower[k]) < margin);
+                        }
                     }
-                }
-                if (FNPT > 0) {
-                    // hand the spikes to the reservoir phase: word (t, warp) = ballot over this warp's 32 channels
-                    unsigned *s_bits = reinterpret_cast<unsigned *>(smem_raw);
-                    const int CW = C >> 5;
-                    for (int k = 0; k < a.K; ++k) {
-                        const unsigned word = __ballot_sync(0xffffffffu, (on >> k) & 1u);
-                        if ((threadIdx.x & 31) == 0) s_bits[(j * a.K + k) * CW + (threadIdx.x >> 5)] = word;
+                    if (FNPT > 0) {
+                        // hand the spikes to the reservoir phase: word (t, warp) = ballot over this warp's 32 channels
+                        unsigned *s_bits = reinterpret_cast<unsigned *>(smem_raw);
+                        const int CW = C >> 5;
+                        for (int k = 0; k < a.K; ++k) {
+                            const unsigned word = __ballot_sync(0xffffffffu, (on >> k) & 1u);
+                            if ((threadIdx.x & 31) == 0) s_bits[(j * a.K + k) * CW + (threadIdx.x >> 5)] = word;
+                        }
                     }
-                }
-                for (int r = 0; row0 && r < a.R; ++r) {
-                    uint8_t *row = row0 + (size_t)r * T + (size_t)j * a.K;
-                    if (a.K == 4) {
-                        // bytes k = 0..3 of column block j, little endian
-                        const unsigned w = (on & 1u) | ((on & 2u) << 7) | ((on & 4u) << 14) | ((on & 8u) << 21);
-                        *reinterpret_cast<uint32_t *>(row) = w;
-                    } else {
-                        for (int k = 0; k < a.K; ++k) row[k] = (on >> k) & 1u;
+                    for (int r = 0; row0 && r < a.R; ++r) {
+                        uint8_t *row = row0 + (size_t)r * T + (size_t)j * a.K;
+                        if (a.K == 4) {
+                            // bytes k = 0..3 of column block j, little endian
+                            const unsigned w = (on & 1u) | ((on & 2u) << 7) | ((on & 4u) << 14) | ((on & 8u) << 21);
+                            *reinterpret_cast<uint32_t *>(row) = w;
+                        } else {
+                            for (int k = 0; k < a.K; ++k) row[k] = (on >> k) & 1u;
+                        }
                     }
                 }
             }
+            if (exact) break;
+            // some comparison of this utterance is too close to call on the speculative plane: filter it again, exactly
+            if (!__syncthreads_or(near ? 1 : 0)) break;
+            if (threadIdx.x == 0) atomicAdd(a.reruns, 1);
+            exact = true;
         }
         if (FNPT > 0) {
             __syncthreads();   // bits complete and visible
@@ -321,6 +435,10 @@ static void fill_args(const lsm_frontend *fe, const float *d_pcm, int B, uint8_t
     a.B = B; a.L = p.n_samples; a.C = p.channels; a.nwin = p.nwin; a.hop = p.hop; a.ncols = fe->ncols;
     a.nbins = p.n_bins; a.K = p.n_thresholds; a.R = p.redundancy;
     for (int k = 0; k < 8; ++k) { a.thr[k] = p.thresholds_desc[k]; a.lower[k] = p.lower_bounds[k]; }
+    // the normalised-spectrogram dump is defined as the exact path's: asking for it selects the exact filter
+    a.mode = d_spec_norm ? 0 : fe->mode;
+    a.spec_delta = fe->spec_delta;
+    a.reruns = fe->d_counters + 64;
 }
 
 // The per-CTA dB planes (grid x ~100 KB) are written and re-read by the same CTA for every utterance.  Mark that

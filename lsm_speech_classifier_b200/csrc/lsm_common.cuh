@@ -32,7 +32,9 @@ struct lsm_frontend {
     double *d_zoom_f = nullptr;    // [n_bins]
     double *d_scratch = nullptr;   // per-CTA [ncols][C] dB plane (stays in L2)
     int grid = 0;
-    int *d_counters = nullptr;     // [64] dynamic work counters, one per in-flight launch
+    int *d_counters = nullptr;     // [64] dynamic work counters, one per in-flight launch; [64] = utterances filtered twice
+    int mode = 1;                  // gammatone: 0 = exact filter only, 1 = speculative filter + exact re-execution of near-ties
+    double spec_delta = 1e-7;      // dB margin of the near-tie test (lsm_frontend_set_mode)
     unsigned counter_next = 0;
     int minb = 5;                  // K1 occupancy target the kernel was instantiated for
     // launches on different streams share the scratch planes: each launch waits for the previous one's event

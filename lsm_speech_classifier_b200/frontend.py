@@ -118,6 +118,22 @@ class Frontend:
         self.ctx.check(self.ctx.lib.lsm_frontend_encode_host(self.ctx.h, self.h, _lib._np_ptr(pcm), B, _lib._np_ptr(spikes)))
         return spikes
 
+    # ---- gammatone only: how the filter bank is evaluated (include/lsm_b200.h, lsm_frontend_set_mode)
+    def set_mode(self, mode: str = "speculative", delta_db: float = 0.0):
+        """"exact": every fp64 operation in the reference's order.  "speculative" (default): a cheaper equivalent
+        arrangement, with utterances whose normalised spectrogram comes within `delta_db` of any encoder comparison
+        filtered again exactly inside the same kernel - the spike trains are the exact path's either way."""
+        modes = {"exact": 0, "speculative": 1}
+        if mode not in modes:
+            raise ValueError(f"mode must be one of {list(modes)}")
+        self.ctx.check(self.ctx.lib.lsm_frontend_set_mode(self.ctx.h, self.h, modes[mode], float(delta_db)))
+
+    def reruns(self, reset: bool = False) -> int:
+        """Utterances the speculative mode had to filter twice (since creation / the last reset)."""
+        out = C.c_int64(0)
+        self.ctx.check(self.ctx.lib.lsm_frontend_reruns(self.ctx.h, self.h, C.byref(out), int(reset)))
+        return int(out.value)
+
     def close(self):
         if getattr(self, "h", None) and getattr(self.ctx, "h", None):
             self.ctx.lib.lsm_frontend_destroy(self.h)

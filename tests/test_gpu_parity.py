@@ -359,3 +359,70 @@ def test_back_to_back_calls_on_different_streams_do_not_race(env, small_set):
         assert np.array_equal(host, want) and np.array_equal(spikes_host, X)
         assert np.array_equal(out.cpu().numpy(), want_big)
         assert np.array_equal(out2.cpu().numpy(), np.concatenate([X] * 30))
+
+
+# ---------------------------------------------------------------- speculative filter (LSM_FILTER_SPECULATIVE)
+def test_speculative_filter_gives_the_exact_spike_trains(env, small_set):
+    """The default mode filters with 13 FMAs per sample and re-filters near-ties exactly: same bytes as the oracle
+    whatever the margin - 0 re-executions (pure speculative plane), the default, and all utterances re-executed."""
+    from lsm_speech_classifier_b200 import synth
+    from lsm_speech_classifier_b200.frontend import Frontend
+    pcm, _ = small_set
+    more, _ = synth.synth_dataset(12, 8)
+    pcm = np.concatenate([pcm, more])
+    fe = Frontend(128, "gammatone")
+    want = oracle_spikes(pcm, fe)
+    fe.set_mode("exact")
+    assert np.array_equal(fe.encode(pcm), want)
+    assert fe.reruns() == 0
+    fe.set_mode("speculative")                       # default margin 1e-7 dB
+    assert np.array_equal(fe.encode(pcm), want)
+    n_default = fe.reruns(reset=True)
+    assert n_default <= 2, n_default                 # ~4e-4 expected per utterance
+    fe.set_mode("speculative", 1e-300)               # no utterance can be flagged: the plain speculative plane
+    assert np.array_equal(fe.encode(pcm), want)
+    assert fe.reruns(reset=True) == 0
+    fe.set_mode("speculative", 1e9)                  # every non-degenerate utterance flagged -> exact re-execution
+    assert np.array_equal(fe.encode(pcm), want)
+    assert fe.reruns(reset=True) >= len(pcm) - 1
+    fe.set_mode("speculative", 1e-3)                 # a mix of both inside one launch
+    assert np.array_equal(fe.encode(pcm), want)
+    n_mix = fe.reruns(reset=True)
+    assert 0 < n_mix < len(pcm), n_mix
+
+
+def test_speculative_plane_is_within_a_thousandth_of_the_margin(env, small_set):
+    """The guarantee behind the speculative mode: its dB plane and the exact one differ by far less than the
+    near-tie margin (1e-7 dB).  The speculative plane itself never leaves the kernel, so ask the question the other
+    way round - with the margin at 1e-10 dB (a thousand times tighter) the spikes still equal the oracle's on every clip."""
+    from lsm_speech_classifier_b200 import synth
+    from lsm_speech_classifier_b200.frontend import Frontend
+    pcm, _ = small_set
+    more, _ = synth.synth_dataset(12, 20, start_utt=500)
+    pcm = np.concatenate([pcm, more])
+    fe = Frontend(128, "gammatone")
+    want = oracle_spikes(pcm, fe)
+    fe.set_mode("speculative", 1e-10)
+    assert np.array_equal(fe.encode(pcm), want)
+
+
+def test_fused_pipeline_same_features_in_both_filter_modes(env, small_set):
+    from lsm_speech_classifier_b200.frontend import Frontend
+    from lsm_speech_classifier_b200.snn import SNN, AudioToFeatures, SimulationParams
+    from lsm_speech_classifier_b200.extract_lsm_features import FEATURE_SETS, calculate_theoretical_w_critico
+    pcm, _ = small_set
+    fe = Frontend(128, "gammatone")
+    spikes = fe.encode(pcm)
+    params = SimulationParams(input_spike_times=spikes[0])
+    params.mean_weight = calculate_theoretical_w_critico(params, spikes, verbose=False) * 0.6
+    lsm = SNN(simulation_params=params)
+    pipe = AudioToFeatures(fe, lsm)
+    assert pipe.fused
+    keys = FEATURE_SETS["original"]
+    fe.set_mode("exact")
+    a = pipe.run_host(pcm, keys)
+    fe.set_mode("speculative")
+    b = pipe.run_host(pcm, keys)
+    fe.set_mode("speculative", 1e9)
+    c = pipe.run_host(pcm, keys)
+    assert np.array_equal(a, b) and np.array_equal(a, c)
