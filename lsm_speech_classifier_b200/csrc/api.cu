@@ -135,12 +135,19 @@ extern "C" int lsm_frontend_create(lsm_ctx *ctx, const lsm_frontend_params *p, c
         for (int c = 0; c < p->channels; ++c)
             if (t[10 * c + 5] != 0.0) { delete fe; LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "gammatone design with A2 != 0"); }
         fe->ncols = 1 + (p->n_samples - p->nwin) / p->hop;
+        for (int c = 0; c < p->channels; ++c) {
+            // same expressions as gt_filter_fast evaluates on the device
+            const double *r = t + 10 * c;
+            for (int k = 0; k < 4; ++k) fe->h_lane_coef[c][k] = r[1 + k] / r[0];
+            fe->h_lane_coef[c][4] = -(r[7] / r[6]);
+            fe->h_lane_coef[c][5] = -(r[8] / r[6]);
+        }
         rc = upload(ctx, &fe->d_coefs, t, (size_t)p->channels * 10);
         fe->minb = lsm_gammatone_minb();
         if (rc == LSM_OK) rc = lsm_gammatone_grid(ctx, p, &fe->grid);
         if (rc == LSM_OK) rc = upload<double>(ctx, &fe->d_scratch, nullptr, (size_t)fe->grid * fe->ncols * p->channels);
-        if (rc == LSM_OK) rc = upload<int>(ctx, &fe->d_counters, nullptr, 72);
-        if (rc == LSM_OK && cudaMemset(fe->d_counters, 0, 72 * sizeof(int)) != cudaSuccess) rc = LSM_ERR_CUDA;
+        if (rc == LSM_OK) rc = upload<int>(ctx, &fe->d_counters, nullptr, 128 + 64 * 256);
+        if (rc == LSM_OK && cudaMemset(fe->d_counters, 0, (128 + 64 * 256) * sizeof(int)) != cudaSuccess) rc = LSM_ERR_CUDA;
         fe->mode = getenv("LSM_EXACT_FILTER") ? LSM_FILTER_EXACT : LSM_FILTER_SPECULATIVE;
     } else if (p->kind == LSM_FILTERBANK_MEL) {
         if (p->n_fft <= 0 || (p->n_fft & (p->n_fft - 1)) || p->mel_hop <= 0) { delete fe; LSM_FAIL(ctx, LSM_ERR_INVALID, "mel n_fft must be a power of two"); }
@@ -169,6 +176,7 @@ extern "C" void lsm_frontend_destroy(lsm_frontend *fe)
     if (!fe) return;
     if (fe->ev_valid) cudaEventSynchronize(fe->ev_last);
     if (fe->ev_last) cudaEventDestroy(fe->ev_last);
+    cudaFree(fe->d_energy);
     cudaFree(fe->d_coefs); cudaFree(fe->d_zoom_i0); cudaFree(fe->d_zoom_f); cudaFree(fe->d_scratch); cudaFree(fe->d_counters);
     lsm_mel_destroy(fe);
     delete fe;

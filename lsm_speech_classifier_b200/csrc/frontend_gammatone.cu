@@ -48,9 +48,13 @@ struct GtArgs {
     uint8_t *spikes;        // [B][C*R][nbins*K]
     double *spec_norm;      // optional [B][C][nbins]
     int B, L, C, nwin, hop, ncols, nbins, K, R;
-    int mode;               // 0 = exact filter only; 1 = speculative filter, exact re-execution of near-ties
+    const double *energy_in; // mode 2: [B][ncols][C] raw energy sums from gammatone_energy_kernel (also this utterance's plane)
+    int mode;               // 0 = exact filter only; 1 = speculative filter (lane = channel) in this kernel, exact re-execution
+                            // of near-ties; 2 = as 1, but the speculative energies were computed by gammatone_energy_kernel
     double spec_delta;      // dB margin of the near-tie test
     int *reruns;            // number of utterances filtered twice (speculative mode)
+    int *sm_rank;           // [256] per-SM arrival counter of this launch (staggered start)
+    int stagger_cycles;     // start delay per CTA rank on its SM, 0 = none
     double thr[8], lower[8];
     ResArgs res;            // fused mode only: the reservoir this utterance's spikes feed
 };
@@ -193,8 +197,7 @@ __device__ __forceinline__ void gt_filter_exact(const GtArgs &a, const float *pc
 //      comes within a.spec_delta dB (default 1e-7) of an encoder threshold, of a hysteresis bound or of the
 //      degenerate-clip test, and those utterances are filtered again by gt_filter_exact: the spike trains that leave the
 //      kernel are the exact path's, byte for byte, as long as the two planes agree to a third of that margin.
-__device__ __forceinline__ void gt_filter_fast(const GtArgs &a, const float *pcm, double *s_x, double *plane, double &tmax,
-                                               double &tmin)
+__device__ __forceinline__ void gt_filter_fast(const GtArgs &a, const float *pcm, double *s_x, double *plane)
 {
     const int ch = threadIdx.x;
     const int C = a.C;
@@ -206,16 +209,13 @@ __device__ __forceinline__ void gt_filter_fast(const GtArgs &a, const float *pcm
     const int n_blocks = (n_used + hop - 1) / hop;
     const int n_chunks = (n_blocks + kChunkBlocks - 1) / kChunkBlocks;
 
-    double c1 = 0, c2 = 0, c3 = 0, c4 = 0, na1 = 0, na2 = 0, g2n = 0;
+    double c1 = 0, c2 = 0, c3 = 0, c4 = 0, na1 = 0, na2 = 0;
     if (live) {
         const double *c = a.coefs + 10 * ch;
         const double a0 = c[6], A0 = c[0];
         c1 = c[1] / A0; c2 = c[2] / A0; c3 = c[3] / A0; c4 = c[4] / A0;
         na1 = -(c[7] / a0);
         na2 = -(c[8] / a0);
-        const double s = A0 / a0;
-        const double G = (s * s) * (s * s) / c[9];
-        g2n = G * G / (double)nwin;
     }
     // stage k at iteration s works on sample s + 4 - k: p_k = its previous output, q_k = the one before
     double xp = 0, p1 = 0, q1 = 0, p2 = 0, q2 = 0, p3 = 0, q3 = 0, p4 = 0, q4 = 0;
@@ -254,7 +254,8 @@ __device__ __forceinline__ void gt_filter_fast(const GtArgs &a, const float *pcm
                 acc = 0.0;
 #pragma unroll 8
                 for (int p = 0; p < n_a; ++p) LSM_FAST_SAMPLE(xb[p]);
-                if (n_a == r_old && m >= 2) emit_db(sqrt(((full2 + full1) + acc) * g2n), plane, m - 2, C, ch, tmax, tmin);
+                // window m-2 complete: its raw energy sum; dB is taken in the epilogue, where the columns give ILP
+                if (n_a == r_old && m >= 2) plane[(size_t)(m - 2) * C + ch] = (full2 + full1) + acc;
 #pragma unroll 8
                 for (int p = n_a; p < n_here; ++p) LSM_FAST_SAMPLE(xb[p]);
                 full2 = full1;
@@ -264,6 +265,293 @@ __device__ __forceinline__ void gt_filter_fast(const GtArgs &a, const float *pcm
         __syncthreads();
     }
 #undef LSM_FAST_SAMPLE
+}
+
+// ---- SPECULATIVE filter, lane = utterance ("lanes" arrangement).  The lane = channel kernel above keeps its per-channel
+//      coefficients in registers, and a DFMA with three distinct register operands issues at only ~75 % of the fp64
+//      pipe's rate on this GPU (tools/fp64_cascade.cu: 14.4 vs 19.2 T lane-ops/s).  Here a warp filters J channels of
+//      32 utterances: the coefficients are the same for every lane, sit in the kernel-parameter constant bank and reach the
+//      DFMAs through uniform registers (two register operands each), so the cascade runs at the pipe's full rate.
+//      Each lane streams its own utterance with 16-byte loads (a sector is consumed by two of them, L1 keeps the line),
+//      no shared memory, no barriers.  Output: raw window energy sums energy[utt][col][ch] (one full 32-byte sector per
+//      lane and window for J = 4); the encoder epilogue of the second kernel takes it from there.
+constexpr int kLanesJ = 4;
+
+struct EnergyArgs {
+    const float *pcm;       // [B][L]
+    double *energy;         // [B][ncols][C] raw energy sums of the normalised cascade
+    int B, L, C, nwin, hop, ncols;
+    int big_groups;         // utterance groups [0, big_groups) are cut into units of kLanesJ channels, the rest into single channels
+    double coef[256][6];    // per channel: c1..c4 (numerator zeros / A0), -a1, -a2
+};
+
+// one unit of work: J channels starting at ch0 for the 32 utterances of group g
+template <int J>
+__device__ __forceinline__ void energy_unit(const EnergyArgs &a, const int g, const int ch0)
+{
+    const int lane = threadIdx.x;
+    const int utt = g * 32 + lane;
+    const bool valid = utt < a.B;
+    const float4 *src = reinterpret_cast<const float4 *>(a.pcm + (size_t)(valid ? utt : a.B - 1) * a.L);
+    const int n4_max = a.L / 4 - 1;
+    const int hop = a.hop, nwin = a.nwin, ncols = a.ncols;
+    const int r_old = nwin - 2 * hop;
+    const int n_used = (ncols - 1) * hop + nwin;
+    const int n_blocks = (n_used + hop - 1) / hop;
+    double *dst = a.energy + (size_t)utt * ncols * a.C + ch0;
+
+    double xp = 0.0;
+    double p1[J], q1[J], p2[J], q2[J], p3[J], q3[J], p4[J], q4[J], acc[J], full1[J], full2[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) { p1[j] = q1[j] = p2[j] = q2[j] = p3[j] = q3[j] = p4[j] = q4[j] = acc[j] = full1[j] = full2[j] = 0.0; }
+
+#define LSM_LANE_SAMPLE(xf)                                                                             \
+    {                                                                                                   \
+        const double x_ = (double)(xf);                                                                 \
+        _Pragma("unroll") for (int j = 0; j < J; ++j) {                                                 \
+            const double *c = a.coef[ch0 + j];                                                          \
+            const double y1 = fma(c[4], p1[j], fma(c[5], q1[j], fma(c[0], xp, x_)));                    \
+            const double y2 = fma(c[4], p2[j], fma(c[5], q2[j], fma(c[1], p1[j], y1)));                 \
+            const double y3 = fma(c[4], p3[j], fma(c[5], q3[j], fma(c[2], p2[j], y2)));                 \
+            const double y4 = fma(c[4], p4[j], fma(c[5], q4[j], fma(c[3], p3[j], y3)));                 \
+            q1[j] = p1[j]; p1[j] = y1; q2[j] = p2[j]; p2[j] = y2;                                       \
+            q3[j] = p3[j]; p3[j] = y3; q4[j] = p4[j]; p4[j] = y4;                                       \
+            acc[j] = fma(y4, y4, acc[j]);                                                               \
+        }                                                                                               \
+        xp = x_;                                                                                        \
+    }
+#define LSM_LANE_8(f0, f1)                                                                              \
+    LSM_LANE_SAMPLE(f0.x) LSM_LANE_SAMPLE(f0.y) LSM_LANE_SAMPLE(f0.z) LSM_LANE_SAMPLE(f0.w)            \
+    LSM_LANE_SAMPLE(f1.x) LSM_LANE_SAMPLE(f1.y) LSM_LANE_SAMPLE(f1.z) LSM_LANE_SAMPLE(f1.w)
+
+    // two 16-byte loads (8 samples) in flight ahead of the arithmetic
+    int i4 = 0;                                        // index of the next float4 to fetch
+    float4 f0 = __ldg(src + 0), f1 = __ldg(src + 1);
+    i4 = 2;
+    for (int m = 0; m < n_blocks; ++m) {
+        const int n_here = min(hop, n_used - m * hop);
+        const int n_a = min(n_here, r_old);
+#pragma unroll
+        for (int j = 0; j < J; ++j) acc[j] = 0.0;
+        for (int p = 0; p < n_a; p += 8) {
+            const float4 g0 = __ldg(src + min(i4, n4_max)), g1 = __ldg(src + min(i4 + 1, n4_max));
+            i4 += 2;
+            LSM_LANE_8(f0, f1)
+            f0 = g0; f1 = g1;
+        }
+        if (n_a == r_old && m >= 2 && valid) {
+            // window m-2 complete: full(m-2) + full(m-1) + head(m)
+            double *o = dst + (size_t)(m - 2) * a.C;
+            if (J == 4) {
+                *reinterpret_cast<double2 *>(o) = make_double2((full2[0] + full1[0]) + acc[0], (full2[1] + full1[1]) + acc[1]);
+                *reinterpret_cast<double2 *>(o + 2) = make_double2((full2[2] + full1[2]) + acc[2], (full2[3] + full1[3]) + acc[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < J; ++j) o[j] = (full2[j] + full1[j]) + acc[j];
+            }
+        }
+        for (int p = n_a; p < n_here; p += 8) {
+            const float4 g0 = __ldg(src + min(i4, n4_max)), g1 = __ldg(src + min(i4 + 1, n4_max));
+            i4 += 2;
+            LSM_LANE_8(f0, f1)
+            f0 = g0; f1 = g1;
+        }
+#pragma unroll
+        for (int j = 0; j < J; ++j) { full2[j] = full1[j]; full1[j] = acc[j]; }
+    }
+#undef LSM_LANE_8
+#undef LSM_LANE_SAMPLE
+}
+
+// Units are dispatched in blockIdx order: first the big ones (kLanesJ channels: one PCM stream and one conversion feed
+// 52 DFMAs), then single-channel units.  A unit is one warp's serial work (0.8 ms for four channels even on an idle SM),
+// so a grid of big units alone ends in a long ragged tail; the small units keep every SM's pipes full to the end.
+__global__ void __launch_bounds__(32) gammatone_energy_kernel(const __grid_constant__ EnergyArgs a)
+{
+    const int n_big = a.big_groups * (a.C / kLanesJ);
+    if ((int)blockIdx.x < n_big) {
+        const int units = a.C / kLanesJ;              // channel blocks per group (fastest index: PCM locality in L2)
+        const int g = blockIdx.x / units;
+        energy_unit<kLanesJ>(a, g, (blockIdx.x - g * units) * kLanesJ);
+    } else {
+        const int s = blockIdx.x - n_big;
+        const int g = s / a.C;
+        energy_unit<1>(a, a.big_groups + g, s - g * a.C);
+    }
+}
+
+// per-utterance max / min over the CTA (create_dataset.py:60,62-63); every thread gets both
+__device__ __forceinline__ void block_minmax(double tmax, double tmin, double (*s_red)[8], double *s_mm, double &mx, double &mn)
+{
+    const double wmax = warp_max_f64(tmax), wmin = warp_min_f64(tmin);
+    if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = wmax; s_red[1][threadIdx.x >> 5] = wmin; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m1 = -INFINITY, m0 = INFINITY;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) { m1 = fmax(m1, s_red[0][w]); m0 = fmin(m0, s_red[1][w]); }
+        s_mm[0] = m1; s_mm[1] = m0;
+    }
+    __syncthreads();
+    mx = s_mm[0];
+    mn = s_mm[1];
+}
+
+// the four (K) Schmitt triggers of one channel for one time bin (create_dataset.py:90-94), bit k of `on` = trigger k
+__device__ __forceinline__ void triggers_step(const GtArgs &a, double v, unsigned &on)
+{
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (k < a.K) {
+            const bool is_on = (on >> k) & 1u;
+            if (!is_on && v > a.thr[k]) on |= (1u << k);
+            else if (is_on && v < a.lower[k]) on &= ~(1u << k);
+        }
+    }
+}
+
+// spikes of time bin j: to the reservoir's bit plane in shared memory (fused kernels) and / or to X_spikes rows
+template <int FNPT>
+__device__ __forceinline__ void put_spikes(const GtArgs &a, unsigned on, int j, uint8_t *row0, unsigned char *smem_raw)
+{
+    if (FNPT > 0) {
+        // word (t, warp) = ballot over this warp's 32 channels
+        unsigned *s_bits = reinterpret_cast<unsigned *>(smem_raw);
+        const int CW = a.C >> 5;
+        for (int k = 0; k < a.K; ++k) {
+            const unsigned word = __ballot_sync(0xffffffffu, (on >> k) & 1u);
+            if ((threadIdx.x & 31) == 0) s_bits[(j * a.K + k) * CW + (threadIdx.x >> 5)] = word;
+        }
+    }
+    const int T = a.nbins * a.K;
+    for (int r = 0; row0 && r < a.R; ++r) {
+        uint8_t *row = row0 + (size_t)r * T + (size_t)j * a.K;
+        if (a.K == 4) {
+            // bytes k = 0..3 of column block j, little endian
+            const unsigned w = (on & 1u) | ((on & 2u) << 7) | ((on & 4u) << 14) | ((on & 8u) << 21);
+            *reinterpret_cast<uint32_t *>(row) = w;
+        } else {
+            for (int k = 0; k < a.K; ++k) row[k] = (on >> k) & 1u;
+        }
+    }
+}
+
+// ---- EXACT epilogue: floor, min-max, zoom, encoder in the reference's operations (create_dataset.py:60-98)
+template <int FNPT>
+__device__ __forceinline__ void exact_epilogue(const GtArgs &a, int utt, double *plane, double tmax, double tmin,
+                                               double (*s_red)[8], double *s_mm, unsigned char *smem_raw)
+{
+    const int ch = threadIdx.x, C = a.C, ncols = a.ncols;
+    double mx, mn0;
+    block_minmax(tmax, tmin, s_red, s_mm, mx, mn0);
+    const double floor_db = sub64(mx, 80.0);
+    const double mn = fmax(mn0, floor_db);             // min of the clamped plane
+    const bool degenerate = sub64(mx, mn) < 1e-8;       // create_dataset.py:64-65 -> all zeros
+    const double den = add64(sub64(mx, mn), 1e-8);
+    if (ch >= C) return;
+    const int T = a.nbins * a.K;
+    uint8_t *row0 = a.spikes ? a.spikes + ((size_t)utt * C * a.R + (size_t)ch * a.R) * T : nullptr;
+    double *dump = a.spec_norm ? a.spec_norm + ((size_t)utt * C + ch) * a.nbins : nullptr;
+    // normalise in place (own column of the plane only)
+    for (int c = 0; c < ncols; ++c) {
+        const double v = fmax(plane[(size_t)c * C + ch], floor_db);
+        plane[(size_t)c * C + ch] = __ddiv_rn(sub64(v, mn), den);
+    }
+    unsigned on = 0;
+    for (int j = 0; j < a.nbins; ++j) {
+        double v;
+        if (degenerate) v = 0.0;
+        else if (ncols == a.nbins) v = plane[(size_t)j * C + ch];
+        else {
+            const int i0 = a.zoom_i0[j];
+            const double f = a.zoom_f[j];
+            v = mul64(plane[(size_t)i0 * C + ch], sub64(1.0, f));
+            if (i0 + 1 < ncols) v = add64(v, mul64(plane[(size_t)(i0 + 1) * C + ch], f));
+        }
+        if (dump) dump[j] = v;
+        triggers_step(a, v, on);
+        put_spikes<FNPT>(a, on, j, row0, smem_raw);
+    }
+}
+
+// ---- SPECULATIVE epilogue: the same chain (dB, floor, min-max, zoom, encoder) on the speculative energy plane, arranged
+//      for throughput - independent columns in flight, library log10, reciprocal instead of division - plus the near-tie
+//      test.  Returns true (per thread) if some comparison was within the margin; the CTA then repeats the utterance exactly.
+template <int FNPT>
+__device__ __forceinline__ bool spec_epilogue(const GtArgs &a, int utt, double *plane, double (*s_red)[8], double *s_mm,
+                                              unsigned char *smem_raw)
+{
+    const int ch = threadIdx.x, C = a.C, ncols = a.ncols;
+    const bool live = ch < C;
+    double tmax = -INFINITY, tmin = INFINITY;
+    if (live) {
+        const double *c = a.coefs + 10 * ch;
+        const double s = c[0] / c[6];
+        const double G = (s * s) * (s * s) / c[9];
+        const double g2n = G * G / (double)a.nwin;      // (A0^4 / gain)^2 / nwin: energy sum -> mean square of the real output
+        double *col = plane + ch;
+        int c0 = 0;
+        for (; c0 + 7 <= ncols; c0 += 7) {
+            double e[7];
+#pragma unroll
+            for (int u = 0; u < 7; ++u) e[u] = col[(size_t)(c0 + u) * C];
+#pragma unroll
+            for (int u = 0; u < 7; ++u) {
+                e[u] = 20.0 * log10(sqrt(e[u] * g2n) + 1e-9);
+                tmax = fmax(tmax, e[u]);
+                tmin = fmin(tmin, e[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 7; ++u) col[(size_t)(c0 + u) * C] = e[u];
+        }
+        for (; c0 < ncols; ++c0) {
+            const double e = 20.0 * log10(sqrt(col[(size_t)c0 * C] * g2n) + 1e-9);
+            tmax = fmax(tmax, e);
+            tmin = fmin(tmin, e);
+            col[(size_t)c0 * C] = e;
+        }
+    }
+    double mx, mn0;
+    block_minmax(tmax, tmin, s_red, s_mm, mx, mn0);
+    const double floor_db = mx - 80.0;
+    const double mn = fmax(mn0, floor_db);
+    const double range = mx - mn;
+    const bool degenerate = range < 1e-8;
+    const double den = range + 1e-8;
+    const double rden = 1.0 / den;
+    // margin in normalised units inside which one of the exact path's comparisons could come out differently
+    const double margin = a.spec_delta * rden;
+    bool near = fabs(range - 1e-8) < a.spec_delta;
+    if (!live) return near;
+    const int T = a.nbins * a.K;
+    uint8_t *row0 = a.spikes ? a.spikes + ((size_t)utt * C * a.R + (size_t)ch * a.R) * T : nullptr;
+    const double *col = plane + ch;
+    unsigned on = 0;
+    for (int j0 = 0; j0 < a.nbins; j0 += 4) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = min(j0 + u, a.nbins - 1);
+            int i0 = j;
+            double f = 0.0;
+            if (ncols != a.nbins) { i0 = __ldg(a.zoom_i0 + j); f = __ldg(a.zoom_f + j); }
+            const int i1 = min(i0 + 1, ncols - 1);
+            const double x0 = (fmax(col[(size_t)i0 * C], floor_db) - mn) * rden;
+            const double x1 = (fmax(col[(size_t)i1 * C], floor_db) - mn) * rden;
+            v[u] = degenerate ? 0.0 : fma(x1 - x0, f, x0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u;
+            if (j < a.nbins) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k < a.K) near |= (fabs(v[u] - a.thr[k]) < margin) | (fabs(v[u] - a.lower[k]) < margin);
+                triggers_step(a, v[u], on);
+                put_spikes<FNPT>(a, on, j, row0, smem_raw);
+            }
+        }
+    }
+    return near;
 }
 
 // FNPT = 0: front end only (spike trains to global memory).  FNPT > 0: fused audio -> features: after
@@ -280,11 +568,18 @@ __global__ void __launch_bounds__(MAXT, MINB) gammatone_encode_kernel(const GtAr
     __shared__ int s_utt;
     __shared__ int s_cnt3[3];
 
-    const int ch = threadIdx.x;
-    const int C = a.C;
-    const bool live = ch < C;
-    const int ncols = a.ncols;
-    double *plane = a.scratch + (size_t)blockIdx.x * ncols * C;     // this CTA's dB plane [ncols][C]
+    // Every utterance costs the same, so the CTAs resident on an SM would march in lockstep: all in the filter loop
+    // (fp64 pipe saturated, issue slots to spare), then all in the encoder / reservoir phases (fp64 pipe idle).  Start
+    // the r-th CTA of each SM r x (utterance period / CTAs per SM) late instead, once; the phases then interleave for the
+    // rest of the launch and the non-fp64 work hides under the other CTAs' filter loops.
+    if (a.stagger_cycles > 0 && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const int r = atomicAdd(a.sm_rank + (smid & 255u), 1);
+        const long long t0 = clock64();
+        const long long wait = (long long)r * a.stagger_cycles;
+        while (clock64() - t0 < wait) __nanosleep(2000);
+    }
 
     for (;;) {
         // dynamic work distribution: utterances are handed out one at a time, so every SM stays busy to the end
@@ -293,90 +588,22 @@ __global__ void __launch_bounds__(MAXT, MINB) gammatone_encode_kernel(const GtAr
         const int utt = s_utt;
         if (utt >= a.B) break;
         const float *pcm = a.pcm + (size_t)utt * a.L;
-        bool exact = a.mode == 0;
-        for (;;) {
-            double tmax = -INFINITY, tmin = INFINITY;
-            if (exact) gt_filter_exact(a, pcm, s_x, plane, tmax, tmin);
-            else gt_filter_fast(a, pcm, s_x, plane, tmax, tmin);
-
-            // ---- per-utterance max / min of the dB plane (create_dataset.py:60,62-63)
-            {
-                const double wmax = warp_max_f64(tmax), wmin = warp_min_f64(tmin);
-                if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = wmax; s_red[1][threadIdx.x >> 5] = wmin; }
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    double mx = -INFINITY, mn = INFINITY;
-                    for (int w = 0; w < (blockDim.x >> 5); ++w) { mx = fmax(mx, s_red[0][w]); mn = fmin(mn, s_red[1][w]); }
-                    s_mm[0] = mx; s_mm[1] = mn;
-                }
-                __syncthreads();
-            }
-            const double mx = s_mm[0];
-            const double floor_db = sub64(mx, 80.0);
-            const double mn = fmax(s_mm[1], floor_db);        // min of the clamped plane
-            const double range = sub64(mx, mn);
-            const bool degenerate = range < 1e-8;              // create_dataset.py:64-65 -> all zeros
-            const double den = add64(range, 1e-8);
-            // speculative pass: margin (in normalised units) inside which a comparison could come out differently
-            const double margin = exact ? 0.0 : a.spec_delta / den;
-            bool near = !exact && fabs(range - 1e-8) < a.spec_delta;
-
-            if (live) {
-                const int T = a.nbins * a.K;
-                uint8_t *row0 = a.spikes ? a.spikes + ((size_t)utt * C * a.R + (size_t)ch * a.R) * T : nullptr;
-                double *dump = a.spec_norm ? a.spec_norm + ((size_t)utt * C + ch) * a.nbins : nullptr;
-                // normalise in place (own column of the plane only)
-                for (int c = 0; c < ncols; ++c) {
-                    const double v = fmax(plane[(size_t)c * C + ch], floor_db);
-                    plane[(size_t)c * C + ch] = __ddiv_rn(sub64(v, mn), den);
-                }
-                unsigned on = 0;   // bit k = state of trigger k
-                for (int j = 0; j < a.nbins; ++j) {
-                    double v;
-                    if (degenerate) v = 0.0;
-                    else if (ncols == a.nbins) v = plane[(size_t)j * C + ch];
-                    else {
-                        const int i0 = a.zoom_i0[j];
-                        const double f = a.zoom_f[j];
-                        v = mul64(plane[(size_t)i0 * C + ch], sub64(1.0, f));
-                        if (i0 + 1 < ncols) v = add64(v, mul64(plane[(size_t)(i0 + 1) * C + ch], f));
-                    }
-                    if (dump) dump[j] = v;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        if (k < a.K) {
-                            const bool is_on = (on >> k) & 1u;
-                            if (!is_on && v > a.thr[k]) on |= (1u << k);
-                            else if (is_on && v < a.lower[k]) on &= ~(1u << k);
-                            if (!exact) near |= (fabs(v - a.thr[k]) < margin) | (fabs(v - a.lower[k]) < margin);
-                        }
-                    }
-                    if (FNPT > 0) {
-                        // hand the spikes to the reservoir phase: word (t, warp) = ballot over this warp's 32 channels
-                        unsigned *s_bits = reinterpret_cast<unsigned *>(smem_raw);
-                        const int CW = C >> 5;
-                        for (int k = 0; k < a.K; ++k) {
-                            const unsigned word = __ballot_sync(0xffffffffu, (on >> k) & 1u);
-                            if ((threadIdx.x & 31) == 0) s_bits[(j * a.K + k) * CW + (threadIdx.x >> 5)] = word;
-                        }
-                    }
-                    for (int r = 0; row0 && r < a.R; ++r) {
-                        uint8_t *row = row0 + (size_t)r * T + (size_t)j * a.K;
-                        if (a.K == 4) {
-                            // bytes k = 0..3 of column block j, little endian
-                            const unsigned w = (on & 1u) | ((on & 2u) << 7) | ((on & 4u) << 14) | ((on & 8u) << 21);
-                            *reinterpret_cast<uint32_t *>(row) = w;
-                        } else {
-                            for (int k = 0; k < a.K; ++k) row[k] = (on >> k) & 1u;
-                        }
-                    }
-                }
-            }
-            if (exact) break;
+        // the utterance's [ncols][C] plane: energies -> dB -> normalised values, in place.  Mode 2 works directly on the
+        // utterance's slice of the energy buffer, the other modes on this CTA's scratch plane (L2-resident).
+        double *plane = a.mode == 2 ? const_cast<double *>(a.energy_in) + (size_t)utt * a.ncols * a.C
+                                    : a.scratch + (size_t)blockIdx.x * a.ncols * a.C;
+        bool settled = false;
+        if (a.mode != 0) {
+            if (a.mode == 1) gt_filter_fast(a, pcm, s_x, plane);
+            const bool near = spec_epilogue<FNPT>(a, utt, plane, s_red, s_mm, smem_raw);
             // some comparison of this utterance is too close to call on the speculative plane: filter it again, exactly
-            if (!__syncthreads_or(near ? 1 : 0)) break;
-            if (threadIdx.x == 0) atomicAdd(a.reruns, 1);
-            exact = true;
+            settled = !__syncthreads_or(near ? 1 : 0);
+            if (!settled && threadIdx.x == 0) atomicAdd(a.reruns, 1);
+        }
+        if (!settled) {
+            double tmax = -INFINITY, tmin = INFINITY;
+            gt_filter_exact(a, pcm, s_x, plane, tmax, tmin);
+            exact_epilogue<FNPT>(a, utt, plane, tmax, tmin, s_red, s_mm, smem_raw);
         }
         if (FNPT > 0) {
             __syncthreads();   // bits complete and visible
@@ -437,6 +664,7 @@ static void fill_args(const lsm_frontend *fe, const float *d_pcm, int B, uint8_t
     for (int k = 0; k < 8; ++k) { a.thr[k] = p.thresholds_desc[k]; a.lower[k] = p.lower_bounds[k]; }
     // the normalised-spectrogram dump is defined as the exact path's: asking for it selects the exact filter
     a.mode = d_spec_norm ? 0 : fe->mode;
+    a.energy_in = nullptr;
     a.spec_delta = fe->spec_delta;
     a.reruns = fe->d_counters + 64;
 }
@@ -472,14 +700,80 @@ static void pin_scratch_in_l2(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st)
     if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
 }
 
-static int next_counter(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st, int **counter)
+// d_counters layout (ints): [0,64) work counters, [64] re-execution count, [128 + 256*slot, +256) per-SM arrival counters
+static int next_counter(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st, int **counter, GtArgs *a, int grid)
 {
     int rc = lsm_frontend_order_before(ctx, fe, st);
     if (rc != LSM_OK) return rc;
     pin_scratch_in_l2(ctx, fe, st);
     // work counter: one int per launch out of a small ring, so back-to-back launches on different streams do not share it
-    *counter = fe->d_counters + (fe->counter_next++ % 64);
+    const unsigned slot = fe->counter_next++ % 64;
+    *counter = fe->d_counters + slot;
     LSM_CUDA(ctx, cudaMemsetAsync(*counter, 0, sizeof(int), st));
+    // staggered start (see the kernel): only when every CTA gets at least two utterances, so the one-off delay pays
+    a->sm_rank = fe->d_counters + 128 + 256 * slot;
+    a->stagger_cycles = 0;
+    if (a->B >= 2 * grid) {
+        const char *e = getenv("LSM_STAGGER");
+        const long long n_used = (long long)(fe->ncols - 1) * fe->p.hop + fe->p.nwin;
+        const long long per_utt = (long long)fe->p.channels * n_used * (a->mode ? 13 : 35) / 64;   // cycles of one SM's fp64 pipe
+        a->stagger_cycles = e ? atoi(e) : (int)(per_utt > 4000000 ? 4000000 : per_utt);
+        if (a->stagger_cycles > 0) LSM_CUDA(ctx, cudaMemsetAsync(a->sm_rank, 0, 256 * sizeof(int), st));
+    }
+    return LSM_OK;
+}
+
+
+// ------------------------------------------------------------------------------------ lanes arrangement (K1a)
+constexpr int kEnergyMaxUtt = 8192;     // utterances per pass of the two-kernel speculative path (energy buffer = 100 KB each)
+
+// Can the speculative filter run lane = utterance?  8-sample steps must tile the window phases, rows must be 16-byte aligned.
+static bool lanes_eligible(const lsm_frontend *fe, const float *d_pcm)
+{
+    const lsm_frontend_params &p = fe->p;
+    // opt-in for now: as two back-to-back kernels (4.2 ms + encoder/reservoir 3.9 ms per 2400 utterances) it does not yet beat
+    // the single fused kernel (7.8 ms); it is the filter half of the pipelined design described in DESIGN.md
+    if (!getenv("LSM_LANES")) return false;
+    const int r_old = p.nwin - 2 * p.hop;
+    return p.kind == LSM_FILTERBANK_GAMMATONE && fe->mode == LSM_FILTER_SPECULATIVE && p.hop % 8 == 0 && r_old % 8 == 0 &&
+           p.n_samples % 4 == 0 && p.channels % kLanesJ == 0 && p.channels <= 256 && (((uintptr_t)d_pcm) & 15) == 0;
+}
+
+static int ensure_energy(lsm_ctx *ctx, lsm_frontend *fe, int B)
+{
+    if (B <= fe->energy_cap) return LSM_OK;
+    if (fe->ev_valid) LSM_CUDA(ctx, cudaEventSynchronize(fe->ev_last));     // nobody is still reading the old buffer
+    if (fe->d_energy) { LSM_CUDA(ctx, cudaFree(fe->d_energy)); fe->d_energy = nullptr; fe->energy_cap = 0; }
+    const size_t bytes = sizeof(double) * (size_t)B * fe->ncols * fe->p.channels;
+    if (cudaMalloc((void **)&fe->d_energy, bytes) != cudaSuccess) LSM_FAIL(ctx, LSM_ERR_NOMEM, "cudaMalloc(%zu) for the energy planes failed", bytes);
+    fe->energy_cap = B;
+    return LSM_OK;
+}
+
+// K1a: raw window energies of the speculative cascade for utterances [0, B) into fe->d_energy
+static int launch_energy(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, cudaStream_t st)
+{
+    const lsm_frontend_params &p = fe->p;
+    int rc;
+    if ((rc = lsm_frontend_order_before(ctx, fe, st)) != LSM_OK) return rc;
+    if ((rc = ensure_energy(ctx, fe, B)) != LSM_OK) return rc;
+    static EnergyArgs ea;       // 12 KB: keep it off the stack; filled and consumed before returning (ctx is single-threaded)
+    ea.pcm = d_pcm; ea.energy = fe->d_energy;
+    ea.B = B; ea.L = p.n_samples; ea.C = p.channels; ea.nwin = p.nwin; ea.hop = p.hop; ea.ncols = fe->ncols;
+    memcpy(ea.coef, fe->h_lane_coef, sizeof(double) * 6 * p.channels);
+    const int groups = (B + 31) / 32;
+    // the last quarter of the groups (at most two resident waves' worth of channels) goes out as single-channel units
+    const char *e = getenv("LSM_LANES_SMALL_PCT");
+    const int pct = e ? atoi(e) : 25;
+    int small_groups = (groups * pct + 99) / 100;
+    const int cap = (2 * 16 * ctx->sm_count + p.channels - 1) / p.channels;
+    if (small_groups > cap && !e) small_groups = cap;
+    if (small_groups > groups) small_groups = groups;
+    ea.big_groups = groups - small_groups;
+    const int grid = ea.big_groups * (p.channels / kLanesJ) + small_groups * p.channels;
+    gammatone_energy_kernel<<<grid, 32, 0, st>>>(ea);
+    ctx->launches += 1;
+    LSM_CUDA(ctx, cudaGetLastError());
     return LSM_OK;
 }
 
@@ -487,15 +781,31 @@ int lsm_launch_gammatone(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int
                          double *d_spec_norm, cudaStream_t st)
 {
     const lsm_frontend_params &p = fe->p;
+    const bool lanes = !d_spec_norm && lanes_eligible(fe, d_pcm);
+    if (lanes && B > kEnergyMaxUtt) {
+        const size_t spk_per = (size_t)p.channels * p.redundancy * p.n_bins * p.n_thresholds;
+        for (int off = 0; off < B; off += kEnergyMaxUtt) {
+            const int n = B - off < kEnergyMaxUtt ? B - off : kEnergyMaxUtt;
+            const int rc = lsm_launch_gammatone(ctx, fe, d_pcm + (size_t)off * p.n_samples, n, d_spikes + off * spk_per, nullptr, st);
+            if (rc != LSM_OK) return rc;
+        }
+        return LSM_OK;
+    }
     GtArgs a;
     fill_args(fe, d_pcm, B, d_spikes, d_spec_norm, &a);
     memset(&a.res, 0, sizeof(a.res));
+    if (lanes && B > 0) {
+        const int rc = launch_energy(ctx, fe, d_pcm, B, st);
+        if (rc != LSM_OK) return rc;
+        a.mode = 2;
+        a.energy_in = fe->d_energy;
+    }
     const int threads = ((p.channels + 31) / 32) * 32;
     const size_t smem = sizeof(double) * 2 * kChunkBlocks * p.hop + k1_pad_smem();
     const int grid = B < fe->grid ? B : fe->grid;
     if (grid <= 0) return LSM_OK;
     int *counter, rc;
-    if ((rc = next_counter(ctx, fe, st, &counter)) != LSM_OK) return rc;
+    if ((rc = next_counter(ctx, fe, st, &counter, &a, grid)) != LSM_OK) return rc;
     if (threads > 128) gammatone_encode_kernel<256, 2, 0, true><<<grid, threads, smem, st>>>(a, counter);
     else if (fe->minb == 4) gammatone_encode_kernel<128, 4, 0, true><<<grid, threads, smem, st>>>(a, counter);
     else if (fe->minb == 5) gammatone_encode_kernel<128, 5, 0, true><<<grid, threads, smem, st>>>(a, counter);
@@ -521,7 +831,7 @@ int lsm_fused_npt(const lsm_frontend *fe, const lsm_reservoir *res)
 
 // launch == false: only report the resident grid (one wave) of this variant through *wave
 template <int MAXT, int MINB, int FNPT>
-static int launch_fused_t(lsm_ctx *ctx, lsm_frontend *fe, const lsm_reservoir *res, const GtArgs &a, int threads, size_t smem,
+static int launch_fused_t(lsm_ctx *ctx, lsm_frontend *fe, const lsm_reservoir *res, GtArgs &a, int threads, size_t smem,
                           cudaStream_t st, bool launch = true, int *wave = nullptr)
 {
     int per_sm = 0, rc;
@@ -535,7 +845,7 @@ static int launch_fused_t(lsm_ctx *ctx, lsm_frontend *fe, const lsm_reservoir *r
     if (!launch) return LSM_OK;
     if (grid > a.B) grid = a.B;
     int *counter;
-    if ((rc = next_counter(ctx, fe, st, &counter)) != LSM_OK) return rc;
+    if ((rc = next_counter(ctx, fe, st, &counter, &a, grid)) != LSM_OK) return rc;
     if (res->lean) gammatone_encode_kernel<MAXT, MINB, FNPT, true><<<grid, threads, smem, st>>>(a, counter);
     else gammatone_encode_kernel<MAXT, MINB, FNPT, false><<<grid, threads, smem, st>>>(a, counter);
     ctx->launches += 1;
@@ -570,9 +880,28 @@ static int fused_dispatch(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, co
     const int npt = lsm_fused_npt(fe, res);
     if (!npt) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "this front end / reservoir pair cannot run fused");
     const lsm_frontend_params &p = fe->p;
+    const bool lanes = launch && lanes_eligible(fe, d_pcm);
+    if (lanes && B > kEnergyMaxUtt) {
+        const size_t spk_per = (size_t)p.channels * p.redundancy * p.n_bins * p.n_thresholds;
+        const size_t feat_per = (size_t)__builtin_popcount(feature_mask & 0xFFu) * res->p.n_out;
+        for (int off = 0; off < B; off += kEnergyMaxUtt) {
+            const int n = B - off < kEnergyMaxUtt ? B - off : kEnergyMaxUtt;
+            const int rc = fused_dispatch(ctx, fe, res, d_pcm + (size_t)off * p.n_samples, n,
+                                          d_spikes_or_null ? d_spikes_or_null + off * spk_per : nullptr, feature_mask, nan_to_num,
+                                          d_features + off * feat_per, st, true, nullptr);
+            if (rc != LSM_OK) return rc;
+        }
+        return LSM_OK;
+    }
     GtArgs a;
     fill_args(fe, d_pcm, B, d_spikes_or_null, nullptr, &a);
     lsm_reservoir_fill_args(res, nullptr, B, feature_mask, nan_to_num, d_features, nullptr, &a.res);
+    if (lanes) {
+        const int rc = launch_energy(ctx, fe, d_pcm, B, st);
+        if (rc != LSM_OK) return rc;
+        a.mode = 2;
+        a.energy_in = fe->d_energy;
+    }
     const int threads = p.channels;
     size_t smem = sizeof(double) * 2 * kChunkBlocks * p.hop;
     const size_t smem_res = lsm_res_smem_bytes(a.res.T, a.res.CW, threads * npt, a.res.N);

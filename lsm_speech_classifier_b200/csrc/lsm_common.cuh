@@ -35,6 +35,9 @@ struct lsm_frontend {
     int *d_counters = nullptr;     // [64] dynamic work counters, one per in-flight launch; [64] = utterances filtered twice
     int mode = 1;                  // gammatone: 0 = exact filter only, 1 = speculative filter + exact re-execution of near-ties
     double spec_delta = 1e-7;      // dB margin of the near-tie test (lsm_frontend_set_mode)
+    double h_lane_coef[256][6] = {};  // per channel c1..c4, -a1, -a2 of the normalised cascade (kernel-parameter table of K1a)
+    double *d_energy = nullptr;    // [energy_cap][ncols][C] raw window energies between K1a and the encoder kernel
+    int energy_cap = 0;
     unsigned counter_next = 0;
     int minb = 5;                  // K1 occupancy target the kernel was instantiated for
     // launches on different streams share the scratch planes: each launch waits for the previous one's event

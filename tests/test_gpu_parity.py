@@ -426,3 +426,22 @@ def test_fused_pipeline_same_features_in_both_filter_modes(env, small_set):
     fe.set_mode("speculative", 1e9)
     c = pipe.run_host(pcm, keys)
     assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+def test_speculative_filter_arrangements_agree(env, small_set, monkeypatch):
+    """Two arrangements of the speculative filter - lane = channel (inside the encoder kernel, the default) and
+    lane = utterance (K1a energy kernel + encoder kernel, LSM_LANES=1) - give the oracle's spike trains for ragged
+    batch sizes (partial 32-utterance groups included)."""
+    from lsm_speech_classifier_b200.frontend import Frontend
+    pcm, _ = small_set
+    fe = Frontend(128, "gammatone")
+    want = oracle_spikes(pcm, fe)
+    for n in (1, 2, 27, len(pcm)):
+        assert np.array_equal(fe.encode(pcm[:n]), want[:n]), n
+    monkeypatch.setenv("LSM_LANES", "1")
+    for n in (1, 27, len(pcm)):
+        assert np.array_equal(fe.encode(pcm[:n]), want[:n]), n
+    fe40 = Frontend(40, "gammatone")
+    assert np.array_equal(fe40.encode(pcm[:9]), oracle_spikes(pcm[:9], fe40))
+    monkeypatch.delenv("LSM_LANES")
+    assert np.array_equal(fe40.encode(pcm[:9]), oracle_spikes(pcm[:9], fe40))
