@@ -390,48 +390,82 @@ extern "C" int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
     int npt, threads;
     lsm_reservoir_geometry(N, &npt, &threads, &res->n_pad);
     if (threads > 1024) { delete res; LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "num_neurons %d > 16384 not supported by the event-driven kernel", N); }
-    // dense presynaptic-major plane: wt[j][i] = weight of j -> i; one extra all-zero row (index N) pads spike lists
-    std::vector<int32_t> wt((size_t)(N + 1) * res->n_pad, 0);
-    std::vector<int64_t> rowabs(N, 0);
-    for (int i = 0; i < N; ++i) {
-        for (int64_t q = h_w_rowptr[i]; q < h_w_rowptr[i + 1]; ++q) {
-            const int j = h_w_col[q];
-            if (j < 0 || j >= N) { delete res; LSM_FAIL(ctx, LSM_ERR_INVALID, "presynaptic index out of range"); }
-            wt[(size_t)j * res->n_pad + i] += h_w_q[q];
-            rowabs[i] += h_w_q[q] < 0 ? -(int64_t)h_w_q[q] : (int64_t)h_w_q[q];
-        }
-        if (rowabs[i] >= (1ll << 31)) { delete res; LSM_FAIL(ctx, LSM_ERR_INVALID, "row %d: sum of |weights| overflows the exact int32 accumulator", i); }
-    }
-    std::vector<int32_t> out_slot(N, -1);
-    for (int o = 0; o < p->n_out; ++o) {
-        if (h_out_idx[o] < 0 || h_out_idx[o] >= N) { delete res; LSM_FAIL(ctx, LSM_ERR_INVALID, "output index out of range"); }
-        out_slot[h_out_idx[o]] = o;
-    }
+    const int n_pad = res->n_pad;
     const int64_t nin = h_in_rowptr[N];
-    std::vector<int32_t> in_row(res->n_pad, -1);
+    for (int64_t q = 0; q < nin; ++q)
+        if (h_in_col[q] < 0 || h_in_col[q] >= p->num_inputs) { delete res; LSM_FAIL(ctx, LSM_ERR_INVALID, "input row out of range"); }
+    std::vector<int32_t> in_row(n_pad, -1);
     for (int i = 0; i < N; ++i) {
         const int d = h_in_rowptr[i + 1] - h_in_rowptr[i];
         if (d > res->max_in_per_neuron) res->max_in_per_neuron = d;
         if (d == 1) in_row[i] = h_in_col[h_in_rowptr[i]];
         else if (d > 1) in_row[i] = -2;
     }
-    // lean kernel variant: uniform leak, uniform input gain (and no -0.0), at most one input row per neuron
-    res->lean = res->max_in_per_neuron <= 1;
+    // lean kernel variant (reservoir_core.cuh): uniform leak, uniform input gain (and no -0.0), every driven neuron has exactly
+    // one input row and no row drives two neurons, the rows fit the "internal neuron 8r" slots, theta > 0, refractory period
+    // fits a 4-bit counter, and the input gain is a multiple of the weight quantum (so the folded constant is exact)
+    res->lean = res->max_in_per_neuron <= 1 && !getenv("LSM_NO_LEAN");
     res->leak0 = h_leak[0];
     res->gain0 = nin > 0 ? h_in_val[0] + 0.0 : 0.0;
     for (int i = 1; i < N && res->lean; ++i)
         if (memcmp(&h_leak[i], &h_leak[0], sizeof(double)) != 0) res->lean = 0;
     for (int64_t q = 0; q < nin && res->lean; ++q)
         if (memcmp(&h_in_val[q], &h_in_val[0], sizeof(double)) != 0) res->lean = 0;
-    for (int64_t q = 0; q < nin; ++q)
-        if (h_in_col[q] < 0 || h_in_col[q] >= p->num_inputs) { delete res; LSM_FAIL(ctx, LSM_ERR_INVALID, "input row out of range"); }
+    if (res->lean) {
+        std::vector<char> seen(p->num_inputs, 0);
+        for (int i = 0; i < N && res->lean; ++i)
+            if (in_row[i] >= 0) { if (seen[in_row[i]]) res->lean = 0; seen[in_row[i]] = 1; }
+        const double g = ldexp(res->gain0, p->w_shift);
+        if (p->num_inputs > n_pad / 8 || !(p->theta > 0.0) || p->refractory > 15 || g != floor(g) ||
+            fabs(res->gain0) > ldexp(1.0, 31 - p->w_shift))
+            res->lean = 0;
+    }
+    // neuron relabelling: perm[external] = internal.  Lean: the neuron driven by input row r becomes internal 8r, the others
+    // fill the remaining slots in ascending order; otherwise the identity.
+    std::vector<int32_t> perm(N), ext_id(n_pad, N);
+    if (res->lean) {
+        std::vector<char> taken(n_pad, 0);
+        for (int i = 0; i < N; ++i)
+            if (in_row[i] >= 0) { perm[i] = 8 * in_row[i]; taken[perm[i]] = 1; }
+        int next = 0;
+        for (int i = 0; i < N; ++i)
+            if (in_row[i] < 0) {
+                while (taken[next]) ++next;
+                perm[i] = next; taken[next] = 1;
+            }
+    } else {
+        for (int i = 0; i < N; ++i) perm[i] = i;
+    }
+    for (int i = 0; i < N; ++i) ext_id[perm[i]] = i;
+    res->zero_row = res->lean ? n_pad : N;
+    res->hi_magic = (1075 - p->w_shift) << 20;
+    res->c_off = ldexp(1.0, 52 - p->w_shift) + ldexp(1.0, 31 - p->w_shift);
+    res->c_on = res->c_off - res->gain0;
+    // dense presynaptic-major plane: wt[j][i] = weight of j -> i (internal labels); one extra all-zero row pads spike lists
+    std::vector<int32_t> wt((size_t)(res->zero_row + 1) * n_pad, 0);
+    std::vector<int64_t> rowabs(N, 0);
+    for (int i = 0; i < N; ++i) {
+        for (int64_t q = h_w_rowptr[i]; q < h_w_rowptr[i + 1]; ++q) {
+            const int j = h_w_col[q];
+            if (j < 0 || j >= N) { delete res; LSM_FAIL(ctx, LSM_ERR_INVALID, "presynaptic index out of range"); }
+            wt[(size_t)perm[j] * n_pad + perm[i]] += h_w_q[q];
+            rowabs[i] += h_w_q[q] < 0 ? -(int64_t)h_w_q[q] : (int64_t)h_w_q[q];
+        }
+        if (rowabs[i] >= (1ll << 31)) { delete res; LSM_FAIL(ctx, LSM_ERR_INVALID, "row %d: sum of |weights| overflows the exact int32 accumulator", i); }
+    }
+    std::vector<int32_t> out_slot(n_pad, -1);
+    for (int o = 0; o < p->n_out; ++o) {
+        if (h_out_idx[o] < 0 || h_out_idx[o] >= N) { delete res; LSM_FAIL(ctx, LSM_ERR_INVALID, "output index out of range"); }
+        out_slot[perm[h_out_idx[o]]] = o;
+    }
     int rc = upload(ctx, &res->d_wt, wt.data(), wt.size());
     if (rc == LSM_OK) rc = upload(ctx, &res->d_in_rowptr, h_in_rowptr, (size_t)N + 1);
     if (rc == LSM_OK) rc = upload(ctx, &res->d_in_col, h_in_col, (size_t)nin);
     if (rc == LSM_OK) rc = upload(ctx, &res->d_in_val, h_in_val, (size_t)nin);
     if (rc == LSM_OK) rc = upload(ctx, &res->d_leak, h_leak, (size_t)N);
-    if (rc == LSM_OK) rc = upload(ctx, &res->d_out_slot, out_slot.data(), (size_t)N);
+    if (rc == LSM_OK) rc = upload(ctx, &res->d_out_slot, out_slot.data(), out_slot.size());
     if (rc == LSM_OK) rc = upload(ctx, &res->d_in_row, in_row.data(), in_row.size());
+    if (rc == LSM_OK) rc = upload(ctx, &res->d_ext_id, ext_id.data(), ext_id.size());
     if (rc != LSM_OK) { lsm_reservoir_destroy(res); return rc; }
     *out = res;
     return LSM_OK;
@@ -441,7 +475,7 @@ extern "C" void lsm_reservoir_destroy(lsm_reservoir *res)
 {
     if (!res) return;
     cudaFree(res->d_wt); cudaFree(res->d_in_rowptr); cudaFree(res->d_in_col); cudaFree(res->d_in_val);
-    cudaFree(res->d_leak); cudaFree(res->d_out_slot); cudaFree(res->d_in_row);
+    cudaFree(res->d_leak); cudaFree(res->d_out_slot); cudaFree(res->d_in_row); cudaFree(res->d_ext_id);
     delete res;
 }
 

@@ -68,7 +68,11 @@ struct lsm_reservoir {
     int32_t *d_out_slot = nullptr; // [N] position in the output list or -1
     int32_t *d_in_row = nullptr;   // [N] single input row, -1 none, -2 several
     int max_in_per_neuron = 0;
-    int lean = 0;                  // uniform leak and gain, <= 1 input row per neuron
+    int lean = 0;                  // uniform leak and gain, one input row per driven neuron, relabelled layout (reservoir_core.cuh)
+    int32_t *d_ext_id = nullptr;   // [n_pad] lean layout: external index of internal neuron slot (>= N: padding)
+    int zero_row = 0;              // index of the all-zero weight row
+    double c_off = 0.0, c_on = 0.0;
+    int hi_magic = 0;
     double leak0 = 0.0, gain0 = 0.0;
 };
 

@@ -77,6 +77,7 @@ void lsm_reservoir_fill_args(const lsm_reservoir *res, const uint8_t *d_spikes, 
     a.spikes = d_spikes; a.wt = res->d_wt; a.in_rowptr = res->d_in_rowptr; a.in_col = res->d_in_col;
     a.in_val = res->d_in_val; a.in_row = res->d_in_row; a.leak = res->d_leak; a.out_slot = res->d_out_slot;
     a.features = d_features; a.raster = d_raster; a.stat_global = nullptr; a.diag = nullptr;
+    a.ext_id = res->d_ext_id; a.c_off = res->c_off; a.c_on = res->c_on; a.hi_magic = res->hi_magic; a.zero_row = res->zero_row;
     a.B = B; a.N = p.num_neurons; a.n_pad = res->n_pad; a.C = p.num_inputs; a.CW = (p.num_inputs + 31) / 32; a.T = p.num_steps;
     a.refractory = p.refractory; a.n_out = p.n_out; a.nan_to_num = nan_to_num;
     a.leak0 = res->leak0; a.gain0 = res->gain0;

@@ -7,17 +7,21 @@
 
 struct ResArgs {
     const uint8_t *spikes;    // [B][C][T]  level signal: any non-zero byte is "on"
-    const int32_t *wt;        // [N+1][n_pad]  row = presynaptic neuron, row N = zeros (list padding)
+    const int32_t *wt;        // [zero_row+1][n_pad]  row = presynaptic neuron, last row = zeros (list padding)
     const int32_t *in_rowptr; // [N+1]
     const int32_t *in_col;
     const double *in_val;
     const int32_t *in_row;    // [n_pad] the single input row of a neuron, -1 none, -2 several (generic CSR walk)
     const double *leak;       // [N]
-    const int32_t *out_slot;  // [N]
+    const int32_t *out_slot;  // [n_pad] position in the output list, -1 = not an output neuron / padding
     double *features;         // [B][nkeys][n_out]
     uint8_t *raster;          // optional [B][T][N]
     int *stat_global;         // per-CTA [6][slots] statistics when they do not fit in shared memory (large N), else null
     int *diag;                // optional [B][2]: neurons that fired at least once, total spikes (run_network_diagnostics)
+    const int32_t *ext_id;    // [n_pad] LEAN layout: external neuron index of an internal slot (>= N for padding), else null
+    double c_off, c_on;       // LEAN: cur = D(acc) - c_off (input off) / - c_on (input on), see lean_current()
+    int hi_magic;             // LEAN: high word of the double whose low word holds acc ^ 0x80000000
+    int zero_row;             // index of the all-zero weight row that pads a group of four list entries
     int B, N, n_pad, C, CW, T, refractory, n_out, nkeys, nan_to_num;
     unsigned feature_mask;
     double theta, scale, leak0, gain0;
@@ -35,8 +39,22 @@ __host__ __device__ inline size_t lsm_res_smem_bytes(int T, int CW, int slots, i
            sizeof(unsigned short) * 2 * (size_t)((N + 7) & ~3);
 }
 
+// LEAN layout and arithmetic (the reference's setup: uniform leak, one input row per driven neuron, theta > 0).
+//  * Neurons are relabelled on the host so that input row r drives internal neuron 8r: the input test is then a static
+//    property of a thread's slot (slot 0 of every thread at 8 neurons per thread), the other slots carry no input code.
+//    Weight rows/columns, output slots and the raster map use the internal labels; padding neurons have no input and
+//    all-zero weight columns, so they never leave V = 0 and need no bounds test.
+//  * I = I_in + acc * 2^-w (spec R6, one rounding) without I2F and DMUL: the bits of acc ^ 0x80000000 are the low word of the
+//    double D = 2^(52-w) + (acc + 2^31) * 2^-w (exact), and I = D - (2^(52-w) + 2^(31-w) - I_in) has the same exact value and
+//    therefore the same single rounding; the host checks that the constant is exact for this gain.
+//  * Refractory counters are 4-bit fields of one register per 8 neurons (decrement-if-nonzero in five integer operations).
+__device__ __forceinline__ double lean_current(int acc, int hi_magic, double c)
+{
+    return __dsub_rn(__hiloint2double(hi_magic, acc ^ (int)0x80000000), c);
+}
+
 // Caller contract: s_bits holds the utterance's input and a __syncthreads() has made it visible.
-// LEAN = uniform leak, uniform input gain, at most one input row per neuron (the reference's setup).
+// LEAN = uniform leak, uniform input gain, at most one input row per neuron, relabelled neurons (see above).
 // STAT_GLOBAL = per-neuron statistics in a.stat_global instead of shared memory (reservoirs too large for it).
 template <int NPT, bool LEAN, bool STAT_GLOBAL = false>
 __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int utt, unsigned char *smem_raw, int *s_cnt)
@@ -60,18 +78,35 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
     // per-neuron state in registers: thread tid owns the NPT consecutive neurons tid*NPT ...
     const int i0 = tid * NPT;
     double V[NPT], lk[NPT];
-    int ref[NPT], in_word[NPT];
-    unsigned in_mask[NPT];
+    int ref[LEAN ? 1 : NPT], in_word[LEAN ? 2 : NPT];
+    unsigned in_mask[LEAN ? 2 : NPT];
+    unsigned refn[(NPT + 7) / 8];                      // LEAN: 4-bit refractory counters, 8 neurons per word
+    if (LEAN) {
 #pragma unroll
-    for (int k = 0; k < NPT; ++k) {
-        const int i = i0 + k;
-        V[k] = 0.0; ref[k] = 0;
-        const int r = __ldg(a.in_row + i);            // padded to n_pad with -1
-        in_word[k] = r >= 0 ? (r >> 5) : (r == -2 ? -2 : 0);
-        in_mask[k] = r >= 0 ? (1u << (r & 31)) : 0u;
-        lk[k] = (LEAN || i >= N) ? a.leak0 : __ldg(a.leak + i);
+        for (int k = 0; k < NPT; ++k) V[k] = 0.0;
+#pragma unroll
+        for (int w = 0; w < (NPT + 7) / 8; ++w) {
+            refn[w] = 0u;
+            const int i = i0 + 8 * w;                  // the only slots that can carry an input: internal index = 8 * row
+            const int row = i >> 3;
+            const bool has = ((i & 7) == 0) && row < a.C;
+            in_word[w] = has ? (row >> 5) : 0;
+            in_mask[w] = has ? (1u << (row & 31)) : 0u;
+        }
+        ref[0] = 0; lk[0] = a.leak0;
+    } else {
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) {
+            const int i = i0 + k;
+            V[k] = 0.0; ref[k] = 0;
+            const int r = __ldg(a.in_row + i);            // padded to n_pad with -1
+            in_word[k] = r >= 0 ? (r >> 5) : (r == -2 ? -2 : 0);
+            in_mask[k] = r >= 0 ? (1u << (r & 31)) : 0u;
+            lk[k] = i >= N ? a.leak0 : __ldg(a.leak + i);
+        }
     }
-    const int32_t *wrow = a.wt + i0;
+    const char *wbase = reinterpret_cast<const char *>(a.wt + i0);
+    const unsigned pitch = (unsigned)a.n_pad * 4u;
     __syncthreads();
 
     int c_cur = 0, c_nxt = 1, c_zero = 2;
@@ -90,36 +125,55 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
             const uint2 jj = *reinterpret_cast<const uint2 *>(list + q);
             // entries past the end of the list select the all-zero weight row (index N)
             const int j0 = jj.x & 0xffff;
-            const int j1 = (q + 1 < n_prev) ? (int)(jj.x >> 16) : N;
-            const int j2 = (q + 2 < n_prev) ? (int)(jj.y & 0xffff) : N;
-            const int j3 = (q + 3 < n_prev) ? (int)(jj.y >> 16) : N;
-            const int32_t *r0 = wrow + j0 * a.n_pad, *r1 = wrow + j1 * a.n_pad;
-            const int32_t *r2 = wrow + j2 * a.n_pad, *r3 = wrow + j3 * a.n_pad;
+            const int j1 = (q + 1 < n_prev) ? (int)(jj.x >> 16) : a.zero_row;
+            const int j2 = (q + 2 < n_prev) ? (int)(jj.y & 0xffff) : a.zero_row;
+            const int j3 = (q + 3 < n_prev) ? (int)(jj.y >> 16) : a.zero_row;
+            const int4 *r0 = reinterpret_cast<const int4 *>(wbase + (size_t)((unsigned)j0 * pitch));
+            const int4 *r1 = reinterpret_cast<const int4 *>(wbase + (size_t)((unsigned)j1 * pitch));
+            const int4 *r2 = reinterpret_cast<const int4 *>(wbase + (size_t)((unsigned)j2 * pitch));
+            const int4 *r3 = reinterpret_cast<const int4 *>(wbase + (size_t)((unsigned)j3 * pitch));
 #pragma unroll
             for (int u = 0; u < NPT / 4; ++u) {
-                const int4 w0 = __ldg(reinterpret_cast<const int4 *>(r0) + u);
-                const int4 w1 = __ldg(reinterpret_cast<const int4 *>(r1) + u);
-                const int4 w2 = __ldg(reinterpret_cast<const int4 *>(r2) + u);
-                const int4 w3 = __ldg(reinterpret_cast<const int4 *>(r3) + u);
+                const int4 w0 = __ldg(r0 + u);
+                const int4 w1 = __ldg(r1 + u);
+                const int4 w2 = __ldg(r2 + u);
+                const int4 w3 = __ldg(r3 + u);
                 acc[4 * u + 0] += (w0.x + w1.x) + (w2.x + w3.x);
                 acc[4 * u + 1] += (w0.y + w1.y) + (w2.y + w3.y);
                 acc[4 * u + 2] += (w0.z + w1.z) + (w2.z + w3.z);
                 acc[4 * u + 3] += (w0.w + w1.w) + (w2.w + w3.w);
             }
         }
-
         // ---- membrane update, threshold, reset, refractory (spec R6), branch-free
         const unsigned *bits_t = s_bits + t * CW;
         unsigned fired = 0;                            // bit k: neuron i0+k fired
+        if (LEAN) {
 #pragma unroll
-        for (int k = 0; k < NPT; ++k) {
-            const int i = i0 + k;
-            double i_in;
-            if (LEAN) {
-                const bool on = (bits_t[in_word[k]] & in_mask[k]) != 0u;
-                i_in = on ? a.gain0 : 0.0;
-            } else {
-                i_in = 0.0;
+            for (int w = 0; w < (NPT + 7) / 8; ++w) {
+                // nz: bit 4j+3 set iff counter j of this word is non-zero (the neuron sits out this step); then count down
+                const unsigned r = refn[w];
+                const unsigned nz = (((r & 0x77777777u) + 0x77777777u) | r) & 0x88888888u;
+                refn[w] = r - (nz >> 3);
+                const bool in_on = (bits_t[in_word[w]] & in_mask[w]) != 0u;
+                unsigned fire_n = 0u;                  // bit 4j: neuron 8w+j fires now
+#pragma unroll
+                for (int j = 0; j < 8 && 8 * w + j < NPT; ++j) {
+                    const int k = 8 * w + j;
+                    const double cur = lean_current(acc[k], a.hi_magic, (j == 0 && in_on) ? a.c_on : a.c_off);
+                    const double v = add64(sub64(V[k], mul64(a.leak0, V[k])), cur);
+                    const bool active = (nz & (8u << (4 * j))) == 0u;
+                    const bool fire = active && (v >= a.theta);
+                    V[k] = (active && !fire) ? v : 0.0;
+                    fire_n |= fire ? (1u << (4 * j)) : 0u;
+                    fired |= fire ? (1u << k) : 0u;
+                }
+                refn[w] += fire_n * (unsigned)a.refractory;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NPT; ++k) {
+                const int i = i0 + k;
+                double i_in = 0.0;
                 if (in_word[k] >= 0) {
                     if (bits_t[in_word[k]] & in_mask[k]) i_in = add64(0.0, __ldg(a.in_val + __ldg(a.in_rowptr + i)));
                 } else {
@@ -129,19 +183,21 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
                         i_in = add64(i_in, mul64(__ldg(a.in_val + p), on));
                     }
                 }
+                const double cur = add64(i_in, mul64((double)acc[k], a.scale));
+                const double v = add64(sub64(V[k], mul64(lk[k], V[k])), cur);
+                const bool active = ref[k] == 0;
+                const bool fire = active && (v >= a.theta) && (i < N);
+                V[k] = (active && !fire) ? v : 0.0;
+                ref[k] = fire ? a.refractory : (active ? 0 : ref[k] - 1);
+                fired |= fire ? (1u << k) : 0u;
             }
-            const double cur = add64(i_in, mul64((double)acc[k], a.scale));
-            const double v = add64(sub64(V[k], mul64(lk[k], V[k])), cur);
-            const bool active = ref[k] == 0;
-            const bool fire = active && (v >= a.theta) && (i < N);
-            V[k] = (active && !fire) ? v : 0.0;
-            ref[k] = fire ? a.refractory : (active ? 0 : ref[k] - 1);
-            fired |= fire ? (1u << k) : 0u;
         }
         if (a.raster) {
 #pragma unroll
-            for (int k = 0; k < NPT; ++k)
-                if (i0 + k < N) a.raster[((size_t)utt * T + t) * N + i0 + k] = (fired >> k) & 1u;
+            for (int k = 0; k < NPT; ++k) {
+                const int e = LEAN ? __ldg(a.ext_id + i0 + k) : i0 + k;     // external (caller's) neuron index
+                if (e < N) a.raster[((size_t)utt * T + t) * N + e] = (fired >> k) & 1u;
+            }
         }
         // ---- spikes are rare: statistics (spec R9) and list compaction only for warps that have one
         if (__any_sync(0xffffffffu, fired != 0u)) {
@@ -178,7 +234,7 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
         int active = 0, total = 0;
 #pragma unroll
         for (int k = 0; k < NPT; ++k) {
-            if (i0 + k < N) { const int c = s_stat[k * nthr + tid]; active += c > 0 ? 1 : 0; total += c; }
+            { const int c = s_stat[k * nthr + tid]; active += c > 0 ? 1 : 0; total += c; }      // padding neurons never fire
         }
         active = __reduce_add_sync(0xffffffffu, active);
         total = __reduce_add_sync(0xffffffffu, total);
@@ -199,7 +255,7 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
         const double nan = __longlong_as_double(0x7ff8000000000000LL);
         int o_k[NPT];
 #pragma unroll
-        for (int k = 0; k < NPT; ++k) o_k[k] = (i0 + k < N) ? __ldg(a.out_slot + i0 + k) : -1;
+        for (int k = 0; k < NPT; ++k) o_k[k] = __ldg(a.out_slot + i0 + k);      // [n_pad], -1 for padding and non-output neurons
         int slot = 0;
         for (int key = 0; key < 8; ++key) {
             if (!(a.feature_mask & (1u << key))) continue;
