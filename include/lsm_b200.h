@@ -189,6 +189,13 @@ int lsm_pipeline_run(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const f
                      int32_t B, uint32_t feature_mask, int32_t nan_to_num, uint8_t *d_spikes_or_null,
                      double *d_features);
 
+/* Asynchronous form of lsm_pipeline_run_host for PINNED host buffers (the zero-copy path; LSM_ERR_UNSUPPORTED otherwise):
+ * the call enqueues the fused kernel on launch lane 0 or 1 of the ctx and returns; the kernel reads the PCM and writes the
+ * feature rows across PCIe.  Calls on alternating lanes overlap (a front end has two scratch slots), which hides the drain
+ * tail of one batch under the start of the next.  lsm_sync_all waits for everything the ctx has enqueued.                 */
+int lsm_pipeline_run_host_async(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *h_pcm, int32_t B,
+                                uint32_t feature_mask, int32_t nan_to_num, double *h_features, int32_t lane);
+int lsm_sync_all(lsm_ctx *ctx);
 /* 1 if lsm_pipeline_run / lsm_pipeline_run_host execute this pair as one fused kernel, else 0. */
 int lsm_pipeline_is_fused(const lsm_frontend *fe, const lsm_reservoir *res);
 

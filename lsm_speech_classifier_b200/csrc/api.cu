@@ -145,7 +145,7 @@ extern "C" int lsm_frontend_create(lsm_ctx *ctx, const lsm_frontend_params *p, c
         rc = upload(ctx, &fe->d_coefs, t, (size_t)p->channels * 10);
         fe->minb = lsm_gammatone_minb();
         if (rc == LSM_OK) rc = lsm_gammatone_grid(ctx, p, &fe->grid);
-        if (rc == LSM_OK) rc = upload<double>(ctx, &fe->d_scratch, nullptr, (size_t)fe->grid * fe->ncols * p->channels);
+        if (rc == LSM_OK) rc = upload<double>(ctx, &fe->d_scratch, nullptr, 2 * (size_t)fe->grid * fe->ncols * p->channels);   // two slots
         if (rc == LSM_OK) rc = upload<int>(ctx, &fe->d_counters, nullptr, 128 + 64 * 256);
         if (rc == LSM_OK && cudaMemset(fe->d_counters, 0, (128 + 64 * 256) * sizeof(int)) != cudaSuccess) rc = LSM_ERR_CUDA;
         fe->mode = getenv("LSM_EXACT_FILTER") ? LSM_FILTER_EXACT : LSM_FILTER_SPECULATIVE;
@@ -174,9 +174,11 @@ extern "C" int lsm_frontend_create(lsm_ctx *ctx, const lsm_frontend_params *p, c
 extern "C" void lsm_frontend_destroy(lsm_frontend *fe)
 {
     if (!fe) return;
-    if (fe->ev_valid) cudaEventSynchronize(fe->ev_last);
-    if (fe->ev_last) cudaEventDestroy(fe->ev_last);
-    cudaFree(fe->d_energy);
+    for (int k = 0; k < 2; ++k) {
+        if (fe->slot_valid[k]) cudaEventSynchronize(fe->ev_slot[k]);
+        if (fe->ev_slot[k]) cudaEventDestroy(fe->ev_slot[k]);
+    }
+    cudaFree(fe->d_energy); cudaFree(fe->d_rerun);
     cudaFree(fe->d_coefs); cudaFree(fe->d_zoom_i0); cudaFree(fe->d_zoom_f); cudaFree(fe->d_scratch); cudaFree(fe->d_counters);
     lsm_mel_destroy(fe);
     delete fe;
@@ -199,7 +201,8 @@ extern "C" int lsm_frontend_reruns(lsm_ctx *ctx, lsm_frontend *fe, int64_t *h_ou
     *h_out = 0;
     if (fe->p.kind != LSM_FILTERBANK_GAMMATONE) return LSM_OK;
     LSM_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (fe->ev_valid) LSM_CUDA(ctx, cudaEventSynchronize(fe->ev_last));
+    int rc = lsm_frontend_wait_idle(ctx, fe);
+    if (rc != LSM_OK) return rc;
     int v = 0;
     LSM_CUDA(ctx, cudaMemcpy(&v, fe->d_counters + 64, sizeof(int), cudaMemcpyDeviceToHost));
     if (reset) LSM_CUDA(ctx, cudaMemset(fe->d_counters + 64, 0, sizeof(int)));
@@ -220,18 +223,30 @@ extern "C" int lsm_frontend_mel_tables(lsm_ctx *ctx, lsm_frontend *fe, const dou
 // The per-CTA scratch planes (and the work-counter ring) of a front end are shared by all its launches.  Launches on one
 // stream are ordered by the stream; when the stream changes (torch's stream for the device-pointer calls, the ctx's
 // own stream for the *_host calls) the new launch first waits for the previous one.
-int lsm_frontend_order_before(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st)
+int lsm_frontend_order_before(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st, int slot)
 {
-    if (fe->ev_valid && fe->last_stream != st) LSM_CUDA(ctx, cudaStreamWaitEvent(st, fe->ev_last, 0));
+    for (int k = 0; k < 2; ++k)
+        if ((slot < 0 || slot == k) && fe->slot_valid[k] && fe->slot_stream[k] != st)
+            LSM_CUDA(ctx, cudaStreamWaitEvent(st, fe->ev_slot[k], 0));
     return LSM_OK;
 }
 
-int lsm_frontend_order_after(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st)
+int lsm_frontend_order_after(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st, int slot)
 {
-    if (!fe->ev_last) LSM_CUDA(ctx, cudaEventCreateWithFlags(&fe->ev_last, cudaEventDisableTiming));
-    LSM_CUDA(ctx, cudaEventRecord(fe->ev_last, st));
-    fe->last_stream = st;
-    fe->ev_valid = 1;
+    for (int k = 0; k < 2; ++k) {
+        if (slot >= 0 && slot != k) continue;
+        if (!fe->ev_slot[k]) LSM_CUDA(ctx, cudaEventCreateWithFlags(&fe->ev_slot[k], cudaEventDisableTiming));
+        LSM_CUDA(ctx, cudaEventRecord(fe->ev_slot[k], st));
+        fe->slot_stream[k] = st;
+        fe->slot_valid[k] = 1;
+    }
+    return LSM_OK;
+}
+
+int lsm_frontend_wait_idle(lsm_ctx *ctx, lsm_frontend *fe)
+{
+    for (int k = 0; k < 2; ++k)
+        if (fe->slot_valid[k]) LSM_CUDA(ctx, cudaEventSynchronize(fe->ev_slot[k]));
     return LSM_OK;
 }
 
@@ -649,6 +664,38 @@ extern "C" int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservo
     LSM_CUDA(ctx, cudaStreamSynchronize(s_out));
     LSM_CUDA(ctx, cudaStreamSynchronize(s_k));
     LSM_CUDA(ctx, cudaStreamSynchronize(s_in));
+    return LSM_OK;
+}
+
+// Asynchronous variant for pinned host buffers only (the zero-copy path): enqueue on one of the ctx's two launch lanes and
+// return.  Two calls on alternating lanes are in flight together (two scratch slots), so the drain tail of one batch overlaps
+// the start of the next.  lsm_sync_all waits for both lanes.
+extern "C" int lsm_pipeline_run_host_async(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *h_pcm,
+                                           int32_t B, uint32_t feature_mask, int32_t nan_to_num, double *h_features,
+                                           int32_t lane)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!fe || !res || B < 0 || (B > 0 && (!h_pcm || !h_features)) || lane < 0 || lane > 1)
+        LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_pipeline_run_host_async: bad argument");
+    if (fe->p.channels * fe->p.redundancy != res->p.num_inputs || fe->p.n_bins * fe->p.n_thresholds != res->p.num_steps)
+        LSM_FAIL(ctx, LSM_ERR_INVALID, "front end emits %dx%d spike trains, reservoir expects %dx%d",
+                 fe->p.channels * fe->p.redundancy, fe->p.n_bins * fe->p.n_thresholds, res->p.num_inputs, res->p.num_steps);
+    if (B == 0) return LSM_OK;
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *dv_pcm = nullptr, *dv_feat = nullptr;
+    if (!lsm_fused_npt(fe, res) || !device_visible(h_pcm, &dv_pcm) || !device_visible(h_features, &dv_feat))
+        LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "lsm_pipeline_run_host_async needs pinned (or device) buffers and a pair that runs fused");
+    return lsm_launch_fused(ctx, fe, res, (const float *)dv_pcm, B, nullptr, feature_mask, nan_to_num, (double *)dv_feat,
+                            lane == 0 ? ctx->own_stream : ctx->copy_stream[0]);
+}
+
+extern "C" int lsm_sync_all(lsm_ctx *ctx)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    LSM_CUDA(ctx, cudaStreamSynchronize(ctx->own_stream));
+    for (int i = 0; i < 2; ++i) LSM_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream[i]));
+    if (ctx->stream != ctx->own_stream) LSM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return LSM_OK;
 }
 

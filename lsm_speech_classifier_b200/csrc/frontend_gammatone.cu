@@ -53,6 +53,9 @@ struct GtArgs {
                             // of near-ties; 2 = as 1, but the speculative energies were computed by gammatone_energy_kernel
     double spec_delta;      // dB margin of the near-tie test
     int *reruns;            // number of utterances filtered twice (speculative mode)
+    const int *utt_list;    // optional indirection: work item i is utterance utt_list[i], i < *utt_count (exact re-execution pass)
+    const int *utt_count;
+    int *rerun_list;        // encode_reservoir_kernel: utterances whose speculative plane was too close to call; [0] = count
     int *sm_rank;           // [256] per-SM arrival counter of this launch (staggered start)
     int stagger_cycles;     // start delay per CTA rank on its SM, 0 = none
     double thr[8], lower[8];
@@ -294,12 +297,14 @@ __device__ __forceinline__ void energy_unit(const EnergyArgs &a, const int g, co
     const bool valid = utt < a.B;
     const float4 *src = reinterpret_cast<const float4 *>(a.pcm + (size_t)(valid ? utt : a.B - 1) * a.L);
     const int n4_max = a.L / 4 - 1;
-    const int hop = a.hop, nwin = a.nwin, ncols = a.ncols;
-    const int r_old = nwin - 2 * hop;
-    const int n_used = (ncols - 1) * hop + nwin;
-    const int n_blocks = (n_used + hop - 1) / hop;
+    const int hop = a.hop, ncols = a.ncols;
+    const int r_old = a.nwin - 2 * hop;
+    const int n_used = (ncols - 1) * hop + a.nwin;
     double *dst = a.energy + (size_t)utt * ncols * a.C + ch0;
 
+    // Stage k works on the sample that stage k-1 finished one iteration earlier (software skew, as in the lane = channel
+    // kernels): per channel four independent 3-FMA chains instead of one of depth eleven.  Iteration i feeds x[i] to stage 1
+    // and completes output i-3; outputs -3..-1 are exact zeros (zero state), so the energy sums need no prologue.
     double xp = 0.0;
     double p1[J], q1[J], p2[J], q2[J], p3[J], q3[J], p4[J], q4[J], acc[J], full1[J], full2[J];
 #pragma unroll
@@ -311,55 +316,52 @@ __device__ __forceinline__ void energy_unit(const EnergyArgs &a, const int g, co
         _Pragma("unroll") for (int j = 0; j < J; ++j) {                                                 \
             const double *c = a.coef[ch0 + j];                                                          \
             const double y1 = fma(c[4], p1[j], fma(c[5], q1[j], fma(c[0], xp, x_)));                    \
-            const double y2 = fma(c[4], p2[j], fma(c[5], q2[j], fma(c[1], p1[j], y1)));                 \
-            const double y3 = fma(c[4], p3[j], fma(c[5], q3[j], fma(c[2], p2[j], y2)));                 \
-            const double y4 = fma(c[4], p4[j], fma(c[5], q4[j], fma(c[3], p3[j], y3)));                 \
+            const double y2 = fma(c[4], p2[j], fma(c[5], q2[j], fma(c[1], q1[j], p1[j])));              \
+            const double y3 = fma(c[4], p3[j], fma(c[5], q3[j], fma(c[2], q2[j], p2[j])));              \
+            const double y4 = fma(c[4], p4[j], fma(c[5], q4[j], fma(c[3], q3[j], p3[j])));              \
             q1[j] = p1[j]; p1[j] = y1; q2[j] = p2[j]; p2[j] = y2;                                       \
             q3[j] = p3[j]; p3[j] = y3; q4[j] = p4[j]; p4[j] = y4;                                       \
             acc[j] = fma(y4, y4, acc[j]);                                                               \
         }                                                                                               \
         xp = x_;                                                                                        \
     }
-#define LSM_LANE_8(f0, f1)                                                                              \
-    LSM_LANE_SAMPLE(f0.x) LSM_LANE_SAMPLE(f0.y) LSM_LANE_SAMPLE(f0.z) LSM_LANE_SAMPLE(f0.w)            \
-    LSM_LANE_SAMPLE(f1.x) LSM_LANE_SAMPLE(f1.y) LSM_LANE_SAMPLE(f1.z) LSM_LANE_SAMPLE(f1.w)
 
-    // two 16-byte loads (8 samples) in flight ahead of the arithmetic
-    int i4 = 0;                                        // index of the next float4 to fetch
-    float4 f0 = __ldg(src + 0), f1 = __ldg(src + 1);
-    i4 = 2;
-    for (int m = 0; m < n_blocks; ++m) {
-        const int n_here = min(hop, n_used - m * hop);
-        const int n_a = min(n_here, r_old);
+    // Groups of 8 iterations aligned with the 16-byte loads; group gi completes outputs 8gi-3 .. 8gi+4, so a window-phase
+    // boundary at sample 8gi (the phases are multiples of 8 samples long) falls after the group's third iteration.
+    int next_b = r_old;                                // next boundary: first the head of hop-block 0 ...
+    int m = 0;                                         // hop-block the boundary belongs to
+    bool head = true;                                  // boundary kind: end of the block's head (window m-2 complete) / end of the block
+    const int n_groups = n_used / 8;                   // the last boundary (sample n_used) is handled after the loop's last group
+    float4 f0 = __ldg(src + 0), f1 = __ldg(src + 1);   // two loads (8 samples) in flight ahead of the arithmetic
+    for (int gi = 0; gi <= n_groups; ++gi) {
+        const float4 g0 = __ldg(src + min(2 * gi + 2, n4_max)), g1 = __ldg(src + min(2 * gi + 3, n4_max));
+        LSM_LANE_SAMPLE(f0.x) LSM_LANE_SAMPLE(f0.y) LSM_LANE_SAMPLE(f0.z)
+        if (8 * gi == next_b) {
+            if (head) {
+                if (m >= 2 && valid) {
+                    // window m-2 complete: full(m-2) + full(m-1) + head(m)
+                    double *o = dst + (size_t)(m - 2) * a.C;
+                    if (J == 4) {
+                        *reinterpret_cast<double2 *>(o) = make_double2((full2[0] + full1[0]) + acc[0], (full2[1] + full1[1]) + acc[1]);
+                        *reinterpret_cast<double2 *>(o + 2) = make_double2((full2[2] + full1[2]) + acc[2], (full2[3] + full1[3]) + acc[3]);
+                    } else {
 #pragma unroll
-        for (int j = 0; j < J; ++j) acc[j] = 0.0;
-        for (int p = 0; p < n_a; p += 8) {
-            const float4 g0 = __ldg(src + min(i4, n4_max)), g1 = __ldg(src + min(i4 + 1, n4_max));
-            i4 += 2;
-            LSM_LANE_8(f0, f1)
-            f0 = g0; f1 = g1;
-        }
-        if (n_a == r_old && m >= 2 && valid) {
-            // window m-2 complete: full(m-2) + full(m-1) + head(m)
-            double *o = dst + (size_t)(m - 2) * a.C;
-            if (J == 4) {
-                *reinterpret_cast<double2 *>(o) = make_double2((full2[0] + full1[0]) + acc[0], (full2[1] + full1[1]) + acc[1]);
-                *reinterpret_cast<double2 *>(o + 2) = make_double2((full2[2] + full1[2]) + acc[2], (full2[3] + full1[3]) + acc[3]);
+                        for (int j = 0; j < J; ++j) o[j] = (full2[j] + full1[j]) + acc[j];
+                    }
+                }
+                next_b += hop - r_old;
+                head = false;
             } else {
 #pragma unroll
-                for (int j = 0; j < J; ++j) o[j] = (full2[j] + full1[j]) + acc[j];
+                for (int j = 0; j < J; ++j) { full2[j] = full1[j]; full1[j] = acc[j]; acc[j] = 0.0; }
+                next_b += r_old;
+                head = true;
+                ++m;
             }
         }
-        for (int p = n_a; p < n_here; p += 8) {
-            const float4 g0 = __ldg(src + min(i4, n4_max)), g1 = __ldg(src + min(i4 + 1, n4_max));
-            i4 += 2;
-            LSM_LANE_8(f0, f1)
-            f0 = g0; f1 = g1;
-        }
-#pragma unroll
-        for (int j = 0; j < J; ++j) { full2[j] = full1[j]; full1[j] = acc[j]; }
+        LSM_LANE_SAMPLE(f0.w) LSM_LANE_SAMPLE(f1.x) LSM_LANE_SAMPLE(f1.y) LSM_LANE_SAMPLE(f1.z) LSM_LANE_SAMPLE(f1.w)
+        f0 = g0; f1 = g1;
     }
-#undef LSM_LANE_8
 #undef LSM_LANE_SAMPLE
 }
 
@@ -583,10 +585,14 @@ __global__ void __launch_bounds__(MAXT, MINB) gammatone_encode_kernel(const GtAr
 
     for (;;) {
         // dynamic work distribution: utterances are handed out one at a time, so every SM stays busy to the end
-        if (threadIdx.x == 0) s_utt = atomicAdd(next_utt, 1);
+        if (threadIdx.x == 0) {
+            const int i = atomicAdd(next_utt, 1);
+            const int n = a.utt_count ? min(*a.utt_count, a.B) : a.B;
+            s_utt = i < n ? (a.utt_list ? a.utt_list[i] : i) : -1;
+        }
         __syncthreads();
         const int utt = s_utt;
-        if (utt >= a.B) break;
+        if (utt < 0) break;
         const float *pcm = a.pcm + (size_t)utt * a.L;
         // the utterance's [ncols][C] plane: energies -> dB -> normalised values, in place.  Mode 2 works directly on the
         // utterance's slice of the energy buffer, the other modes on this CTA's scratch plane (L2-resident).
@@ -622,6 +628,38 @@ static int k1_minb()
     const int v = e ? atoi(e) : 5;
     return v < 4 ? 4 : (v > 6 ? 6 : v);
 }
+
+namespace {
+// Second kernel of the lanes arrangement: encoder epilogue on the energy planes of gammatone_energy_kernel, then the
+// utterance's reservoir and feature readout.  No filter code, so it runs at a higher occupancy than the fused kernel above
+// (the reservoir phase is latency / issue bound).  Utterances whose speculative plane is too close to call are finished
+// like the others and also appended to a list; the host follows up with gammatone_encode_kernel in exact mode on that list
+// (typically 0-1 utterances per 2400), which overwrites their spike trains and feature rows.
+template <int MINB, int FNPT, bool LEAN>
+__global__ void __launch_bounds__(128, MINB) encode_reservoir_kernel(const GtArgs a, int *next_utt)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double s_red[2][8];
+    __shared__ double s_mm[2];
+    __shared__ int s_utt;
+    __shared__ int s_cnt3[3];
+    for (;;) {
+        if (threadIdx.x == 0) s_utt = atomicAdd(next_utt, 1);
+        __syncthreads();
+        const int utt = s_utt;
+        if (utt >= a.B) break;
+        double *plane = const_cast<double *>(a.energy_in) + (size_t)utt * a.ncols * a.C;
+        const bool near = spec_epilogue<FNPT>(a, utt, plane, s_red, s_mm, smem_raw);
+        if (__syncthreads_or(near ? 1 : 0) && threadIdx.x == 0) {
+            a.rerun_list[1 + atomicAdd(a.rerun_list, 1)] = utt;
+            atomicAdd(a.reruns, 1);
+        }
+        __syncthreads();   // bits complete and visible
+        reservoir_simulate<FNPT, LEAN>(a.res, utt, smem_raw, s_cnt3);
+        __syncthreads();
+    }
+}
+}  // namespace
 
 template <int MAXT, int MINB, int FNPT, bool LEAN>
 static int k1_grid(lsm_ctx *ctx, int threads, size_t smem, int *per_sm)
@@ -665,6 +703,7 @@ static void fill_args(const lsm_frontend *fe, const float *d_pcm, int B, uint8_t
     // the normalised-spectrogram dump is defined as the exact path's: asking for it selects the exact filter
     a.mode = d_spec_norm ? 0 : fe->mode;
     a.energy_in = nullptr;
+    a.utt_list = nullptr; a.utt_count = nullptr; a.rerun_list = nullptr;
     a.spec_delta = fe->spec_delta;
     a.reruns = fe->d_counters + 64;
 }
@@ -674,7 +713,7 @@ static void fill_args(const lsm_frontend *fe, const float *d_pcm, int B, uint8_t
 static void pin_scratch_in_l2(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st)
 {
     if (getenv("LSM_NO_L2_PIN")) return;
-    const size_t bytes = sizeof(double) * (size_t)fe->grid * fe->ncols * fe->p.channels;
+    const size_t bytes = 2 * sizeof(double) * (size_t)fe->grid * fe->ncols * fe->p.channels;   // both slots
     if (!fe->l2_window_ready) {
         int max_persist = 0, max_window = 0;
         cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
@@ -701,17 +740,18 @@ static void pin_scratch_in_l2(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st)
 }
 
 // d_counters layout (ints): [0,64) work counters, [64] re-execution count, [128 + 256*slot, +256) per-SM arrival counters
-static int next_counter(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st, int **counter, GtArgs *a, int grid)
+static int next_counter(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st, int **counter, GtArgs *a, int grid, int slot)
 {
-    int rc = lsm_frontend_order_before(ctx, fe, st);
+    int rc = lsm_frontend_order_before(ctx, fe, st, slot);
     if (rc != LSM_OK) return rc;
+    a->scratch = fe->d_scratch + (slot > 0 ? (size_t)fe->grid * fe->ncols * fe->p.channels : 0);
     pin_scratch_in_l2(ctx, fe, st);
     // work counter: one int per launch out of a small ring, so back-to-back launches on different streams do not share it
-    const unsigned slot = fe->counter_next++ % 64;
-    *counter = fe->d_counters + slot;
+    const unsigned cslot = fe->counter_next++ % 64;
+    *counter = fe->d_counters + cslot;
     LSM_CUDA(ctx, cudaMemsetAsync(*counter, 0, sizeof(int), st));
     // staggered start (see the kernel): only when every CTA gets at least two utterances, so the one-off delay pays
-    a->sm_rank = fe->d_counters + 128 + 256 * slot;
+    a->sm_rank = fe->d_counters + 128 + 256 * cslot;
     a->stagger_cycles = 0;
     if (a->B >= 2 * grid) {
         const char *e = getenv("LSM_STAGGER");
@@ -744,10 +784,12 @@ static bool lanes_eligible(const lsm_frontend *fe, const float *d_pcm)
 static int ensure_energy(lsm_ctx *ctx, lsm_frontend *fe, int B)
 {
     if (B <= fe->energy_cap) return LSM_OK;
-    if (fe->ev_valid) LSM_CUDA(ctx, cudaEventSynchronize(fe->ev_last));     // nobody is still reading the old buffer
+    { const int rc = lsm_frontend_wait_idle(ctx, fe); if (rc != LSM_OK) return rc; }     // nobody is still reading the old buffer
     if (fe->d_energy) { LSM_CUDA(ctx, cudaFree(fe->d_energy)); fe->d_energy = nullptr; fe->energy_cap = 0; }
     const size_t bytes = sizeof(double) * (size_t)B * fe->ncols * fe->p.channels;
     if (cudaMalloc((void **)&fe->d_energy, bytes) != cudaSuccess) LSM_FAIL(ctx, LSM_ERR_NOMEM, "cudaMalloc(%zu) for the energy planes failed", bytes);
+    if (fe->d_rerun) { cudaFree(fe->d_rerun); fe->d_rerun = nullptr; }
+    if (cudaMalloc((void **)&fe->d_rerun, sizeof(int) * ((size_t)B + 1)) != cudaSuccess) LSM_FAIL(ctx, LSM_ERR_NOMEM, "cudaMalloc for the re-execution list failed");
     fe->energy_cap = B;
     return LSM_OK;
 }
@@ -764,13 +806,19 @@ static int launch_energy(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int
     ea.B = B; ea.L = p.n_samples; ea.C = p.channels; ea.nwin = p.nwin; ea.hop = p.hop; ea.ncols = fe->ncols;
     memcpy(ea.coef, fe->h_lane_coef, sizeof(double) * 6 * p.channels);
     const int groups = (B + 31) / 32;
-    // the last quarter of the groups (at most two resident waves' worth of channels) goes out as single-channel units
+    // Big units fill whole resident waves (they start together and, sharing the pipes evenly, finish together); what is left
+    // over after the last full wave goes out as single-channel units, which pack the tail four times finer.
+    if (!fe->lanes_slots) {
+        int per_sm = 0;
+        LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gammatone_energy_kernel, 32, 0));
+        fe->lanes_slots = (per_sm > 0 ? per_sm : 1) * ctx->sm_count;
+    }
+    const int upg = p.channels / kLanesJ;                       // big units per group
+    const long long big_units = (long long)groups * upg;
+    int big_groups = (int)((big_units / fe->lanes_slots) * fe->lanes_slots / upg);
     const char *e = getenv("LSM_LANES_SMALL_PCT");
-    const int pct = e ? atoi(e) : 25;
-    int small_groups = (groups * pct + 99) / 100;
-    const int cap = (2 * 16 * ctx->sm_count + p.channels - 1) / p.channels;
-    if (small_groups > cap && !e) small_groups = cap;
-    if (small_groups > groups) small_groups = groups;
+    if (e) big_groups = groups - (groups * atoi(e) + 99) / 100;
+    int small_groups = groups - big_groups;
     ea.big_groups = groups - small_groups;
     const int grid = ea.big_groups * (p.channels / kLanesJ) + small_groups * p.channels;
     gammatone_energy_kernel<<<grid, 32, 0, st>>>(ea);
@@ -807,14 +855,15 @@ int lsm_launch_gammatone(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int
     const int grid = B < fe->grid ? B : fe->grid;
     if (grid <= 0) return LSM_OK;
     int *counter, rc;
-    if ((rc = next_counter(ctx, fe, st, &counter, &a, grid)) != LSM_OK) return rc;
+    const int slot = lanes ? -1 : (int)(fe->slot_next++ & 1u);
+    if ((rc = next_counter(ctx, fe, st, &counter, &a, grid, slot)) != LSM_OK) return rc;
     if (threads > 128) gammatone_encode_kernel<256, 2, 0, true><<<grid, threads, smem, st>>>(a, counter);
     else if (fe->minb == 4) gammatone_encode_kernel<128, 4, 0, true><<<grid, threads, smem, st>>>(a, counter);
     else if (fe->minb == 5) gammatone_encode_kernel<128, 5, 0, true><<<grid, threads, smem, st>>>(a, counter);
     else gammatone_encode_kernel<128, 6, 0, true><<<grid, threads, smem, st>>>(a, counter);
     ctx->launches += 1;
     LSM_CUDA(ctx, cudaGetLastError());
-    return lsm_frontend_order_after(ctx, fe, st);
+    return lsm_frontend_order_after(ctx, fe, st, slot);
 }
 
 // Can this (front end, reservoir) pair run as one fused kernel?  Gammatone, no redundancy, one thread
@@ -834,7 +883,7 @@ int lsm_fused_npt(const lsm_frontend *fe, const lsm_reservoir *res)
 // launch == false: only report the resident grid (one wave) of this variant through *wave
 template <int MAXT, int MINB, int FNPT>
 static int launch_fused_t(lsm_ctx *ctx, lsm_frontend *fe, const lsm_reservoir *res, GtArgs &a, int threads, size_t smem,
-                          cudaStream_t st, bool launch = true, int *wave = nullptr)
+                          cudaStream_t st, bool launch = true, int *wave = nullptr, int max_grid = 0)
 {
     int per_sm = 0, rc;
     if (res->lean) rc = k1_grid<MAXT, MINB, FNPT, true>(ctx, threads, smem, &per_sm);
@@ -846,13 +895,16 @@ static int launch_fused_t(lsm_ctx *ctx, lsm_frontend *fe, const lsm_reservoir *r
     if (wave) *wave = grid;
     if (!launch) return LSM_OK;
     if (grid > a.B) grid = a.B;
+    if (max_grid > 0 && grid > max_grid) grid = max_grid;
     int *counter;
-    if ((rc = next_counter(ctx, fe, st, &counter, &a, grid)) != LSM_OK) return rc;
+    // the lanes arrangement shares one energy buffer: exclusive; the single-kernel path alternates the two scratch slots
+    const int slot = (a.mode == 2 || a.utt_list) ? -1 : (int)(fe->slot_next++ & 1u);
+    if ((rc = next_counter(ctx, fe, st, &counter, &a, grid, slot)) != LSM_OK) return rc;
     if (res->lean) gammatone_encode_kernel<MAXT, MINB, FNPT, true><<<grid, threads, smem, st>>>(a, counter);
     else gammatone_encode_kernel<MAXT, MINB, FNPT, false><<<grid, threads, smem, st>>>(a, counter);
     ctx->launches += 1;
     LSM_CUDA(ctx, cudaGetLastError());
-    return lsm_frontend_order_after(ctx, fe, st);
+    return lsm_frontend_order_after(ctx, fe, st, slot);
 }
 
 static int fused_dispatch(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B,
@@ -908,6 +960,29 @@ static int fused_dispatch(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, co
     size_t smem = sizeof(double) * 2 * kChunkBlocks * p.hop;
     const size_t smem_res = lsm_res_smem_bytes(a.res.T, a.res.CW, threads * npt, a.res.N);
     if (smem_res > smem) smem = smem_res;
+    if (lanes && threads == 128 && npt == 8 && res->lean && !getenv("LSM_LANES_OLD_KERNEL")) {
+        // lanes arrangement, default shape: K1a (above) -> encode_reservoir_kernel -> exact pass over the flagged utterances
+        int rc, per_sm = 0, *counter;
+        if (smem_res > 48 * 1024)
+            LSM_CUDA(ctx, cudaFuncSetAttribute(encode_reservoir_kernel<6, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res));
+        LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_reservoir_kernel<6, 8, true>, 128, smem_res));
+        if (per_sm < 1) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "encode_reservoir_kernel does not fit on an SM");
+        if (const char *e = getenv("LSM_ER_PER_SM")) { const int v = atoi(e); if (v > 0 && v < per_sm) per_sm = v; }   // experiment knob
+        int grid = per_sm * ctx->sm_count;
+        if (grid > B) grid = B;
+        a.rerun_list = fe->d_rerun;
+        LSM_CUDA(ctx, cudaMemsetAsync(fe->d_rerun, 0, sizeof(int), st));
+        if ((rc = next_counter(ctx, fe, st, &counter, &a, grid, -1)) != LSM_OK) return rc;
+        a.stagger_cycles = 0;
+        encode_reservoir_kernel<6, 8, true><<<grid, 128, smem_res, st>>>(a, counter);
+        ctx->launches += 1;
+        LSM_CUDA(ctx, cudaGetLastError());
+        // exact pass: same kernel as the single-kernel path, exact mode, reading its work list from the device
+        GtArgs x = a;
+        x.mode = 0; x.energy_in = nullptr; x.rerun_list = nullptr;
+        x.utt_list = fe->d_rerun + 1; x.utt_count = fe->d_rerun;
+        return launch_fused_t<128, 5, 8>(ctx, fe, res, x, threads, smem, st, true, nullptr, 8);
+    }
     if (threads == 256) return launch_fused_t<256, 2, 4>(ctx, fe, res, a, threads, smem, st, launch, wave);
     if (npt == 8) {
         if (fe->minb >= 5) return launch_fused_t<128, 5, 8>(ctx, fe, res, a, threads, smem, st, launch, wave);

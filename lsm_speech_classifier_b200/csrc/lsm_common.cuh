@@ -38,12 +38,17 @@ struct lsm_frontend {
     double h_lane_coef[256][6] = {};  // per channel c1..c4, -a1, -a2 of the normalised cascade (kernel-parameter table of K1a)
     double *d_energy = nullptr;    // [energy_cap][ncols][C] raw window energies between K1a and the encoder kernel
     int energy_cap = 0;
+    int *d_rerun = nullptr;        // [1 + energy_cap] count + utterances the encoder kernel flagged for the exact pass
+    int lanes_slots = 0;           // resident warps of K1a on this device (one wave of units)
     unsigned counter_next = 0;
     int minb = 5;                  // K1 occupancy target the kernel was instantiated for
     // launches on different streams share the scratch planes: each launch waits for the previous one's event
-    cudaEvent_t ev_last = nullptr;
-    cudaStream_t last_stream = nullptr;
-    int ev_valid = 0;
+    // two scratch slots: launch n uses slot n & 1 and only has to wait for launch n-2, so two launches (on two streams) can be
+    // in flight and the drain tail of one overlaps the start of the next; slot -1 = exclusive (waits for / blocks both)
+    cudaEvent_t ev_slot[2] = {nullptr, nullptr};
+    cudaStream_t slot_stream[2] = {nullptr, nullptr};
+    int slot_valid[2] = {0, 0};
+    unsigned slot_next = 0;
     int l2_window_ready = 0;       // L2 persisting window for the scratch planes
     size_t l2_window_bytes = 0;
     float l2_hit_ratio = 1.0f;
@@ -99,8 +104,9 @@ int lsm_launch_gammatone(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int
                          double *d_spec_norm, cudaStream_t st);
 int lsm_gammatone_grid(lsm_ctx *ctx, const lsm_frontend_params *p, int *grid);
 int lsm_gammatone_minb(void);
-int lsm_frontend_order_before(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st);   // call before a launch that uses fe's scratch
-int lsm_frontend_order_after(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st);    // ... and right after it
+int lsm_frontend_order_before(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st, int slot = -1);   // call before a launch that uses fe's scratch
+int lsm_frontend_order_after(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st, int slot = -1);    // ... and right after it
+int lsm_frontend_wait_idle(lsm_ctx *ctx, lsm_frontend *fe);                                      // host waits for every launch of fe
 int lsm_fused_npt(const lsm_frontend *fe, const lsm_reservoir *res);
 int lsm_launch_fused(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B,
                      uint8_t *d_spikes_or_null, uint32_t feature_mask, int nan_to_num, double *d_features, cudaStream_t st);

@@ -188,6 +188,19 @@ class AudioToFeatures:
             C.c_void_p(ptr(out)), C.c_void_p(spikes_out.ctypes.data) if spikes_out is not None else None))
         return out
 
+    def run_host_async(self, pcm, feature_keys, out, lane: int = 0, nan_to_num: bool = True):
+        """Pinned host buffers only: enqueue and return (lsm_pipeline_run_host_async).  Alternate `lane` 0/1 between
+        consecutive batches and finish with `self.ctx.sync_all()`; `out` holds the feature rows after that."""
+        keys = list(feature_keys)
+        mask = _lib.feature_mask(keys)
+        if _lib.mask_keys(mask) != keys:
+            raise ValueError("feature keys must be in FEATURE_SETS order")
+        ptr = (lambda a: a.data_ptr() if _is_torch(a) else a.ctypes.data)
+        self.ctx.check(self.ctx.lib.lsm_pipeline_run_host_async(
+            self.ctx.h, self.frontend.h, self.snn.h, C.c_void_p(ptr(pcm)), pcm.shape[0], mask, int(nan_to_num),
+            C.c_void_p(ptr(out)), int(lane)))
+        return out
+
     def run(self, pcm, feature_keys, nan_to_num: bool = True, spikes=None, out=None, want_spikes: bool = True):
         """torch CUDA tensors, asynchronous on the current stream.  One fused kernel when the pair allows it;
         with want_spikes=False the spike trains then never leave the SM."""

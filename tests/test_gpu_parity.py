@@ -445,3 +445,70 @@ def test_speculative_filter_arrangements_agree(env, small_set, monkeypatch):
     assert np.array_equal(fe40.encode(pcm[:9]), oracle_spikes(pcm[:9], fe40))
     monkeypatch.delenv("LSM_LANES")
     assert np.array_equal(fe40.encode(pcm[:9]), oracle_spikes(pcm[:9], fe40))
+
+
+def test_lanes_arrangement_fused_pipeline(env, small_set, monkeypatch):
+    """LSM_LANES=1, default shape: energy kernel -> encoder + reservoir kernel -> exact pass over the flagged utterances.
+    Same features as the single fused kernel in exact mode, whatever fraction of the batch takes the exact pass."""
+    from lsm_speech_classifier_b200 import synth
+    from lsm_speech_classifier_b200.frontend import Frontend
+    from lsm_speech_classifier_b200.snn import SNN, AudioToFeatures, SimulationParams
+    from lsm_speech_classifier_b200.extract_lsm_features import FEATURE_SETS, calculate_theoretical_w_critico
+    pcm, _ = small_set
+    more, _ = synth.synth_dataset(12, 6, start_utt=40)
+    pcm = np.concatenate([pcm, more])
+    fe = Frontend(128, "gammatone")
+    fe.set_mode("exact")
+    spikes = fe.encode(pcm)
+    params = SimulationParams(input_spike_times=spikes[0])
+    params.mean_weight = calculate_theoretical_w_critico(params, spikes, verbose=False) * 0.6
+    lsm = SNN(simulation_params=params)
+    pipe = AudioToFeatures(fe, lsm)
+    keys = FEATURE_SETS["original"]
+    want = pipe.run_host(pcm, keys)
+    monkeypatch.setenv("LSM_LANES", "1")
+    for delta, lo, hi in ((0.0, 0, 2), (1e-300, 0, 0), (1e-3, 1, len(pcm) - 1), (1e9, len(pcm) - 1, len(pcm))):
+        fe.set_mode("speculative", delta)
+        fe.reruns(reset=True)
+        spk = np.zeros_like(spikes)
+        got = pipe.run_host(pcm, keys, spikes_out=spk)
+        assert np.array_equal(got, want), delta
+        assert np.array_equal(spk, spikes), delta
+        assert lo <= fe.reruns() <= hi, (delta, fe.reruns())
+    fe.set_mode("speculative", 1e-7)
+    import torch
+    out, _ = pipe.run(torch.from_numpy(pcm).cuda(), keys, want_spikes=False)
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_async_host_calls_on_two_lanes(env, small_set):
+    """lsm_pipeline_run_host_async: consecutive pinned batches alternate the two launch lanes (two scratch slots, two launches
+    in flight) and give the synchronous call's feature rows; three launches on the same lane pair reuse the slots correctly."""
+    import torch
+    from lsm_speech_classifier_b200 import synth, _lib
+    from lsm_speech_classifier_b200.frontend import Frontend
+    from lsm_speech_classifier_b200.snn import SNN, AudioToFeatures, SimulationParams
+    from lsm_speech_classifier_b200.extract_lsm_features import FEATURE_SETS, calculate_theoretical_w_critico
+    pcm, _ = small_set
+    more, _ = synth.synth_dataset(12, 70, start_utt=900)           # 840 utterances: more than one resident wave
+    batches = [np.concatenate([pcm, more[:400]]), more[400:], more[:333][::-1].copy(), pcm[:5]]
+    fe = Frontend(128, "gammatone")
+    spikes = fe.encode(pcm)
+    params = SimulationParams(input_spike_times=spikes[0])
+    params.mean_weight = calculate_theoretical_w_critico(params, spikes, verbose=False) * 0.6
+    lsm = SNN(simulation_params=params)
+    pipe = AudioToFeatures(fe, lsm)
+    keys = FEATURE_SETS["original"]
+    want = [pipe.run_host(b, keys) for b in batches]
+    pinned_in = [torch.from_numpy(b).pin_memory() for b in batches]
+    pinned_out = [torch.empty((len(b), want[0].shape[1]), dtype=torch.float64).pin_memory() for b in batches]
+    for rep in range(2):
+        for o in pinned_out:
+            o.zero_()
+        for i, (x, o) in enumerate(zip(pinned_in, pinned_out)):
+            pipe.run_host_async(x, keys, out=o, lane=i & 1)
+        fe.ctx.sync_all()
+        for i, (o, w) in enumerate(zip(pinned_out, want)):
+            assert np.array_equal(o.numpy(), w), (rep, i)
+    with pytest.raises(_lib.LsmError):
+        pipe.run_host_async(batches[3], keys, out=np.empty((5, want[0].shape[1])), lane=0)      # pageable buffers
