@@ -162,8 +162,10 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
                     const double cur = lean_current(acc[k], a.hi_magic, (j == 0 && in_on) ? a.c_on : a.c_off);
                     const double v = add64(sub64(V[k], mul64(a.leak0, V[k])), cur);
                     const bool active = (nz & (8u << (4 * j))) == 0u;
-                    const bool fire = active && (v >= a.theta);
-                    V[k] = (active && !fire) ? v : 0.0;
+                    const bool ge = v >= a.theta;              // one comparison; fire and keep are predicate logic on it
+                    const bool fire = active && ge;
+                    const bool keep = active && !ge;
+                    V[k] = keep ? v : 0.0;
                     fire_n |= fire ? (1u << (4 * j)) : 0u;
                     fired |= fire ? (1u << k) : 0u;
                 }
