@@ -368,7 +368,7 @@ __device__ __forceinline__ void energy_unit(const EnergyArgs &a, const int g, co
 // Units are dispatched in blockIdx order: first the big ones (kLanesJ channels: one PCM stream and one conversion feed
 // 52 DFMAs), then single-channel units.  A unit is one warp's serial work (0.8 ms for four channels even on an idle SM),
 // so a grid of big units alone ends in a long ragged tail; the small units keep every SM's pipes full to the end.
-__global__ void __launch_bounds__(32) gammatone_energy_kernel(const __grid_constant__ EnergyArgs a)
+__global__ void __launch_bounds__(32, 16) gammatone_energy_kernel(const __grid_constant__ EnergyArgs a)
 {
     const int n_big = a.big_groups * (a.C / kLanesJ);
     if ((int)blockIdx.x < n_big) {
@@ -630,6 +630,40 @@ static int k1_minb()
 }
 
 namespace {
+// Speculative-only form of the fused kernel (default shape): fast filter, speculative epilogue, reservoir, readout - and nothing
+// of the exact path, which keeps the kernel's code and register footprint down.  Flagged utterances are completed like the
+// others and appended to the device work list; the host follows with gammatone_encode_kernel in exact mode on that list.
+template <int MINB, int FNPT, bool LEAN>
+__global__ void __launch_bounds__(128, MINB) spec_fused_kernel(const GtArgs a, int *next_utt)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_x = reinterpret_cast<double *>(smem_raw);
+    __shared__ double s_red[2][8];
+    __shared__ double s_mm[2];
+    __shared__ int s_utt;
+    __shared__ int s_cnt3[3];
+    double *plane = a.scratch + (size_t)blockIdx.x * a.ncols * a.C;
+    for (;;) {
+        if (threadIdx.x == 0) s_utt = atomicAdd(next_utt, 1);
+        __syncthreads();
+        const int utt = s_utt;
+        if (utt >= a.B) break;
+        gt_filter_fast(a, a.pcm + (size_t)utt * a.L, s_x, plane);
+        const bool near = spec_epilogue<FNPT>(a, utt, plane, s_red, s_mm, smem_raw);
+        if (__syncthreads_or(near ? 1 : 0) && threadIdx.x == 0) {
+            a.rerun_list[1 + atomicAdd(a.rerun_list, 1)] = utt;
+            atomicAdd(a.reruns, 1);
+        }
+        if (FNPT > 0) {
+            __syncthreads();
+            reservoir_simulate<(FNPT > 0 ? FNPT : 4), LEAN>(a.res, utt, smem_raw, s_cnt3);
+        }
+        __syncthreads();
+    }
+}
+}  // namespace
+
+namespace {
 // Second kernel of the lanes arrangement: encoder epilogue on the energy planes of gammatone_energy_kernel, then the
 // utterance's reservoir and feature readout.  No filter code, so it runs at a higher occupancy than the fused kernel above
 // (the reservoir phase is latency / issue bound).  Utterances whose speculative plane is too close to call are finished
@@ -781,6 +815,18 @@ static bool lanes_eligible(const lsm_frontend *fe, const float *d_pcm)
            p.n_samples % 4 == 0 && p.channels % kLanesJ == 0 && p.channels <= 256 && (((uintptr_t)d_pcm) & 15) == 0;
 }
 
+// device work list of the exact pass: [0] = count, then utterance indices
+static int ensure_rerun(lsm_ctx *ctx, lsm_frontend *fe, int B)
+{
+    if (B <= fe->rerun_cap) return LSM_OK;
+    { const int rc = lsm_frontend_wait_idle(ctx, fe); if (rc != LSM_OK) return rc; }
+    if (fe->d_rerun) { cudaFree(fe->d_rerun); fe->d_rerun = nullptr; fe->rerun_cap = 0; }
+    // two lists: one per scratch slot (two launches in flight)
+    if (cudaMalloc((void **)&fe->d_rerun, 2 * sizeof(int) * ((size_t)B + 1)) != cudaSuccess) LSM_FAIL(ctx, LSM_ERR_NOMEM, "cudaMalloc for the re-execution list failed");
+    fe->rerun_cap = B;
+    return LSM_OK;
+}
+
 static int ensure_energy(lsm_ctx *ctx, lsm_frontend *fe, int B)
 {
     if (B <= fe->energy_cap) return LSM_OK;
@@ -788,10 +834,8 @@ static int ensure_energy(lsm_ctx *ctx, lsm_frontend *fe, int B)
     if (fe->d_energy) { LSM_CUDA(ctx, cudaFree(fe->d_energy)); fe->d_energy = nullptr; fe->energy_cap = 0; }
     const size_t bytes = sizeof(double) * (size_t)B * fe->ncols * fe->p.channels;
     if (cudaMalloc((void **)&fe->d_energy, bytes) != cudaSuccess) LSM_FAIL(ctx, LSM_ERR_NOMEM, "cudaMalloc(%zu) for the energy planes failed", bytes);
-    if (fe->d_rerun) { cudaFree(fe->d_rerun); fe->d_rerun = nullptr; }
-    if (cudaMalloc((void **)&fe->d_rerun, sizeof(int) * ((size_t)B + 1)) != cudaSuccess) LSM_FAIL(ctx, LSM_ERR_NOMEM, "cudaMalloc for the re-execution list failed");
     fe->energy_cap = B;
-    return LSM_OK;
+    return ensure_rerun(ctx, fe, B);
 }
 
 // K1a: raw window energies of the speculative cascade for utterances [0, B) into fe->d_energy
@@ -806,16 +850,12 @@ static int launch_energy(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int
     ea.B = B; ea.L = p.n_samples; ea.C = p.channels; ea.nwin = p.nwin; ea.hop = p.hop; ea.ncols = fe->ncols;
     memcpy(ea.coef, fe->h_lane_coef, sizeof(double) * 6 * p.channels);
     const int groups = (B + 31) / 32;
-    // Big units fill whole resident waves (they start together and, sharing the pipes evenly, finish together); what is left
-    // over after the last full wave goes out as single-channel units, which pack the tail four times finer.
-    if (!fe->lanes_slots) {
-        int per_sm = 0;
-        LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gammatone_energy_kernel, 32, 0));
-        fe->lanes_slots = (per_sm > 0 ? per_sm : 1) * ctx->sm_count;
-    }
+    // Units share an SM's fp64 pipes evenly, so an SM's finishing time is proportional to the work placed on it: hand every SM
+    // the same number of big units (a multiple of the SM count; blocks are dealt round-robin) and cut what is left over into
+    // single-channel units, which balance four times finer (all-big grid 4.8 ms, balanced 4.1 ms per 2400 utterances).
     const int upg = p.channels / kLanesJ;                       // big units per group
     const long long big_units = (long long)groups * upg;
-    int big_groups = (int)((big_units / fe->lanes_slots) * fe->lanes_slots / upg);
+    int big_groups = (int)((big_units / ctx->sm_count) * ctx->sm_count / upg);
     const char *e = getenv("LSM_LANES_SMALL_PCT");
     if (e) big_groups = groups - (groups * atoi(e) + 99) / 100;
     int small_groups = groups - big_groups;
@@ -883,7 +923,7 @@ int lsm_fused_npt(const lsm_frontend *fe, const lsm_reservoir *res)
 // launch == false: only report the resident grid (one wave) of this variant through *wave
 template <int MAXT, int MINB, int FNPT>
 static int launch_fused_t(lsm_ctx *ctx, lsm_frontend *fe, const lsm_reservoir *res, GtArgs &a, int threads, size_t smem,
-                          cudaStream_t st, bool launch = true, int *wave = nullptr, int max_grid = 0)
+                          cudaStream_t st, bool launch = true, int *wave = nullptr, int max_grid = 0, int forced_slot = -2)
 {
     int per_sm = 0, rc;
     if (res->lean) rc = k1_grid<MAXT, MINB, FNPT, true>(ctx, threads, smem, &per_sm);
@@ -898,7 +938,7 @@ static int launch_fused_t(lsm_ctx *ctx, lsm_frontend *fe, const lsm_reservoir *r
     if (max_grid > 0 && grid > max_grid) grid = max_grid;
     int *counter;
     // the lanes arrangement shares one energy buffer: exclusive; the single-kernel path alternates the two scratch slots
-    const int slot = (a.mode == 2 || a.utt_list) ? -1 : (int)(fe->slot_next++ & 1u);
+    const int slot = forced_slot != -2 ? forced_slot : ((a.mode == 2 || a.utt_list) ? -1 : (int)(fe->slot_next++ & 1u));
     if ((rc = next_counter(ctx, fe, st, &counter, &a, grid, slot)) != LSM_OK) return rc;
     if (res->lean) gammatone_encode_kernel<MAXT, MINB, FNPT, true><<<grid, threads, smem, st>>>(a, counter);
     else gammatone_encode_kernel<MAXT, MINB, FNPT, false><<<grid, threads, smem, st>>>(a, counter);
@@ -970,7 +1010,7 @@ static int fused_dispatch(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, co
         if (const char *e = getenv("LSM_ER_PER_SM")) { const int v = atoi(e); if (v > 0 && v < per_sm) per_sm = v; }   // experiment knob
         int grid = per_sm * ctx->sm_count;
         if (grid > B) grid = B;
-        a.rerun_list = fe->d_rerun;
+        a.rerun_list = fe->d_rerun;          // exclusive launch: list of slot 0
         LSM_CUDA(ctx, cudaMemsetAsync(fe->d_rerun, 0, sizeof(int), st));
         if ((rc = next_counter(ctx, fe, st, &counter, &a, grid, -1)) != LSM_OK) return rc;
         a.stagger_cycles = 0;
@@ -983,6 +1023,31 @@ static int fused_dispatch(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, co
         x.utt_list = fe->d_rerun + 1; x.utt_count = fe->d_rerun;
         return launch_fused_t<128, 5, 8>(ctx, fe, res, x, threads, smem, st, true, nullptr, 8);
     }
+    if (launch && !lanes && a.mode == 1 && threads == 128 && npt == 8 && res->lean && getenv("LSM_SPLIT_EXACT")) {
+        // opt-in variant: spec_fused_kernel (no exact-path code in the hot kernel), then the exact pass over the utterances it
+        // flagged.  Measured slower than re-executing inside the kernel (6.37 vs 6.24 ms per step): the follow-up launch is a
+        // one-CTA tail per step, and the smaller kernel (92 vs 96 registers) gains no occupancy.
+        int rc, per_sm = 0, *counter;
+        if ((rc = ensure_rerun(ctx, fe, B)) != LSM_OK) return rc;
+        if (smem > 48 * 1024)
+            LSM_CUDA(ctx, cudaFuncSetAttribute(spec_fused_kernel<5, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spec_fused_kernel<5, 8, true>, 128, smem));
+        if (per_sm < 1) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "spec_fused_kernel does not fit on an SM");
+        int grid = per_sm * ctx->sm_count;
+        if (grid > fe->grid) grid = fe->grid;
+        if (grid > B) grid = B;
+        const int slot = (int)(fe->slot_next++ & 1u);
+        int *list = fe->d_rerun + (size_t)slot * (fe->rerun_cap + 1);
+        if ((rc = next_counter(ctx, fe, st, &counter, &a, grid, slot)) != LSM_OK) return rc;
+        LSM_CUDA(ctx, cudaMemsetAsync(list, 0, sizeof(int), st));
+        a.rerun_list = list;
+        spec_fused_kernel<5, 8, true><<<grid, 128, smem, st>>>(a, counter);
+        ctx->launches += 1;
+        LSM_CUDA(ctx, cudaGetLastError());
+        GtArgs x = a;
+        x.mode = 0; x.rerun_list = nullptr; x.utt_list = list + 1; x.utt_count = list;
+        return launch_fused_t<128, 5, 8>(ctx, fe, res, x, threads, smem, st, true, nullptr, 8, slot);
+    }
     if (threads == 256) return launch_fused_t<256, 2, 4>(ctx, fe, res, a, threads, smem, st, launch, wave);
     if (npt == 8) {
         if (fe->minb >= 5) return launch_fused_t<128, 5, 8>(ctx, fe, res, a, threads, smem, st, launch, wave);
@@ -992,3 +1057,4 @@ static int fused_dispatch(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, co
 }
 
 int lsm_gammatone_minb(void) { return k1_minb(); }
+

@@ -39,6 +39,7 @@ struct lsm_frontend {
     double *d_energy = nullptr;    // [energy_cap][ncols][C] raw window energies between K1a and the encoder kernel
     int energy_cap = 0;
     int *d_rerun = nullptr;        // [1 + energy_cap] count + utterances the encoder kernel flagged for the exact pass
+    int rerun_cap = 0;
     int lanes_slots = 0;           // resident warps of K1a on this device (one wave of units)
     unsigned counter_next = 0;
     int minb = 5;                  // K1 occupancy target the kernel was instantiated for

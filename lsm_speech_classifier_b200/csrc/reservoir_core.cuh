@@ -121,6 +121,7 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
         int acc[NPT];
 #pragma unroll
         for (int k = 0; k < NPT; ++k) acc[k] = 0;
+#pragma unroll 1   // keep the step loop small: the unrolled form (16 rows per trip) made instruction fetch a top stall
         for (int q = 0; q < n_prev; q += 4) {
             const uint2 jj = *reinterpret_cast<const uint2 *>(list + q);
             // entries past the end of the list select the all-zero weight row (index N)

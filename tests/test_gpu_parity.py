@@ -406,7 +406,10 @@ def test_speculative_plane_is_within_a_thousandth_of_the_margin(env, small_set):
     assert np.array_equal(fe.encode(pcm), want)
 
 
-def test_fused_pipeline_same_features_in_both_filter_modes(env, small_set):
+@pytest.mark.parametrize("split_exact", [False, True])
+def test_fused_pipeline_same_features_in_both_filter_modes(env, small_set, monkeypatch, split_exact):
+    if split_exact:
+        monkeypatch.setenv("LSM_SPLIT_EXACT", "1")       # exact pass as a follow-up launch over a device work list
     from lsm_speech_classifier_b200.frontend import Frontend
     from lsm_speech_classifier_b200.snn import SNN, AudioToFeatures, SimulationParams
     from lsm_speech_classifier_b200.extract_lsm_features import FEATURE_SETS, calculate_theoretical_w_critico
@@ -425,7 +428,9 @@ def test_fused_pipeline_same_features_in_both_filter_modes(env, small_set):
     b = pipe.run_host(pcm, keys)
     fe.set_mode("speculative", 1e9)
     c = pipe.run_host(pcm, keys)
-    assert np.array_equal(a, b) and np.array_equal(a, c)
+    fe.set_mode("speculative", 1e-3)
+    d = pipe.run_host(pcm, keys)
+    assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, d)
 
 
 def test_speculative_filter_arrangements_agree(env, small_set, monkeypatch):
