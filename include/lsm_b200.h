@@ -196,6 +196,9 @@ int lsm_pipeline_run(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const f
 int lsm_pipeline_run_host_async(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *h_pcm, int32_t B,
                                 uint32_t feature_mask, int32_t nan_to_num, double *h_features, int32_t lane);
 int lsm_sync_all(lsm_ctx *ctx);
+/* The cudaStream_t of launch lane 0 / 1, so that a caller can order its own work (an NCCL all-gather of the feature rows, a copy)
+ * after an asynchronous call on that lane.  NULL for a bad argument.                                                       */
+void *lsm_lane_stream(lsm_ctx *ctx, int32_t lane);
 /* 1 if lsm_pipeline_run / lsm_pipeline_run_host execute this pair as one fused kernel, else 0. */
 int lsm_pipeline_is_fused(const lsm_frontend *fe, const lsm_reservoir *res);
 

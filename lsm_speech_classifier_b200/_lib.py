@@ -23,7 +23,7 @@ EXPORTS = [
     "lsm_frontend_encode_host", "lsm_reservoir_create", "lsm_reservoir_destroy", "lsm_reservoir_run",
     "lsm_reservoir_run_host", "lsm_pipeline_run_host", "lsm_pipeline_run", "lsm_spike_density",
     "lsm_hysteresis_encode", "lsm_fp64_peak_gops", "lsm_pipeline_is_fused", "lsm_frontend_mel_tables", "lsm_reservoir_diagnostics", "lsm_gammatone_design", "lsm_zoom_table", "lsm_standardize_fit", "lsm_standardize_transform",
-    "lsm_frontend_set_mode", "lsm_frontend_reruns", "lsm_pipeline_run_host_async", "lsm_sync_all",
+    "lsm_frontend_set_mode", "lsm_frontend_reruns", "lsm_pipeline_run_host_async", "lsm_sync_all", "lsm_lane_stream",
 ]
 
 
@@ -90,6 +90,8 @@ def load():
     lib.lsm_zoom_table.argtypes = [i32, i32, vp, vp]
     lib.lsm_pipeline_run_host_async.argtypes = [vp, vp, vp, vp, i32, u32, i32, vp, i32]
     lib.lsm_sync_all.argtypes = [vp]
+    lib.lsm_lane_stream.argtypes = [vp, i32]
+    lib.lsm_lane_stream.restype = vp
     lib.lsm_frontend_set_mode.argtypes = [vp, vp, i32, C.c_double]
     lib.lsm_frontend_reruns.argtypes = [vp, vp, vp, i32]
     lib.lsm_standardize_fit.argtypes = [vp, vp, i32, i32, vp, vp, vp]
@@ -140,6 +142,13 @@ class Context:
 
     def sync(self):
         self.check(self.lib.lsm_sync(self.h))
+
+    def lane_stream(self, lane: int) -> int:
+        """cudaStream_t handle of launch lane 0 / 1 (wrap with torch.cuda.ExternalStream to order other work after it)."""
+        h = self.lib.lsm_lane_stream(self.h, int(lane))
+        if not h:
+            raise LsmError("lane must be 0 or 1")
+        return int(h)
 
     def sync_all(self):
         """Wait for everything enqueued through this ctx (both launch lanes of the asynchronous host calls)."""

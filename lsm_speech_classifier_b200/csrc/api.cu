@@ -689,6 +689,12 @@ extern "C" int lsm_pipeline_run_host_async(lsm_ctx *ctx, lsm_frontend *fe, lsm_r
                             lane == 0 ? ctx->own_stream : ctx->copy_stream[0]);
 }
 
+extern "C" void *lsm_lane_stream(lsm_ctx *ctx, int32_t lane)
+{
+    if (!ctx || lane < 0 || lane > 1) return nullptr;
+    return (void *)(lane == 0 ? ctx->own_stream : ctx->copy_stream[0]);
+}
+
 extern "C" int lsm_sync_all(lsm_ctx *ctx)
 {
     if (!ctx) return LSM_ERR_INVALID;
