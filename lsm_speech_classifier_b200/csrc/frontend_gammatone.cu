@@ -80,7 +80,8 @@ constexpr int kSkew = 3;
 // PCM -> fp64 in shared memory; buffer element i of chunk k holds sample k*chunk + i + kSkew
 __device__ __forceinline__ void stage_pcm(double *dst, const float *pcm, int base, int chunk, int L)
 {
-    for (int i = threadIdx.x; i < chunk; i += blockDim.x) dst[i] = (base + i < L) ? (double)__ldg(pcm + base + i) : 0.0;
+    // streaming loads (evict-first): every PCM sample is read once and must not push the CTAs' scratch planes out of L2
+    for (int i = threadIdx.x; i < chunk; i += blockDim.x) dst[i] = (base + i < L) ? (double)__ldcs(pcm + base + i) : 0.0;
 }
 
 // sqrt(mean) -> dB of one finished window (create_dataset.py:59) into the CTA's plane
@@ -430,7 +431,7 @@ __device__ __forceinline__ void put_spikes(const GtArgs &a, unsigned on, int j, 
         if (a.K == 4) {
             // bytes k = 0..3 of column block j, little endian
             const unsigned w = (on & 1u) | ((on & 2u) << 7) | ((on & 4u) << 14) | ((on & 8u) << 21);
-            *reinterpret_cast<uint32_t *>(row) = w;
+            __stcs(reinterpret_cast<unsigned *>(row), w);        // streaming store: written once, never read here
         } else {
             for (int k = 0; k < a.K; ++k) row[k] = (on >> k) & 1u;
         }
@@ -746,7 +747,10 @@ static void fill_args(const lsm_frontend *fe, const float *d_pcm, int B, uint8_t
 // region L2-persisting on the launch stream so it is not evicted to HBM by the PCM / spike streams passing through.
 static void pin_scratch_in_l2(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st)
 {
-    if (getenv("LSM_NO_L2_PIN")) return;
+    // Off by default since the streaming (evict-first) hints on the PCM loads and the spike / feature stores: with two scratch
+    // slots the window (118 MB) no longer fits the persisting carve-out and made things worse (ncu, 2400 utterances per launch:
+    // 775 MB of DRAM traffic with the window, 472 MB without; algorithmic 315 MB).  LSM_L2_PIN=1 turns it back on.
+    if (!getenv("LSM_L2_PIN")) return;
     const size_t bytes = 2 * sizeof(double) * (size_t)fe->grid * fe->ncols * fe->p.channels;   // both slots
     if (!fe->l2_window_ready) {
         int max_persist = 0, max_window = 0;

@@ -290,7 +290,7 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
                 }
                 __syncthreads();
                 const int n_here = min(cap, a.n_out - tile);
-                for (int idx = tid; idx < n_here; idx += nthr) f[(size_t)slot * a.n_out + tile + idx] = s_buf[idx];
+                for (int idx = tid; idx < n_here; idx += nthr) __stcs(f + (size_t)slot * a.n_out + tile + idx, s_buf[idx]);
                 __syncthreads();
             }
             ++slot;
