@@ -214,6 +214,17 @@ int lsm_standardize_fit(lsm_ctx *ctx, const double *d_X, int32_t n, int32_t F, d
 int lsm_standardize_transform(lsm_ctx *ctx, const double *d_X, int32_t n, int32_t F, const double *d_mean,
                               const double *d_scale, double *d_out);
 
+/* Multinomial logistic regression readout on the device (train_classifier.py:36-47: LogisticRegression(max_iter=1000).fit /
+ * .predict).  scikit-learn's lbfgs objective: mean multinomial log-loss + ||W||^2 / (2 C n), intercept unpenalised; L-BFGS until
+ * max|grad| <= tol.  d_X: double[n][F] (standardised features), d_y: int32[n] class indices 0..n_classes-1 (<= 16 classes).
+ * h_coef: double[n_classes][F], h_intercept: double[n_classes] (host, scikit-learn's coef_ / intercept_ layout).
+ * The unique optimum is reached to solver tolerance, not scikit-learn's iterates bit for bit: the parity bar is the reference's
+ * own metric, test accuracy (tests/test_gpu_readout.py: within 0.5 points and >= 99 % identical predictions).                    */
+int lsm_logreg_fit(lsm_ctx *ctx, const double *d_X, const int32_t *d_y, int32_t n, int32_t F, int32_t n_classes, double C_reg,
+                   int32_t max_iter, double tol, double *h_coef, double *h_intercept, int32_t *h_n_iter);
+int lsm_logreg_predict(lsm_ctx *ctx, const double *d_X, int32_t n, int32_t F, int32_t n_classes, const double *h_coef,
+                       const double *h_intercept, int32_t *d_pred);
+
 /* Diagnostic: measured ceiling of the fp64 pipe on this device, in 1e9 DADD/DMUL lane-operations per
  * second (independent register chains, 8 warps per scheduler).  K1's roofline denominator in bench.py. */
 int lsm_fp64_peak_gops(lsm_ctx *ctx, double *h_out);

@@ -7,7 +7,7 @@ import argparse
 
 
 def run_pipeline(n_filters: int, filterbank: str, feature_set: str, multiplier: float, synthetic=None,
-                 train: bool = True):
+                 train: bool = True, readout: str = "sklearn"):
     from . import create_dataset as cd, extract_lsm_features as ex
     from .distributed import init_from_env, is_main
     init_from_env()
@@ -23,7 +23,7 @@ def run_pipeline(n_filters: int, filterbank: str, feature_set: str, multiplier: 
     if train and is_main():
         print("\n--- Step 3: Training and Evaluating Classifier ---")
         from .train_classifier import train_and_evaluate_classifier
-        train_and_evaluate_classifier()
+        train_and_evaluate_classifier(readout=readout)
     if is_main():
         print("\n--- Pipeline Finished ---")
 
@@ -46,9 +46,11 @@ def _cli(argv=None):
     parser.add_argument("--synthetic", type=int, nargs=2, metavar=("CLASSES", "PER_CLASS"), default=None,
                         help="(extension) synthetic utterances instead of speech_commands_v0.02/")
     parser.add_argument("--no-train", action="store_true", help="(extension) stop after the feature file")
+    parser.add_argument("--readout", type=str, default="sklearn", choices=["sklearn", "device"],
+                        help="(extension) fit the logistic-regression readout with scikit-learn (reference) or on the GPU")
     args = parser.parse_args(argv)
     run_pipeline(n_filters=args.n_filters, filterbank=args.filterbank, feature_set=args.feature_set,
-                 multiplier=args.multiplier, synthetic=args.synthetic, train=not args.no_train)
+                 multiplier=args.multiplier, synthetic=args.synthetic, train=not args.no_train, readout=args.readout)
 
 
 if __name__ == "__main__":

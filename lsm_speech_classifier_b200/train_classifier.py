@@ -12,8 +12,14 @@ import numpy as np
 CLASS_NAMES = ["yes", "no", "up", "visual", "backward", "stop", "bird", "cat", "nine", "eight", "zero", "follow"]
 
 
-def train_and_evaluate_classifier(dataset_filename: str = "lsm_features_larger.npz", verbose: bool = True):
-    from sklearn.linear_model import LogisticRegression
+def train_and_evaluate_classifier(dataset_filename: str = "lsm_features_larger.npz", verbose: bool = True,
+                                  readout: str = "sklearn"):
+    """readout="sklearn": the reference's classifier; readout="device": the same multinomial objective fitted on the GPU
+    (readout.LogisticRegression / lsm_logreg_fit; needs at least three classes)."""
+    if readout == "device":
+        from .readout import LogisticRegression
+    else:
+        from sklearn.linear_model import LogisticRegression
     from sklearn.metrics import accuracy_score, classification_report
     if not Path(dataset_filename).exists():
         print("Error: Dataset file not found. Please run 'extract_lsm_features.py' first.")

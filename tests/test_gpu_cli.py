@@ -84,6 +84,9 @@ def test_reference_train_classifier_settings_consume_the_file(workdir):
     from lsm_speech_classifier_b200.train_classifier import train_and_evaluate_classifier
     acc = train_and_evaluate_classifier(str(d / "lsm_features_larger.npz"), verbose=False)
     assert acc is not None and acc > 0.5          # 4 synthetic classes: far above chance (0.25)
+    # the same file through the device readout (multinomial logistic regression on the GPU): the reference's metric agrees
+    acc_dev = train_and_evaluate_classifier(str(d / "lsm_features_larger.npz"), verbose=False, readout="device")
+    assert abs(acc_dev - acc) <= 0.005 + 1.0 / 80
 
 
 def test_stage_scripts_and_missing_file_behaviour(tmp_path):
