@@ -285,6 +285,7 @@ struct EnergyArgs {
     const float *pcm;       // [B][L]
     double *energy;         // [B][ncols][C] raw energy sums of the normalised cascade
     int B, L, C, nwin, hop, ncols;
+    int n_units;            // big units + single-channel units
     int big_groups;         // utterance groups [0, big_groups) are cut into units of kLanesJ channels, the rest into single channels
     double coef[256][6];    // per channel: c1..c4 (numerator zeros / A0), -a1, -a2
 };
@@ -369,17 +370,22 @@ __device__ __forceinline__ void energy_unit(const EnergyArgs &a, const int g, co
 // Units are dispatched in blockIdx order: first the big ones (kLanesJ channels: one PCM stream and one conversion feed
 // 52 DFMAs), then single-channel units.  A unit is one warp's serial work (0.8 ms for four channels even on an idle SM),
 // so a grid of big units alone ends in a long ragged tail; the small units keep every SM's pipes full to the end.
+// The unit index is blockIdx.x + k * gridDim.x: with a grid as large as the unit count every CTA runs one unit (k = 0), with a
+// smaller grid (LSM_K1A_PER_SM resident warps per SM, the co-residency experiment) a CTA walks a static list - either way the
+// index is provably CTA-uniform for the compiler, which is what puts the coefficients in uniform registers.
 __global__ void __launch_bounds__(32, 16) gammatone_energy_kernel(const __grid_constant__ EnergyArgs a)
 {
     const int n_big = a.big_groups * (a.C / kLanesJ);
-    if ((int)blockIdx.x < n_big) {
-        const int units = a.C / kLanesJ;              // channel blocks per group (fastest index: PCM locality in L2)
-        const int g = blockIdx.x / units;
-        energy_unit<kLanesJ>(a, g, (blockIdx.x - g * units) * kLanesJ);
-    } else {
-        const int s = blockIdx.x - n_big;
-        const int g = s / a.C;
-        energy_unit<1>(a, a.big_groups + g, s - g * a.C);
+    for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+        if (u < n_big) {
+            const int units = a.C / kLanesJ;              // channel blocks per group (fastest index: PCM locality in L2)
+            const int g = u / units;
+            energy_unit<kLanesJ>(a, g, (u - g * units) * kLanesJ);
+        } else {
+            const int s = u - n_big;
+            const int g = s / a.C;
+            energy_unit<1>(a, a.big_groups + g, s - g * a.C);
+        }
     }
 }
 
@@ -864,10 +870,21 @@ static int launch_energy(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int
     if (e) big_groups = groups - (groups * atoi(e) + 99) / 100;
     int small_groups = groups - big_groups;
     ea.big_groups = groups - small_groups;
-    const int grid = ea.big_groups * (p.channels / kLanesJ) + small_groups * p.channels;
+    ea.n_units = ea.big_groups * (p.channels / kLanesJ) + small_groups * p.channels;
+    int grid = ea.n_units;
+    if (const char *k = getenv("LSM_K1A_PER_SM")) { const int v = atoi(k) * ctx->sm_count; if (v > 0 && v < grid) grid = v; }
+    // co-residency experiment (LSM_K1A_CHAIN): energy kernels of one ctx run one after the other whatever their streams, so that
+    // energy kernel i+1 starts together with the encoder/reservoir kernel of batch i instead of beside energy kernel i
+    static cudaEvent_t ev_chain = nullptr;
+    const bool chain = getenv("LSM_K1A_CHAIN") != nullptr;
+    if (chain) {
+        if (!ev_chain) LSM_CUDA(ctx, cudaEventCreateWithFlags(&ev_chain, cudaEventDisableTiming));
+        else LSM_CUDA(ctx, cudaStreamWaitEvent(st, ev_chain, 0));
+    }
     gammatone_energy_kernel<<<grid, 32, 0, st>>>(ea);
     ctx->launches += 1;
     LSM_CUDA(ctx, cudaGetLastError());
+    if (chain) LSM_CUDA(ctx, cudaEventRecord(ev_chain, st));
     return LSM_OK;
 }
 
