@@ -106,3 +106,48 @@ def init_from_env():
         else:
             dist.init_process_group("gloo")
     return dist.get_rank(), dist.get_world_size(), local_rank
+
+
+class PeerAllGather:
+    """All-gather of equal row blocks by peer-to-peer copies over NVLink (copy engines, no SM use).
+
+    The compute kernels of this path are persistent and fill every SM, so an NCCL all-gather kernel has to find CTA slots
+    between them.  Here every rank maps the gather buffers of all ranks (CUDA IPC, exchanged once through the process
+    group) and writes its block straight into each of them with cudaMemcpyPeerAsync on a side stream; the SMs never see
+    the collective.  Measured at N = 2: 6.68 ms per step against 6.72 ms with NCCL's asynchronous all-gather - the
+    collective was not what separates N = 2 from N = 1 (6.3 ms; the step time is the maximum over ranks), so bench.py keeps
+    NCCL by default and uses this class with LSM_BENCH_P2P=1; both give identical matrices (checked in bench.py).
+    `n_buffers` gather buffers per rank alternate between steps; the caller synchronises ranks (a barrier) before it reads."""
+
+    def __init__(self, rows: int, width: int, dtype, device, n_buffers: int = 2):
+        import torch
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.rows = rows
+        self.bufs = [torch.empty((self.world * rows, width), dtype=dtype, device=device) for _ in range(n_buffers)]
+        mine = [reduce_tensor(b) for b in self.bufs]
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine)
+        # peer[r][k]: rank r's gather buffer k, addressable from this process (this rank's own buffers are used directly)
+        self.peer = [[(self.bufs[k] if r == self.rank else fn(*args)) for k, (fn, args) in enumerate(everyone[r])]
+                     for r in range(self.world)]
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(n_buffers)]
+
+    def gather_async(self, k: int, local, after_stream):
+        """Write `local` (this rank's [rows, width] block) into slot `rank` of every rank's buffer k, ordered after the
+        work already enqueued on `after_stream`.  Returns the side stream the copies run on."""
+        import torch
+        st = self.streams[k]
+        st.wait_stream(after_stream)
+        lo = self.rank * self.rows
+        with torch.cuda.stream(st):
+            for d in range(self.world):
+                r = (self.rank + d) % self.world              # start with the own buffer, then round the ring
+                self.peer[r][k][lo:lo + self.rows].copy_(local, non_blocking=True)
+        return st
+
+    def wait(self, k: int, stream=None):
+        """Make `stream` (default: the current one) wait for this rank's outstanding copies into buffers k."""
+        import torch
+        (stream or torch.cuda.current_stream()).wait_stream(self.streams[k])
