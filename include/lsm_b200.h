@@ -196,6 +196,15 @@ int lsm_pipeline_run(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const f
 int lsm_pipeline_run_host_async(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *h_pcm, int32_t B,
                                 uint32_t feature_mask, int32_t nan_to_num, double *h_features, int32_t lane);
 int lsm_sync_all(lsm_ctx *ctx);
+/* PCM16 input - the samples as a 16 kHz mono WAV file holds them (the ingest step
+ * create_dataset.py:22-36 performs with librosa.load).  The kernel converts int16 -> sample / 32768 exactly as the float32
+ * path would have received it, so spike trains and features are the same bytes; half as many bytes cross PCIe.
+ * lsm_pipeline_run_i16: device (or pinned host) pointers on the ctx stream, like lsm_pipeline_run; d_spikes optional.
+ * lsm_pipeline_run_host_async_i16: like lsm_pipeline_run_host_async.  Both need a pair that runs fused.                  */
+int lsm_pipeline_run_i16(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const int16_t *d_pcm16, int32_t B,
+                         uint32_t feature_mask, int32_t nan_to_num, uint8_t *d_spikes, double *d_features);
+int lsm_pipeline_run_host_async_i16(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const int16_t *h_pcm16, int32_t B,
+                                    uint32_t feature_mask, int32_t nan_to_num, double *h_features, int32_t lane);
 /* The cudaStream_t of launch lane 0 / 1, so that a caller can order its own work (an NCCL all-gather of the feature rows, a copy)
  * after an asynchronous call on that lane.  NULL for a bad argument.                                                       */
 void *lsm_lane_stream(lsm_ctx *ctx, int32_t lane);

@@ -46,6 +46,7 @@ extern "C" void lsm_ctx_destroy(lsm_ctx *ctx)
     for (int i = 0; i < 8; ++i) if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
     for (int i = 0; i < 4; ++i) if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
     for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
     for (int i = 0; i < 2; ++i) if (ctx->copy_stream[i]) cudaStreamDestroy(ctx->copy_stream[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -665,6 +666,47 @@ extern "C" int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservo
     LSM_CUDA(ctx, cudaStreamSynchronize(s_k));
     LSM_CUDA(ctx, cudaStreamSynchronize(s_in));
     return LSM_OK;
+}
+
+// PCM16 input (what a Speech Commands WAV file holds): the int16 -> float32 conversion of the ingest
+// (create_dataset.py:22-36, librosa.load) happens in the kernel, exactly; half the bytes cross PCIe.  Fused pairs only.
+static int run_i16(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const int16_t *pcm16, int32_t B, uint32_t feature_mask,
+                   int32_t nan_to_num, uint8_t *d_spikes, double *d_features, cudaStream_t st, const char *who)
+{
+    if (fe->p.channels * fe->p.redundancy != res->p.num_inputs || fe->p.n_bins * fe->p.n_thresholds != res->p.num_steps)
+        LSM_FAIL(ctx, LSM_ERR_INVALID, "front end emits %dx%d spike trains, reservoir expects %dx%d",
+                 fe->p.channels * fe->p.redundancy, fe->p.n_bins * fe->p.n_thresholds, res->p.num_inputs, res->p.num_steps);
+    if (!lsm_fused_npt(fe, res)) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "%s: PCM16 input needs a front end / reservoir pair that runs fused", who);
+    fe->next_pcm16 = pcm16;
+    const int rc = lsm_launch_fused(ctx, fe, res, nullptr, B, d_spikes, feature_mask, nan_to_num, d_features, st);
+    fe->next_pcm16 = nullptr;
+    return rc;
+}
+
+extern "C" int lsm_pipeline_run_i16(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const int16_t *d_pcm16, int32_t B,
+                                    uint32_t feature_mask, int32_t nan_to_num, uint8_t *d_spikes, double *d_features)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!fe || !res || B < 0 || (B > 0 && (!d_pcm16 || !d_features))) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_pipeline_run_i16: bad argument");
+    if (B == 0) return LSM_OK;
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    return run_i16(ctx, fe, res, d_pcm16, B, feature_mask, nan_to_num, d_spikes, d_features, ctx->stream, "lsm_pipeline_run_i16");
+}
+
+extern "C" int lsm_pipeline_run_host_async_i16(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const int16_t *h_pcm16,
+                                               int32_t B, uint32_t feature_mask, int32_t nan_to_num, double *h_features,
+                                               int32_t lane)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!fe || !res || B < 0 || (B > 0 && (!h_pcm16 || !h_features)) || lane < 0 || lane > 1)
+        LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_pipeline_run_host_async_i16: bad argument");
+    if (B == 0) return LSM_OK;
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *dv_pcm = nullptr, *dv_feat = nullptr;
+    if (!device_visible(h_pcm16, &dv_pcm) || !device_visible(h_features, &dv_feat))
+        LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "lsm_pipeline_run_host_async_i16 needs pinned (or device) buffers");
+    return run_i16(ctx, fe, res, (const int16_t *)dv_pcm, B, feature_mask, nan_to_num, nullptr, (double *)dv_feat,
+                   lane == 0 ? ctx->own_stream : ctx->copy_stream[0], "lsm_pipeline_run_host_async_i16");
 }
 
 // Asynchronous variant for pinned host buffers only (the zero-copy path): enqueue on one of the ctx's two launch lanes and

@@ -20,6 +20,9 @@
 // (oracle/lsm_oracle.c gammatone_energy / db_normalise_zoom / hysteresis_encode_f64).
 #include <stdlib.h>
 
+#include <memory>
+#include <new>
+
 #include "reservoir_core.cuh"
 
 namespace {
@@ -40,7 +43,8 @@ __device__ __forceinline__ double div_by_const(double x, double g, double r)
 }
 
 struct GtArgs {
-    const float *pcm;       // [B][L]
+    const float *pcm;       // [B][L] float32 samples, or null when pcm16 is given
+    const int16_t *pcm16;   // [B][L] PCM16 samples (optional alternative input)
     const double *coefs;    // [C][10]
     const int32_t *zoom_i0; // [nbins]
     const double *zoom_f;   // [nbins]
@@ -77,11 +81,23 @@ struct GtArgs {
 // output of iteration s is the cascade output for sample s.
 constexpr int kSkew = 3;
 
+// One utterance's samples: float32 (the load_audio_file contract, create_dataset.py:22-36) or the PCM16 a WAV file holds.
+// (double)int16 * 2^-15 is exactly the double of float32(int16 / 32768), what librosa/soundfile hand to the reference, so both
+// forms give the same bits downstream (the int16 -> float32 step of the ingest, done where the sample is used).
+struct PcmRow {
+    const float *f;
+    const int16_t *h;
+    __device__ __forceinline__ double at(int i) const
+    {
+        return h ? __dmul_rn((double)__ldcs(h + i), 0x1p-15) : (double)__ldcs(f + i);
+    }
+};
+
 // PCM -> fp64 in shared memory; buffer element i of chunk k holds sample k*chunk + i + kSkew
-__device__ __forceinline__ void stage_pcm(double *dst, const float *pcm, int base, int chunk, int L)
+__device__ __forceinline__ void stage_pcm(double *dst, const PcmRow pcm, int base, int chunk, int L)
 {
     // streaming loads (evict-first): every PCM sample is read once and must not push the CTAs' scratch planes out of L2
-    for (int i = threadIdx.x; i < chunk; i += blockDim.x) dst[i] = (base + i < L) ? (double)__ldcs(pcm + base + i) : 0.0;
+    for (int i = threadIdx.x; i < chunk; i += blockDim.x) dst[i] = (base + i < L) ? pcm.at(base + i) : 0.0;
 }
 
 // sqrt(mean) -> dB of one finished window (create_dataset.py:59) into the CTA's plane
@@ -95,7 +111,7 @@ __device__ __forceinline__ void emit_db(double y2w, double *plane, int col, int 
 
 // ---- EXACT filter: the reference's operations in the reference's order (scipy lfilter x4, /gain, square,
 //      left-to-right window sums).  35 fp64 operations per channel-sample, none of them fused.
-__device__ __forceinline__ void gt_filter_exact(const GtArgs &a, const float *pcm, double *s_x, double *plane, double &tmax,
+__device__ __forceinline__ void gt_filter_exact(const GtArgs &a, const PcmRow pcm, double *s_x, double *plane, double &tmax,
                                                 double &tmin)
 {
     const int ch = threadIdx.x;
@@ -130,7 +146,7 @@ __device__ __forceinline__ void gt_filter_exact(const GtArgs &a, const float *pc
         // prologue: iterations s = -3, -2, -1 fill the skewed pipeline (outputs belong to no sample)
 #pragma unroll
         for (int s = 0; s < kSkew; ++s) {
-            const double x = (double)__ldg(pcm + s);
+            const double x = pcm.at(s);
             double t1, t2, t3;
             LSM_BIQUAD(t1, x, z0_0, z1_0, b1_0);
             LSM_BIQUAD(t2, y1, z0_1, z1_1, b1_1);
@@ -201,7 +217,7 @@ __device__ __forceinline__ void gt_filter_exact(const GtArgs &a, const float *pc
 //      comes within a.spec_delta dB (default 1e-7) of an encoder threshold, of a hysteresis bound or of the
 //      degenerate-clip test, and those utterances are filtered again by gt_filter_exact: the spike trains that leave the
 //      kernel are the exact path's, byte for byte, as long as the two planes agree to a third of that margin.
-__device__ __forceinline__ void gt_filter_fast(const GtArgs &a, const float *pcm, double *s_x, double *plane)
+__device__ __forceinline__ void gt_filter_fast(const GtArgs &a, const PcmRow pcm, double *s_x, double *plane)
 {
     const int ch = threadIdx.x;
     const int C = a.C;
@@ -240,7 +256,7 @@ __device__ __forceinline__ void gt_filter_fast(const GtArgs &a, const float *pcm
     stage_pcm(s_x, pcm, kSkew, chunk, a.L);
     if (live) {
 #pragma unroll
-        for (int s = 0; s < kSkew; ++s) LSM_FAST_SAMPLE((double)__ldg(pcm + s));
+        for (int s = 0; s < kSkew; ++s) LSM_FAST_SAMPLE(pcm.at(s));
         acc = 0.0;   // (already zero: stage 4 has seen no sample yet)
     }
     __syncthreads();
@@ -600,7 +616,7 @@ __global__ void __launch_bounds__(MAXT, MINB) gammatone_encode_kernel(const GtAr
         __syncthreads();
         const int utt = s_utt;
         if (utt < 0) break;
-        const float *pcm = a.pcm + (size_t)utt * a.L;
+        const PcmRow pcm = {a.pcm ? a.pcm + (size_t)utt * a.L : nullptr, a.pcm16 ? a.pcm16 + (size_t)utt * a.L : nullptr};
         // the utterance's [ncols][C] plane: energies -> dB -> normalised values, in place.  Mode 2 works directly on the
         // utterance's slice of the energy buffer, the other modes on this CTA's scratch plane (L2-resident).
         double *plane = a.mode == 2 ? const_cast<double *>(a.energy_in) + (size_t)utt * a.ncols * a.C
@@ -655,7 +671,8 @@ __global__ void __launch_bounds__(128, MINB) spec_fused_kernel(const GtArgs a, i
         __syncthreads();
         const int utt = s_utt;
         if (utt >= a.B) break;
-        gt_filter_fast(a, a.pcm + (size_t)utt * a.L, s_x, plane);
+        const PcmRow pcm = {a.pcm ? a.pcm + (size_t)utt * a.L : nullptr, a.pcm16 ? a.pcm16 + (size_t)utt * a.L : nullptr};
+        gt_filter_fast(a, pcm, s_x, plane);
         const bool near = spec_epilogue<FNPT>(a, utt, plane, s_red, s_mm, smem_raw);
         if (__syncthreads_or(near ? 1 : 0) && threadIdx.x == 0) {
             a.rerun_list[1 + atomicAdd(a.rerun_list, 1)] = utt;
@@ -736,7 +753,7 @@ static void fill_args(const lsm_frontend *fe, const float *d_pcm, int B, uint8_t
 {
     const lsm_frontend_params &p = fe->p;
     GtArgs &a = *out;
-    a.pcm = d_pcm; a.coefs = fe->d_coefs; a.zoom_i0 = fe->d_zoom_i0; a.zoom_f = fe->d_zoom_f;
+    a.pcm = d_pcm; a.pcm16 = d_pcm ? nullptr : fe->next_pcm16; a.coefs = fe->d_coefs; a.zoom_i0 = fe->d_zoom_i0; a.zoom_f = fe->d_zoom_f;
     a.scratch = fe->d_scratch; a.spikes = d_spikes; a.spec_norm = d_spec_norm;
     a.B = B; a.L = p.n_samples; a.C = p.channels; a.nwin = p.nwin; a.hop = p.hop; a.ncols = fe->ncols;
     a.nbins = p.n_bins; a.K = p.n_thresholds; a.R = p.redundancy;
@@ -819,7 +836,7 @@ static bool lanes_eligible(const lsm_frontend *fe, const float *d_pcm)
     const lsm_frontend_params &p = fe->p;
     // opt-in for now: as two back-to-back kernels (4.2 ms + encoder/reservoir 3.9 ms per 2400 utterances) it does not yet beat
     // the single fused kernel (7.8 ms); it is the filter half of the pipelined design described in DESIGN.md
-    if (!getenv("LSM_LANES")) return false;
+    if (!getenv("LSM_LANES") || !d_pcm) return false;
     const int r_old = p.nwin - 2 * p.hop;
     return p.kind == LSM_FILTERBANK_GAMMATONE && fe->mode == LSM_FILTER_SPECULATIVE && p.hop % 8 == 0 && r_old % 8 == 0 &&
            p.n_samples % 4 == 0 && p.channels % kLanesJ == 0 && p.channels <= 256 && (((uintptr_t)d_pcm) & 15) == 0;
@@ -855,7 +872,9 @@ static int launch_energy(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int
     int rc;
     if ((rc = lsm_frontend_order_before(ctx, fe, st)) != LSM_OK) return rc;
     if ((rc = ensure_energy(ctx, fe, B)) != LSM_OK) return rc;
-    static EnergyArgs ea;       // 12 KB: keep it off the stack; filled and consumed before returning (ctx is single-threaded)
+    std::unique_ptr<EnergyArgs> ea_holder(new (std::nothrow) EnergyArgs);     // 12 KB of kernel parameters: not on the stack
+    if (!ea_holder) LSM_FAIL(ctx, LSM_ERR_NOMEM, "out of host memory");
+    EnergyArgs &ea = *ea_holder;
     ea.pcm = d_pcm; ea.energy = fe->d_energy;
     ea.B = B; ea.L = p.n_samples; ea.C = p.channels; ea.nwin = p.nwin; ea.hop = p.hop; ea.ncols = fe->ncols;
     memcpy(ea.coef, fe->h_lane_coef, sizeof(double) * 6 * p.channels);
@@ -875,16 +894,15 @@ static int launch_energy(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int
     if (const char *k = getenv("LSM_K1A_PER_SM")) { const int v = atoi(k) * ctx->sm_count; if (v > 0 && v < grid) grid = v; }
     // co-residency experiment (LSM_K1A_CHAIN): energy kernels of one ctx run one after the other whatever their streams, so that
     // energy kernel i+1 starts together with the encoder/reservoir kernel of batch i instead of beside energy kernel i
-    static cudaEvent_t ev_chain = nullptr;
     const bool chain = getenv("LSM_K1A_CHAIN") != nullptr;
     if (chain) {
-        if (!ev_chain) LSM_CUDA(ctx, cudaEventCreateWithFlags(&ev_chain, cudaEventDisableTiming));
-        else LSM_CUDA(ctx, cudaStreamWaitEvent(st, ev_chain, 0));
+        if (!ctx->ev_chain) LSM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming));
+        else LSM_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_chain, 0));
     }
     gammatone_energy_kernel<<<grid, 32, 0, st>>>(ea);
     ctx->launches += 1;
     LSM_CUDA(ctx, cudaGetLastError());
-    if (chain) LSM_CUDA(ctx, cudaEventRecord(ev_chain, st));
+    if (chain) LSM_CUDA(ctx, cudaEventRecord(ctx->ev_chain, st));
     return LSM_OK;
 }
 

@@ -15,6 +15,7 @@ struct lsm_ctx {
     cudaStream_t stream = nullptr;       // where work goes (own_stream or the caller's)
     cudaStream_t copy_stream[2] = {nullptr, nullptr};  // pipeline_run_host: H2D / D2H legs
     cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_chain = nullptr;      // LSM_K1A_CHAIN experiment: orders the energy kernels of this ctx across streams
     int64_t launches = 0;
     char err[512] = {0};
     // staging owned by the ctx for the *_host entry points (grown on demand)
@@ -40,6 +41,7 @@ struct lsm_frontend {
     int energy_cap = 0;
     int *d_rerun = nullptr;        // [1 + energy_cap] count + utterances the encoder kernel flagged for the exact pass
     int rerun_cap = 0;
+    const int16_t *next_pcm16 = nullptr;   // set by the *_i16 entry points for the launch they make (d_pcm == nullptr), then cleared
     int lanes_slots = 0;           // resident warps of K1a on this device (one wave of units)
     unsigned counter_next = 0;
     int minb = 5;                  // K1 occupancy target the kernel was instantiated for

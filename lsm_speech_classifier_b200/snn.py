@@ -29,6 +29,10 @@ def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch")
 
 
+def _is_int16(x) -> bool:
+    return str(x.dtype) in ("int16", "torch.int16")
+
+
 class SNN:
     def __init__(self, simulation_params: SimulationParams | None = None, reservoir: ReservoirDef | None = None,
                  ctx: _lib.Context | None = None, device: int | None = None):
@@ -190,13 +194,15 @@ class AudioToFeatures:
 
     def run_host_async(self, pcm, feature_keys, out, lane: int = 0, nan_to_num: bool = True):
         """Pinned host buffers only: enqueue and return (lsm_pipeline_run_host_async).  Alternate `lane` 0/1 between
-        consecutive batches and finish with `self.ctx.sync_all()`; `out` holds the feature rows after that."""
+        consecutive batches and finish with `self.ctx.sync_all()`; `out` holds the feature rows after that.
+        `pcm` may be float32[B, 16000] or int16[B, 16000] (PCM16 as stored in a WAV file; converted in the kernel)."""
         keys = list(feature_keys)
         mask = _lib.feature_mask(keys)
         if _lib.mask_keys(mask) != keys:
             raise ValueError("feature keys must be in FEATURE_SETS order")
         ptr = (lambda a: a.data_ptr() if _is_torch(a) else a.ctypes.data)
-        self.ctx.check(self.ctx.lib.lsm_pipeline_run_host_async(
+        fn = self.ctx.lib.lsm_pipeline_run_host_async_i16 if _is_int16(pcm) else self.ctx.lib.lsm_pipeline_run_host_async
+        self.ctx.check(fn(
             self.ctx.h, self.frontend.h, self.snn.h, C.c_void_p(ptr(pcm)), pcm.shape[0], mask, int(nan_to_num),
             C.c_void_p(ptr(out)), int(lane)))
         return out
@@ -216,7 +222,8 @@ class AudioToFeatures:
         if out is None:
             out = torch.empty((B, len(keys) * self.snn.num_output_neurons), dtype=torch.float64, device=pcm.device)
         self.ctx.set_stream(torch.cuda.current_stream(pcm.device).cuda_stream)
-        self.ctx.check(self.ctx.lib.lsm_pipeline_run(
+        fn = self.ctx.lib.lsm_pipeline_run_i16 if _is_int16(pcm) else self.ctx.lib.lsm_pipeline_run
+        self.ctx.check(fn(
             self.ctx.h, fe.h, self.snn.h, C.c_void_p(pcm.data_ptr()), B, mask, int(nan_to_num),
             C.c_void_p(spikes.data_ptr()) if spikes is not None else None, C.c_void_p(out.data_ptr())))
         return out, spikes

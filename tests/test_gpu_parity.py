@@ -517,3 +517,38 @@ def test_async_host_calls_on_two_lanes(env, small_set):
             assert np.array_equal(o.numpy(), w), (rep, i)
     with pytest.raises(_lib.LsmError):
         pipe.run_host_async(batches[3], keys, out=np.empty((5, want[0].shape[1])), lane=0)      # pageable buffers
+
+
+def test_pcm16_input_gives_the_float32_results(env, small_set):
+    """PCM16 ingest (what a 16 kHz WAV holds; create_dataset.py:22-36 via librosa.load -> sample / 32768): the kernel's
+    int16 path gives the features and spike trains of the float32 path on the same samples, and both equal the oracle."""
+    import torch
+    from lsm_speech_classifier_b200 import _lib
+    from lsm_speech_classifier_b200.frontend import Frontend
+    from lsm_speech_classifier_b200.snn import SNN, AudioToFeatures, SimulationParams
+    from lsm_speech_classifier_b200.extract_lsm_features import FEATURE_SETS, calculate_theoretical_w_critico
+    pcm, _ = small_set
+    i16 = np.clip(np.round(pcm * 32768.0), -32768, 32767).astype(np.int16)
+    as_f32 = (i16.astype(np.float32) / np.float32(32768.0))               # what soundfile/librosa hand to the reference
+    fe = Frontend(128, "gammatone")
+    want_spikes = oracle_spikes(as_f32, fe)
+    params = SimulationParams(input_spike_times=want_spikes[0])
+    params.mean_weight = calculate_theoretical_w_critico(params, want_spikes, verbose=False) * 0.6
+    lsm = SNN(simulation_params=params)
+    pipe = AudioToFeatures(fe, lsm)
+    keys = FEATURE_SETS["original"]
+    want = pipe.run_host(as_f32, keys)
+    for mode in ("speculative", "exact"):
+        fe.set_mode(mode)
+        out, spk = pipe.run(torch.from_numpy(i16).cuda(), keys)
+        torch.cuda.synchronize()
+        assert np.array_equal(spk.cpu().numpy(), want_spikes), mode
+        assert np.array_equal(out.cpu().numpy(), want), mode
+    h_in = torch.from_numpy(i16).pin_memory()
+    h_out = torch.zeros((len(i16), want.shape[1]), dtype=torch.float64).pin_memory()
+    pipe.run_host_async(h_in, keys, out=h_out, lane=1)
+    fe.ctx.sync_all()
+    assert np.array_equal(h_out.numpy(), want)
+    femel = Frontend(128, "mel")
+    with pytest.raises(_lib.LsmError):
+        AudioToFeatures(femel, lsm).run(torch.from_numpy(i16).cuda(), keys)       # not a fused pair
