@@ -550,6 +550,8 @@ __device__ __forceinline__ bool spec_epilogue(const GtArgs &a, int utt, double *
     const int T = a.nbins * a.K;
     uint8_t *row0 = a.spikes ? a.spikes + ((size_t)utt * C * a.R + (size_t)ch * a.R) * T : nullptr;
     const double *col = plane + ch;
+    // diagnostic only (LSM_SPEC_DUMP): the speculative normalised spectrogram, to measure its distance from the exact one
+    double *dump = a.spec_norm ? a.spec_norm + ((size_t)utt * C + ch) * a.nbins : nullptr;
     unsigned on = 0;
     for (int j0 = 0; j0 < a.nbins; j0 += 4) {
         double v[4];
@@ -568,6 +570,7 @@ __device__ __forceinline__ bool spec_epilogue(const GtArgs &a, int utt, double *
         for (int u = 0; u < 4; ++u) {
             const int j = j0 + u;
             if (j < a.nbins) {
+                if (dump) dump[j] = v[u];
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
                     if (k < a.K) near |= (fabs(v[u] - a.thr[k]) < margin) | (fabs(v[u] - a.lower[k]) < margin);
@@ -759,7 +762,7 @@ static void fill_args(const lsm_frontend *fe, const float *d_pcm, int B, uint8_t
     a.nbins = p.n_bins; a.K = p.n_thresholds; a.R = p.redundancy;
     for (int k = 0; k < 8; ++k) { a.thr[k] = p.thresholds_desc[k]; a.lower[k] = p.lower_bounds[k]; }
     // the normalised-spectrogram dump is defined as the exact path's: asking for it selects the exact filter
-    a.mode = d_spec_norm ? 0 : fe->mode;
+    a.mode = (d_spec_norm && !getenv("LSM_SPEC_DUMP")) ? 0 : fe->mode;
     a.energy_in = nullptr;
     a.utt_list = nullptr; a.utt_count = nullptr; a.rerun_list = nullptr;
     a.spec_delta = fe->spec_delta;

@@ -552,3 +552,30 @@ def test_pcm16_input_gives_the_float32_results(env, small_set):
     femel = Frontend(128, "mel")
     with pytest.raises(_lib.LsmError):
         AudioToFeatures(femel, lsm).run(torch.from_numpy(i16).cuda(), keys)       # not a fused pair
+
+
+def test_speculative_plane_distance_measured(env, small_set, monkeypatch):
+    """Direct measurement behind the speculative mode's margin: the normalised spectrogram of the speculative pass
+    (diagnostic dump, LSM_SPEC_DUMP) against the exact one, in dB (difference x (max - min + 1e-8)), over speech-like and
+    pathological clips.  The near-tie margin is 1e-7 dB; the planes must agree at least a hundred times better."""
+    import torch
+    from lsm_speech_classifier_b200 import synth
+    from lsm_speech_classifier_b200.frontend import Frontend
+    pcm, _ = small_set
+    more, _ = synth.synth_dataset(12, 40, start_utt=300)
+    tone = (np.sin(2 * np.pi * 3000 * np.arange(16000) / 16000) * 0.5).astype(np.float32)[None]
+    pcm = np.concatenate([pcm, more, tone])
+    fe = Frontend(128, "gammatone")
+    d = torch.from_numpy(pcm).cuda()
+    fe.set_mode("exact")
+    _, exact = fe.encode(d, return_spectrogram=True)
+    monkeypatch.setenv("LSM_SPEC_DUMP", "1")
+    fe.set_mode("speculative", 1e-300)               # nothing is re-executed: the dump is the speculative plane
+    _, spec = fe.encode(d, return_spectrogram=True)
+    monkeypatch.delenv("LSM_SPEC_DUMP")
+    torch.cuda.synchronize()
+    assert fe.reruns(reset=True) == 0
+    exact, spec = exact.cpu().numpy(), spec.cpu().numpy()
+    diff = np.abs(spec - exact).max(axis=(1, 2)) * 80.0      # normalised units -> dB, with the largest possible range (80 dB floor)
+    print(f"\nspeculative vs exact plane: max {diff.max():.3e} dB, median {np.median(diff):.3e} dB over {len(pcm)} clips")
+    assert diff.max() < 1e-9
