@@ -105,7 +105,6 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
             lk[k] = i >= N ? a.leak0 : __ldg(a.leak + i);
         }
     }
-    const char *wbase = reinterpret_cast<const char *>(a.wt + i0);
     const unsigned pitch = (unsigned)a.n_pad * 4u;
     __syncthreads();
 
@@ -129,10 +128,11 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
             const int j1 = (q + 1 < n_prev) ? (int)(jj.x >> 16) : a.zero_row;
             const int j2 = (q + 2 < n_prev) ? (int)(jj.y & 0xffff) : a.zero_row;
             const int j3 = (q + 3 < n_prev) ? (int)(jj.y >> 16) : a.zero_row;
-            const int4 *r0 = reinterpret_cast<const int4 *>(wbase + (size_t)((unsigned)j0 * pitch));
-            const int4 *r1 = reinterpret_cast<const int4 *>(wbase + (size_t)((unsigned)j1 * pitch));
-            const int4 *r2 = reinterpret_cast<const int4 *>(wbase + (size_t)((unsigned)j2 * pitch));
-            const int4 *r3 = reinterpret_cast<const int4 *>(wbase + (size_t)((unsigned)j3 * pitch));
+            // 32-bit int4 indices off the uniform base pointer: one IMAD per row instead of 64-bit address arithmetic
+            const int4 *w4 = reinterpret_cast<const int4 *>(a.wt);
+            const unsigned p4 = pitch >> 4, t4 = (unsigned)i0 >> 2;
+            const int4 *r0 = w4 + ((unsigned)j0 * p4 + t4), *r1 = w4 + ((unsigned)j1 * p4 + t4);
+            const int4 *r2 = w4 + ((unsigned)j2 * p4 + t4), *r3 = w4 + ((unsigned)j3 * p4 + t4);
 #pragma unroll
             for (int u = 0; u < NPT / 4; ++u) {
                 const int4 w0 = __ldg(r0 + u);
