@@ -21,7 +21,7 @@ template <int NPT, bool LEAN, bool STAT_GLOBAL>
 __global__ void __launch_bounds__(1024) reservoir_kernel(const ResArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_cnt[3];
+    __shared__ int s_cnt[4];
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int T = a.T, CW = a.CW;
     unsigned *s_bits = reinterpret_cast<unsigned *>(smem_raw);

@@ -74,6 +74,7 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
         s_stat[i] = 0; s_stat[S + i] = 0; s_stat[2 * S + i] = -1; s_stat[3 * S + i] = -1; s_stat[4 * S + i] = 0; s_stat[5 * S + i] = 0;
     }
     if (tid < 3) s_cnt[tid] = 0;
+    if (tid == 3) s_cnt[3] = T;                        // first step with an input spike (see below)
 
     // per-neuron state in registers: thread tid owns the NPT consecutive neurons tid*NPT ...
     const int i0 = tid * NPT;
@@ -108,8 +109,19 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
     const unsigned pitch = (unsigned)a.n_pad * 4u;
     __syncthreads();
 
+    // Dead time: until the first input spike every membrane potential is exactly +0, nobody fires and no statistic changes
+    // ((0 - leak*0) + 0 = +0), so the simulation starts at that step - the leading silence of an utterance, typically a
+    // quarter of the 400 steps, costs nothing.  (With a raster dump the silent steps are simulated, which writes their zeros.)
+    int t_first = 0;
+    if (!a.raster) {
+        for (int i = tid; i < T * CW; i += nthr)
+            if (s_bits[i]) atomicMin(&s_cnt[3], i / CW);
+        __syncthreads();
+        t_first = s_cnt[3];
+    }
+
     int c_cur = 0, c_nxt = 1, c_zero = 2;
-    for (int t = 0; t < T; ++t) {
+    for (int t = t_first; t < T; ++t) {
         const unsigned short *list = s_list + (t & 1) * NL;
         unsigned short *list_next = s_list + ((t + 1) & 1) * NL;
         const int n_prev = s_cnt[c_cur];
