@@ -454,6 +454,9 @@ extern "C" int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
     }
     for (int i = 0; i < N; ++i) ext_id[perm[i]] = i;
     res->zero_row = res->lean ? n_pad : N;
+    res->skip_dead_time = (p->theta > 0.0 && !getenv("LSM_NO_DEAD_TIME_SKIP")) ? 1 : 0;
+    for (int i = 0; i < N; ++i)
+        if (!(h_leak[i] >= 0.0 && h_leak[i] <= 1.0)) res->skip_dead_time = 0;
     res->hi_magic = (1075 - p->w_shift) << 20;
     res->c_off = ldexp(1.0, 52 - p->w_shift) + ldexp(1.0, 31 - p->w_shift);
     res->c_on = res->c_off - res->gain0;

@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(MAXT, MINB) gammatone_encode_kernel(const GtAr
     __shared__ double s_red[2][8];
     __shared__ double s_mm[2];
     __shared__ int s_utt;
-    __shared__ int s_cnt3[4];
+    __shared__ int s_cnt3[5];
 
     // Every utterance costs the same, so the CTAs resident on an SM would march in lockstep: all in the filter loop
     // (fp64 pipe saturated, issue slots to spare), then all in the encoder / reservoir phases (fp64 pipe idle).  Start
@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(128, MINB) spec_fused_kernel(const GtArgs a, i
     __shared__ double s_red[2][8];
     __shared__ double s_mm[2];
     __shared__ int s_utt;
-    __shared__ int s_cnt3[4];
+    __shared__ int s_cnt3[5];
     double *plane = a.scratch + (size_t)blockIdx.x * a.ncols * a.C;
     for (;;) {
         if (threadIdx.x == 0) s_utt = atomicAdd(next_utt, 1);
@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(128, MINB) encode_reservoir_kernel(const GtArg
     __shared__ double s_red[2][8];
     __shared__ double s_mm[2];
     __shared__ int s_utt;
-    __shared__ int s_cnt3[4];
+    __shared__ int s_cnt3[5];
     for (;;) {
         if (threadIdx.x == 0) s_utt = atomicAdd(next_utt, 1);
         __syncthreads();

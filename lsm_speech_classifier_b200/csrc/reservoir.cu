@@ -21,7 +21,7 @@ template <int NPT, bool LEAN, bool STAT_GLOBAL>
 __global__ void __launch_bounds__(1024) reservoir_kernel(const ResArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_cnt[4];
+    __shared__ int s_cnt[5];
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int T = a.T, CW = a.CW;
     unsigned *s_bits = reinterpret_cast<unsigned *>(smem_raw);
@@ -78,6 +78,7 @@ void lsm_reservoir_fill_args(const lsm_reservoir *res, const uint8_t *d_spikes, 
     a.in_val = res->d_in_val; a.in_row = res->d_in_row; a.leak = res->d_leak; a.out_slot = res->d_out_slot;
     a.features = d_features; a.raster = d_raster; a.stat_global = nullptr; a.diag = nullptr;
     a.ext_id = res->d_ext_id; a.c_off = res->c_off; a.c_on = res->c_on; a.hi_magic = res->hi_magic; a.zero_row = res->zero_row;
+    a.skip_dead_time = res->skip_dead_time;
     a.B = B; a.N = p.num_neurons; a.n_pad = res->n_pad; a.C = p.num_inputs; a.CW = (p.num_inputs + 31) / 32; a.T = p.num_steps;
     a.refractory = p.refractory; a.n_out = p.n_out; a.nan_to_num = nan_to_num;
     a.leak0 = res->leak0; a.gain0 = res->gain0;

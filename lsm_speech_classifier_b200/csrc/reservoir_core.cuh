@@ -22,6 +22,7 @@ struct ResArgs {
     double c_off, c_on;       // LEAN: cur = D(acc) - c_off (input off) / - c_on (input on), see lean_current()
     int hi_magic;             // LEAN: high word of the double whose low word holds acc ^ 0x80000000
     int zero_row;             // index of the all-zero weight row that pads a group of four list entries
+    int skip_dead_time;       // 1: theta > 0 and every leak in [0, 1], so silent stretches may be skipped (exactly)
     int B, N, n_pad, C, CW, T, refractory, n_out, nkeys, nan_to_num;
     unsigned feature_mask;
     double theta, scale, leak0, gain0;
@@ -74,7 +75,7 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
         s_stat[i] = 0; s_stat[S + i] = 0; s_stat[2 * S + i] = -1; s_stat[3 * S + i] = -1; s_stat[4 * S + i] = 0; s_stat[5 * S + i] = 0;
     }
     if (tid < 3) s_cnt[tid] = 0;
-    if (tid == 3) s_cnt[3] = T;                        // first step with an input spike (see below)
+    if (tid == 3) { s_cnt[3] = T; s_cnt[4] = -1; }     // first / last step with an input spike (see below)
 
     // per-neuron state in registers: thread tid owns the NPT consecutive neurons tid*NPT ...
     const int i0 = tid * NPT;
@@ -109,15 +110,18 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
     const unsigned pitch = (unsigned)a.n_pad * 4u;
     __syncthreads();
 
-    // Dead time: until the first input spike every membrane potential is exactly +0, nobody fires and no statistic changes
-    // ((0 - leak*0) + 0 = +0), so the simulation starts at that step - the leading silence of an utterance, typically a
-    // quarter of the 400 steps, costs nothing.  (With a raster dump the silent steps are simulated, which writes their zeros.)
-    int t_first = 0;
-    if (!a.raster) {
+    // Dead time.  Until the first input spike every membrane potential is exactly +0, nobody fires and no statistic changes
+    // ((0 - leak*0) + 0 = +0), so the simulation starts at that step.  And once the input has ended and a step passes without
+    // a spike, no neuron can fire again (without current |V| only shrinks: 0 <= leak <= 1, theta > 0 - checked on the host), so
+    // the rasters and statistics are final and the loop stops.  Leading and trailing silence of an utterance cost nothing; the
+    // result is exactly that of simulating all T steps.  (With a raster dump all steps are simulated, which writes their zeros.)
+    int t_first = 0, t_last_in = T;
+    if (!a.raster && a.skip_dead_time) {
         for (int i = tid; i < T * CW; i += nthr)
-            if (s_bits[i]) atomicMin(&s_cnt[3], i / CW);
+            if (s_bits[i]) { atomicMin(&s_cnt[3], i / CW); atomicMax(&s_cnt[4], i / CW); }
         __syncthreads();
         t_first = s_cnt[3];
+        t_last_in = s_cnt[4];
     }
 
     int c_cur = 0, c_nxt = 1, c_zero = 2;
@@ -125,6 +129,7 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
         const unsigned short *list = s_list + (t & 1) * NL;
         unsigned short *list_next = s_list + ((t + 1) & 1) * NL;
         const int n_prev = s_cnt[c_cur];
+        if (t > t_last_in && n_prev == 0) break;      // input over and the reservoir has fallen silent (uniform across the CTA)
         if (tid == 0) s_cnt[c_zero] = 0;
 
         // ---- recurrent current: exact integer sum over the neurons that fired at t-1; one 16-byte
