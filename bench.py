@@ -487,13 +487,22 @@ def main():
         t0 = time.perf_counter()
         ref = oracle_pipeline(sample, tables, lsm.reservoir, mask, 0)
         dt = time.perf_counter() - t0
+        # the two stages separately: front end + encoder, reservoir + features
+        ta = time.perf_counter()
+        spk_cpu = coracle.gammatone_encode(sample, *tables, [0.70, 0.80, 0.90, 0.95], 0.1, nthreads=0)
+        tb = time.perf_counter()
+        coracle.reservoir_run(lsm.reservoir, spk_cpu, mask, True, False, nthreads=0)
+        tc = time.perf_counter()
         t1 = time.perf_counter()
         oracle_pipeline(sample[:16], tables, lsm.reservoir, mask, 1)
         dt1 = time.perf_counter() - t1
         got = path.run_host(np.ascontiguousarray(sample), keys)
         out["cpu_baseline"] = {"value": len(sample) / dt, "unit": "utterances/s", "cores": cores, "kind": "port",
                                "sample": f"{len(sample)} of the step's {B} utterances, oracle C port, {cores} threads",
-                               "value_1core": 16 / dt1, "gpu_matches_cpu_bit_exact": bool(np.array_equal(got, ref))}
+                               "value_1core": 16 / dt1, "stage1_frontend_encoder": len(sample) / (tb - ta),
+                               "stage23_reservoir_features": len(sample) / (tc - tb),
+                               "neuron_steps_per_s": len(sample) / dt * N_NEURONS * T_STEPS,
+                               "gpu_matches_cpu_bit_exact": bool(np.array_equal(got, ref))}
     emit(out)
     if world > 1:
         dist.destroy_process_group()
