@@ -454,7 +454,9 @@ def main():
                      "peak_source": f"{peak_kind} MEASURED_PEAKS.json hbm_gbs",
                      "note": "this kernel is bound by the fp64 pipe / instruction issue, not HBM (SURVEY.md 8d): see roofline_fp64; "
                              "traffic = dram read+write bytes per launch from ncu (profiles/r1_traffic.json)"},
-        "roofline_fp64": {"kernel": "gammatone_encode_kernel (K1, stand-alone launch)", "bound": "fp64 pipe",
+        "roofline_fp64": {"kernel": "stand-alone front end (K1): gammatone_energy_kernel (lane = utterance, uniform-register coefficients) + "
+                                    "encoder kernel" if spec else "gammatone_encode_kernel (K1, stand-alone launch, exact filter)",
+                          "bound": "fp64 pipe",
                           "achieved": k1_gops, "peak": fp64_peak,
                           "unit": "G fp64 lane-ops/s (DADD, DMUL, DFMA each count 1)", "frac": k1_gops / fp64_peak,
                           "lane_ops_per_utterance": k1_ops,
@@ -463,8 +465,8 @@ def main():
                                               "note": "filter-bank lane-ops only, over one launch of the fused kernel (reservoir and readout included in the time)"},
                           "over_timed_steps": {"achieved": k1_ops * B / (step_ms / 1e3) / 1e9, "frac": k1_ops * B / (step_ms / 1e3) / 1e9 / fp64_peak},
                           "three_register_dfma_ceiling": {"value": 14400.0, "note": "tools/fp64_cascade.cu: a DFMA with three distinct register "
-                                                          "operands (per-lane coefficients) issues at 75 % of the pipe's rate; with uniform-register "
-                                                          "coefficients 19200"},
+                                                          "operands (per-lane coefficients, the fused kernel's filter) issues at 75 % of the pipe's rate; "
+                                                          "with uniform-register coefficients (the stand-alone front end's energy kernel) 19200"},
                           "peak_source": "measured live by lsm_fp64_peak_gops (independent DADD/DMUL register chains); "
                                          "nominal 148 SMs x 64 lanes x 1.965 GHz = 18612"},
         "kernel_ms": {"K1_gammatone_encode": k1_ms, "K2_reservoir_features": k2_ms, "fused_audio_to_features": fused_ms,

@@ -837,12 +837,14 @@ static int next_counter(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st, int **c
 constexpr int kEnergyMaxUtt = 8192;     // utterances per pass of the two-kernel speculative path (energy buffer = 100 KB each)
 
 // Can the speculative filter run lane = utterance?  8-sample steps must tile the window phases, rows must be 16-byte aligned.
-static bool lanes_eligible(const lsm_frontend *fe, const float *d_pcm)
+static bool lanes_eligible(const lsm_frontend *fe, const float *d_pcm, bool standalone = false)
 {
     const lsm_frontend_params &p = fe->p;
-    // opt-in for now: as two back-to-back kernels (4.2 ms + encoder/reservoir 3.9 ms per 2400 utterances) it does not yet beat
-    // the single fused kernel (7.8 ms); it is the filter half of the pipelined design described in DESIGN.md
-    if (!getenv("LSM_LANES") || !d_pcm) return false;
+    // Stand-alone front end (stage 1 only: lsm_frontend_encode): on by default, 4.7 ms vs 5.5 ms per 2400 utterances.
+    // Whole path: opt-in (LSM_LANES=1) - as two kernels it only ties with the single fused kernel (6.5 vs 6.5 ms per launch,
+    // 5.7 vs 5.7 ms per step with two launches in flight) and gives up the zero-copy host path; see DESIGN.md.
+    if (getenv("LSM_NO_LANES") || !d_pcm) return false;
+    if (!standalone && !getenv("LSM_LANES")) return false;
     const int r_old = p.nwin - 2 * p.hop;
     return p.kind == LSM_FILTERBANK_GAMMATONE && fe->mode == LSM_FILTER_SPECULATIVE && p.hop % 8 == 0 && r_old % 8 == 0 &&
            p.n_samples % 4 == 0 && p.channels % kLanesJ == 0 && p.channels <= 256 && (((uintptr_t)d_pcm) & 15) == 0;
@@ -916,7 +918,7 @@ int lsm_launch_gammatone(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int
                          double *d_spec_norm, cudaStream_t st)
 {
     const lsm_frontend_params &p = fe->p;
-    const bool lanes = !d_spec_norm && lanes_eligible(fe, d_pcm);
+    const bool lanes = !d_spec_norm && lanes_eligible(fe, d_pcm, true);
     if (lanes && B > kEnergyMaxUtt) {
         const size_t spk_per = (size_t)p.channels * p.redundancy * p.n_bins * p.n_thresholds;
         for (int off = 0; off < B; off += kEnergyMaxUtt) {

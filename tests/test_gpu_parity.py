@@ -434,22 +434,26 @@ def test_fused_pipeline_same_features_in_both_filter_modes(env, small_set, monke
 
 
 def test_speculative_filter_arrangements_agree(env, small_set, monkeypatch):
-    """Two arrangements of the speculative filter - lane = channel (inside the encoder kernel, the default) and
-    lane = utterance (K1a energy kernel + encoder kernel, LSM_LANES=1) - give the oracle's spike trains for ragged
-    batch sizes (partial 32-utterance groups included)."""
+    """Two arrangements of the speculative filter in the stand-alone front end - lane = utterance (energy kernel + encoder
+    kernel, the default there) and lane = channel (inside the encoder kernel, LSM_NO_LANES=1 or shapes the energy kernel does
+    not take) - give the oracle's spike trains for ragged batch sizes (partial 32-utterance groups included)."""
     from lsm_speech_classifier_b200.frontend import Frontend
     pcm, _ = small_set
     fe = Frontend(128, "gammatone")
     want = oracle_spikes(pcm, fe)
+    launches = fe.ctx.launches
     for n in (1, 2, 27, len(pcm)):
         assert np.array_equal(fe.encode(pcm[:n]), want[:n]), n
-    monkeypatch.setenv("LSM_LANES", "1")
+    assert fe.ctx.launches - launches == 8                    # two kernels per call: the lanes arrangement ran
+    fe40 = Frontend(40, "gammatone")
+    want40 = oracle_spikes(pcm[:9], fe40)
+    assert np.array_equal(fe40.encode(pcm[:9]), want40)
+    monkeypatch.setenv("LSM_NO_LANES", "1")
+    launches = fe.ctx.launches
     for n in (1, 27, len(pcm)):
         assert np.array_equal(fe.encode(pcm[:n]), want[:n]), n
-    fe40 = Frontend(40, "gammatone")
-    assert np.array_equal(fe40.encode(pcm[:9]), oracle_spikes(pcm[:9], fe40))
-    monkeypatch.delenv("LSM_LANES")
-    assert np.array_equal(fe40.encode(pcm[:9]), oracle_spikes(pcm[:9], fe40))
+    assert fe.ctx.launches - launches == 3                    # one kernel per call
+    assert np.array_equal(fe40.encode(pcm[:9]), want40)
 
 
 def test_lanes_arrangement_fused_pipeline(env, small_set, monkeypatch):
