@@ -610,6 +610,18 @@ extern "C" int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservo
             void *d_spk = nullptr;
             int rc0;
             if (h_spikes_or_null && (rc0 = lsm_stage_device(ctx, 1, (size_t)B * spk_per, &d_spk)) != LSM_OK) return rc0;
+            const int wave = lsm_fused_wave(ctx, fe, res);
+            if (!h_spikes_or_null && wave > 0 && B >= 2 * wave && !getenv("LSM_NO_SPLIT")) {
+                // two launches on the two lanes (two scratch slots): the second half fills the drain tail of the first
+                const int n0 = B / 2;
+                if ((rc0 = lsm_launch_fused(ctx, fe, res, (const float *)dv_pcm, n0, nullptr, feature_mask, nan_to_num,
+                                            (double *)dv_feat, ctx->own_stream)) != LSM_OK) return rc0;
+                if ((rc0 = lsm_launch_fused(ctx, fe, res, (const float *)dv_pcm + (size_t)n0 * L, B - n0, nullptr, feature_mask, nan_to_num,
+                                            (double *)dv_feat + (size_t)n0 * feat_per, ctx->copy_stream[0])) != LSM_OK) return rc0;
+                LSM_CUDA(ctx, cudaStreamSynchronize(ctx->own_stream));
+                LSM_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream[0]));
+                return LSM_OK;
+            }
             if ((rc0 = lsm_launch_fused(ctx, fe, res, (const float *)dv_pcm, B, (uint8_t *)d_spk, feature_mask, nan_to_num,
                                         (double *)dv_feat, ctx->stream)) != LSM_OK) return rc0;
             if (h_spikes_or_null)

@@ -583,3 +583,40 @@ def test_speculative_plane_distance_measured(env, small_set, monkeypatch):
     diff = np.abs(spec - exact).max(axis=(1, 2)) * 80.0      # normalised units -> dB, with the largest possible range (80 dB floor)
     print(f"\nspeculative vs exact plane: max {diff.max():.3e} dB, median {np.median(diff):.3e} dB over {len(pcm)} clips")
     assert diff.max() < 1e-9
+
+
+def test_large_pinned_batch_is_split_across_the_two_lanes(env, monkeypatch):
+    """lsm_pipeline_run_host with pinned buffers and at least two resident waves of utterances launches the two halves on
+    the two lanes; the feature rows are those of the unsplit call (LSM_NO_SPLIT=1) and of the oracle."""
+    import torch
+    from oracle import coracle
+    from lsm_speech_classifier_b200 import synth, _lib
+    from lsm_speech_classifier_b200.frontend import Frontend
+    from lsm_speech_classifier_b200.snn import SNN, AudioToFeatures, SimulationParams
+    from lsm_speech_classifier_b200.extract_lsm_features import FEATURE_SETS, calculate_theoretical_w_critico
+    base, _ = synth.synth_dataset(12, 20)
+    pcm = np.concatenate([base] * 8)[:1900]                      # > 2 x 888 resident CTAs
+    pcm[7] = 0.0                                                 # a silent clip in the first half
+    fe = Frontend(128, "gammatone")
+    spikes = fe.encode(base)
+    params = SimulationParams(input_spike_times=spikes[0])
+    params.mean_weight = calculate_theoretical_w_critico(params, spikes, verbose=False) * 0.6
+    lsm = SNN(simulation_params=params)
+    pipe = AudioToFeatures(fe, lsm)
+    keys = FEATURE_SETS["original"]
+    h_in = torch.from_numpy(pcm).pin_memory()
+    h_out = torch.zeros((len(pcm), 2000), dtype=torch.float64).pin_memory()
+    launches = fe.ctx.launches
+    pipe.run_host(h_in.numpy(), keys, out=h_out.numpy())
+    assert fe.ctx.launches - launches == 2
+    split = h_out.numpy().copy()
+    monkeypatch.setenv("LSM_NO_SPLIT", "1")
+    h_out.zero_()
+    launches = fe.ctx.launches
+    pipe.run_host(h_in.numpy(), keys, out=h_out.numpy())
+    assert fe.ctx.launches - launches == 1
+    assert np.array_equal(split, h_out.numpy())
+    want_spk = oracle_spikes(base, fe)
+    want, _ = coracle.reservoir_run(lsm.reservoir, want_spk, _lib.feature_mask(keys), True, False)
+    assert np.array_equal(split[240:480], want) and np.array_equal(split[1680:1900], want[:220])
+    assert not split[7].any()
