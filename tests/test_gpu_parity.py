@@ -620,3 +620,20 @@ def test_large_pinned_batch_is_split_across_the_two_lanes(env, monkeypatch):
     want, _ = coracle.reservoir_run(lsm.reservoir, want_spk, _lib.feature_mask(keys), True, False)
     assert np.array_equal(split[240:480], want) and np.array_equal(split[1680:1900], want[:220])
     assert not split[7].any()
+
+
+def test_front_end_batches_beyond_one_energy_pass(env):
+    """The stand-alone front end works in passes of 8192 utterances (energy planes); a batch of 8200 crosses that boundary."""
+    import torch
+    from lsm_speech_classifier_b200 import synth
+    from lsm_speech_classifier_b200.frontend import Frontend
+    base, _ = synth.synth_dataset(4, 10)
+    reps = 8200 // len(base) + 1
+    pcm = np.concatenate([base] * reps)[:8200]
+    fe = Frontend(128, "gammatone")
+    want = oracle_spikes(base, fe)
+    got = fe.encode(torch.from_numpy(pcm).cuda()).cpu().numpy()
+    assert got.shape == (8200, 128, 400)
+    tiled = np.concatenate([want] * reps)[:8200]
+    assert np.array_equal(got[:80], tiled[:80]) and np.array_equal(got[8150:], tiled[8150:])
+    assert np.array_equal(got, tiled)
