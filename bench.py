@@ -248,7 +248,8 @@ def main():
     d_feats = [torch.empty((B, F), dtype=torch.float64, device="cuda") for _ in range(2)]
     d_feat = d_feats[0]
     # feature all-gather: NCCL (asynchronous, double-buffered); LSM_BENCH_P2P=1 switches to peer-to-peer copies over NVLink
-    # (distributed.PeerAllGather, copy engines only) - measured equal at N = 2 (6.68 vs 6.72 ms per step), so NCCL stays the default
+    # (distributed.PeerAllGather, copy engines only) - measured equal at N = 2 (6.68 vs 6.72 ms per step) and much worse at N = 8
+    # (25.5 vs 7.0 ms), so NCCL stays the default
     use_p2p = world > 1 and bool(os.environ.get("LSM_BENCH_P2P"))
     pag = None
     if use_p2p:

@@ -115,8 +115,10 @@ class PeerAllGather:
     between them.  Here every rank maps the gather buffers of all ranks (CUDA IPC, exchanged once through the process
     group) and writes its block straight into each of them with cudaMemcpyPeerAsync on a side stream; the SMs never see
     the collective.  Measured at N = 2: 6.68 ms per step against 6.72 ms with NCCL's asynchronous all-gather - the
-    collective was not what separates N = 2 from N = 1 (6.3 ms; the step time is the maximum over ranks), so bench.py keeps
-    NCCL by default and uses this class with LSM_BENCH_P2P=1; both give identical matrices (checked in bench.py).
+    collective was not what separates N = 2 from N = 1 (6.3 ms; the step time is the maximum over ranks).  At N = 8 this
+    simple form is far worse than NCCL (25.5 vs 7.0 ms per step: seven serial 38 MB peer copies per rank and step through
+    IPC-mapped buffers), so bench.py keeps NCCL and uses this class only with LSM_BENCH_P2P=1; both give identical matrices
+    (checked in bench.py).
     `n_buffers` gather buffers per rank alternate between steps; the caller synchronises ranks (a barrier) before it reads."""
 
     def __init__(self, rows: int, width: int, dtype, device, n_buffers: int = 2):
