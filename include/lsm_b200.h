@@ -171,6 +171,13 @@ int lsm_reservoir_run_host(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *h_sp
 /* Network diagnostics of run_network_diagnostics (extract_lsm_features.py:92-152) reduced on the device instead of
  * shipping the raster: for each utterance, d_diag[2*b] = neurons (of all N) that fired at least once,
  * d_diag[2*b+1] = total spikes.  Participation % = 100*d_diag[2b]/N, average spikes per neuron = d_diag[2b+1]/N. */
+/* Fused feature all-gather (the one collective of the path): from now on every launch that computes features
+ * with this reservoir also stores the row of utterance u at row (row0 + u) of each of the n <= 8 matrices d_gather[k]
+ * (double[total_rows][n_keys*n_out], device pointers - typically every rank's gather matrix, mapped through CUDA IPC, the
+ * caller's own included) directly from the readout epilogue, over NVLink: no collective kernel, nothing to schedule beside the
+ * persistent kernels.  The rows are complete when the launch has completed; ranks synchronise (a barrier) before reading.
+ * n = 0 switches it off.  The setting is read when a launch is enqueued.                                                    */
+int lsm_reservoir_set_gather(lsm_ctx *ctx, lsm_reservoir *res, double *const *d_gather, int32_t n, int64_t row0);
 int lsm_reservoir_diagnostics(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int32_t B, int32_t *d_diag);
 
 /* ---------------------------------------------------------------- the whole path, host buffers

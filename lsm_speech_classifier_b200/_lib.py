@@ -23,7 +23,7 @@ EXPORTS = [
     "lsm_frontend_encode_host", "lsm_reservoir_create", "lsm_reservoir_destroy", "lsm_reservoir_run",
     "lsm_reservoir_run_host", "lsm_pipeline_run_host", "lsm_pipeline_run", "lsm_spike_density",
     "lsm_hysteresis_encode", "lsm_fp64_peak_gops", "lsm_pipeline_is_fused", "lsm_frontend_mel_tables", "lsm_reservoir_diagnostics", "lsm_gammatone_design", "lsm_zoom_table", "lsm_standardize_fit", "lsm_standardize_transform",
-    "lsm_frontend_set_mode", "lsm_frontend_reruns", "lsm_pipeline_run_host_async", "lsm_sync_all", "lsm_lane_stream", "lsm_logreg_fit", "lsm_logreg_predict", "lsm_pipeline_run_i16", "lsm_pipeline_run_host_async_i16",
+    "lsm_frontend_set_mode", "lsm_frontend_reruns", "lsm_pipeline_run_host_async", "lsm_sync_all", "lsm_lane_stream", "lsm_logreg_fit", "lsm_logreg_predict", "lsm_pipeline_run_i16", "lsm_pipeline_run_host_async_i16", "lsm_reservoir_set_gather",
 ]
 
 
@@ -90,6 +90,7 @@ def load():
     lib.lsm_zoom_table.argtypes = [i32, i32, vp, vp]
     lib.lsm_pipeline_run_host_async.argtypes = [vp, vp, vp, vp, i32, u32, i32, vp, i32]
     lib.lsm_sync_all.argtypes = [vp]
+    lib.lsm_reservoir_set_gather.argtypes = [vp, vp, vp, i32, i64]
     lib.lsm_pipeline_run_i16.argtypes = [vp, vp, vp, vp, i32, u32, i32, vp, vp]
     lib.lsm_pipeline_run_host_async_i16.argtypes = [vp, vp, vp, vp, i32, u32, i32, vp, i32]
     lib.lsm_logreg_fit.argtypes = [vp, vp, vp, i32, i32, i32, C.c_double, i32, C.c_double, vp, vp, vp]

@@ -498,6 +498,18 @@ extern "C" void lsm_reservoir_destroy(lsm_reservoir *res)
     delete res;
 }
 
+extern "C" int lsm_reservoir_set_gather(lsm_ctx *ctx, lsm_reservoir *res, double *const *d_gather, int32_t n, int64_t row0)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!res || n < 0 || n > 8 || (n > 0 && !d_gather) || row0 < 0) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_set_gather: bad argument (at most 8 destinations)");
+    for (int k = 0; k < n; ++k)
+        if (!d_gather[k]) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_set_gather: null destination %d", k);
+    res->n_gather = n;
+    res->gather_row0 = row0;
+    for (int k = 0; k < 8; ++k) res->gather_out[k] = k < n ? d_gather[k] : nullptr;
+    return LSM_OK;
+}
+
 extern "C" int lsm_reservoir_run(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int32_t B,
                                  uint32_t feature_mask, int32_t nan_to_num, double *d_features,
                                  uint8_t *d_raster_or_null)

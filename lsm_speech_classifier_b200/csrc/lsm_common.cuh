@@ -79,6 +79,9 @@ struct lsm_reservoir {
     int lean = 0;                  // uniform leak and gain, one input row per driven neuron, relabelled layout (reservoir_core.cuh)
     int32_t *d_ext_id = nullptr;   // [n_pad] lean layout: external index of internal neuron slot (>= N: padding)
     int zero_row = 0;              // index of the all-zero weight row
+    double *gather_out[8] = {};    // fused all-gather destinations (lsm_reservoir_set_gather), n_gather = 0: off
+    long long gather_row0 = 0;
+    int n_gather = 0;
     int skip_dead_time = 0;        // theta > 0 and 0 <= leak <= 1 everywhere: silent stretches of an utterance are exact no-ops
     double c_off = 0.0, c_on = 0.0;
     int hi_magic = 0;

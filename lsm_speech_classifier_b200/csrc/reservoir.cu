@@ -79,6 +79,8 @@ void lsm_reservoir_fill_args(const lsm_reservoir *res, const uint8_t *d_spikes, 
     a.features = d_features; a.raster = d_raster; a.stat_global = nullptr; a.diag = nullptr;
     a.ext_id = res->d_ext_id; a.c_off = res->c_off; a.c_on = res->c_on; a.hi_magic = res->hi_magic; a.zero_row = res->zero_row;
     a.skip_dead_time = res->skip_dead_time;
+    a.n_gather = res->n_gather; a.gather_row0 = res->gather_row0;
+    for (int k = 0; k < 8; ++k) a.gather_out[k] = k < res->n_gather ? res->gather_out[k] : nullptr;
     a.B = B; a.N = p.num_neurons; a.n_pad = res->n_pad; a.C = p.num_inputs; a.CW = (p.num_inputs + 31) / 32; a.T = p.num_steps;
     a.refractory = p.refractory; a.n_out = p.n_out; a.nan_to_num = nan_to_num;
     a.leak0 = res->leak0; a.gain0 = res->gain0;

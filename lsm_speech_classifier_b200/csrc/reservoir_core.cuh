@@ -23,6 +23,11 @@ struct ResArgs {
     int hi_magic;             // LEAN: high word of the double whose low word holds acc ^ 0x80000000
     int zero_row;             // index of the all-zero weight row that pads a group of four list entries
     int skip_dead_time;       // 1: theta > 0 and every leak in [0, 1], so silent stretches may be skipped (exactly)
+    // fused all-gather: the feature row of utterance u also goes to row gather_row0 + u of every rank's gather matrix, as
+    // direct stores over NVLink into IPC-mapped peer memory (lsm_reservoir_set_gather); n_gather = 0: off
+    double *gather_out[8];
+    long long gather_row0;
+    int n_gather;
     int B, N, n_pad, C, CW, T, refractory, n_out, nkeys, nan_to_num;
     unsigned feature_mask;
     double theta, scale, leak0, gain0;
@@ -308,6 +313,12 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
                 __syncthreads();
                 const int n_here = min(cap, a.n_out - tile);
                 for (int idx = tid; idx < n_here; idx += nthr) __stcs(f + (size_t)slot * a.n_out + tile + idx, s_buf[idx]);
+                if (a.n_gather > 0) {
+                    // the collective, fused: the same coalesced run into every rank's gather matrix (own one included)
+                    const size_t off = ((size_t)(a.gather_row0 + utt) * a.nkeys + slot) * a.n_out + tile;
+                    for (int p = 0; p < a.n_gather; ++p)
+                        for (int idx = tid; idx < n_here; idx += nthr) __stcs(a.gather_out[p] + off + idx, s_buf[idx]);
+                }
                 __syncthreads();
             }
             ++slot;

@@ -149,6 +149,11 @@ class PeerAllGather:
                 self.peer[r][k][lo:lo + self.rows].copy_(local, non_blocking=True)
         return st
 
+    def pointers(self, k: int):
+        """Device addresses of every rank's gather buffer k (rank order), for SNN.set_gather: the fused all-gather, where the
+        readout epilogue of the kernel stores the rows into all of them itself."""
+        return [self.peer[r][k].data_ptr() for r in range(self.world)]
+
     def wait(self, k: int, stream=None):
         """Make `stream` (default: the current one) wait for this rank's outstanding copies into buffers k."""
         import torch

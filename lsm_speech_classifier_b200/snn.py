@@ -116,6 +116,14 @@ class SNN:
         n = self.num_neurons
         return d[:, 0] / n * 100.0, n - d[:, 0], d[:, 1] / n
 
+    def set_gather(self, pointers, row0: int = 0):
+        """Fused all-gather (lsm_reservoir_set_gather): launches enqueued from now on also store utterance u's feature row at
+        row row0 + u of every matrix in `pointers` (device addresses, e.g. `distributed.PeerAllGather.pointers(k)`); an empty
+        list switches it off."""
+        ptrs = [int(p) for p in pointers]
+        arr = (C.c_void_p * max(1, len(ptrs)))(*ptrs)
+        self.ctx.check(self.ctx.lib.lsm_reservoir_set_gather(self.ctx.h, self.h, arr, len(ptrs), int(row0)))
+
     @staticmethod
     def _reorder(feats, order, keys, n_out):
         """The kernel emits keys in bit order; FEATURE_SETS lists are already in that order, but honour any."""

@@ -637,3 +637,37 @@ def test_front_end_batches_beyond_one_energy_pass(env):
     tiled = np.concatenate([want] * reps)[:8200]
     assert np.array_equal(got[:80], tiled[:80]) and np.array_equal(got[8150:], tiled[8150:])
     assert np.array_equal(got, tiled)
+
+
+def test_fused_gather_writes_rows_into_every_destination(env, small_set):
+    """lsm_reservoir_set_gather: the readout epilogue also stores each feature row at row0 + u of every destination matrix
+    (on one GPU here: two local matrices stand in for the ranks' IPC-mapped gather buffers); off again with an empty list."""
+    import torch
+    from lsm_speech_classifier_b200.frontend import Frontend
+    from lsm_speech_classifier_b200.snn import SNN, AudioToFeatures, SimulationParams
+    from lsm_speech_classifier_b200.extract_lsm_features import FEATURE_SETS, calculate_theoretical_w_critico
+    pcm, _ = small_set
+    fe = Frontend(128, "gammatone")
+    spikes = fe.encode(pcm)
+    params = SimulationParams(input_spike_times=spikes[0])
+    params.mean_weight = calculate_theoretical_w_critico(params, spikes, verbose=False) * 0.6
+    lsm = SNN(simulation_params=params)
+    pipe = AudioToFeatures(fe, lsm)
+    keys = FEATURE_SETS["original"]
+    d_pcm = torch.from_numpy(pcm).cuda()
+    want, _ = pipe.run(d_pcm, keys)
+    B, F = want.shape
+    dst = [torch.full((3 * B + 5, F), -1.0, dtype=torch.float64, device="cuda") for _ in range(2)]
+    lsm.set_gather([d.data_ptr() for d in dst], B + 5)
+    got, _ = pipe.run(d_pcm, keys)                         # fused kernel
+    got2 = lsm.simulate_batch(torch.from_numpy(spikes).cuda(), keys)      # stand-alone reservoir kernel: same epilogue
+    torch.cuda.synchronize()
+    lsm.set_gather([], 0)
+    assert torch.equal(got, want) and torch.equal(got2, want)
+    for d in dst:
+        assert torch.equal(d[B + 5:2 * B + 5], want)
+        assert bool((d[:B + 5] == -1).all()) and bool((d[2 * B + 5:] == -1).all())
+    dst[0].fill_(-1.0)
+    pipe.run(d_pcm, keys)
+    torch.cuda.synchronize()
+    assert bool((dst[0] == -1).all())
