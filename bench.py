@@ -170,9 +170,7 @@ def workload_config():
             "utterances_per_step_per_gpu": N_CLASSES * PER_CLASS, "n_filters": N_FILTERS, "filterbank": FILTERBANK,
             "feature_set": FEATURE_SET, "multiplier": MULTIPLIER, "n_neurons": N_NEURONS,
             "l2_policy": "inputs larger than L2 (153.6 MB PCM per step > 126 MB L2)",
-            "parallelism": "utterance-sharded, one process per GPU; feature rows all-gathered inside the timed region ("
-                           + ("stored into every rank's matrix by the kernel's readout epilogue over NVLink" if os.environ.get("LSM_BENCH_FUSED_GATHER")
-                              else "NCCL") + ")"}
+            "parallelism": "utterance-sharded, one process per GPU; feature rows all-gathered over NCCL inside the timed region"}
 
 
 _REAL_STDOUT = None
@@ -252,10 +250,9 @@ def main():
     # feature all-gather: NCCL (asynchronous, double-buffered); LSM_BENCH_P2P=1 switches to peer-to-peer copies over NVLink
     # (distributed.PeerAllGather, copy engines only) - measured equal at N = 2 (6.68 vs 6.72 ms per step) and much worse at N = 8
     # (25.5 vs 7.0 ms), so NCCL stays the default
-    use_p2p = world > 1 and bool(os.environ.get("LSM_BENCH_P2P") or os.environ.get("LSM_BENCH_FUSED_GATHER"))
-    # LSM_BENCH_FUSED_GATHER=1: no collective call at all - the readout epilogue of the fused kernel stores every feature row
-    # into all ranks' gather matrices itself (lsm_reservoir_set_gather, NVLink stores into IPC-mapped peer memory)
-    fused_gather = world > 1 and bool(os.environ.get("LSM_BENCH_FUSED_GATHER"))
+    use_p2p = world > 1 and bool(os.environ.get("LSM_BENCH_P2P"))
+    # (lsm_reservoir_set_gather - the readout epilogue storing the rows into every rank's matrix itself - is not wired in here:
+    # with CUDA-IPC-mapped destinations of another process the kernel faulted in the N = 2 trial)
     pag = None
     if use_p2p:
         from lsm_speech_classifier_b200.distributed import PeerAllGather
@@ -276,14 +273,10 @@ def main():
         with torch.cuda.stream(streams[b]):
             if pending[b] is not None:
                 pending[b].wait()          # the all-gather that last read this buffer pair
-            if pag is not None and not fused_gather:
+            if pag is not None:
                 pag.wait(b)                # this rank's copies out of d_feats[b] two steps ago
-            if fused_gather:
-                lsm.set_gather(pag.pointers(b), rank * B)
             path.run(d_pcm, keys, spikes=d_spikes2[b], out=d_feats[b])
-            if fused_gather:
-                pass                       # the kernel has already been told where the rows go
-            elif pag is not None:
+            if pag is not None:
                 pag.gather_async(b, d_feats[b], streams[b])
             elif world > 1:
                 pending[b] = dist.all_gather_into_tensor(d_alls[b], d_feats[b], async_op=True)
@@ -341,8 +334,6 @@ def main():
         b.record(); torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
-    if fused_gather:
-        lsm.set_gather([], 0)
     reps = max(3, min(args.steps, 10))
     reruns_value = fe.reruns(reset=True) / max(1, max(args.warmup, 3) + args.steps + 1)   # per step (+1: the w_critico head)
     k1_ms = time_kernel(lambda: fe.encode(d_pcm), reps)
@@ -383,14 +374,10 @@ def main():
                 with torch.cuda.stream(ext[b]):
                     if pend[b] is not None:
                         pend[b].wait()
-                    if pag is not None and not fused_gather:
+                    if pag is not None:
                         pag.wait(b, ext[b])
-                    if fused_gather:
-                        lsm.set_gather(pag.pointers(b), rank * B)
                     path.run_host_async(h_in, keys, out=d_feats[b], lane=b)
-                    if fused_gather:
-                        pass
-                    elif pag is not None:
+                    if pag is not None:
                         pag.gather_async(b, d_feats[b], ext[b])
                     else:
                         pend[b] = dist.all_gather_into_tensor(d_alls[b], d_feats[b], async_op=True)
@@ -402,8 +389,6 @@ def main():
             if pag is not None:
                 pag.wait(b, ext[b])
         ctx.sync_all()
-        if fused_gather:
-            lsm.set_gather([], 0)
         fence()
         dt = time.perf_counter() - t0
         te = torch.tensor([dt], dtype=torch.float64, device="cuda")

@@ -502,8 +502,34 @@ extern "C" int lsm_reservoir_set_gather(lsm_ctx *ctx, lsm_reservoir *res, double
 {
     if (!ctx) return LSM_ERR_INVALID;
     if (!res || n < 0 || n > 8 || (n > 0 && !d_gather) || row0 < 0) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_set_gather: bad argument (at most 8 destinations)");
-    for (int k = 0; k < n; ++k)
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int k = 0; k < n; ++k) {
         if (!d_gather[k]) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_set_gather: null destination %d", k);
+        // a destination in another GPU's memory (IPC-mapped): kernels of this device may only store there once peer access is on
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, d_gather[k]) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+            cudaGetLastError();
+            LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_set_gather: destination %d is not device memory", k);
+        }
+        if (at.device != ctx->device) {
+            int can = 0;
+            LSM_CUDA(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, at.device));
+            if (!can) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "lsm_reservoir_set_gather: device %d cannot access device %d", ctx->device, at.device);
+        }
+    }
+    if (n > 0) {
+        // peer access from this device to every other visible device (idempotent; IPC-mapped destinations report their owner)
+        int ndev = 0;
+        LSM_CUDA(ctx, cudaGetDeviceCount(&ndev));
+        for (int d = 0; d < ndev; ++d) {
+            if (d == ctx->device) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, ctx->device, d) != cudaSuccess || !can) { cudaGetLastError(); continue; }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(d, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); LSM_FAIL(ctx, LSM_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) -> %s", d, cudaGetErrorString(e)); }
+            cudaGetLastError();
+        }
+    }
     res->n_gather = n;
     res->gather_row0 = row0;
     for (int k = 0; k < 8; ++k) res->gather_out[k] = k < n ? d_gather[k] : nullptr;
