@@ -125,21 +125,48 @@ def _collect_wavs():
     return clips, labels
 
 
-def create_dataset(n_filters: int, filterbank: str, synthetic: tuple | None = None):
-    """reference :107-177.  `synthetic=(n_classes, per_class)` replaces the directory walk with the
-    deterministic generator (synth.py) - there is no Speech Commands copy in this environment."""
-    from .distributed import is_main
-    print(f"Creating dataset with filterbank: {filterbank}, filters: {n_filters}")
+PACKED_FILE = "speech_spike_dataset_packed.npz"
+
+
+def save_packed_spikes(filename, X_spikes: np.ndarray, y_labels: np.ndarray):
+    """(extension) the spike trains as bits: X_spikes_bits uint8[S, C, ceil(T/8)] (np.packbits along the
+    time axis), n_steps, y_labels - an eighth of the reference file before compression.  `load_spike_dataset` reads it back to
+    exactly the reference's arrays when the reference-schema file is absent."""
+    X = np.asarray(X_spikes)
+    if X.dtype != np.uint8 or X.ndim != 3 or (X > 1).any():
+        raise ValueError("X_spikes must be uint8[S, C, T] of zeros and ones")
+    np.savez_compressed(filename, X_spikes_bits=np.packbits(X, axis=2), n_steps=np.int32(X.shape[2]),
+                        y_labels=np.asarray(y_labels, dtype=np.int32))
+
+
+def load_packed_spikes(filename):
+    data = np.load(filename)
+    T = int(data["n_steps"])
+    return np.unpackbits(data["X_spikes_bits"], axis=2, count=T), data["y_labels"]
+
+
+def collect_pcm(synthetic: tuple | None = None):
+    """The utterances of a run as float32[S, 16000] + labels: the synthetic generator or the reference's directory walk."""
     if synthetic is not None:
         from . import synth
         import os
-        pcm, labels = synth.synth_dataset(int(synthetic[0]), int(synthetic[1]), workers=os.cpu_count() or 1)
-    else:
-        clips, labels = _collect_wavs()
-        if not clips:
-            print("\nERROR: No audio files were successfully processed.")
-            return
-        pcm = np.stack(clips)
+        return synth.synth_dataset(int(synthetic[0]), int(synthetic[1]), workers=os.cpu_count() or 1)
+    clips, labels = _collect_wavs()
+    if not clips:
+        print("\nERROR: No audio files were successfully processed.")
+        return None, None
+    return np.stack(clips), np.array(labels, dtype=np.int32)
+
+
+def create_dataset(n_filters: int, filterbank: str, synthetic: tuple | None = None, packed: bool = False):
+    """reference :107-177.  `synthetic=(n_classes, per_class)` replaces the directory walk with the
+    deterministic generator (synth.py) - there is no Speech Commands copy in this environment.
+    `packed=True` writes the bit-packed file (save_packed_spikes) instead of the reference-schema one."""
+    from .distributed import is_main
+    print(f"Creating dataset with filterbank: {filterbank}, filters: {n_filters}")
+    pcm, labels = collect_pcm(synthetic)
+    if pcm is None:
+        return
     X_spikes = encode_batch(pcm, n_filters, filterbank)
     y_labels = np.array(labels, dtype=np.int32)
     if not is_main():
@@ -148,6 +175,10 @@ def create_dataset(n_filters: int, filterbank: str, synthetic: tuple | None = No
     print("\nDataset created successfully.")
     print(f"  Shape: {X_spikes.shape}")
     print(f"  Avg spikes per sample: {np.mean(counts):.1f}")
+    if packed:
+        save_packed_spikes(PACKED_FILE, X_spikes, y_labels)
+        print(f"Saved to '{PACKED_FILE}' (bit-packed)")
+        return
     np.savez_compressed(OUTPUT_FILE, X_spikes=X_spikes, y_labels=y_labels)
     print(f"Saved to '{OUTPUT_FILE}'")
 
@@ -159,8 +190,9 @@ def _cli(argv=None):
                         help="Type of filterbank to use.")
     parser.add_argument("--synthetic", type=int, nargs=2, metavar=("CLASSES", "PER_CLASS"), default=None,
                         help="(extension) use the deterministic synthetic generator instead of speech_commands_v0.02/")
+    parser.add_argument("--packed", action="store_true", help="(extension) write the bit-packed spike file instead")
     args = parser.parse_args(argv)
-    create_dataset(n_filters=args.n_filters, filterbank=args.filterbank, synthetic=args.synthetic)
+    create_dataset(n_filters=args.n_filters, filterbank=args.filterbank, synthetic=args.synthetic, packed=args.packed)
 
 
 if __name__ == "__main__":

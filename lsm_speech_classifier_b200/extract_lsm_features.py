@@ -57,8 +57,17 @@ def calculate_theoretical_w_critico(lsm_params, input_data, verbose: bool = True
     return w_critico
 
 
+PACKED_SPIKE_FILE = "speech_spike_dataset_packed.npz"
+
+
 def load_spike_dataset(filename=SPIKE_FILE):
     if not Path(filename).exists():
+        if filename == SPIKE_FILE and Path(PACKED_SPIKE_FILE).exists():
+            # (extension) the bit-packed form written by create_dataset --packed: same arrays after unpacking
+            from .create_dataset import load_packed_spikes
+            X_spikes, y_labels = load_packed_spikes(PACKED_SPIKE_FILE)
+            print(f"Loaded {len(X_spikes)} samples from '{PACKED_SPIKE_FILE}' (bit-packed)")
+            return X_spikes, y_labels
         print(f"Error: Dataset not found at '{filename}'")
         return None, None
     data = np.load(filename)
@@ -146,6 +155,40 @@ def main(feature_set: str, multiplier: float, leak_variance_divisor: float = Non
     X_test_feat = extract_all_features(lsm, X_test, feature_keys, "Testing")
     if not is_main():
         return
+    scaler = StandardScaler()
+    X_train_scaled = scaler.fit_transform(X_train_feat)
+    X_test_scaled = scaler.transform(X_test_feat)
+    np.savez_compressed(FEATURE_FILE, X_train_features=X_train_scaled, y_train=y_train,
+                        X_test_features=X_test_scaled, y_test=y_test, feature_set=feature_set,
+                        leak_variance_divisor=leak_variance_divisor)
+    print(f"Extraction complete. Features saved to '{FEATURE_FILE}'")
+
+
+def main_fused(pcm, y_labels, n_filters: int, filterbank: str, feature_set: str, multiplier: float,
+               leak_variance_divisor: float = None, num_neurons: int = NUM_NEURONS):
+    """(extension) stages 1 and 2 without the spike file in between: audio -> features through the fused
+    path, same split, same reservoir, same feature file as create_dataset + main (bit for bit; tests/test_gpu_cli.py).  Only
+    the first <= 500 training utterances are encoded on their own, for w_critico (reference :40-49, :160-162)."""
+    from sklearn.model_selection import train_test_split
+    from sklearn.preprocessing import StandardScaler
+    from .distributed import world
+    from .frontend import Frontend
+    from .snn import AudioToFeatures
+    if world()[1] > 1:
+        raise RuntimeError("main_fused is single-process; under torchrun use create_dataset + main (utterance-sharded)")
+    pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+    y_labels = np.asarray(y_labels, dtype=np.int32)
+    idx = np.arange(len(pcm))
+    tr, te, y_train, y_test = train_test_split(idx, y_labels, test_size=0.2, random_state=42, stratify=y_labels)
+    fe = Frontend(n_filters, filterbank)
+    head = fe.encode(pcm[tr[:500]])
+    lsm = build_lsm(head, multiplier, leak_variance_divisor, num_neurons)
+    run_network_diagnostics(lsm, head)
+    feature_keys = FEATURE_SETS[feature_set]
+    print(f"Extracting feature set: '{feature_set}' (fused audio -> features)")
+    path = AudioToFeatures(fe, lsm)
+    X_train_feat = path.run_host(np.ascontiguousarray(pcm[tr]), feature_keys)
+    X_test_feat = path.run_host(np.ascontiguousarray(pcm[te]), feature_keys)
     scaler = StandardScaler()
     X_train_scaled = scaler.fit_transform(X_train_feat)
     X_test_scaled = scaler.transform(X_test_feat)

@@ -7,18 +7,26 @@ import argparse
 
 
 def run_pipeline(n_filters: int, filterbank: str, feature_set: str, multiplier: float, synthetic=None,
-                 train: bool = True, readout: str = "sklearn"):
+                 train: bool = True, readout: str = "sklearn", fused: bool = False, packed: bool = False):
     from . import create_dataset as cd, extract_lsm_features as ex
     from .distributed import init_from_env, is_main
     init_from_env()
     if is_main():
         print("--- Running Pipeline ---")
-        print("\n--- Step 1: Creating Spike Train Dataset ---")
-    cd.create_dataset(n_filters=n_filters, filterbank=filterbank, synthetic=synthetic)
-    _barrier()
-    if is_main():
-        print("\n--- Step 2: Extracting LSM Features ---")
-    ex.main(feature_set=feature_set, multiplier=multiplier)
+    if fused:
+        # (extension) no spike file between the stages: audio -> features in one pass
+        print("\n--- Steps 1+2: Audio -> LSM Features (fused) ---")
+        pcm, labels = cd.collect_pcm(synthetic)
+        if pcm is not None:
+            ex.main_fused(pcm, labels, n_filters, filterbank, feature_set, multiplier)
+    else:
+        if is_main():
+            print("\n--- Step 1: Creating Spike Train Dataset ---")
+        cd.create_dataset(n_filters=n_filters, filterbank=filterbank, synthetic=synthetic, packed=packed)
+        _barrier()
+        if is_main():
+            print("\n--- Step 2: Extracting LSM Features ---")
+        ex.main(feature_set=feature_set, multiplier=multiplier)
     _barrier()
     if train and is_main():
         print("\n--- Step 3: Training and Evaluating Classifier ---")
@@ -48,9 +56,13 @@ def _cli(argv=None):
     parser.add_argument("--no-train", action="store_true", help="(extension) stop after the feature file")
     parser.add_argument("--readout", type=str, default="sklearn", choices=["sklearn", "device"],
                         help="(extension) fit the logistic-regression readout with scikit-learn (reference) or on the GPU")
+    parser.add_argument("--fused", action="store_true",
+                        help="(extension) audio -> features in one pass, no spike file between the stages (same feature file)")
+    parser.add_argument("--packed", action="store_true", help="(extension) bit-packed spike file between the stages")
     args = parser.parse_args(argv)
     run_pipeline(n_filters=args.n_filters, filterbank=args.filterbank, feature_set=args.feature_set,
-                 multiplier=args.multiplier, synthetic=args.synthetic, train=not args.no_train, readout=args.readout)
+                 multiplier=args.multiplier, synthetic=args.synthetic, train=not args.no_train, readout=args.readout,
+                 fused=args.fused, packed=args.packed)
 
 
 if __name__ == "__main__":

@@ -109,3 +109,21 @@ def test_stage_scripts_and_missing_file_behaviour(tmp_path):
     f2 = np.load(tmp_path / "lsm_features_larger.npz", allow_pickle=True)
     assert f2["X_train_features"].shape[1] == 8 * 400 and str(f2["feature_set"]) == "all"
     assert float(f2["leak_variance_divisor"]) == 4.0
+
+
+def test_fused_and_packed_cli_modes_write_the_same_feature_file(workdir, tmp_path_factory):
+    """--fused (no spike file between the stages) and --packed (bit-packed spike file) end in the feature file of the
+    reference-schema run, array for array."""
+    d0, _ = workdir
+    ref = np.load(d0 / "lsm_features_larger.npz", allow_pickle=True)
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    for flag in ("--fused", "--packed"):
+        d = tmp_path_factory.mktemp("cli" + flag.strip("-"))
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "main.py"), "--synthetic", "4", "100", "--no-train", flag],
+                           cwd=d, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        got = np.load(d / "lsm_features_larger.npz", allow_pickle=True)
+        for k in ("X_train_features", "y_train", "X_test_features", "y_test"):
+            assert np.array_equal(got[k], ref[k]), (flag, k)
+        assert not (d / "speech_spike_dataset_pure_redundancy.npz").exists()
+        assert (d / "speech_spike_dataset_packed.npz").exists() == (flag == "--packed")

@@ -90,3 +90,26 @@ def test_readout_has_no_cpu_fallback():
     for cls in (StandardScaler, LogisticRegression):
         with pytest.raises(_lib.LsmError):
             cls()
+
+
+def test_packed_spike_file_round_trip(tmp_path, monkeypatch):
+    """create_dataset --packed: bits on disk, the reference's arrays back through load_spike_dataset."""
+    import os
+    from lsm_speech_classifier_b200 import create_dataset as cd, extract_lsm_features as ex
+    rng = np.random.default_rng(7)
+    X = (rng.random((9, 128, 400)) < 0.03).astype(np.uint8)
+    X[3] = 0
+    X[4] = 1
+    y = np.arange(9, dtype=np.int32) % 4
+    monkeypatch.chdir(tmp_path)
+    cd.save_packed_spikes(cd.PACKED_FILE, X, y)
+    ref = tmp_path / "ref.npz"
+    np.savez_compressed(ref, X_spikes=X, y_labels=y)
+    assert os.path.getsize(cd.PACKED_FILE) < os.path.getsize(ref)
+    Xb, yb = ex.load_spike_dataset()                              # reference-schema file absent -> packed file
+    assert Xb.dtype == np.uint8 and Xb.shape == X.shape and np.array_equal(Xb, X) and np.array_equal(yb, y) and yb.dtype == np.int32
+    Xo = (rng.random((2, 3, 13)) < 0.5).astype(np.uint8)          # a step count that is not a multiple of 8
+    cd.save_packed_spikes("odd.npz", Xo, np.zeros(2, np.int32))
+    assert np.array_equal(cd.load_packed_spikes("odd.npz")[0], Xo)
+    with pytest.raises(ValueError):
+        cd.save_packed_spikes("bad.npz", X * 2, y)
