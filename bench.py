@@ -170,7 +170,9 @@ def workload_config():
             "utterances_per_step_per_gpu": N_CLASSES * PER_CLASS, "n_filters": N_FILTERS, "filterbank": FILTERBANK,
             "feature_set": FEATURE_SET, "multiplier": MULTIPLIER, "n_neurons": N_NEURONS,
             "l2_policy": "inputs larger than L2 (153.6 MB PCM per step > 126 MB L2)",
-            "parallelism": "utterance-sharded, one process per GPU; feature rows all-gathered over NCCL inside the timed region"}
+            "parallelism": "utterance-sharded, one process per GPU; feature rows all-gathered inside the timed region, "
+                           + ("by the kernel's readout epilogue (NVLink stores into every rank's matrix)" if os.environ.get("LSM_BENCH_FUSED_GATHER")
+                              else "over NCCL")}
 
 
 _REAL_STDOUT = None
@@ -250,13 +252,16 @@ def main():
     # feature all-gather: NCCL (asynchronous, double-buffered); LSM_BENCH_P2P=1 switches to peer-to-peer copies over NVLink
     # (distributed.PeerAllGather, copy engines only) - measured equal at N = 2 (6.68 vs 6.72 ms per step) and much worse at N = 8
     # (25.5 vs 7.0 ms), so NCCL stays the default
-    use_p2p = world > 1 and bool(os.environ.get("LSM_BENCH_P2P"))
-    # (lsm_reservoir_set_gather - the readout epilogue storing the rows into every rank's matrix itself - is not wired in here:
-    # with CUDA-IPC-mapped destinations of another process the kernel faulted in the N = 2 trial)
+    # LSM_BENCH_FUSED_GATHER=1: no collective call at all - the readout epilogue of the fused kernel stores every feature row into
+    # all ranks' gather matrices itself (lsm_reservoir_set_gather; the peers' matrices are mapped through CUDA IPC on the local
+    # device).  Validated at N = 2 (tools/fused_gather_exp.py: 5.74 vs 6.16 ms per step, identical matrices); NCCL stays the
+    # default until it has been run at N = 8.
+    fused_gather = world > 1 and bool(os.environ.get("LSM_BENCH_FUSED_GATHER"))
+    use_p2p = world > 1 and bool(os.environ.get("LSM_BENCH_P2P") or fused_gather)
     pag = None
     if use_p2p:
         from lsm_speech_classifier_b200.distributed import PeerAllGather
-        pag = PeerAllGather(B, F, torch.float64, torch.device("cuda", local_rank))
+        pag = PeerAllGather(B, F, torch.float64, torch.device("cuda", local_rank), map_on_local_device=fused_gather)
         d_alls = pag.bufs
     else:
         d_alls = [torch.empty((world * B, F), dtype=torch.float64, device="cuda") for _ in range(2)] if world > 1 else None
@@ -273,10 +278,12 @@ def main():
         with torch.cuda.stream(streams[b]):
             if pending[b] is not None:
                 pending[b].wait()          # the all-gather that last read this buffer pair
-            if pag is not None:
+            if pag is not None and not fused_gather:
                 pag.wait(b)                # this rank's copies out of d_feats[b] two steps ago
+            if fused_gather:
+                lsm.set_gather(pag.pointers(b), rank * B)      # read when the launch is enqueued
             path.run(d_pcm, keys, spikes=d_spikes2[b], out=d_feats[b])
-            if pag is not None:
+            if pag is not None and not fused_gather:
                 pag.gather_async(b, d_feats[b], streams[b])
             elif world > 1:
                 pending[b] = dist.all_gather_into_tensor(d_alls[b], d_feats[b], async_op=True)
@@ -334,6 +341,8 @@ def main():
         b.record(); torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
+    if fused_gather:
+        lsm.set_gather([], 0)              # the stand-alone timings below do not gather
     reps = max(3, min(args.steps, 10))
     reruns_value = fe.reruns(reset=True) / max(1, max(args.warmup, 3) + args.steps + 1)   # per step (+1: the w_critico head)
     k1_ms = time_kernel(lambda: fe.encode(d_pcm), reps)
@@ -374,10 +383,12 @@ def main():
                 with torch.cuda.stream(ext[b]):
                     if pend[b] is not None:
                         pend[b].wait()
-                    if pag is not None:
+                    if pag is not None and not fused_gather:
                         pag.wait(b, ext[b])
+                    if fused_gather:
+                        lsm.set_gather(pag.pointers(b), rank * B)
                     path.run_host_async(h_in, keys, out=d_feats[b], lane=b)
-                    if pag is not None:
+                    if pag is not None and not fused_gather:
                         pag.gather_async(b, d_feats[b], ext[b])
                     else:
                         pend[b] = dist.all_gather_into_tensor(d_alls[b], d_feats[b], async_op=True)
@@ -389,6 +400,8 @@ def main():
             if pag is not None:
                 pag.wait(b, ext[b])
         ctx.sync_all()
+        if fused_gather:
+            lsm.set_gather([], 0)
         fence()
         dt = time.perf_counter() - t0
         te = torch.tensor([dt], dtype=torch.float64, device="cuda")

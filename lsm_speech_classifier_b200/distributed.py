@@ -121,7 +121,7 @@ class PeerAllGather:
     (checked in bench.py).
     `n_buffers` gather buffers per rank alternate between steps; the caller synchronises ranks (a barrier) before it reads."""
 
-    def __init__(self, rows: int, width: int, dtype, device, n_buffers: int = 2):
+    def __init__(self, rows: int, width: int, dtype, device, n_buffers: int = 2, map_on_local_device: bool = False):
         import torch
         import torch.distributed as dist
         from torch.multiprocessing.reductions import reduce_tensor
@@ -131,8 +131,17 @@ class PeerAllGather:
         mine = [reduce_tensor(b) for b in self.bufs]
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine)
-        # peer[r][k]: rank r's gather buffer k, addressable from this process (this rank's own buffers are used directly)
-        self.peer = [[(self.bufs[k] if r == self.rank else fn(*args)) for k, (fn, args) in enumerate(everyone[r])]
+        # peer[r][k]: rank r's gather buffer k, addressable from this process (this rank's own buffers are used directly).
+        # map_on_local_device: open the IPC handles with THIS rank's device current (rebuild_cuda_tensor's storage_device
+        # argument), so that the mapping belongs to the context kernels of this rank run in - what kernels that store into the
+        # peers' buffers (SNN.set_gather) need; torch then labels those tensors with the local device.
+        def rebuild(fn, args):
+            if map_on_local_device:
+                args = list(args)
+                args[6] = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+                args = tuple(args)
+            return fn(*args)
+        self.peer = [[(self.bufs[k] if r == self.rank else rebuild(fn, args)) for k, (fn, args) in enumerate(everyone[r])]
                      for r in range(self.world)]
         self.streams = [torch.cuda.Stream(device=device) for _ in range(n_buffers)]
 
