@@ -10,14 +10,17 @@
 //   convert_spectrogram_to_spikes_hysteresis     :81-98
 //   create_pure_redundancy                       :101-104
 //
-// Mapping: one CTA per utterance in flight (persistent grid, CTAs stride over the batch), one thread
-// per channel.  The IIR recurrences are inherently sequential in the reference's rounding order, so
-// parallelism is (utterance x channel): 128 chains per utterance, thousands of utterances.  The
-// kernel is bound by the fp64 pipe (~35 DADD/DMUL/DFMA per channel-sample), not by HBM: per
-// utterance it reads 64 000 B of PCM and writes 51 200 B of spikes.
-//
-// Bit-exactness: every fp64 operation is an explicit __d*_rn intrinsic in the oracle's order
-// (oracle/lsm_oracle.c gammatone_energy / db_normalise_zoom / hysteresis_encode_f64).
+// Kernels in this file:
+//   gammatone_encode_kernel<MAXT, MINB, FNPT, LEAN>  persistent, one CTA per utterance in flight, one thread per channel.  FNPT = 0:
+//       front end only; FNPT > 0: fused audio -> features (the CTA then simulates the utterance's reservoir, reservoir_core.cuh).
+//       Filter modes: exact (gt_filter_exact: every fp64 operation an explicit __d*_rn intrinsic in the oracle's order -
+//       oracle/lsm_oracle.c gammatone_energy / db_normalise_zoom / hysteresis_encode_f64 - 35 operations per channel-sample) and,
+//       by default, speculative (gt_filter_fast: the same cascade in 13 FMAs; spec_epilogue flags near-ties, which are filtered
+//       again exactly inside the kernel, so the spike trains are the exact path's either way).
+//   gammatone_energy_kernel + encode_reservoir_kernel / gammatone_encode_kernel in mode 2: the lanes arrangement (lane =
+//       utterance, coefficients in uniform registers); default for the stand-alone front end, opt-in for the whole path.
+//   spec_fused_kernel: speculative-only variant with the exact pass as a follow-up launch (opt-in, measured slower).
+// The filter is bound by the fp64 pipe, not by HBM: per utterance it reads 64 000 B of PCM and writes 51 200 B of spikes.
 #include <stdlib.h>
 
 #include <memory>
