@@ -138,7 +138,8 @@ def reference_arm(args, rank, world):
     from lsm_speech_classifier_b200._lib import feature_mask
     from lsm_speech_classifier_b200.extract_lsm_features import FEATURE_SETS
     cores = coracle.num_threads()
-    per_class = max(1, (cores * 8 + N_CLASSES - 1) // N_CLASSES)
+    # the whole 2400-utterance step when the host gets through it in a few seconds (>= 16 threads), else a bounded sample
+    per_class = PER_CLASS if cores >= 16 else max(1, (cores * 8 + N_CLASSES - 1) // N_CLASSES)
     pcm, _ = synth.synth_dataset(N_CLASSES, per_class, workers=cores)
     tables = host_tables()
     spikes = coracle.gammatone_encode(pcm[:64], *tables, [0.70, 0.80, 0.90, 0.95], 0.1)
@@ -152,7 +153,8 @@ def reference_arm(args, rank, world):
         oracle_pipeline(pcm, tables, res, mask, 0)
     dt = time.perf_counter() - t0
     val = len(pcm) * args.steps / dt
-    sample = f"{len(pcm)} utterances per step (bounded sample of the {N_CLASSES * PER_CLASS}-utterance workload), all host threads"
+    sample = (f"the full {len(pcm)}-utterance step, all host threads" if len(pcm) == N_CLASSES * PER_CLASS else
+              f"{len(pcm)} utterances per step (bounded sample of the {N_CLASSES * PER_CLASS}-utterance workload), all host threads")
     emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "utterances/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
@@ -171,8 +173,8 @@ def workload_config():
             "feature_set": FEATURE_SET, "multiplier": MULTIPLIER, "n_neurons": N_NEURONS,
             "l2_policy": "inputs larger than L2 (153.6 MB PCM per step > 126 MB L2)",
             "parallelism": "utterance-sharded, one process per GPU; feature rows all-gathered inside the timed region, "
-                           + ("by the kernel's readout epilogue (NVLink stores into every rank's matrix)" if os.environ.get("LSM_BENCH_FUSED_GATHER")
-                              else "over NCCL")}
+                           + ("over NCCL" if os.environ.get("LSM_BENCH_NCCL_GATHER")
+                              else "by the kernel's readout epilogue (NVLink stores into every rank's matrix; no collective kernel)")}
 
 
 _REAL_STDOUT = None
@@ -249,19 +251,22 @@ def main():
     d_spikes = d_spikes2[0]
     d_feats = [torch.empty((B, F), dtype=torch.float64, device="cuda") for _ in range(2)]
     d_feat = d_feats[0]
-    # feature all-gather: NCCL (asynchronous, double-buffered); LSM_BENCH_P2P=1 switches to peer-to-peer copies over NVLink
-    # (distributed.PeerAllGather, copy engines only) - measured equal at N = 2 (6.68 vs 6.72 ms per step) and much worse at N = 8
-    # (25.5 vs 7.0 ms), so NCCL stays the default
-    # LSM_BENCH_FUSED_GATHER=1: no collective call at all - the readout epilogue of the fused kernel stores every feature row into
-    # all ranks' gather matrices itself (lsm_reservoir_set_gather; the peers' matrices are mapped through CUDA IPC on the local
-    # device).  Validated at N = 2 (tools/fused_gather_exp.py: 5.74 vs 6.16 ms per step, identical matrices); NCCL stays the
-    # default until it has been run at N = 8.
-    fused_gather = world > 1 and bool(os.environ.get("LSM_BENCH_FUSED_GATHER"))
+    # Feature all-gather (the path's one collective).  Default: fused into the readout epilogue - every rank's kernel stores its
+    # feature rows into all ranks' gather matrices itself (lsm_reservoir_set_gather; the peers' matrices are mapped through CUDA
+    # IPC), so no collective kernel has to find room beside the persistent kernels.  Checked against one NCCL all-gather after the
+    # timed regions.  LSM_BENCH_NCCL_GATHER=1: NCCL's asynchronous all-gather instead; LSM_BENCH_P2P=1: copy-engine peer copies.
+    fused_gather = world > 1 and not os.environ.get("LSM_BENCH_NCCL_GATHER") and not os.environ.get("LSM_BENCH_P2P")
     use_p2p = world > 1 and bool(os.environ.get("LSM_BENCH_P2P") or fused_gather)
     pag = None
     if use_p2p:
         from lsm_speech_classifier_b200.distributed import PeerAllGather
-        pag = PeerAllGather(B, F, torch.float64, torch.device("cuda", local_rank), map_on_local_device=fused_gather)
+        try:
+            pag = PeerAllGather(B, F, torch.float64, torch.device("cuda", local_rank), ctx=ctx)
+        except RuntimeError as e:        # raised on every rank alike: no peer access here, the collective goes over NCCL
+            log(f"[bench] rank {rank}: {e}; feature all-gather over NCCL")
+            pag, fused_gather, use_p2p = None, False, False
+            os.environ["LSM_BENCH_NCCL_GATHER"] = "1"
+    if pag is not None:
         d_alls = pag.bufs
     else:
         d_alls = [torch.empty((world * B, F), dtype=torch.float64, device="cuda") for _ in range(2)] if world > 1 else None
@@ -285,7 +290,7 @@ def main():
             path.run(d_pcm, keys, spikes=d_spikes2[b], out=d_feats[b])
             if pag is not None and not fused_gather:
                 pag.gather_async(b, d_feats[b], streams[b])
-            elif world > 1:
+            elif world > 1 and not fused_gather:
                 pending[b] = dist.all_gather_into_tensor(d_alls[b], d_feats[b], async_op=True)
 
     def drain():
@@ -324,12 +329,29 @@ def main():
     e1.record()
     fence()
     ms_total = e0.elapsed_time(e1)
-    gpu_launches = ctx.launches - launches0 + (args.steps if (world > 1 and pag is None) else 0)      # + NCCL's kernels
+    gpu_launches = ctx.launches - launches0 + (args.steps if (world > 1 and pag is None) else 0)      # + NCCL's kernels, if it gathers
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     value = world * B * args.steps / (ms_total / 1e3)
+
+    # ---- the same steps for >= 2 s: the sustained figure beside the K-step burst (clocks settle under the power cap)
+    n_sus = max(args.steps, int(2200.0 / max(ms_total / args.steps, 1e-3)) + 1)
+    fence()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for st in streams:
+        st.wait_event(s0)
+    for _ in range(n_sus):
+        step_device()
+    drain()
+    s1.record()
+    fence()
+    ts = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+    sustained_ms = float(ts.item())
 
     # ---- per-kernel durations (K1 alone, K2 alone) for the roofline: CUDA events, same stream
     def time_kernel(fn, reps):
@@ -390,7 +412,7 @@ def main():
                     path.run_host_async(h_in, keys, out=d_feats[b], lane=b)
                     if pag is not None and not fused_gather:
                         pag.gather_async(b, d_feats[b], ext[b])
-                    else:
+                    elif not fused_gather:
                         pend[b] = dist.all_gather_into_tensor(d_alls[b], d_feats[b], async_op=True)
                     h_feats[b].copy_(d_feats[b], non_blocking=True)
         for b in (0, 1):
@@ -415,6 +437,18 @@ def main():
     ctx.sync_all()
     e2e_i16_val = e2e_loop(h_pcm16)
     e2e_val = e2e_loop(h_pcm)
+    # the same step from PAGEABLE numpy arrays through the synchronous public call (what create_dataset / extract_all_features
+    # style callers hand over): the copies are staged by the driver
+    e2e_pageable_val = None
+    if world == 1:
+        out_np = np.empty((B, F), dtype=np.float64)
+        path.run_host(pcm_np, keys, out=out_np)
+        t0 = time.perf_counter()
+        n_pg = max(2, min(args.steps, 5))
+        for _ in range(n_pg):
+            path.run_host(pcm_np, keys, out=out_np)
+        e2e_pageable_val = B * n_pg / (time.perf_counter() - t0)
+        assert np.array_equal(out_np, d_feats[0].cpu().numpy()), "pageable host path and device path disagree"
     if pag is not None:
         # the peer-to-peer gather against NCCL's, once, outside the timed regions
         ref_all = torch.empty_like(pag.bufs[0])
@@ -438,61 +472,65 @@ def main():
     hbm_peak = float(peaks["hbm_gbs"])
     step_ms = ms_total / args.steps
     fused = bool(path.fused)
-    # dominant kernel: the fused audio->features kernel (one launch per step) when the pair fuses, else K1
-    dom_ms = fused_ms if fused else k1_ms
-    dom_bytes = (FUSED_BYTES_PER_UTT if fused else K1_BYTES_PER_UTT) * B
-    dom_gbs = dom_bytes / (dom_ms / 1e3) / 1e9
+    # Dominant kernel: pipeline_kernel (warp-specialised audio -> features; two launches share the SMs, so the per-launch figure
+    # is taken over the timed steps: kernels run back to back on the two launch lanes for the whole region).  Binding resource:
+    # the fp64 pipe (13 DFMA per channel-sample); HBM is the secondary key.
+    dom_bytes = FUSED_BYTES_PER_UTT * B
+    dom_gbs = dom_bytes / (step_ms / 1e3) / 1e9
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             tj = json.load(f)
-        if fused and tj.get("utterances_per_launch") == B:
+        if tj.get("utterances_per_step") == B:
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     except Exception:
         pass
     spec = args.filter_mode == "speculative"
     k1_ops = K1_FP64_OPS_PER_UTT_SPEC if spec else K1_FP64_OPS_PER_UTT
     k1_gops = k1_ops * B / (k1_ms / 1e3) / 1e9
+    step_gops = k1_ops * B / (step_ms / 1e3) / 1e9
+    sus_step_ms = sustained_ms / n_sus
     out = {
         "metric": METRIC, "value": value, "unit": "utterances/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(),
         "neuron_steps_per_s": value * N_NEURONS * T_STEPS,
-        "e2e": {"value": e2e_val, "unit": "utterances/s", "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * F * 8},
+        "sustained": {"value": world * B * n_sus / (sustained_ms / 1e3), "unit": "utterances/s", "steps": n_sus, "seconds": sustained_ms / 1e3,
+                      "ms_per_step": sus_step_ms, "note": "the same steps for >= 2 s, CUDA events, max over ranks"},
+        "e2e": {"value": e2e_val, "unit": "utterances/s", "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * F * 8,
+                "note": "pinned host buffers through lsm_pipeline_run_host_async on alternating launch lanes: PCM by the copy engine, "
+                        "feature rows written by the kernel into the pinned host matrix"},
         "e2e_pcm16": {"value": e2e_i16_val, "unit": "utterances/s", "h2d_bytes_per_step": B * L * 2, "d2h_bytes_per_step": B * F * 8,
                       "note": "same steps with int16 PCM host buffers (lsm_pipeline_run_host_async_i16): the WAV-file sample format, "
                               "converted exactly in the kernel; e2e above keeps the float32 contract of load_audio_file"},
+        "e2e_pageable": {"value": e2e_pageable_val, "unit": "utterances/s", "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * F * 8,
+                         "note": "pageable numpy arrays through the synchronous lsm_pipeline_run_host (the reference-style call)"},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
-        "roofline": {"kernel": "gammatone_encode_kernel fused audio->features (K1+K2+K3)" if fused else "gammatone_encode_kernel (K1)",
-                     "bound": "hbm", "achieved": dom_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": dom_gbs / hbm_peak,
-                     "traffic": traffic, "algorithmic_bytes_per_launch": dom_bytes,
-                     "peak_source": f"{peak_kind} MEASURED_PEAKS.json hbm_gbs",
-                     "note": "this kernel is bound by the fp64 pipe / instruction issue, not HBM (SURVEY.md 8d): see roofline_fp64; "
-                             "traffic = dram read+write bytes per launch from ncu (profiles/r1_traffic.json)"},
-        "roofline_fp64": {"kernel": "stand-alone front end (K1): gammatone_energy_kernel (lane = utterance, uniform-register coefficients) + "
-                                    "encoder kernel" if spec else "gammatone_encode_kernel (K1, stand-alone launch, exact filter)",
-                          "bound": "fp64 pipe",
-                          "achieved": k1_gops, "peak": fp64_peak,
-                          "unit": "G fp64 lane-ops/s (DADD, DMUL, DFMA each count 1)", "frac": k1_gops / fp64_peak,
-                          "lane_ops_per_utterance": k1_ops,
-                          "in_fused_kernel": {"achieved": k1_ops * B / (fused_ms / 1e3) / 1e9,
-                                              "frac": k1_ops * B / (fused_ms / 1e3) / 1e9 / fp64_peak,
-                                              "note": "filter-bank lane-ops only, over one launch of the fused kernel (reservoir and readout included in the time)"},
-                          "over_timed_steps": {"achieved": k1_ops * B / (step_ms / 1e3) / 1e9, "frac": k1_ops * B / (step_ms / 1e3) / 1e9 / fp64_peak},
-                          "three_register_dfma_ceiling": {"value": 14400.0, "note": "tools/fp64_cascade.cu: a DFMA with three distinct register "
-                                                          "operands (per-lane coefficients, the fused kernel's filter) issues at 75 % of the pipe's rate; "
-                                                          "with uniform-register coefficients (the stand-alone front end's energy kernel) 19200"},
-                          "peak_source": "measured live by lsm_fp64_peak_gops (independent DADD/DMUL register chains); "
-                                         "nominal 148 SMs x 64 lanes x 1.965 GHz = 18612"},
-        "kernel_ms": {"K1_gammatone_encode": k1_ms, "K2_reservoir_features": k2_ms, "fused_audio_to_features": fused_ms,
-                      "note": "stand-alone launches on one stream; the timed steps alternate two streams, so ms_per_step < fused"},
+        "roofline": {"kernel": "pipeline_kernel (warp-specialised audio->features: lane = utterance filter warps + encoder/reservoir units)"
+                               if fused else "gammatone_encode_kernel (K1)",
+                     "bound": "fp64", "achieved": step_gops, "peak": fp64_peak, "unit": "G fp64 lane-ops/s (DFMA = 1)",
+                     "frac": step_gops / fp64_peak, "traffic": traffic,
+                     "lane_ops_per_utterance": k1_ops, "launch_duration_ms": step_ms,
+                     "peak_source": "measured live by lsm_fp64_peak_gops (independent DADD/DMUL register chains); nominal 148 SMs x 64 "
+                                    "lanes x 1.965 GHz = 18612; MEASURED_PEAKS.json has no fp64 entry",
+                     "note": "filter-bank lane-ops only (the reservoir's and the encoder's fp64 work, ~7 % more, is not counted) over the "
+                             "timed steps; two launches share every SM throughout, so the step time is the per-launch time of the kernel pair",
+                     "sustained_frac": k1_ops * B / (sus_step_ms / 1e3) / 1e9 / fp64_peak},
+        "roofline_hbm": {"bound": "hbm", "achieved": dom_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": dom_gbs / hbm_peak,
+                         "algorithmic_bytes_per_step": dom_bytes, "peak_source": f"{peak_kind} MEASURED_PEAKS.json hbm_gbs",
+                         "note": "64 000 B PCM in + 51 200 B spikes + 16 000 B features out per utterance: this path is nowhere near HBM-bound"},
+        "kernel_ms": {"K1_gammatone_encode": k1_ms, "K2_reservoir_features": k2_ms, "whole_step_one_caller_stream": fused_ms,
+                      "K1_fp64_frac": k1_gops / fp64_peak,
+                      "note": "stand-alone launches; K1 = lsm_frontend_encode (energy kernel + encoder kernel), K2 = lsm_reservoir_run, "
+                              "whole step = lsm_pipeline_run back to back on one caller stream"},
         "filter_mode": {"mode": args.filter_mode, "exact_reruns_per_step": reruns_value,
                         "other_mode": other, "other_mode_K1_ms": k1_other_ms, "other_mode_step_ms": step_other_ms,
                         "other_mode_value": B / (step_other_ms / 1e3),
                         "both_modes_identical_spikes_and_features": modes_agree,
-                        "note": "speculative = 13-FMA arrangement of the gammatone cascade + exact re-execution of near-tie "
-                                "utterances in-kernel; exact = the reference's 35 separately rounded operations per sample"},
+                        "note": "speculative = 13-FMA arrangement of the gammatone cascade + exact re-execution of every utterance in which "
+                                "the derived distance bound could change an encoder comparison; exact = the reference's 35 separately "
+                                "rounded operations per sample"},
     }
     if not args.no_cpu_baseline and world == 1:
         from oracle import coracle

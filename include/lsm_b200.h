@@ -99,15 +99,20 @@ int lsm_frontend_mel_tables(lsm_ctx *ctx, lsm_frontend *fe, const double *h_wind
  * gammatone.gtgram), byte for byte.
  *   LSM_FILTER_EXACT        every fp64 operation in the reference's order (35 separate roundings per channel-sample).
  *   LSM_FILTER_SPECULATIVE  (default) a mathematically equivalent arrangement of the same cascade in 13 fused
- *                           multiply-adds; an utterance in which any normalised value comes within delta_db decibels of an
- *                           encoder threshold / hysteresis bound / the silent-clip test is filtered again in exact mode
- *                           inside the same kernel.  delta_db = 0 keeps the current margin (1e-7 dB by default; the two
- *                           arrangements differ by < 1e-10 dB).  The optional d_spec_norm dump always uses the exact path.
+ *                           multiply-adds.  The library derives, per channel, a worst-case bound on the distance between the
+ *                           two arrangements (lsm_gammatone_error_bound) and carries it through dB,
+ *                           floor, min-max and zoom: an utterance in which that bound could change the outcome of any
+ *                           encoder comparison (threshold, hysteresis bound, silent-clip test) is filtered again in exact
+ *                           mode.  delta_db >= 0 widens the test by that many decibels on top of the bound (default 0).
+ *                           The optional d_spec_norm dump always uses the exact path.
+ * lsm_frontend_set_bound_scale: diagnostic - multiplies the derived bound (1 = the guarantee; 0 switches the bound off, so
+ *                           that tests can look at the speculative plane alone).
  * lsm_frontend_reruns: number of utterances that were filtered twice since creation / the last reset (waits for the
  * front end's last launch).                                                                                          */
 #define LSM_FILTER_EXACT 0
 #define LSM_FILTER_SPECULATIVE 1
 int lsm_frontend_set_mode(lsm_ctx *ctx, lsm_frontend *fe, int mode, double delta_db);
+int lsm_frontend_set_bound_scale(lsm_ctx *ctx, lsm_frontend *fe, double scale);
 int lsm_frontend_reruns(lsm_ctx *ctx, lsm_frontend *fe, int64_t *h_out, int reset);
 /* d_pcm: float[B][n_samples].  d_spikes: uint8[B][channels*redundancy][n_bins*n_thresholds] — the
  * X_spikes layout of speech_spike_dataset_pure_redundancy.npz (create_dataset.py:168).
@@ -118,6 +123,16 @@ int lsm_frontend_encode(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int3
 /* Same through host buffers: H2D, kernel, D2H, synchronous. */
 int lsm_frontend_encode_host(lsm_ctx *ctx, lsm_frontend *fe, const float *h_pcm, int32_t B,
                              uint8_t *h_spikes);
+
+/* Diagnostic behind the speculative mode: filters every utterance with BOTH arrangements and reports, per utterance,
+ * d_out[8*b + ...]: [0] largest |dB_speculative - dB_exact| over the 98 x channels window cells, [1] the largest ratio of
+ * that distance to the cell's derived bound (the guarantee is [1] <= 1), [2] and [3] the same ratio for the plane's maximum
+ * and (floored) minimum, [4] and [5] those two bounds in dB, [6] max |sample|, [7] the plane's range in dB.             */
+int lsm_frontend_audit(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int32_t B, double *d_out);
+/* The bound itself (host code, no device work): h_kappa[c] bounds |window amplitude (speculative) - window amplitude
+ * (reference order)| of channel c for an utterance with max |sample| = 1; it scales linearly with the peak level.
+ * h_table as for lsm_frontend_create.                                                                               */
+int lsm_gammatone_error_bound(const double *h_table, int32_t channels, int32_t n_samples, double *h_kappa);
 
 /* Host-side design helpers for callers without numpy (plain libm; no device work).
  * lsm_gammatone_design: the table gammatone.gtgram.gtgram_xe filters with - make_erb_filters(fs, centre_freqs(fs,
@@ -178,6 +193,13 @@ int lsm_reservoir_run_host(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *h_sp
  * persistent kernels.  The rows are complete when the launch has completed; ranks synchronise (a barrier) before reading.
  * n = 0 switches it off.  The setting is read when a launch is enqueued.                                                    */
 int lsm_reservoir_set_gather(lsm_ctx *ctx, lsm_reservoir *res, double *const *d_gather, int32_t n, int64_t row0);
+/* Gather matrices for the above across processes: device memory of this ctx's device exported as a 64-byte CUDA IPC handle
+ * (create), mapped into another rank's process with that rank's device current (open; the pointer then goes into that
+ * rank's d_gather list), unmapped (close) and freed by its owner (destroy).  Peer access over NVLink is enabled on open. */
+int lsm_peer_buffer_create(lsm_ctx *ctx, int64_t bytes, void **d_ptr, void *h_handle64);
+int lsm_peer_buffer_open(lsm_ctx *ctx, const void *h_handle64, void **d_ptr);
+int lsm_peer_buffer_close(lsm_ctx *ctx, void *d_ptr);
+int lsm_peer_buffer_destroy(lsm_ctx *ctx, void *d_ptr);
 int lsm_reservoir_diagnostics(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int32_t B, int32_t *d_diag);
 
 /* ---------------------------------------------------------------- the whole path, host buffers

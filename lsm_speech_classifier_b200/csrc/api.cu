@@ -33,7 +33,7 @@ extern "C" int lsm_ctx_create(lsm_ctx **out, int device_ordinal)
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LSM_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
     for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&ctx->copy_stream[i], cudaStreamNonBlocking);
-    for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < 12; ++i) cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming);
     *out = ctx;
     return LSM_OK;
 }
@@ -43,10 +43,9 @@ extern "C" void lsm_ctx_destroy(lsm_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 8; ++i) if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
+    for (int i = 0; i < 16; ++i) if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
     for (int i = 0; i < 4; ++i) if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
-    for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-    if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
+    for (int i = 0; i < 12; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 2; ++i) if (ctx->copy_stream[i]) cudaStreamDestroy(ctx->copy_stream[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -81,7 +80,8 @@ extern "C" int lsm_sm_count(const lsm_ctx *ctx) { return ctx ? ctx->sm_count : 0
 int lsm_stage_device(lsm_ctx *ctx, int slot, size_t bytes, void **out)
 {
     if (ctx->d_stage_bytes[slot] < bytes) {
-        if (ctx->d_stage[slot]) { LSM_CUDA(ctx, cudaFree(ctx->d_stage[slot])); ctx->d_stage[slot] = nullptr; ctx->d_stage_bytes[slot] = 0; }
+        // growing: asynchronous work (the launch lanes) may still be using the old buffer
+        if (ctx->d_stage[slot]) { LSM_CUDA(ctx, cudaDeviceSynchronize()); LSM_CUDA(ctx, cudaFree(ctx->d_stage[slot])); ctx->d_stage[slot] = nullptr; ctx->d_stage_bytes[slot] = 0; }
         if (cudaMalloc(&ctx->d_stage[slot], bytes) != cudaSuccess) LSM_FAIL(ctx, LSM_ERR_NOMEM, "cudaMalloc(%zu) failed", bytes);
         ctx->d_stage_bytes[slot] = bytes;
     }
@@ -144,7 +144,12 @@ extern "C" int lsm_frontend_create(lsm_ctx *ctx, const lsm_frontend_params *p, c
             fe->h_lane_coef[c][5] = -(r[8] / r[6]);
         }
         rc = upload(ctx, &fe->d_coefs, t, (size_t)p->channels * 10);
-        fe->minb = lsm_gammatone_minb();
+        // worst-case distance between the speculative and the reference-order arrangement of this design (error_bound.cu)
+        if (rc == LSM_OK && lsm_gammatone_error_bound(t, p->channels, p->n_samples, fe->h_kappa) != LSM_OK) {
+            rc = LSM_ERR_INVALID;
+            snprintf(ctx->err, sizeof(ctx->err), "gammatone design: the error bound of the speculative filter is not finite");
+        }
+        if (rc == LSM_OK) rc = upload(ctx, &fe->d_kappa, fe->h_kappa, (size_t)p->channels);
         if (rc == LSM_OK) rc = lsm_gammatone_grid(ctx, p, &fe->grid);
         if (rc == LSM_OK) rc = upload<double>(ctx, &fe->d_scratch, nullptr, 2 * (size_t)fe->grid * fe->ncols * p->channels);   // two slots
         if (rc == LSM_OK) rc = upload<int>(ctx, &fe->d_counters, nullptr, 128 + 64 * 256);
@@ -179,7 +184,7 @@ extern "C" void lsm_frontend_destroy(lsm_frontend *fe)
         if (fe->slot_valid[k]) cudaEventSynchronize(fe->ev_slot[k]);
         if (fe->ev_slot[k]) cudaEventDestroy(fe->ev_slot[k]);
     }
-    cudaFree(fe->d_energy); cudaFree(fe->d_rerun);
+    cudaFree(fe->d_energy); cudaFree(fe->d_rerun); cudaFree(fe->d_kappa); cudaFree(fe->d_xmax); cudaFree(fe->d_pipe_sync);
     cudaFree(fe->d_coefs); cudaFree(fe->d_zoom_i0); cudaFree(fe->d_zoom_f); cudaFree(fe->d_scratch); cudaFree(fe->d_counters);
     lsm_mel_destroy(fe);
     delete fe;
@@ -188,11 +193,29 @@ extern "C" void lsm_frontend_destroy(lsm_frontend *fe)
 extern "C" int lsm_frontend_set_mode(lsm_ctx *ctx, lsm_frontend *fe, int mode, double delta_db)
 {
     if (!ctx) return LSM_ERR_INVALID;
-    if (!fe || (mode != LSM_FILTER_EXACT && mode != LSM_FILTER_SPECULATIVE) || !(delta_db >= 0.0))
-        LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_frontend_set_mode: mode must be 0 or 1 and delta_db >= 0");
+    if (!fe || (mode != LSM_FILTER_EXACT && mode != LSM_FILTER_SPECULATIVE) || !(delta_db >= 0.0) || !(delta_db < 1e300))
+        LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_frontend_set_mode: mode must be 0 or 1 and 0 <= delta_db < 1e300");
     fe->mode = mode;
-    if (delta_db > 0.0) fe->spec_delta = delta_db;
+    fe->spec_delta = delta_db;
     return LSM_OK;
+}
+
+extern "C" int lsm_frontend_set_bound_scale(lsm_ctx *ctx, lsm_frontend *fe, double scale)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!fe || !(scale >= 0.0) || !(scale < 1e30)) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_frontend_set_bound_scale: 0 <= scale < 1e30");
+    fe->bound_scale = scale;
+    return LSM_OK;
+}
+
+extern "C" int lsm_frontend_audit(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int32_t B, double *d_out)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!fe || B < 0 || (B > 0 && (!d_pcm || !d_out))) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_frontend_audit: bad argument");
+    if (fe->p.kind != LSM_FILTERBANK_GAMMATONE) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "lsm_frontend_audit: gammatone front ends only");
+    if (B == 0) return LSM_OK;
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    return lsm_launch_audit(ctx, fe, d_pcm, B, d_out, ctx->stream);
 }
 
 extern "C" int lsm_frontend_reruns(lsm_ctx *ctx, lsm_frontend *fe, int64_t *h_out, int reset)
@@ -536,6 +559,60 @@ extern "C" int lsm_reservoir_set_gather(lsm_ctx *ctx, lsm_reservoir *res, double
     return LSM_OK;
 }
 
+// ------------------------------------------------------------------------------------ peer buffers (fused all-gather)
+// Gather matrices that other ranks' kernels store into: plain cudaMalloc memory exported / imported through CUDA IPC.
+extern "C" int lsm_peer_buffer_create(lsm_ctx *ctx, int64_t bytes, void **d_ptr, void *h_handle64)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!d_ptr || !h_handle64 || bytes <= 0) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_peer_buffer_create: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    *d_ptr = nullptr;
+    if (cudaMalloc(d_ptr, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); LSM_FAIL(ctx, LSM_ERR_NOMEM, "cudaMalloc(%lld) for a peer buffer failed", (long long)bytes); }
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*d_ptr); *d_ptr = nullptr; cudaGetLastError();
+        LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "cudaIpcGetMemHandle -> %s", cudaGetErrorString(e));
+    }
+    memcpy(h_handle64, &h, 64);
+    return LSM_OK;
+}
+
+extern "C" int lsm_peer_buffer_open(lsm_ctx *ctx, const void *h_handle64, void **d_ptr)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!d_ptr || !h_handle64) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_peer_buffer_open: bad argument");
+    // the mapping must belong to the context this ctx's kernels run in: open it with the ctx's device current
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, h_handle64, 64);
+    *d_ptr = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "cudaIpcOpenMemHandle -> %s", cudaGetErrorString(e)); }
+    return LSM_OK;
+}
+
+extern "C" int lsm_peer_buffer_close(lsm_ctx *ctx, void *d_ptr)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!d_ptr) return LSM_OK;
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    LSM_CUDA(ctx, cudaDeviceSynchronize());
+    LSM_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return LSM_OK;
+}
+
+extern "C" int lsm_peer_buffer_destroy(lsm_ctx *ctx, void *d_ptr)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!d_ptr) return LSM_OK;
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    LSM_CUDA(ctx, cudaDeviceSynchronize());
+    LSM_CUDA(ctx, cudaFree(d_ptr));
+    return LSM_OK;
+}
+
 extern "C" int lsm_reservoir_run(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int32_t B,
                                  uint32_t feature_mask, int32_t nan_to_num, double *d_features,
                                  uint8_t *d_raster_or_null)
@@ -583,7 +660,121 @@ extern "C" int lsm_reservoir_run_host(lsm_ctx *ctx, lsm_reservoir *res, const ui
     return LSM_OK;
 }
 
+// Can the device address this buffer directly?  Pinned/registered host memory (UVA alias) or device/managed memory.
+static bool device_visible(const void *h, void **d)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return false; }
+    if ((at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) && at.devicePointer) {
+        *d = at.devicePointer;
+        return true;
+    }
+    return false;
+}
+
 // ------------------------------------------------------------------------------------ whole path
+static cudaStream_t lane_stream(lsm_ctx *ctx, int lane) { return lane == 0 ? ctx->own_stream : ctx->copy_stream[0]; }
+
+// The warp-specialised kernel's units give up (and say so) if a group never completes; surfaced at the synchronous calls.
+static int check_pipe_error(lsm_ctx *ctx, lsm_frontend *fe)
+{
+    if (!fe->d_pipe_sync) return LSM_OK;
+    int flag = 0;
+    LSM_CUDA(ctx, cudaMemcpy(&flag, fe->d_pipe_sync + 2 * ((size_t)fe->energy_cap / 32 + 8), sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) LSM_FAIL(ctx, LSM_ERR_CUDA, "pipeline kernel: an encoder unit timed out waiting for its filter units");
+    return LSM_OK;
+}
+
+// Utterances per launch of the warp-specialised kernel: half the batch (two launches share the SMs), in whole 32-utterance
+// groups, at most 8192 (the energy planes between the two roles take 100 KB per utterance).
+static int lanes_piece(int B)
+{
+    int n = ((B / 2 + 31) / 32) * 32;
+    if (B < 64) n = B;
+    return n > 8192 ? 8192 : n;
+}
+
+// The warp-specialised kernel on device-resident PCM (float32, or PCM16 when d_pcm is null and fe->next_pcm16 is set), ordered
+// after / before the work on `st`.  A launch has one CTA per SM and two launches share an SM, so the batch goes out in pieces
+// that alternate between the two launch lanes: the fill and drain phases of one overlap the steady state of the other.
+int lsm_pipeline_lanes_device(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B, uint8_t *d_spikes,
+                              uint32_t feature_mask, int nan_to_num, double *d_features, cudaStream_t st)
+{
+    const int L = fe->p.n_samples;
+    const size_t spk_per = (size_t)res->p.num_inputs * res->p.num_steps;
+    const size_t feat_per = (size_t)__builtin_popcount(feature_mask & 0xFFu) * res->p.n_out;
+    const int16_t *pcm16 = d_pcm ? nullptr : fe->next_pcm16;
+    cudaStream_t l0 = lane_stream(ctx, 0), l1 = lane_stream(ctx, 1);
+    const bool on_lane = st == l0 || st == l1;
+    const int piece = on_lane ? (B > 8192 ? 8192 : B) : lanes_piece(B);
+    int rc = LSM_OK, used = 0;
+    if (!on_lane && B > piece) LSM_CUDA(ctx, cudaEventRecord(ctx->ev[8], st));
+    for (int off = 0, k = 0; off < B && rc == LSM_OK; off += piece, ++k) {
+        const int n = B - off < piece ? B - off : piece;
+        int lane = k & 1;
+        cudaStream_t ls = lane == 0 ? l0 : l1;
+        if (on_lane) { lane = st == l1 ? 1 : 0; ls = st; }
+        else if (B <= piece) { lane = 0; ls = st; }          // a single small launch stays on the caller's stream
+        else if (k < 2) LSM_CUDA(ctx, cudaStreamWaitEvent(ls, ctx->ev[8], 0));
+        fe->next_pcm16 = pcm16 ? pcm16 + (size_t)off * L : nullptr;
+        rc = lsm_launch_pipeline_lanes(ctx, fe, res, d_pcm ? d_pcm + (size_t)off * L : nullptr, n,
+                                       d_spikes ? d_spikes + (size_t)off * spk_per : nullptr, feature_mask, nan_to_num,
+                                       d_features + (size_t)off * feat_per, ls, lane, off);
+        if (ls != st) used |= 1 << lane;
+    }
+    fe->next_pcm16 = pcm16;
+    if (rc != LSM_OK) return rc;
+    for (int lane = 0; lane < 2; ++lane)
+        if (used & (1 << lane)) {
+            LSM_CUDA(ctx, cudaEventRecord(ctx->ev[9 + lane], lane == 0 ? l0 : l1));
+            LSM_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[9 + lane], 0));
+        }
+    return LSM_OK;
+}
+
+// Host buffers through the warp-specialised kernel: the batch goes out in pieces that alternate between the two launch lanes,
+// each piece copied to the device by the copy engine (the kernel reads every sample sixteen times, from L2), filtered, and
+// its feature rows written straight to the host buffer when the device can address it (pinned), else copied back.
+// only_lane < 0: both lanes, then wait; 0 / 1: that lane only, asynchronous.
+static int pipeline_lanes_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const void *h_pcm, bool i16, int B,
+                               uint32_t feature_mask, int nan_to_num, double *h_features, uint8_t *h_spikes_or_null, int only_lane)
+{
+    const int L = fe->p.n_samples;
+    const size_t esz = i16 ? sizeof(int16_t) : sizeof(float);
+    const size_t spk_per = (size_t)res->p.num_inputs * res->p.num_steps;
+    const size_t feat_per = (size_t)__builtin_popcount(feature_mask & 0xFFu) * res->p.n_out;
+    void *dv_feat = nullptr;
+    const bool feat_direct = device_visible(h_features, &dv_feat);
+    const int piece = only_lane >= 0 ? (B > 8192 ? 8192 : B) : lanes_piece(B);
+    int rc;
+    for (int off = 0, k = 0; off < B; off += piece, ++k) {
+        const int n = B - off < piece ? B - off : piece;
+        const int lane = only_lane >= 0 ? only_lane : (k & 1);
+        cudaStream_t ls = lane_stream(ctx, lane);
+        void *d_in = nullptr, *d_feat = nullptr, *d_spk = nullptr;
+        if ((rc = lsm_stage_device(ctx, 8 + lane, (size_t)piece * L * esz, &d_in)) != LSM_OK) return rc;
+        if (!feat_direct && (rc = lsm_stage_device(ctx, 10 + lane, (size_t)piece * feat_per * sizeof(double), &d_feat)) != LSM_OK) return rc;
+        if (h_spikes_or_null && (rc = lsm_stage_device(ctx, 12 + lane, (size_t)piece * spk_per, &d_spk)) != LSM_OK) return rc;
+        LSM_CUDA(ctx, cudaMemcpyAsync(d_in, (const char *)h_pcm + (size_t)off * L * esz, (size_t)n * L * esz, cudaMemcpyDefault, ls));
+        double *out = feat_direct ? (double *)dv_feat + (size_t)off * feat_per : (double *)d_feat;
+        fe->next_pcm16 = i16 ? (const int16_t *)d_in : nullptr;
+        rc = lsm_launch_pipeline_lanes(ctx, fe, res, i16 ? nullptr : (const float *)d_in, n, (uint8_t *)d_spk, feature_mask, nan_to_num,
+                                       out, ls, lane, off);
+        fe->next_pcm16 = nullptr;
+        if (rc != LSM_OK) return rc;
+        if (!feat_direct)
+            LSM_CUDA(ctx, cudaMemcpyAsync(h_features + (size_t)off * feat_per, d_feat, (size_t)n * feat_per * sizeof(double), cudaMemcpyDeviceToHost, ls));
+        if (h_spikes_or_null)
+            LSM_CUDA(ctx, cudaMemcpyAsync(h_spikes_or_null + (size_t)off * spk_per, d_spk, (size_t)n * spk_per, cudaMemcpyDeviceToHost, ls));
+    }
+    if (only_lane < 0) {
+        LSM_CUDA(ctx, cudaStreamSynchronize(lane_stream(ctx, 0)));
+        LSM_CUDA(ctx, cudaStreamSynchronize(lane_stream(ctx, 1)));
+        return check_pipe_error(ctx, fe);
+    }
+    return LSM_OK;
+}
+
 extern "C" int lsm_pipeline_run(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm,
                                 int32_t B, uint32_t feature_mask, int32_t nan_to_num, uint8_t *d_spikes,
                                 double *d_features)
@@ -596,25 +787,16 @@ extern "C" int lsm_pipeline_run(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *r
                  fe->p.channels * fe->p.redundancy, fe->p.n_bins * fe->p.n_thresholds, res->p.num_inputs, res->p.num_steps);
     if (B == 0) return LSM_OK;
     LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    // default shape: the warp-specialised kernel, two half batches on the ctx's two launch lanes (they share the SMs)
+    if (lsm_pipeline_lanes_eligible(fe, res, d_pcm, false))
+        return lsm_pipeline_lanes_device(ctx, fe, res, d_pcm, B, d_spikes, feature_mask, nan_to_num, d_features, ctx->stream);
     // one fused kernel when the pair allows it (spikes handed over in shared memory; d_spikes optional)
     if (lsm_fused_npt(fe, res))
-        return lsm_launch_fused(ctx, fe, res, d_pcm, B, d_spikes, feature_mask, nan_to_num, d_features, ctx->stream);
+        return lsm_launch_fused(ctx, fe, res, d_pcm, B, d_spikes, feature_mask, nan_to_num, d_features, ctx->stream, 0);
     if (!d_spikes) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_pipeline_run: this configuration runs as two kernels and needs a d_spikes buffer");
     int rc = frontend_launch(ctx, fe, d_pcm, B, d_spikes, nullptr, ctx->stream);
     if (rc != LSM_OK) return rc;
     return lsm_launch_reservoir(ctx, res, d_spikes, B, feature_mask, nan_to_num, d_features, nullptr, ctx->stream);
-}
-
-// Can the device address this buffer directly?  Pinned/registered host memory (UVA alias) or device/managed memory.
-static bool device_visible(const void *h, void **d)
-{
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return false; }
-    if ((at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) && at.devicePointer) {
-        *d = at.devicePointer;
-        return true;
-    }
-    return false;
 }
 
 extern "C" int lsm_pipeline_is_fused(const lsm_frontend *fe, const lsm_reservoir *res)
@@ -638,6 +820,9 @@ extern "C" int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservo
     const size_t spk_per = (size_t)res->p.num_inputs * res->p.num_steps;
     const int nkeys = __builtin_popcount(feature_mask & 0xFFu);
     const size_t feat_per = (size_t)nkeys * res->p.n_out;
+    // Default shape: the warp-specialised kernel, fed by the copy engine, two halves on the two launch lanes
+    if (lsm_pipeline_lanes_eligible(fe, res, (const void *)256, false))
+        return pipeline_lanes_host(ctx, fe, res, h_pcm, false, B, feature_mask, nan_to_num, h_features, h_spikes_or_null, -1);
     // Zero-copy path: with pinned host buffers the one fused persistent kernel reads each PCM sample exactly once
     // straight over PCIe as it consumes it (~15 GB/s at full speed) and writes the feature rows straight back, so
     // there is no staging copy, no chunking and no per-chunk drain tail.  Pageable buffers take the staged path below.
@@ -653,15 +838,15 @@ extern "C" int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservo
                 // two launches on the two lanes (two scratch slots): the second half fills the drain tail of the first
                 const int n0 = B / 2;
                 if ((rc0 = lsm_launch_fused(ctx, fe, res, (const float *)dv_pcm, n0, nullptr, feature_mask, nan_to_num,
-                                            (double *)dv_feat, ctx->own_stream)) != LSM_OK) return rc0;
+                                            (double *)dv_feat, ctx->own_stream, 0)) != LSM_OK) return rc0;
                 if ((rc0 = lsm_launch_fused(ctx, fe, res, (const float *)dv_pcm + (size_t)n0 * L, B - n0, nullptr, feature_mask, nan_to_num,
-                                            (double *)dv_feat + (size_t)n0 * feat_per, ctx->copy_stream[0])) != LSM_OK) return rc0;
+                                            (double *)dv_feat + (size_t)n0 * feat_per, ctx->copy_stream[0], n0)) != LSM_OK) return rc0;
                 LSM_CUDA(ctx, cudaStreamSynchronize(ctx->own_stream));
                 LSM_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream[0]));
                 return LSM_OK;
             }
             if ((rc0 = lsm_launch_fused(ctx, fe, res, (const float *)dv_pcm, B, (uint8_t *)d_spk, feature_mask, nan_to_num,
-                                        (double *)dv_feat, ctx->stream)) != LSM_OK) return rc0;
+                                        (double *)dv_feat, ctx->stream, 0)) != LSM_OK) return rc0;
             if (h_spikes_or_null)
                 LSM_CUDA(ctx, cudaMemcpyAsync(h_spikes_or_null, d_spk, (size_t)B * spk_per, cudaMemcpyDeviceToHost, ctx->stream));
             LSM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -702,11 +887,11 @@ extern "C" int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservo
         if (c >= 2) LSM_CUDA(ctx, cudaStreamWaitEvent(s_k, ctx->ev[4 + b], 0));    // D2H of chunk c-2 released d_spk/d_feat[b]
         if (fused) {
             if ((rc = lsm_launch_fused(ctx, fe, res, (const float *)d_pcm[b], n, h_spikes_or_null ? (uint8_t *)d_spk[b] : nullptr,
-                                       feature_mask, nan_to_num, (double *)d_feat[b], s_k)) != LSM_OK) return rc;
+                                       feature_mask, nan_to_num, (double *)d_feat[b], s_k, (long long)off)) != LSM_OK) return rc;
         } else {
             if ((rc = frontend_launch(ctx, fe, (const float *)d_pcm[b], n, (uint8_t *)d_spk[b], nullptr, s_k)) != LSM_OK) return rc;
             if ((rc = lsm_launch_reservoir(ctx, res, (const uint8_t *)d_spk[b], n, feature_mask, nan_to_num,
-                                           (double *)d_feat[b], nullptr, s_k)) != LSM_OK) return rc;
+                                           (double *)d_feat[b], nullptr, s_k, nullptr, (long long)off)) != LSM_OK) return rc;
         }
         LSM_CUDA(ctx, cudaEventRecord(ctx->ev[2 + b], s_k));
         LSM_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->ev[2 + b], 0));
@@ -731,7 +916,17 @@ static int run_i16(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const int
                  fe->p.channels * fe->p.redundancy, fe->p.n_bins * fe->p.n_thresholds, res->p.num_inputs, res->p.num_steps);
     if (!lsm_fused_npt(fe, res)) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "%s: PCM16 input needs a front end / reservoir pair that runs fused", who);
     fe->next_pcm16 = pcm16;
-    const int rc = lsm_launch_fused(ctx, fe, res, nullptr, B, d_spikes, feature_mask, nan_to_num, d_features, st);
+    {
+        cudaPointerAttributes at;
+        const bool on_device = cudaPointerGetAttributes(&at, pcm16) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+        cudaGetLastError();
+        if (on_device && lsm_pipeline_lanes_eligible(fe, res, pcm16, true)) {
+            const int rc = lsm_pipeline_lanes_device(ctx, fe, res, nullptr, B, d_spikes, feature_mask, nan_to_num, d_features, st);
+            fe->next_pcm16 = nullptr;
+            return rc;
+        }
+    }
+    const int rc = lsm_launch_fused(ctx, fe, res, nullptr, B, d_spikes, feature_mask, nan_to_num, d_features, st, 0);
     fe->next_pcm16 = nullptr;
     return rc;
 }
@@ -758,6 +953,9 @@ extern "C" int lsm_pipeline_run_host_async_i16(lsm_ctx *ctx, lsm_frontend *fe, l
     void *dv_pcm = nullptr, *dv_feat = nullptr;
     if (!device_visible(h_pcm16, &dv_pcm) || !device_visible(h_features, &dv_feat))
         LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "lsm_pipeline_run_host_async_i16 needs pinned (or device) buffers");
+    if (fe->p.channels * fe->p.redundancy == res->p.num_inputs && fe->p.n_bins * fe->p.n_thresholds == res->p.num_steps &&
+        lsm_pipeline_lanes_eligible(fe, res, (const void *)256, true))
+        return pipeline_lanes_host(ctx, fe, res, h_pcm16, true, B, feature_mask, nan_to_num, h_features, nullptr, lane);
     return run_i16(ctx, fe, res, (const int16_t *)dv_pcm, B, feature_mask, nan_to_num, nullptr, (double *)dv_feat,
                    lane == 0 ? ctx->own_stream : ctx->copy_stream[0], "lsm_pipeline_run_host_async_i16");
 }
@@ -780,8 +978,10 @@ extern "C" int lsm_pipeline_run_host_async(lsm_ctx *ctx, lsm_frontend *fe, lsm_r
     void *dv_pcm = nullptr, *dv_feat = nullptr;
     if (!lsm_fused_npt(fe, res) || !device_visible(h_pcm, &dv_pcm) || !device_visible(h_features, &dv_feat))
         LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "lsm_pipeline_run_host_async needs pinned (or device) buffers and a pair that runs fused");
+    if (lsm_pipeline_lanes_eligible(fe, res, (const void *)256, false))
+        return pipeline_lanes_host(ctx, fe, res, h_pcm, false, B, feature_mask, nan_to_num, h_features, nullptr, lane);
     return lsm_launch_fused(ctx, fe, res, (const float *)dv_pcm, B, nullptr, feature_mask, nan_to_num, (double *)dv_feat,
-                            lane == 0 ? ctx->own_stream : ctx->copy_stream[0]);
+                            lane == 0 ? ctx->own_stream : ctx->copy_stream[0], 0);
 }
 
 extern "C" void *lsm_lane_stream(lsm_ctx *ctx, int32_t lane)

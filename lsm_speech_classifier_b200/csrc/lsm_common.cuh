@@ -14,13 +14,12 @@ struct lsm_ctx {
     cudaStream_t own_stream = nullptr;   // created by the ctx
     cudaStream_t stream = nullptr;       // where work goes (own_stream or the caller's)
     cudaStream_t copy_stream[2] = {nullptr, nullptr};  // pipeline_run_host: H2D / D2H legs
-    cudaEvent_t ev[8] = {};
-    cudaEvent_t ev_chain = nullptr;      // LSM_K1A_CHAIN experiment: orders the energy kernels of this ctx across streams
+    cudaEvent_t ev[12] = {};             // [0,6): chunked host pipeline; 8: fork, 9-10: join of the two launch lanes
     int64_t launches = 0;
     char err[512] = {0};
     // staging owned by the ctx for the *_host entry points (grown on demand)
-    void *d_stage[8] = {};
-    size_t d_stage_bytes[8] = {};
+    void *d_stage[16] = {};
+    size_t d_stage_bytes[16] = {};
     void *h_pin[4] = {};
     size_t h_pin_bytes[4] = {};
 };
@@ -35,16 +34,19 @@ struct lsm_frontend {
     int grid = 0;
     int *d_counters = nullptr;     // [64] dynamic work counters, one per in-flight launch; [64] = utterances filtered twice
     int mode = 1;                  // gammatone: 0 = exact filter only, 1 = speculative filter + exact re-execution of near-ties
-    double spec_delta = 1e-7;      // dB margin of the near-tie test (lsm_frontend_set_mode)
+    double spec_delta = 0.0;       // extra dB margin of the near-tie test on top of the derived bound (lsm_frontend_set_mode)
+    double bound_scale = 1.0;      // multiplier of the derived bound (lsm_frontend_set_bound_scale; diagnostics only)
+    double h_kappa[256] = {};      // per channel: bound on |amplitude(speculative) - amplitude(exact)| per unit max|x| (lsm_gammatone_error_bound)
+    double *d_kappa = nullptr;     // [C] the same on the device
+    float *d_xmax = nullptr;       // [2][energy_cap] max |sample| per utterance, written by the filter warps (lanes arrangements)
+    int *d_pipe_sync = nullptr;    // pipeline kernel: per launch lane work counter + group completion counters; error flag last
     double h_lane_coef[256][6] = {};  // per channel c1..c4, -a1, -a2 of the normalised cascade (kernel-parameter table of K1a)
-    double *d_energy = nullptr;    // [energy_cap][ncols][C] raw window energies between K1a and the encoder kernel
+    double *d_energy = nullptr;    // [2][energy_cap][ncols][C] raw window energies between the filter warps and the encoder (one set per launch lane)
     int energy_cap = 0;
     int *d_rerun = nullptr;        // [1 + energy_cap] count + utterances the encoder kernel flagged for the exact pass
     int rerun_cap = 0;
     const int16_t *next_pcm16 = nullptr;   // set by the *_i16 entry points for the launch they make (d_pcm == nullptr), then cleared
-    int lanes_slots = 0;           // resident warps of K1a on this device (one wave of units)
     unsigned counter_next = 0;
-    int minb = 5;                  // K1 occupancy target the kernel was instantiated for
     // launches on different streams share the scratch planes: each launch waits for the previous one's event
     // two scratch slots: launch n uses slot n & 1 and only has to wait for launch n-2, so two launches (on two streams) can be
     // in flight and the drain tail of one overlaps the start of the next; slot -1 = exclusive (waits for / blocks both)
@@ -52,9 +54,6 @@ struct lsm_frontend {
     cudaStream_t slot_stream[2] = {nullptr, nullptr};
     int slot_valid[2] = {0, 0};
     unsigned slot_next = 0;
-    int l2_window_ready = 0;       // L2 persisting window for the scratch planes
-    size_t l2_window_bytes = 0;
-    float l2_hit_ratio = 1.0f;
     // mel
     float *d_mel_w = nullptr;      // packed non-zero mel weights
     int32_t *d_mel_lo = nullptr;   // [C] first non-zero bin
@@ -110,13 +109,28 @@ int lsm_stage_pinned(lsm_ctx *ctx, int slot, size_t bytes, void **out);
 int lsm_launch_gammatone(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, uint8_t *d_spikes,
                          double *d_spec_norm, cudaStream_t st);
 int lsm_gammatone_grid(lsm_ctx *ctx, const lsm_frontend_params *p, int *grid);
-int lsm_gammatone_minb(void);
+struct GtArgs;
+void lsm_gammatone_fill_args(const lsm_frontend *fe, const float *d_pcm, int B, uint8_t *d_spikes, double *d_spec_norm, GtArgs *out);
+bool lsm_lanes_eligible(const lsm_frontend *fe, const void *d_pcm);
+int lsm_frontend_ensure_energy(lsm_ctx *ctx, lsm_frontend *fe, int B);
+int lsm_frontend_ensure_rerun(lsm_ctx *ctx, lsm_frontend *fe, int B);
+bool lsm_pipeline_lanes_eligible(const lsm_frontend *fe, const lsm_reservoir *res, const void *d_pcm, bool i16);
+int lsm_launch_pipeline_lanes(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B,
+                              uint8_t *d_spikes_or_null, uint32_t feature_mask, int nan_to_num, double *d_features,
+                              cudaStream_t st, int lane, long long row0);
+int lsm_pipeline_lanes_device(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B, uint8_t *d_spikes,
+                              uint32_t feature_mask, int nan_to_num, double *d_features, cudaStream_t st);
+int lsm_launch_audit(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, double *d_out, cudaStream_t st);
+extern "C" int lsm_gammatone_error_bound(const double *h_table, int32_t channels, int32_t n_samples, double *h_kappa);
 int lsm_frontend_order_before(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st, int slot = -1);   // call before a launch that uses fe's scratch
 int lsm_frontend_order_after(lsm_ctx *ctx, lsm_frontend *fe, cudaStream_t st, int slot = -1);    // ... and right after it
 int lsm_frontend_wait_idle(lsm_ctx *ctx, lsm_frontend *fe);                                      // host waits for every launch of fe
 int lsm_fused_npt(const lsm_frontend *fe, const lsm_reservoir *res);
 int lsm_launch_fused(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B,
-                     uint8_t *d_spikes_or_null, uint32_t feature_mask, int nan_to_num, double *d_features, cudaStream_t st);
+                     uint8_t *d_spikes_or_null, uint32_t feature_mask, int nan_to_num, double *d_features, cudaStream_t st,
+                     long long row0);
+int lsm_launch_fused_args(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, GtArgs &a, cudaStream_t st, bool launch, int *wave,
+                          int max_grid, int forced_slot);
 int lsm_fused_wave(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res);
 struct ResArgs;
 void lsm_reservoir_fill_args(const lsm_reservoir *res, const uint8_t *d_spikes, int B, uint32_t feature_mask,
@@ -125,7 +139,7 @@ int lsm_launch_mel(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, ui
                    double *d_spec_norm, cudaStream_t st);
 int lsm_launch_reservoir(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int B,
                          uint32_t feature_mask, int nan_to_num, double *d_features, uint8_t *d_raster,
-                         cudaStream_t st, int *d_diag = nullptr);
+                         cudaStream_t st, int *d_diag = nullptr, long long row0 = 0);
 void lsm_reservoir_geometry(int N, int *npt, int *threads, int *n_pad);
 int lsm_mel_create(lsm_ctx *ctx, lsm_frontend *fe, const float *h_basis);
 void lsm_mel_destroy(lsm_frontend *fe);

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(1024) reservoir_kernel(const ResArgs a)
         }
     }
     __syncthreads();
-    reservoir_simulate<NPT, LEAN, STAT_GLOBAL>(a, utt, smem_raw, s_cnt);
+    reservoir_simulate<NPT, LEAN, STAT_GLOBAL>(a, utt, smem_raw, s_cnt, threadIdx.x, blockDim.x, blockIdx.x);
 }
 
 }  // namespace
@@ -92,13 +92,14 @@ void lsm_reservoir_fill_args(const lsm_reservoir *res, const uint8_t *d_spikes, 
 
 int lsm_launch_reservoir(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int B,
                          uint32_t feature_mask, int nan_to_num, double *d_features, uint8_t *d_raster,
-                         cudaStream_t st, int *d_diag)
+                         cudaStream_t st, int *d_diag, long long row0)
 {
     const lsm_reservoir_params &p = res->p;
     if (B <= 0) return LSM_OK;
     ResArgs a;
     lsm_reservoir_fill_args(res, d_spikes, B, feature_mask, nan_to_num, d_features, d_raster, &a);
     a.diag = d_diag;
+    a.gather_row0 += row0;
     const int N = p.num_neurons;
     int npt, threads, n_pad;
     lsm_reservoir_geometry(N, &npt, &threads, &n_pad);

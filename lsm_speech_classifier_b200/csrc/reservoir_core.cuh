@@ -41,7 +41,8 @@ struct ResArgs {
 //                           the end select the all-zero weight row)
 __host__ __device__ inline size_t lsm_res_smem_bytes(int T, int CW, int slots, int N, bool stat_in_smem = true)
 {
-    return sizeof(unsigned) * (size_t)T * CW + (stat_in_smem ? sizeof(int) * 6 * (size_t)slots : 0) +
+    // the bit plane is rounded up to whole 8-byte words: the spike list behind it is read with 8-byte loads
+    return sizeof(unsigned) * (((size_t)T * CW + 1) & ~(size_t)1) + (stat_in_smem ? sizeof(int) * 6 * (size_t)slots : 0) +
            sizeof(unsigned short) * 2 * (size_t)((N + 7) & ~3);
 }
 
@@ -59,21 +60,31 @@ __device__ __forceinline__ double lean_current(int acc, int hi_magic, double c)
     return __dsub_rn(__hiloint2double(hi_magic, acc ^ (int)0x80000000), c);
 }
 
-// Caller contract: s_bits holds the utterance's input and a __syncthreads() has made it visible.
+// Barrier of the thread group that simulates one utterance: the whole CTA (BAR = 0, __syncthreads) or, in the
+// warp-specialised kernel, the nthr threads that own named barrier BAR.
+template <int BAR>
+__device__ __forceinline__ void res_sync(int nthr)
+{
+    if (BAR == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(BAR), "r"(nthr) : "memory");
+}
+
+// Caller contract: s_bits holds the utterance's input and a barrier of the group has made it visible.
 // LEAN = uniform leak, uniform input gain, at most one input row per neuron, relabelled neurons (see above).
 // STAT_GLOBAL = per-neuron statistics in a.stat_global instead of shared memory (reservoirs too large for it).
-template <int NPT, bool LEAN, bool STAT_GLOBAL = false>
-__device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int utt, unsigned char *smem_raw, int *s_cnt)
+// tid / nthr: this thread's index in the group and the group's size (whole warps); slab: the group's index for STAT_GLOBAL.
+template <int NPT, bool LEAN, bool STAT_GLOBAL = false, int BAR = 0>
+__device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int utt, unsigned char *smem_raw, int *s_cnt,
+                                                   const int tid, const int nthr, const int slab = 0)
 {
-    const int tid = threadIdx.x;
-    const int nthr = blockDim.x;
     const int lane = tid & 31;
     const int N = a.N, T = a.T, CW = a.CW;
     const int S = nthr * NPT;
     const int NL = (N + 7) & ~3;                       // list capacity, multiple of 4
     unsigned *s_bits = reinterpret_cast<unsigned *>(smem_raw);
-    int *s_stat = STAT_GLOBAL ? a.stat_global + (size_t)blockIdx.x * 6 * S : reinterpret_cast<int *>(s_bits + (size_t)T * CW);
-    unsigned short *s_list = reinterpret_cast<unsigned short *>(reinterpret_cast<int *>(s_bits + (size_t)T * CW) +
+    const size_t bits_words = ((size_t)T * CW + 1) & ~(size_t)1;      // lsm_res_smem_bytes: 8-byte aligned list
+    int *s_stat = STAT_GLOBAL ? a.stat_global + (size_t)slab * 6 * S : reinterpret_cast<int *>(s_bits + bits_words);
+    unsigned short *s_list = reinterpret_cast<unsigned short *>(reinterpret_cast<int *>(s_bits + bits_words) +
                                                                 (STAT_GLOBAL ? 0 : 6 * (size_t)S));
 
     for (int i = tid; i < S; i += nthr) {
@@ -113,7 +124,7 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
         }
     }
     const unsigned pitch = (unsigned)a.n_pad * 4u;
-    __syncthreads();
+    res_sync<BAR>(nthr);
 
     // Dead time.  Until the first input spike every membrane potential is exactly +0, nobody fires and no statistic changes
     // ((0 - leak*0) + 0 = +0), so the simulation starts at that step.  And once the input has ended and a step passes without
@@ -124,7 +135,7 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
     if (!a.raster && a.skip_dead_time) {
         for (int i = tid; i < T * CW; i += nthr)
             if (s_bits[i]) { atomicMin(&s_cnt[3], i / CW); atomicMax(&s_cnt[4], i / CW); }
-        __syncthreads();
+        res_sync<BAR>(nthr);
         t_first = s_cnt[3];
         t_last_in = s_cnt[4];
     }
@@ -250,7 +261,7 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
                 }
             }
         }
-        __syncthreads();
+        res_sync<BAR>(nthr);
         const int tmp = c_cur; c_cur = c_nxt; c_nxt = c_zero; c_zero = tmp;
     }
 
@@ -264,9 +275,9 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
         active = __reduce_add_sync(0xffffffffu, active);
         total = __reduce_add_sync(0xffffffffu, total);
         if (tid < 2) s_cnt[tid] = 0;
-        __syncthreads();
+        res_sync<BAR>(nthr);
         if (lane == 0) { atomicAdd(&s_cnt[0], active); atomicAdd(&s_cnt[1], total); }
-        __syncthreads();
+        res_sync<BAR>(nthr);
         if (tid < 2) a.diag[(size_t)utt * 2 + tid] = s_cnt[tid];
     }
 
@@ -310,7 +321,7 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
                     if (a.nan_to_num && v != v) v = 0.0;
                     s_buf[o - tile] = v;
                 }
-                __syncthreads();
+                res_sync<BAR>(nthr);
                 const int n_here = min(cap, a.n_out - tile);
                 for (int idx = tid; idx < n_here; idx += nthr) __stcs(f + (size_t)slot * a.n_out + tile + idx, s_buf[idx]);
                 if (a.n_gather > 0) {
@@ -319,7 +330,7 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
                     for (int p = 0; p < a.n_gather; ++p)
                         for (int idx = tid; idx < n_here; idx += nthr) __stcs(a.gather_out[p] + off + idx, s_buf[idx]);
                 }
-                __syncthreads();
+                res_sync<BAR>(nthr);
             }
             ++slot;
         }

@@ -108,41 +108,79 @@ def init_from_env():
     return dist.get_rank(), dist.get_world_size(), local_rank
 
 
+class _DeviceBlock:
+    """A device allocation owned by the C library, viewable as a torch tensor (CUDA array interface)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
 class PeerAllGather:
-    """All-gather of equal row blocks by peer-to-peer copies over NVLink (copy engines, no SM use).
+    """The feature all-gather without a collective kernel.
 
     The compute kernels of this path are persistent and fill every SM, so an NCCL all-gather kernel has to find CTA slots
-    between them.  Here every rank maps the gather buffers of all ranks (CUDA IPC, exchanged once through the process
-    group) and writes its block straight into each of them with cudaMemcpyPeerAsync on a side stream; the SMs never see
-    the collective.  Measured at N = 2: 6.68 ms per step against 6.72 ms with NCCL's asynchronous all-gather - the
-    collective was not what separates N = 2 from N = 1 (6.3 ms; the step time is the maximum over ranks).  At N = 8 this
-    simple form is far worse than NCCL (25.5 vs 7.0 ms per step: seven serial 38 MB peer copies per rank and step through
-    IPC-mapped buffers), so bench.py keeps NCCL and uses this class only with LSM_BENCH_P2P=1; both give identical matrices
-    (checked in bench.py).
-    `n_buffers` gather buffers per rank alternate between steps; the caller synchronises ranks (a barrier) before it reads."""
+    between them (round 1: 7.0 vs 5.8 ms per step at N = 8).  Here every rank owns `n_buffers` gather matrices allocated by
+    the C library (lsm_peer_buffer_create), exports them as CUDA IPC handles, and maps the other ranks' matrices into its own
+    process with its own device current (lsm_peer_buffer_open).  `pointers(k)` is then what `SNN.set_gather` takes: the
+    readout epilogue of the kernel stores every feature row into all ranks' matrices itself, as NVLink stores.
+    `gather_async` is the copy-engine form of the same collective (cudaMemcpyPeerAsync through the same mappings).
+    The caller synchronises ranks (a barrier) before it reads `bufs[k]`."""
 
-    def __init__(self, rows: int, width: int, dtype, device, n_buffers: int = 2, map_on_local_device: bool = False):
+    def __init__(self, rows: int, width: int, dtype, device, n_buffers: int = 2, ctx=None):
+        import ctypes as C
         import torch
         import torch.distributed as dist
-        from torch.multiprocessing.reductions import reduce_tensor
+        from . import _lib
+        if dtype != torch.float64:
+            raise ValueError("PeerAllGather holds float64 feature rows")
+        self.ctx = ctx or _lib.context(torch.device(device).index)
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
-        self.rows = rows
-        self.bufs = [torch.empty((self.world * rows, width), dtype=dtype, device=device) for _ in range(n_buffers)]
-        mine = [reduce_tensor(b) for b in self.bufs]
+        self.rows, self.width = rows, width
+        nbytes = self.world * rows * width * 8
+        # Every rank walks through the same collectives whatever fails locally; the outcome is agreed on at the end, so that
+        # either all ranks hold a working mapping or all of them raise.
+        self._own, self._opened, handles, err = [], [], [], None
+        try:
+            for _ in range(n_buffers):
+                ptr, h = C.c_void_p(), C.create_string_buffer(64)
+                self.ctx.check(self.ctx.lib.lsm_peer_buffer_create(self.ctx.h, nbytes, C.byref(ptr), h))
+                self._own.append(int(ptr.value))
+                handles.append(h.raw)
+        except Exception as e:
+            err, handles = e, None
         everyone = [None] * self.world
-        dist.all_gather_object(everyone, mine)
-        # peer[r][k]: rank r's gather buffer k, addressable from this process (this rank's own buffers are used directly).
-        # map_on_local_device: open the IPC handles with THIS rank's device current (rebuild_cuda_tensor's storage_device
-        # argument), so that the mapping belongs to the context kernels of this rank run in - what kernels that store into the
-        # peers' buffers (SNN.set_gather) need; torch then labels those tensors with the local device.
-        def rebuild(fn, args):
-            if map_on_local_device:
-                args = list(args)
-                args[6] = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
-                args = tuple(args)
-            return fn(*args)
-        self.peer = [[(self.bufs[k] if r == self.rank else rebuild(fn, args)) for k, (fn, args) in enumerate(everyone[r])]
-                     for r in range(self.world)]
+        dist.all_gather_object(everyone, handles)
+        self._ptr = [[0] * n_buffers for _ in range(self.world)]
+        if err is None and all(h is not None for h in everyone):
+            try:
+                for r in range(self.world):
+                    for k in range(n_buffers):
+                        if r == self.rank:
+                            self._ptr[r][k] = self._own[k]
+                        else:
+                            ptr = C.c_void_p()
+                            self.ctx.check(self.ctx.lib.lsm_peer_buffer_open(self.ctx.h, C.c_char_p(everyone[r][k]), C.byref(ptr)))
+                            self._ptr[r][k] = int(ptr.value)
+                            self._opened.append(int(ptr.value))
+            except Exception as e:
+                err = e
+        elif err is None:
+            err = RuntimeError("another rank could not create its gather buffers")
+        ok = torch.tensor([0.0 if err is not None else 1.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)      # doubles as the barrier: every rank has mapped every buffer
+        if ok.item() < 1.0:
+            for p in self._opened:
+                self.ctx.lib.lsm_peer_buffer_close(self.ctx.h, p)
+            dist.barrier()
+            for p in self._own:
+                self.ctx.lib.lsm_peer_buffer_destroy(self.ctx.h, p)
+            self._own = None
+            raise RuntimeError(f"PeerAllGather: peer mapping unavailable on some rank ({err})")
+        self.bufs = [torch.as_tensor(_DeviceBlock(p, (self.world * rows, width), "<f8"), device=device) for p in self._own]
+        self.peer = [[(self.bufs[k] if r == self.rank else
+                       torch.as_tensor(_DeviceBlock(self._ptr[r][k], (self.world * rows, width), "<f8"), device=device))
+                      for k in range(n_buffers)] for r in range(self.world)]
         self.streams = [torch.cuda.Stream(device=device) for _ in range(n_buffers)]
 
     def gather_async(self, k: int, local, after_stream):
@@ -161,9 +199,23 @@ class PeerAllGather:
     def pointers(self, k: int):
         """Device addresses of every rank's gather buffer k (rank order), for SNN.set_gather: the fused all-gather, where the
         readout epilogue of the kernel stores the rows into all of them itself."""
-        return [self.peer[r][k].data_ptr() for r in range(self.world)]
+        return [self._ptr[r][k] for r in range(self.world)]
 
     def wait(self, k: int, stream=None):
         """Make `stream` (default: the current one) wait for this rank's outstanding copies into buffers k."""
         import torch
         (stream or torch.cuda.current_stream()).wait_stream(self.streams[k])
+
+    def close(self):
+        """Unmap the peers' matrices and free this rank's own (collective: every rank calls it)."""
+        import torch.distributed as dist
+        if getattr(self, "_own", None) is None:
+            return
+        dist.barrier()
+        for p in self._opened:
+            self.ctx.lib.lsm_peer_buffer_close(self.ctx.h, p)
+        dist.barrier()
+        for p in self._own:
+            self.ctx.lib.lsm_peer_buffer_destroy(self.ctx.h, p)
+        self._own = None
+        self.bufs = self.peer = []

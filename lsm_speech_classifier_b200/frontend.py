@@ -121,12 +121,40 @@ class Frontend:
     # ---- gammatone only: how the filter bank is evaluated (include/lsm_b200.h, lsm_frontend_set_mode)
     def set_mode(self, mode: str = "speculative", delta_db: float = 0.0):
         """"exact": every fp64 operation in the reference's order.  "speculative" (default): a cheaper equivalent
-        arrangement, with utterances whose normalised spectrogram comes within `delta_db` of any encoder comparison
-        filtered again exactly inside the same kernel - the spike trains are the exact path's either way."""
+        arrangement; utterances in which the derived distance bound between the two arrangements (plus `delta_db`
+        decibels) could change any encoder comparison are filtered again exactly - the spike trains are the exact
+        path's either way."""
         modes = {"exact": 0, "speculative": 1}
         if mode not in modes:
             raise ValueError(f"mode must be one of {list(modes)}")
         self.ctx.check(self.ctx.lib.lsm_frontend_set_mode(self.ctx.h, self.h, modes[mode], float(delta_db)))
+
+    def set_bound_scale(self, scale: float = 1.0):
+        """Diagnostic: multiply the derived error bound of the speculative mode (1 = the guarantee, 0 = off)."""
+        self.ctx.check(self.ctx.lib.lsm_frontend_set_bound_scale(self.ctx.h, self.h, float(scale)))
+
+    def error_bound(self) -> np.ndarray:
+        """Per channel: bound on |window amplitude (speculative) - window amplitude (reference order)| for max |sample| = 1
+        (lsm_gammatone_error_bound; gammatone only)."""
+        out = np.zeros(self.n_filters, dtype=np.float64)
+        rc = self.ctx.lib.lsm_gammatone_error_bound(_lib._np_ptr(self.table), self.n_filters, self.n_samples, _lib._np_ptr(out))
+        if rc != 0:
+            raise _lib.LsmError(f"lsm_gammatone_error_bound failed with status {rc}")
+        return out
+
+    def audit(self, pcm):
+        """Both filter arrangements on every utterance (lsm_frontend_audit): float64[B, 8] =
+        [max |dB difference|, max difference / bound, same for the plane's maximum, for its minimum, bound on the maximum,
+        bound on the minimum, max |sample|, range in dB]."""
+        import torch
+        if not _is_torch(pcm):
+            pcm = torch.from_numpy(_lib.as_host(pcm, np.float32)).cuda(self.ctx.device)
+        pcm = pcm.contiguous()
+        out = torch.zeros((pcm.shape[0], 8), dtype=torch.float64, device=pcm.device)
+        self.ctx.set_stream(torch.cuda.current_stream(pcm.device).cuda_stream)
+        self.ctx.check(self.ctx.lib.lsm_frontend_audit(self.ctx.h, self.h, C.c_void_p(pcm.data_ptr()), pcm.shape[0],
+                                                       C.c_void_p(out.data_ptr())))
+        return out.cpu().numpy()
 
     def reruns(self, reset: bool = False) -> int:
         """Utterances the speculative mode had to filter twice (since creation / the last reset)."""

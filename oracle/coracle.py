@@ -141,3 +141,18 @@ def reservoir_run(r, spikes, feature_mask=0xFF, nan_to_num=False, want_raster=Fa
 
 def num_threads():
     return int(lib().oracle_num_threads())
+
+
+def two_arrangements(pcm, coefs, nwin, hop, ncols):
+    """One utterance -> (amp_exact, amp_fast), float64[C, ncols] each: the window amplitudes of the reference-order
+    cascade and of the product's speculative arrangement restated with the same FMAs (oracle_gammatone_two_arrangements)."""
+    pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+    coefs = np.ascontiguousarray(coefs, dtype=np.float64)
+    Cc = coefs.shape[0]
+    a = np.zeros((Cc, ncols), dtype=np.float64)
+    b = np.zeros((Cc, ncols), dtype=np.float64)
+    f = lib().oracle_gammatone_two_arrangements
+    f.restype = None
+    f(_p(pcm, C.c_float), C.c_int(len(pcm)), _p(coefs, C.c_double), C.c_int(Cc), C.c_int(nwin), C.c_int(hop),
+      C.c_int(ncols), _p(a, C.c_double), _p(b, C.c_double))
+    return a, b

@@ -166,6 +166,56 @@ static void gammatone_energy(const float *pcm, int L, const double *coefs, int C
     }
 }
 
+/* The product's SPECULATIVE arrangement of the same cascade (csrc/gammatone_core.cuh gt_filter_fast), restated with the
+ * same fused multiply-adds so that tests/test_error_bound.py can check, without a GPU, that its window amplitudes stay
+ * within the derived bound (csrc/error_bound.cu) of the reference-order ones above.  Test infrastructure like the rest
+ * of this file.  amp_exact / amp_fast: [C][ncols].                                                                   */
+void oracle_gammatone_two_arrangements(const float *pcm, int L, const double *coefs, int C, int nwin, int hop,
+                                       int ncols, double *amp_exact, double *amp_fast)
+{
+    gammatone_energy(pcm, L, coefs, C, nwin, hop, ncols, amp_exact);
+    const int r_old = nwin - 2 * hop;
+    const int n_used = (ncols - 1) * hop + nwin;
+    const int n_blocks = (n_used + hop - 1) / hop;
+    for (int ch = 0; ch < C; ++ch) {
+        const double *c = coefs + 10 * ch;
+        const double A0 = c[0], a0 = c[6];
+        const double c1 = c[1] / A0, c2 = c[2] / A0, c3 = c[3] / A0, c4 = c[4] / A0;
+        const double na1 = -(c[7] / a0), na2 = -(c[8] / a0);
+        const double sc = c[0] / c[6];
+        const double G = (sc * sc) * (sc * sc) / c[9];
+        const double g2n = G * G / (double)nwin;
+        double xp = 0, p1 = 0, q1 = 0, p2 = 0, q2 = 0, p3 = 0, q3 = 0, p4 = 0, q4 = 0;
+        double acc = 0, full1 = 0, full2 = 0;
+        for (int m = 0; m < n_blocks; ++m) {
+            const int n_here = (n_used - m * hop) < hop ? (n_used - m * hop) : hop;
+            acc = 0.0;
+            for (int p = 0; p < n_here; ++p) {
+                if (p == r_old && m >= 2) amp_fast[(size_t)ch * ncols + (m - 2)] = sqrt(((full2 + full1) + acc) * g2n);
+                const int n = m * hop + p;
+                const double x = n < L ? (double)pcm[n] : 0.0;
+                /* unskewed evaluation: the same values as the skewed loop of the kernel, stage by stage.  Stage k consumes
+                 * the stage k-1 outputs of this sample and of the previous one (o1..o3 = p1..p3 before their update). */
+                const double n1 = fma(na1, p1, fma(na2, q1, fma(c1, xp, x)));
+                const double o1 = p1;
+                xp = x; q1 = p1; p1 = n1;
+                const double n2 = fma(na1, p2, fma(na2, q2, fma(c2, o1, n1)));
+                const double o2 = p2;
+                q2 = p2; p2 = n2;
+                const double n3 = fma(na1, p3, fma(na2, q3, fma(c3, o2, n2)));
+                const double o3 = p3;
+                q3 = p3; p3 = n3;
+                const double n4 = fma(na1, p4, fma(na2, q4, fma(c4, o3, n3)));
+                q4 = p4; p4 = n4;
+                acc = fma(n4, n4, acc);
+            }
+            if (n_here == r_old && m >= 2) amp_fast[(size_t)ch * ncols + (m - 2)] = sqrt(((full2 + full1) + acc) * g2n);
+            full2 = full1;
+            full1 = acc;
+        }
+    }
+}
+
 /* create_dataset.py:59-78 on a [C][ncols] energy matrix -> spec_norm [C][nbins] (fp64).
  * zi0/zf: zoom table (source index, fraction) for each output bin.  Returns 0 if degenerate
  * (all-zero output, create_dataset.py:64-65).                                                 */

@@ -363,8 +363,9 @@ def test_back_to_back_calls_on_different_streams_do_not_race(env, small_set):
 
 # ---------------------------------------------------------------- speculative filter (LSM_FILTER_SPECULATIVE)
 def test_speculative_filter_gives_the_exact_spike_trains(env, small_set):
-    """The default mode filters with 13 FMAs per sample and re-filters near-ties exactly: same bytes as the oracle
-    whatever the margin - 0 re-executions (pure speculative plane), the default, and all utterances re-executed."""
+    """The default mode filters with 13 FMAs per sample and re-filters exactly every utterance in which the derived distance
+    bound could change a comparison: same bytes as the oracle whatever the extra margin - none, a mix, everything re-executed -
+    and, on these ordinary clips, even with the bound switched off (the plain speculative plane)."""
     from lsm_speech_classifier_b200 import synth
     from lsm_speech_classifier_b200.frontend import Frontend
     pcm, _ = small_set
@@ -375,13 +376,14 @@ def test_speculative_filter_gives_the_exact_spike_trains(env, small_set):
     fe.set_mode("exact")
     assert np.array_equal(fe.encode(pcm), want)
     assert fe.reruns() == 0
-    fe.set_mode("speculative")                       # default margin 1e-7 dB
+    fe.set_mode("speculative")                       # the derived bound alone
     assert np.array_equal(fe.encode(pcm), want)
     n_default = fe.reruns(reset=True)
-    assert n_default <= 2, n_default                 # ~4e-4 expected per utterance
-    fe.set_mode("speculative", 1e-300)               # no utterance can be flagged: the plain speculative plane
+    assert n_default <= 3, n_default                 # ~1e-3 expected per utterance
+    fe.set_bound_scale(0.0)                          # no utterance can be flagged: the plain speculative plane
     assert np.array_equal(fe.encode(pcm), want)
     assert fe.reruns(reset=True) == 0
+    fe.set_bound_scale(1.0)
     fe.set_mode("speculative", 1e9)                  # every non-degenerate utterance flagged -> exact re-execution
     assert np.array_equal(fe.encode(pcm), want)
     assert fe.reruns(reset=True) >= len(pcm) - 1
@@ -389,27 +391,71 @@ def test_speculative_filter_gives_the_exact_spike_trains(env, small_set):
     assert np.array_equal(fe.encode(pcm), want)
     n_mix = fe.reruns(reset=True)
     assert 0 < n_mix < len(pcm), n_mix
+    with pytest.raises(Exception):
+        fe.set_mode("speculative", -1.0)
 
 
-def test_speculative_plane_is_within_a_thousandth_of_the_margin(env, small_set):
-    """The guarantee behind the speculative mode: its dB plane and the exact one differ by far less than the
-    near-tie margin (1e-7 dB).  The speculative plane itself never leaves the kernel, so ask the question the other
-    way round - with the margin at 1e-10 dB (a thousand times tighter) the spikes still equal the oracle's on every clip."""
+def _audit_report(tag, a):
+    print(f"\n{tag}: {len(a)} clips; largest |dB_spec - dB_exact| {a[:, 0].max():.3e} dB (median {np.median(a[:, 0]):.3e}); "
+          f"largest distance/bound: cells {a[:, 1].max():.3e}, maximum {a[:, 2].max():.3e}, minimum {a[:, 3].max():.3e}; "
+          f"bound on the minimum: median {np.median(a[:, 5]):.3e} dB, max {a[:, 5].max():.3e} dB")
+
+
+def test_speculative_distance_is_inside_the_derived_bound(env, small_set):
+    """The guarantee behind the speculative mode, measured: both arrangements run on the same clips (lsm_frontend_audit) and
+    every window cell, the plane's maximum and its floored minimum of the speculative pass lie within the derived bound of
+    the exact pass's.  Speech-like clips here; ten thousand adversarial ones below."""
     from lsm_speech_classifier_b200 import synth
     from lsm_speech_classifier_b200.frontend import Frontend
     pcm, _ = small_set
-    more, _ = synth.synth_dataset(12, 20, start_utt=500)
-    pcm = np.concatenate([pcm, more])
+    more, _ = synth.synth_dataset(12, 40, start_utt=300)
+    tone = (np.sin(2 * np.pi * 3000 * np.arange(16000) / 16000) * 0.5).astype(np.float32)[None]
+    pcm = np.concatenate([pcm, more, tone])
     fe = Frontend(128, "gammatone")
-    want = oracle_spikes(pcm, fe)
-    fe.set_mode("speculative", 1e-10)
-    assert np.array_equal(fe.encode(pcm), want)
+    a = fe.audit(pcm)
+    _audit_report("speech-like", a)
+    assert a[:, 1].max() <= 1.0 and a[:, 2].max() <= 1.0 and a[:, 3].max() <= 1.0
+    assert a[:, 0].max() < 1e-6
+    silent = a[24]                                    # all-zero clip: both planes are exactly -180 dB
+    assert silent[0] == 0.0 and silent[6] == 0.0
 
 
-@pytest.mark.parametrize("split_exact", [False, True])
-def test_fused_pipeline_same_features_in_both_filter_modes(env, small_set, monkeypatch, split_exact):
-    if split_exact:
-        monkeypatch.setenv("LSM_SPLIT_EXACT", "1")       # exact pass as a follow-up launch over a device work list
+def test_ten_thousand_adversarial_clips_stay_inside_the_bound(env):
+    """>= 10 000 clips built to separate the two arrangements (out-of-band tone + in-band component at
+    -60..-79 dB, full-scale clipping, PCM16 extremes, 80 dB chirps, impulses, resonances, l1-attaining sign patterns):
+    (a) no cell, maximum or minimum leaves the derived bound (largest ratio reported), (b) the default mode's spike trains
+    equal the exact mode's on all of them, (c) the re-execution rate the bound costs is reported."""
+    import adversarial
+    from lsm_speech_classifier_b200.frontend import Frontend
+    fe = Frontend(128, "gammatone")
+    worst = np.zeros(4)
+    reruns = total = 0
+    audits = []
+    for start in range(0, 10080, 1008):
+        pcm = adversarial.clips(start, 1008, seed=11, coefs=fe.table)
+        a = fe.audit(pcm)
+        audits.append(a)
+        assert a[:, 1].max() <= 1.0 and a[:, 2].max() <= 1.0 and a[:, 3].max() <= 1.0, (start, a[:, 1:4].max(axis=0))
+        fe.set_mode("exact")
+        want = fe.encode(pcm)
+        fe.set_mode("speculative")
+        fe.reruns(reset=True)
+        got = fe.encode(pcm)
+        reruns += fe.reruns(reset=True)
+        total += len(pcm)
+        assert np.array_equal(got, want), start
+    a = np.concatenate(audits)
+    _audit_report("adversarial", a)
+    print(f"exact re-executions under the derived bound: {reruns} of {total} adversarial clips ({100.0 * reruns / total:.2f} %)")
+    assert total >= 10000
+    # the fixed 1e-7 dB margin of round 1 would not have covered these clips: the planes differ by more than a third of it
+    assert a[:, 0].max() > 3e-8
+
+
+@pytest.mark.parametrize("no_pipeline", [False, True])
+def test_fused_pipeline_same_features_in_both_filter_modes(env, small_set, monkeypatch, no_pipeline):
+    if no_pipeline:
+        monkeypatch.setenv("LSM_NO_PIPELINE", "1")       # the lane = channel fused kernel instead of the warp-specialised one
     from lsm_speech_classifier_b200.frontend import Frontend
     from lsm_speech_classifier_b200.snn import SNN, AudioToFeatures, SimulationParams
     from lsm_speech_classifier_b200.extract_lsm_features import FEATURE_SETS, calculate_theoretical_w_critico
@@ -456,16 +502,19 @@ def test_speculative_filter_arrangements_agree(env, small_set, monkeypatch):
     assert np.array_equal(fe40.encode(pcm[:9]), want40)
 
 
-def test_lanes_arrangement_fused_pipeline(env, small_set, monkeypatch):
-    """LSM_LANES=1, default shape: energy kernel -> encoder + reservoir kernel -> exact pass over the flagged utterances.
-    Same features as the single fused kernel in exact mode, whatever fraction of the batch takes the exact pass."""
+def test_warp_specialised_kernel_equals_the_lane_channel_kernel(env, small_set, monkeypatch):
+    """Default shape: the warp-specialised kernel (lane = utterance filter warps + encoder/reservoir units in one CTA, flagged
+    utterances finished by the exact kernel) against the lane = channel fused kernel in exact mode (LSM_NO_PIPELINE=1):
+    same features and spike trains for ragged batch sizes, whatever fraction of the batch takes the exact pass, float32 and
+    PCM16, device and host buffers."""
+    import torch
     from lsm_speech_classifier_b200 import synth
     from lsm_speech_classifier_b200.frontend import Frontend
     from lsm_speech_classifier_b200.snn import SNN, AudioToFeatures, SimulationParams
     from lsm_speech_classifier_b200.extract_lsm_features import FEATURE_SETS, calculate_theoretical_w_critico
     pcm, _ = small_set
-    more, _ = synth.synth_dataset(12, 6, start_utt=40)
-    pcm = np.concatenate([pcm, more])
+    more, _ = synth.synth_dataset(12, 30, start_utt=40)
+    pcm = np.concatenate([pcm, more])                      # 388 utterances
     fe = Frontend(128, "gammatone")
     fe.set_mode("exact")
     spikes = fe.encode(pcm)
@@ -474,20 +523,41 @@ def test_lanes_arrangement_fused_pipeline(env, small_set, monkeypatch):
     lsm = SNN(simulation_params=params)
     pipe = AudioToFeatures(fe, lsm)
     keys = FEATURE_SETS["original"]
+    monkeypatch.setenv("LSM_NO_PIPELINE", "1")
     want = pipe.run_host(pcm, keys)
-    monkeypatch.setenv("LSM_LANES", "1")
-    for delta, lo, hi in ((0.0, 0, 2), (1e-300, 0, 0), (1e-3, 1, len(pcm) - 1), (1e9, len(pcm) - 1, len(pcm))):
+    monkeypatch.delenv("LSM_NO_PIPELINE")
+    d_pcm = torch.from_numpy(pcm).cuda()
+    for delta, lo, hi in ((0.0, 0, 3), (1e-3, 1, len(pcm) - 1), (1e9, len(pcm) - 1, len(pcm))):
         fe.set_mode("speculative", delta)
         fe.reruns(reset=True)
+        launches = fe.ctx.launches
         spk = np.zeros_like(spikes)
         got = pipe.run_host(pcm, keys, spikes_out=spk)
+        assert fe.ctx.launches - launches == 4, "two pieces on the two lanes: pipeline kernel + exact pass each"
         assert np.array_equal(got, want), delta
         assert np.array_equal(spk, spikes), delta
         assert lo <= fe.reruns() <= hi, (delta, fe.reruns())
-    fe.set_mode("speculative", 1e-7)
-    import torch
-    out, _ = pipe.run(torch.from_numpy(pcm).cuda(), keys, want_spikes=False)
-    assert np.array_equal(out.cpu().numpy(), want)
+    fe.set_mode("speculative")
+    for n in (1, 31, 33, 64, 100, len(pcm)):               # partial groups, one piece / two pieces
+        out, dspk = pipe.run(d_pcm[:n], keys)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), want[:n]), n
+        assert np.array_equal(dspk.cpu().numpy(), spikes[:n]), n
+    out, none = pipe.run(d_pcm, keys, want_spikes=False)
+    assert none is None and np.array_equal(out.cpu().numpy(), want)
+    # PCM16 through the same kernel
+    i16 = np.clip(np.round(pcm * 32768.0), -32768, 32767).astype(np.int16)
+    as_f32 = i16.astype(np.float32) / np.float32(32768.0)
+    monkeypatch.setenv("LSM_NO_PIPELINE", "1")
+    want16 = pipe.run_host(as_f32, keys)
+    monkeypatch.delenv("LSM_NO_PIPELINE")
+    out16, _ = pipe.run(torch.from_numpy(i16).cuda(), keys)
+    assert np.array_equal(out16.cpu().numpy(), want16)
+    h_in = torch.from_numpy(i16).pin_memory()
+    h_out = torch.zeros((len(i16), want.shape[1]), dtype=torch.float64).pin_memory()
+    pipe.run_host_async(h_in, keys, out=h_out, lane=1)
+    fe.ctx.sync_all()
+    assert np.array_equal(h_out.numpy(), want16)
 
 
 def test_async_host_calls_on_two_lanes(env, small_set):
@@ -558,37 +628,12 @@ def test_pcm16_input_gives_the_float32_results(env, small_set):
         AudioToFeatures(femel, lsm).run(torch.from_numpy(i16).cuda(), keys)       # not a fused pair
 
 
-def test_speculative_plane_distance_measured(env, small_set, monkeypatch):
-    """Direct measurement behind the speculative mode's margin: the normalised spectrogram of the speculative pass
-    (diagnostic dump, LSM_SPEC_DUMP) against the exact one, in dB (difference x (max - min + 1e-8)), over speech-like and
-    pathological clips.  The near-tie margin is 1e-7 dB; the planes must agree at least a hundred times better."""
-    import torch
-    from lsm_speech_classifier_b200 import synth
-    from lsm_speech_classifier_b200.frontend import Frontend
-    pcm, _ = small_set
-    more, _ = synth.synth_dataset(12, 40, start_utt=300)
-    tone = (np.sin(2 * np.pi * 3000 * np.arange(16000) / 16000) * 0.5).astype(np.float32)[None]
-    pcm = np.concatenate([pcm, more, tone])
-    fe = Frontend(128, "gammatone")
-    d = torch.from_numpy(pcm).cuda()
-    fe.set_mode("exact")
-    _, exact = fe.encode(d, return_spectrogram=True)
-    monkeypatch.setenv("LSM_SPEC_DUMP", "1")
-    fe.set_mode("speculative", 1e-300)               # nothing is re-executed: the dump is the speculative plane
-    _, spec = fe.encode(d, return_spectrogram=True)
-    monkeypatch.delenv("LSM_SPEC_DUMP")
-    torch.cuda.synchronize()
-    assert fe.reruns(reset=True) == 0
-    exact, spec = exact.cpu().numpy(), spec.cpu().numpy()
-    diff = np.abs(spec - exact).max(axis=(1, 2)) * 80.0      # normalised units -> dB, with the largest possible range (80 dB floor)
-    print(f"\nspeculative vs exact plane: max {diff.max():.3e} dB, median {np.median(diff):.3e} dB over {len(pcm)} clips")
-    assert diff.max() < 1e-9
-
-
 def test_large_pinned_batch_is_split_across_the_two_lanes(env, monkeypatch):
     """lsm_pipeline_run_host with pinned buffers and at least two resident waves of utterances launches the two halves on
-    the two lanes; the feature rows are those of the unsplit call (LSM_NO_SPLIT=1) and of the oracle."""
+    the two lanes; the feature rows are those of the unsplit call (LSM_NO_SPLIT=1), of the warp-specialised kernel and of
+    the oracle.  (LSM_NO_PIPELINE=1 selects the lane = channel kernel, the zero-copy one.)"""
     import torch
+    monkeypatch.setenv("LSM_NO_PIPELINE", "1")
     from oracle import coracle
     from lsm_speech_classifier_b200 import synth, _lib
     from lsm_speech_classifier_b200.frontend import Frontend
@@ -615,6 +660,10 @@ def test_large_pinned_batch_is_split_across_the_two_lanes(env, monkeypatch):
     launches = fe.ctx.launches
     pipe.run_host(h_in.numpy(), keys, out=h_out.numpy())
     assert fe.ctx.launches - launches == 1
+    assert np.array_equal(split, h_out.numpy())
+    monkeypatch.delenv("LSM_NO_PIPELINE")
+    h_out.zero_()
+    pipe.run_host(h_in.numpy(), keys, out=h_out.numpy())        # default: warp-specialised kernel, copy-engine staging
     assert np.array_equal(split, h_out.numpy())
     want_spk = oracle_spikes(base, fe)
     want, _ = coracle.reservoir_run(lsm.reservoir, want_spk, _lib.feature_mask(keys), True, False)
