@@ -56,6 +56,15 @@ int lsm_set_stream(lsm_ctx *ctx, void *cuda_stream);
 /* Go back to the non-blocking stream the ctx created for itself (the initial state). */
 int lsm_reset_stream(lsm_ctx *ctx);
 int lsm_sync(lsm_ctx *ctx);
+/* How the asynchronous host-buffer calls (lsm_pipeline_run_host_async*) bring pinned PCM to the kernel:
+ * LSM_FEED_ZERO_COPY (default) - the fused kernel reads the pinned host buffer itself, sample by sample as it filters (every
+ *   sample crosses PCIe exactly once, no staging buffer);
+ * LSM_FEED_COPY_ENGINE - one cudaMemcpyAsync per call into a device staging buffer on the launch lane, then the kernel on
+ *   device memory; the copy of one lane overlaps the kernel of the other.  Better when many GPUs pull from one host
+ *   (zero-copy loads of eight GPUs share the host's read bandwidth at small request size).                             */
+#define LSM_FEED_ZERO_COPY 0
+#define LSM_FEED_COPY_ENGINE 1
+int lsm_ctx_set_host_feed(lsm_ctx *ctx, int32_t mode);
 /* Kernels launched by this ctx since creation (bench.py's gpu_launches). */
 int64_t lsm_launch_count(const lsm_ctx *ctx);
 int lsm_sm_count(const lsm_ctx *ctx);

@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_PKG, "liblsmb200.so")
+SO_PATH = os.path.join(_PKG, os.environ.get("LSM_SO_NAME", "liblsmb200.so"))      # LSM_SO_NAME: build experiments only
 
 LSM_OK = 0
 FILTERBANK_KINDS = {"gammatone": 0, "mel": 1}
@@ -25,7 +25,7 @@ EXPORTS = [
     "lsm_hysteresis_encode", "lsm_fp64_peak_gops", "lsm_pipeline_is_fused", "lsm_frontend_mel_tables", "lsm_reservoir_diagnostics", "lsm_gammatone_design", "lsm_zoom_table", "lsm_standardize_fit", "lsm_standardize_transform",
     "lsm_frontend_set_mode", "lsm_frontend_reruns", "lsm_pipeline_run_host_async", "lsm_sync_all", "lsm_lane_stream", "lsm_logreg_fit", "lsm_logreg_predict", "lsm_pipeline_run_i16", "lsm_pipeline_run_host_async_i16", "lsm_reservoir_set_gather",
     "lsm_frontend_set_bound_scale", "lsm_frontend_audit", "lsm_gammatone_error_bound",
-    "lsm_peer_buffer_create", "lsm_peer_buffer_open", "lsm_peer_buffer_close", "lsm_peer_buffer_destroy",
+    "lsm_ctx_set_host_feed", "lsm_peer_buffer_create", "lsm_peer_buffer_open", "lsm_peer_buffer_close", "lsm_peer_buffer_destroy",
 ]
 
 
@@ -104,6 +104,7 @@ def load():
     lib.lsm_frontend_set_bound_scale.argtypes = [vp, vp, C.c_double]
     lib.lsm_frontend_audit.argtypes = [vp, vp, vp, i32, vp]
     lib.lsm_gammatone_error_bound.argtypes = [vp, i32, i32, vp]
+    lib.lsm_ctx_set_host_feed.argtypes = [vp, i32]
     lib.lsm_peer_buffer_create.argtypes = [vp, i64, C.POINTER(vp), vp]
     lib.lsm_peer_buffer_open.argtypes = [vp, vp, C.POINTER(vp)]
     lib.lsm_peer_buffer_close.argtypes = [vp, vp]
@@ -156,6 +157,14 @@ class Context:
 
     def sync(self):
         self.check(self.lib.lsm_sync(self.h))
+
+    def set_host_feed(self, mode: str = "zero_copy"):
+        """How run_host_async brings pinned PCM to the kernel: "zero_copy" (the kernel reads the host buffer itself) or
+        "copy_engine" (one cudaMemcpyAsync into a device staging buffer per call, overlapped with the other lane's kernel)."""
+        modes = {"zero_copy": 0, "copy_engine": 1}
+        if mode not in modes:
+            raise ValueError(f"mode must be one of {list(modes)}")
+        self.check(self.lib.lsm_ctx_set_host_feed(self.h, modes[mode]))
 
     def lane_stream(self, lane: int) -> int:
         """cudaStream_t handle of launch lane 0 / 1 (wrap with torch.cuda.ExternalStream to order other work after it)."""

@@ -9,7 +9,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-SO = os.path.join(PKG, "liblsmb200.so")
+SO = os.path.join(PKG, os.environ.get("LSM_SO_NAME", "liblsmb200.so"))
 SOURCES = ["api.cu", "error_bound.cu", "frontend_gammatone.cu", "pipeline_lanes.cu", "frontend_mel.cu", "reservoir.cu", "standardize.cu", "logreg.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "--fmad=false",            # never contract a*b+c: bit parity with the CPU oracle
@@ -38,6 +38,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         cmd = [nvcc(), *FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
+        if os.environ.get("LSM_PIPE_J"):      # experiment: channels per filter warp of the warp-specialised kernel (default 1)
+            cmd.insert(1, "-DLSM_PIPE_J=" + os.environ["LSM_PIPE_J"])
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.check_call(cmd)

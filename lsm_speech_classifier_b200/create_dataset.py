@@ -162,8 +162,10 @@ def create_dataset(n_filters: int, filterbank: str, synthetic: tuple | None = No
     """reference :107-177.  `synthetic=(n_classes, per_class)` replaces the directory walk with the
     deterministic generator (synth.py) - there is no Speech Commands copy in this environment.
     `packed=True` writes the bit-packed file (save_packed_spikes) instead of the reference-schema one."""
-    from .distributed import is_main
-    print(f"Creating dataset with filterbank: {filterbank}, filters: {n_filters}")
+    from .distributed import init_from_env, is_main
+    init_from_env()             # under torchrun (also when this stage is run on its own): one rank per GPU, utterances sharded
+    if is_main():
+        print(f"Creating dataset with filterbank: {filterbank}, filters: {n_filters}")
     pcm, labels = collect_pcm(synthetic)
     if pcm is None:
         return

@@ -74,6 +74,14 @@ extern "C" int lsm_sync(lsm_ctx *ctx)
     return LSM_OK;
 }
 
+extern "C" int lsm_ctx_set_host_feed(lsm_ctx *ctx, int32_t mode)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (mode != LSM_FEED_ZERO_COPY && mode != LSM_FEED_COPY_ENGINE) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_ctx_set_host_feed: mode must be 0 or 1");
+    ctx->host_feed = mode;
+    return LSM_OK;
+}
+
 extern "C" int64_t lsm_launch_count(const lsm_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int lsm_sm_count(const lsm_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 
@@ -689,6 +697,7 @@ static int check_pipe_error(lsm_ctx *ctx, lsm_frontend *fe)
 // groups, at most 8192 (the energy planes between the two roles take 100 KB per utterance).
 static int lanes_piece(int B)
 {
+    if (getenv("LSM_PIPE_ONE_PIECE")) return B > 8192 ? 8192 : B;       // experiment: no split across the two lanes
     int n = ((B / 2 + 31) / 32) * 32;
     if (B < 64) n = B;
     return n > 8192 ? 8192 : n;
@@ -737,7 +746,8 @@ int lsm_pipeline_lanes_device(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res
 // its feature rows written straight to the host buffer when the device can address it (pinned), else copied back.
 // only_lane < 0: both lanes, then wait; 0 / 1: that lane only, asynchronous.
 static int pipeline_lanes_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const void *h_pcm, bool i16, int B,
-                               uint32_t feature_mask, int nan_to_num, double *h_features, uint8_t *h_spikes_or_null, int only_lane)
+                               uint32_t feature_mask, int nan_to_num, double *h_features, uint8_t *h_spikes_or_null, int only_lane,
+                               bool warp_specialised = true)
 {
     const int L = fe->p.n_samples;
     const size_t esz = i16 ? sizeof(int16_t) : sizeof(float);
@@ -758,8 +768,11 @@ static int pipeline_lanes_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *re
         LSM_CUDA(ctx, cudaMemcpyAsync(d_in, (const char *)h_pcm + (size_t)off * L * esz, (size_t)n * L * esz, cudaMemcpyDefault, ls));
         double *out = feat_direct ? (double *)dv_feat + (size_t)off * feat_per : (double *)d_feat;
         fe->next_pcm16 = i16 ? (const int16_t *)d_in : nullptr;
-        rc = lsm_launch_pipeline_lanes(ctx, fe, res, i16 ? nullptr : (const float *)d_in, n, (uint8_t *)d_spk, feature_mask, nan_to_num,
-                                       out, ls, lane, off);
+        if (warp_specialised)
+            rc = lsm_launch_pipeline_lanes(ctx, fe, res, i16 ? nullptr : (const float *)d_in, n, (uint8_t *)d_spk, feature_mask, nan_to_num,
+                                           out, ls, lane, off);
+        else       // the lane = channel fused kernel on the staged copy
+            rc = lsm_launch_fused(ctx, fe, res, i16 ? nullptr : (const float *)d_in, n, (uint8_t *)d_spk, feature_mask, nan_to_num, out, ls, off);
         fe->next_pcm16 = nullptr;
         if (rc != LSM_OK) return rc;
         if (!feat_direct)
@@ -956,6 +969,9 @@ extern "C" int lsm_pipeline_run_host_async_i16(lsm_ctx *ctx, lsm_frontend *fe, l
     if (fe->p.channels * fe->p.redundancy == res->p.num_inputs && fe->p.n_bins * fe->p.n_thresholds == res->p.num_steps &&
         lsm_pipeline_lanes_eligible(fe, res, (const void *)256, true))
         return pipeline_lanes_host(ctx, fe, res, h_pcm16, true, B, feature_mask, nan_to_num, h_features, nullptr, lane);
+    if (ctx->host_feed == LSM_FEED_COPY_ENGINE && lsm_fused_npt(fe, res) &&
+        fe->p.channels * fe->p.redundancy == res->p.num_inputs && fe->p.n_bins * fe->p.n_thresholds == res->p.num_steps)
+        return pipeline_lanes_host(ctx, fe, res, h_pcm16, true, B, feature_mask, nan_to_num, h_features, nullptr, lane, false);
     return run_i16(ctx, fe, res, (const int16_t *)dv_pcm, B, feature_mask, nan_to_num, nullptr, (double *)dv_feat,
                    lane == 0 ? ctx->own_stream : ctx->copy_stream[0], "lsm_pipeline_run_host_async_i16");
 }
@@ -980,6 +996,8 @@ extern "C" int lsm_pipeline_run_host_async(lsm_ctx *ctx, lsm_frontend *fe, lsm_r
         LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "lsm_pipeline_run_host_async needs pinned (or device) buffers and a pair that runs fused");
     if (lsm_pipeline_lanes_eligible(fe, res, (const void *)256, false))
         return pipeline_lanes_host(ctx, fe, res, h_pcm, false, B, feature_mask, nan_to_num, h_features, nullptr, lane);
+    if (ctx->host_feed == LSM_FEED_COPY_ENGINE)
+        return pipeline_lanes_host(ctx, fe, res, h_pcm, false, B, feature_mask, nan_to_num, h_features, nullptr, lane, false);
     return lsm_launch_fused(ctx, fe, res, (const float *)dv_pcm, B, nullptr, feature_mask, nan_to_num, (double *)dv_feat,
                             lane == 0 ? ctx->own_stream : ctx->copy_stream[0], 0);
 }

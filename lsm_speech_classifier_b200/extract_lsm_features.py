@@ -138,8 +138,11 @@ def build_lsm(X_train, multiplier: float, leak_variance_divisor=None, num_neuron
 def main(feature_set: str, multiplier: float, leak_variance_divisor: float = None, num_neurons: int = NUM_NEURONS):
     from sklearn.model_selection import train_test_split
     from sklearn.preprocessing import StandardScaler
-    from .distributed import is_main
+    from .distributed import _dist, init_from_env, is_main
 
+    init_from_env()             # under torchrun (also when this stage is run on its own): one rank per GPU, samples sharded
+    if _dist() is not None:
+        _dist().barrier()       # the spike file is written by rank 0 of the previous stage
     X_spikes, y_labels = load_spike_dataset()
     if X_spikes is None:
         return

@@ -452,10 +452,10 @@ def test_ten_thousand_adversarial_clips_stay_inside_the_bound(env):
     assert a[:, 0].max() > 3e-8
 
 
-@pytest.mark.parametrize("no_pipeline", [False, True])
-def test_fused_pipeline_same_features_in_both_filter_modes(env, small_set, monkeypatch, no_pipeline):
-    if no_pipeline:
-        monkeypatch.setenv("LSM_NO_PIPELINE", "1")       # the lane = channel fused kernel instead of the warp-specialised one
+@pytest.mark.parametrize("pipeline", [False, True])
+def test_fused_pipeline_same_features_in_both_filter_modes(env, small_set, monkeypatch, pipeline):
+    if pipeline:
+        monkeypatch.setenv("LSM_PIPELINE", "1")          # the warp-specialised kernel instead of the lane = channel fused one
     from lsm_speech_classifier_b200.frontend import Frontend
     from lsm_speech_classifier_b200.snn import SNN, AudioToFeatures, SimulationParams
     from lsm_speech_classifier_b200.extract_lsm_features import FEATURE_SETS, calculate_theoretical_w_critico
@@ -503,8 +503,8 @@ def test_speculative_filter_arrangements_agree(env, small_set, monkeypatch):
 
 
 def test_warp_specialised_kernel_equals_the_lane_channel_kernel(env, small_set, monkeypatch):
-    """Default shape: the warp-specialised kernel (lane = utterance filter warps + encoder/reservoir units in one CTA, flagged
-    utterances finished by the exact kernel) against the lane = channel fused kernel in exact mode (LSM_NO_PIPELINE=1):
+    """Default shape, LSM_PIPELINE=1: the warp-specialised kernel (lane = utterance filter warps + encoder/reservoir units in
+    one CTA, flagged utterances finished by the exact kernel) against the lane = channel fused kernel in exact mode:
     same features and spike trains for ragged batch sizes, whatever fraction of the batch takes the exact pass, float32 and
     PCM16, device and host buffers."""
     import torch
@@ -523,9 +523,8 @@ def test_warp_specialised_kernel_equals_the_lane_channel_kernel(env, small_set, 
     lsm = SNN(simulation_params=params)
     pipe = AudioToFeatures(fe, lsm)
     keys = FEATURE_SETS["original"]
-    monkeypatch.setenv("LSM_NO_PIPELINE", "1")
     want = pipe.run_host(pcm, keys)
-    monkeypatch.delenv("LSM_NO_PIPELINE")
+    monkeypatch.setenv("LSM_PIPELINE", "1")
     d_pcm = torch.from_numpy(pcm).cuda()
     for delta, lo, hi in ((0.0, 0, 3), (1e-3, 1, len(pcm) - 1), (1e9, len(pcm) - 1, len(pcm))):
         fe.set_mode("speculative", delta)
@@ -533,7 +532,7 @@ def test_warp_specialised_kernel_equals_the_lane_channel_kernel(env, small_set, 
         launches = fe.ctx.launches
         spk = np.zeros_like(spikes)
         got = pipe.run_host(pcm, keys, spikes_out=spk)
-        assert fe.ctx.launches - launches == 4, "two pieces on the two lanes: pipeline kernel + exact pass each"
+        assert fe.ctx.launches - launches == 6, "two pieces on the two lanes: peak pre-pass + pipeline kernel + exact pass each"
         assert np.array_equal(got, want), delta
         assert np.array_equal(spk, spikes), delta
         assert lo <= fe.reruns() <= hi, (delta, fe.reruns())
@@ -548,9 +547,9 @@ def test_warp_specialised_kernel_equals_the_lane_channel_kernel(env, small_set, 
     # PCM16 through the same kernel
     i16 = np.clip(np.round(pcm * 32768.0), -32768, 32767).astype(np.int16)
     as_f32 = i16.astype(np.float32) / np.float32(32768.0)
-    monkeypatch.setenv("LSM_NO_PIPELINE", "1")
+    monkeypatch.delenv("LSM_PIPELINE")
     want16 = pipe.run_host(as_f32, keys)
-    monkeypatch.delenv("LSM_NO_PIPELINE")
+    monkeypatch.setenv("LSM_PIPELINE", "1")
     out16, _ = pipe.run(torch.from_numpy(i16).cuda(), keys)
     assert np.array_equal(out16.cpu().numpy(), want16)
     h_in = torch.from_numpy(i16).pin_memory()
@@ -631,9 +630,8 @@ def test_pcm16_input_gives_the_float32_results(env, small_set):
 def test_large_pinned_batch_is_split_across_the_two_lanes(env, monkeypatch):
     """lsm_pipeline_run_host with pinned buffers and at least two resident waves of utterances launches the two halves on
     the two lanes; the feature rows are those of the unsplit call (LSM_NO_SPLIT=1), of the warp-specialised kernel and of
-    the oracle.  (LSM_NO_PIPELINE=1 selects the lane = channel kernel, the zero-copy one.)"""
+    the oracle."""
     import torch
-    monkeypatch.setenv("LSM_NO_PIPELINE", "1")
     from oracle import coracle
     from lsm_speech_classifier_b200 import synth, _lib
     from lsm_speech_classifier_b200.frontend import Frontend
@@ -661,9 +659,11 @@ def test_large_pinned_batch_is_split_across_the_two_lanes(env, monkeypatch):
     pipe.run_host(h_in.numpy(), keys, out=h_out.numpy())
     assert fe.ctx.launches - launches == 1
     assert np.array_equal(split, h_out.numpy())
-    monkeypatch.delenv("LSM_NO_PIPELINE")
+    monkeypatch.delenv("LSM_NO_SPLIT")
+    monkeypatch.setenv("LSM_PIPELINE", "1")
     h_out.zero_()
-    pipe.run_host(h_in.numpy(), keys, out=h_out.numpy())        # default: warp-specialised kernel, copy-engine staging
+    pipe.run_host(h_in.numpy(), keys, out=h_out.numpy())        # warp-specialised kernel, copy-engine staging
+    monkeypatch.delenv("LSM_PIPELINE")
     assert np.array_equal(split, h_out.numpy())
     want_spk = oracle_spikes(base, fe)
     want, _ = coracle.reservoir_run(lsm.reservoir, want_spk, _lib.feature_mask(keys), True, False)
