@@ -34,6 +34,7 @@ extern "C" int lsm_ctx_create(lsm_ctx **out, int device_ordinal)
     ctx->stream = ctx->own_stream;
     for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&ctx->copy_stream[i], cudaStreamNonBlocking);
     for (int i = 0; i < 12; ++i) cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < 4; ++i) { cudaEventCreateWithFlags(&ctx->ev_stage_full[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_stage_free[i], cudaEventDisableTiming); }
     *out = ctx;
     return LSM_OK;
 }
@@ -46,6 +47,7 @@ extern "C" void lsm_ctx_destroy(lsm_ctx *ctx)
     for (int i = 0; i < 16; ++i) if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
     for (int i = 0; i < 4; ++i) if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
     for (int i = 0; i < 12; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 4; ++i) { if (ctx->ev_stage_full[i]) cudaEventDestroy(ctx->ev_stage_full[i]); if (ctx->ev_stage_free[i]) cudaEventDestroy(ctx->ev_stage_free[i]); }
     for (int i = 0; i < 2; ++i) if (ctx->copy_stream[i]) cudaStreamDestroy(ctx->copy_stream[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -762,10 +764,24 @@ static int pipeline_lanes_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *re
         const int lane = only_lane >= 0 ? only_lane : (k & 1);
         cudaStream_t ls = lane_stream(ctx, lane);
         void *d_in = nullptr, *d_feat = nullptr, *d_spk = nullptr;
-        if ((rc = lsm_stage_device(ctx, 8 + lane, (size_t)piece * L * esz, &d_in)) != LSM_OK) return rc;
-        if (!feat_direct && (rc = lsm_stage_device(ctx, 10 + lane, (size_t)piece * feat_per * sizeof(double), &d_feat)) != LSM_OK) return rc;
-        if (h_spikes_or_null && (rc = lsm_stage_device(ctx, 12 + lane, (size_t)piece * spk_per, &d_spk)) != LSM_OK) return rc;
-        LSM_CUDA(ctx, cudaMemcpyAsync(d_in, (const char *)h_pcm + (size_t)off * L * esz, (size_t)n * L * esz, cudaMemcpyDefault, ls));
+        // PCM staging: a ring of four device buffers filled by the copy engine on its own stream, so that the copy of piece
+        // k+1 (and k+2) runs while the kernels of piece k are busy whatever lane they are on; events hand a buffer from the
+        // copy to its kernel and back
+        const int slot = (int)(ctx->stage_next++ & 3u);
+        {
+            // all four buffers at once, so that growing one never frees memory another piece is still using
+            const size_t need = (size_t)piece * L * esz;
+            if (ctx->d_stage_bytes[8] < need)
+                for (int q = 0; q < 4; ++q) { void *tmp; if ((rc = lsm_stage_device(ctx, 8 + q, need, &tmp)) != LSM_OK) return rc; }
+            d_in = ctx->d_stage[8 + slot];
+        }
+        if (!feat_direct && (rc = lsm_stage_device(ctx, 12 + lane, (size_t)piece * feat_per * sizeof(double), &d_feat)) != LSM_OK) return rc;
+        if (h_spikes_or_null && (rc = lsm_stage_device(ctx, 14 + lane, (size_t)piece * spk_per, &d_spk)) != LSM_OK) return rc;
+        cudaStream_t cs = ctx->copy_stream[1];
+        if (ctx->stage_busy[slot]) LSM_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_stage_free[slot], 0));      // its last kernel has read it
+        LSM_CUDA(ctx, cudaMemcpyAsync(d_in, (const char *)h_pcm + (size_t)off * L * esz, (size_t)n * L * esz, cudaMemcpyDefault, cs));
+        LSM_CUDA(ctx, cudaEventRecord(ctx->ev_stage_full[slot], cs));
+        LSM_CUDA(ctx, cudaStreamWaitEvent(ls, ctx->ev_stage_full[slot], 0));
         double *out = feat_direct ? (double *)dv_feat + (size_t)off * feat_per : (double *)d_feat;
         fe->next_pcm16 = i16 ? (const int16_t *)d_in : nullptr;
         if (warp_specialised)
@@ -775,6 +791,8 @@ static int pipeline_lanes_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *re
             rc = lsm_launch_fused(ctx, fe, res, i16 ? nullptr : (const float *)d_in, n, (uint8_t *)d_spk, feature_mask, nan_to_num, out, ls, off);
         fe->next_pcm16 = nullptr;
         if (rc != LSM_OK) return rc;
+        LSM_CUDA(ctx, cudaEventRecord(ctx->ev_stage_free[slot], ls));
+        ctx->stage_busy[slot] = 1;
         if (!feat_direct)
             LSM_CUDA(ctx, cudaMemcpyAsync(h_features + (size_t)off * feat_per, d_feat, (size_t)n * feat_per * sizeof(double), cudaMemcpyDeviceToHost, ls));
         if (h_spikes_or_null)

@@ -16,6 +16,9 @@ struct lsm_ctx {
     cudaStream_t copy_stream[2] = {nullptr, nullptr};  // pipeline_run_host: H2D / D2H legs
     cudaEvent_t ev[12] = {};             // [0,6): chunked host pipeline; 8: fork, 9-10: join of the two launch lanes
     int64_t launches = 0;
+    cudaEvent_t ev_stage_full[4] = {}, ev_stage_free[4] = {};   // copy-engine feed: staging ring hand-over
+    int stage_busy[4] = {};
+    unsigned stage_next = 0;
     int host_feed = 0;                   // lsm_ctx_set_host_feed: 0 = the kernel reads pinned host PCM itself, 1 = copy engine first
     char err[512] = {0};
     // staging owned by the ctx for the *_host entry points (grown on demand)
