@@ -191,6 +191,23 @@ int lsm_reservoir_run(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes,
 int lsm_reservoir_run_host(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *h_spikes, int32_t B,
                            uint32_t feature_mask, int32_t nan_to_num, double *h_features,
                            uint8_t *h_raster_or_null);
+/* How lsm_reservoir_run / lsm_reservoir_run_host form the recurrent current of lsm.simulate() (extract_lsm_features.py:81;
+ * BASELINE.json north star, kernel 2: "event-driven gather ... or ... a tensor-core tile, choosing whichever ncu shows wins").
+ * Both arms produce the same rasters and features bit for bit (integer weights: the sum is exact in any order).
+ *   LSM_RESERVOIR_EVENT (default)  one CTA per utterance, all steps in one launch, state in registers / shared memory; work per
+ *                                  step = (neurons that fired at t-1) x N integer adds.
+ *   LSM_RESERVOIR_DENSE            one launch per time step for the whole batch: spikes[B,N] . W[N,N] on the integer tensor cores
+ *                                  (tcgen05.mma kind::i8 over 8-bit digit planes of the weights, int32 accumulators in TMEM),
+ *                                  membrane update as the epilogue; work per step = N x N regardless of activity.  Needs at most
+ *                                  one input row per neuron; the fused all-gather is not available (LSM_ERR_UNSUPPORTED).
+ * profiles/r2_config4.md holds the measured comparison; the event-driven arm wins at every operating point of the reference. */
+#define LSM_RESERVOIR_EVENT 0
+#define LSM_RESERVOIR_DENSE 1
+int lsm_reservoir_set_mode(lsm_ctx *ctx, lsm_reservoir *res, int32_t mode);
+/* Diagnostic of the dense arm: one contraction.  d_s: uint8[B][N] spike bytes (any non-zero = fired) in the caller's neuron
+ * order, B <= 8192; d_acc: int32[B][N], d_acc[b][i] = sum_j Wq[i][j] * s[b][j] exactly as the tensor cores and the digit-plane
+ * recombination form it (tests compare it with the integer matrix product).                                              */
+int lsm_reservoir_dense_probe(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_s, int32_t B, int32_t *d_acc);
 
 /* Network diagnostics of run_network_diagnostics (extract_lsm_features.py:92-152) reduced on the device instead of
  * shipping the raster: for each utterance, d_diag[2*b] = neurons (of all N) that fired at least once,

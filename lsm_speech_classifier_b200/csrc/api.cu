@@ -464,6 +464,9 @@ extern "C" int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
         std::vector<char> seen(p->num_inputs, 0);
         for (int i = 0; i < N && res->lean; ++i)
             if (in_row[i] >= 0) { if (seen[in_row[i]]) res->lean = 0; seen[in_row[i]] = 1; }
+        // the lean kernel treats internal slot 8r as driven by row r: every row must drive a neuron
+        for (int r = 0; r < p->num_inputs && res->lean; ++r)
+            if (!seen[r]) res->lean = 0;
         const double g = ldexp(res->gain0, p->w_shift);
         if (p->num_inputs > n_pad / 8 || !(p->theta > 0.0) || p->refractory > 15 || g != floor(g) ||
             fabs(res->gain0) > ldexp(1.0, 31 - p->w_shift))
@@ -510,6 +513,28 @@ extern "C" int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
         if (h_out_idx[o] < 0 || h_out_idx[o] >= N) { delete res; LSM_FAIL(ctx, LSM_ERR_INVALID, "output index out of range"); }
         out_slot[perm[h_out_idx[o]]] = o;
     }
+    // dense arm (reservoir_dense.cu): per-neuron tables in internal order and the number of 8-bit digit planes the weights need
+    res->h_dense_in_row = (int32_t *)malloc(sizeof(int32_t) * n_pad);
+    res->h_dense_gain = (double *)malloc(sizeof(double) * n_pad);
+    res->h_dense_leak = (double *)malloc(sizeof(double) * n_pad);
+    res->h_dense_out_int = (int32_t *)malloc(sizeof(int32_t) * (p->n_out > 0 ? p->n_out : 1));
+    if (!res->h_dense_in_row || !res->h_dense_gain || !res->h_dense_leak || !res->h_dense_out_int) {
+        lsm_reservoir_destroy(res);
+        LSM_FAIL(ctx, LSM_ERR_NOMEM, "out of host memory");
+    }
+    for (int i = 0; i < n_pad; ++i) { res->h_dense_in_row[i] = -1; res->h_dense_gain[i] = 0.0; res->h_dense_leak[i] = 0.0; }
+    for (int i = 0; i < N; ++i) {
+        res->h_dense_in_row[perm[i]] = in_row[i];
+        res->h_dense_gain[perm[i]] = in_row[i] >= 0 ? h_in_val[h_in_rowptr[i]] : 0.0;
+        res->h_dense_leak[perm[i]] = h_leak[i];
+    }
+    for (int o = 0; o < p->n_out; ++o) res->h_dense_out_int[o] = perm[h_out_idx[o]];
+    {
+        int32_t lo = 0, hi = 0;
+        for (size_t q = 0; q < wt.size(); ++q) { if (wt[q] < lo) lo = wt[q]; if (wt[q] > hi) hi = wt[q]; }
+        if (lo < 0 || hi >= (1 << 24)) { res->dense_planes = 4; res->dense_top_signed = 1; }
+        else res->dense_planes = hi >= (1 << 16) ? 3 : (hi >= (1 << 8) ? 2 : 1);
+    }
     int rc = upload(ctx, &res->d_wt, wt.data(), wt.size());
     if (rc == LSM_OK) rc = upload(ctx, &res->d_in_rowptr, h_in_rowptr, (size_t)N + 1);
     if (rc == LSM_OK) rc = upload(ctx, &res->d_in_col, h_in_col, (size_t)nin);
@@ -528,6 +553,8 @@ extern "C" void lsm_reservoir_destroy(lsm_reservoir *res)
     if (!res) return;
     cudaFree(res->d_wt); cudaFree(res->d_in_rowptr); cudaFree(res->d_in_col); cudaFree(res->d_in_val);
     cudaFree(res->d_leak); cudaFree(res->d_out_slot); cudaFree(res->d_in_row); cudaFree(res->d_ext_id);
+    free(res->h_dense_in_row); free(res->h_dense_gain); free(res->h_dense_leak); free(res->h_dense_out_int);
+    lsm_dense_ws_free(res->dense);
     delete res;
 }
 
@@ -623,6 +650,15 @@ extern "C" int lsm_peer_buffer_destroy(lsm_ctx *ctx, void *d_ptr)
     return LSM_OK;
 }
 
+// stage 2+3 by the arm lsm_reservoir_set_mode selected (event-driven by default)
+static int launch_reservoir_by_mode(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int B, uint32_t feature_mask,
+                                    int nan_to_num, double *d_features, uint8_t *d_raster, cudaStream_t st)
+{
+    if (res->mode == LSM_RESERVOIR_DENSE)
+        return lsm_launch_reservoir_dense(ctx, res, d_spikes, B, feature_mask, nan_to_num, d_features, d_raster, st);
+    return lsm_launch_reservoir(ctx, res, d_spikes, B, feature_mask, nan_to_num, d_features, d_raster, st);
+}
+
 extern "C" int lsm_reservoir_run(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int32_t B,
                                  uint32_t feature_mask, int32_t nan_to_num, double *d_features,
                                  uint8_t *d_raster_or_null)
@@ -631,7 +667,26 @@ extern "C" int lsm_reservoir_run(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t
     if (!res || B < 0 || (B > 0 && !d_spikes)) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_run: bad argument");
     if (B == 0) return LSM_OK;
     LSM_CUDA(ctx, cudaSetDevice(ctx->device));
-    return lsm_launch_reservoir(ctx, res, d_spikes, B, feature_mask, nan_to_num, d_features, d_raster_or_null, ctx->stream);
+    return launch_reservoir_by_mode(ctx, res, d_spikes, B, feature_mask, nan_to_num, d_features, d_raster_or_null, ctx->stream);
+}
+
+extern "C" int lsm_reservoir_set_mode(lsm_ctx *ctx, lsm_reservoir *res, int32_t mode)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!res || (mode != LSM_RESERVOIR_EVENT && mode != LSM_RESERVOIR_DENSE)) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_set_mode: bad argument");
+    if (mode == LSM_RESERVOIR_DENSE)
+        if (const char *why = lsm_dense_unsupported(res)) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "dense reservoir arm: %s", why);
+    res->mode = mode;
+    return LSM_OK;
+}
+
+extern "C" int lsm_reservoir_dense_probe(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_s, int32_t B, int32_t *d_acc)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!res || B < 0 || (B > 0 && (!d_s || !d_acc))) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_dense_probe: bad argument");
+    if (B == 0) return LSM_OK;
+    LSM_CUDA(ctx, cudaSetDevice(ctx->device));
+    return lsm_reservoir_dense_probe_launch(ctx, res, d_s, B, d_acc, ctx->stream);
 }
 
 extern "C" int lsm_reservoir_diagnostics(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int32_t B, int32_t *d_diag)
@@ -662,8 +717,8 @@ extern "C" int lsm_reservoir_run_host(lsm_ctx *ctx, lsm_reservoir *res, const ui
     if (h_features && (rc = lsm_stage_device(ctx, 2, feat_bytes, &d_feat)) != LSM_OK) return rc;
     if (h_raster_or_null && (rc = lsm_stage_device(ctx, 3, ras_bytes, &d_ras)) != LSM_OK) return rc;
     LSM_CUDA(ctx, cudaMemcpyAsync(d_spk, h_spikes, spk_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = lsm_launch_reservoir(ctx, res, (const uint8_t *)d_spk, B, feature_mask, nan_to_num,
-                                   (double *)d_feat, (uint8_t *)d_ras, ctx->stream)) != LSM_OK) return rc;
+    if ((rc = launch_reservoir_by_mode(ctx, res, (const uint8_t *)d_spk, B, feature_mask, nan_to_num,
+                                       (double *)d_feat, (uint8_t *)d_ras, ctx->stream)) != LSM_OK) return rc;
     if (h_features) LSM_CUDA(ctx, cudaMemcpyAsync(h_features, d_feat, feat_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (h_raster_or_null) LSM_CUDA(ctx, cudaMemcpyAsync(h_raster_or_null, d_ras, ras_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     LSM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -89,6 +89,12 @@ struct lsm_reservoir {
     double c_off = 0.0, c_on = 0.0;
     int hi_magic = 0;
     double leak0 = 0.0, gain0 = 0.0;
+    // dense (tensor-core) arm, reservoir_dense.cu: host tables in internal neuron order, digit-plane count, workspace
+    int mode = 0;                  // lsm_reservoir_set_mode: 0 event-driven, 1 dense
+    int32_t *h_dense_in_row = nullptr, *h_dense_out_int = nullptr;   // [n_pad] input row or -1 / [n_out] internal index of output o
+    double *h_dense_gain = nullptr, *h_dense_leak = nullptr;         // [n_pad]
+    int dense_planes = 0, dense_top_signed = 0;
+    struct lsm_dense_ws *dense = nullptr;
 };
 
 #define LSM_FAIL(ctx, code, ...)                                  \
@@ -145,6 +151,12 @@ int lsm_launch_reservoir(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spik
                          uint32_t feature_mask, int nan_to_num, double *d_features, uint8_t *d_raster,
                          cudaStream_t st, int *d_diag = nullptr, long long row0 = 0);
 void lsm_reservoir_geometry(int N, int *npt, int *threads, int *n_pad);
+// dense arm (reservoir_dense.cu)
+const char *lsm_dense_unsupported(const lsm_reservoir *res);
+void lsm_dense_ws_free(struct lsm_dense_ws *w);
+int lsm_launch_reservoir_dense(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int B, uint32_t feature_mask,
+                               int nan_to_num, double *d_features, uint8_t *d_raster, cudaStream_t st);
+int lsm_reservoir_dense_probe_launch(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_s, int B, int32_t *d_acc, cudaStream_t st);
 int lsm_mel_create(lsm_ctx *ctx, lsm_frontend *fe, const float *h_basis);
 void lsm_mel_destroy(lsm_frontend *fe);
 int lsm_mel_set_tables(lsm_ctx *ctx, lsm_frontend *fe, const double *h_win, const double *h_tw, const double *h_tw2);

@@ -116,6 +116,28 @@ class SNN:
         n = self.num_neurons
         return d[:, 0] / n * 100.0, n - d[:, 0], d[:, 1] / n
 
+    RESERVOIR_MODES = {"event": 0, "dense": 1}
+
+    def set_mode(self, mode: str = "event"):
+        """Which arm forms the recurrent current (lsm_reservoir_set_mode): "event" - the event-driven gather over the neurons
+        that fired (default) - or "dense" - spikes[B,N] . W[N,N] on the integer tensor cores, one launch per time step.
+        Same rasters and features bit for bit."""
+        if mode not in self.RESERVOIR_MODES:
+            raise ValueError(f"mode must be one of {list(self.RESERVOIR_MODES)}")
+        self.ctx.check(self.ctx.lib.lsm_reservoir_set_mode(self.ctx.h, self.h, self.RESERVOIR_MODES[mode]))
+
+    def dense_probe(self, s):
+        """Diagnostic (lsm_reservoir_dense_probe): s uint8[B, N] spike bytes -> int32[B, N] recurrent sums W . s of the dense arm."""
+        import torch
+        s = torch.as_tensor(s, dtype=torch.uint8).cuda(self.ctx.device).contiguous()
+        if s.dim() != 2 or s.shape[1] != self.num_neurons:
+            raise ValueError(f"s must be uint8[B,{self.num_neurons}]")
+        acc = torch.zeros(s.shape, dtype=torch.int32, device=s.device)
+        self.ctx.set_stream(torch.cuda.current_stream(s.device).cuda_stream)
+        self.ctx.check(self.ctx.lib.lsm_reservoir_dense_probe(self.ctx.h, self.h, C.c_void_p(s.data_ptr()), s.shape[0],
+                                                              C.c_void_p(acc.data_ptr())))
+        return acc
+
     def set_gather(self, pointers, row0: int = 0):
         """Fused all-gather (lsm_reservoir_set_gather): launches enqueued from now on also store utterance u's feature row at
         row row0 + u of every matrix in `pointers` (device addresses, e.g. `distributed.PeerAllGather.pointers(k)`); an empty
