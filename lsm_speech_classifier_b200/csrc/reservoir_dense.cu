@@ -14,15 +14,19 @@
 //
 // Shape of the computation.  Time steps are sequential (the spikes of step t are the A operand of step t+1), so one launch
 // advances the whole batch by one step:
-//     grid = (Bp / 128 utterance tiles) x (NP / 128 neuron tiles), 192 threads per CTA
-//     warp 4   producer: TMA 2-D tiles (128 rows x 128 bytes of K, SWIZZLE_128B) of the spike matrix S[Bp][NK] (A, K-major)
-//              and of each digit plane Wd[p][NP][NK] (B, K-major) into a shared-memory ring, full / empty mbarriers
-//     warp 5   one thread issues tcgen05.mma (M = 128, N = 128, K = 32 per instruction), one accumulator block of 128 TMEM
+//     grid = (Bp / 128 utterance tiles) x (NP / 64 neuron tiles), 320 threads per CTA, two CTAs per SM (the TMA / MMA phase of
+//     one overlaps the epilogue of the other: 256 of the 512 TMEM columns and ~80 KB of shared memory each)
+//     warp 8   producer: TMA 2-D tiles (rows x 128 bytes of K, SWIZZLE_128B) of the spike matrix S[Bp][NK] (A, K-major, 128
+//              rows) and of each digit plane Wd[p][NP][NK] (B, K-major, 64 rows) into a two-slot shared-memory ring,
+//              full / empty mbarriers
+//     warp 9   one thread issues tcgen05.mma (M = 128, N = 64, K = 32 per instruction), one accumulator block of 64 TMEM
 //              columns per digit plane; tcgen05.commit releases ring slots and finally signals the epilogue
-//     warps 0-3 epilogue: thread = utterance (TMEM lane), tcgen05.ld 16 columns x planes at a time, recombine, then for each
-//              neuron the LIF update on V[n][b] / refractory[n][b] (neuron-major planes: coalesced across the warp), spike
-//              statistics for the readout (touched only on a spike) and the spike byte of S_next[b][n] (16-byte stores)
-// The readout (K3, spec R9) is a small kernel over the statistics planes after the last step.
+//     warps 0-7 epilogue: thread = utterance (TMEM lane; lane quarter = warp & 3) x 32 of the tile's neurons (warp >> 2),
+//              tcgen05.ld 8 columns x planes at a time, recombine, then the LIF update on V[n][b] / refractory[n][b]
+//              (neuron-major planes: coalesced across the warp; the next block's state is requested while the current one is
+//              computed, the first block's before the accumulators are complete), the spike statistics of the readout
+//              (two 16-byte records per neuron-utterance, touched only on a spike) and the spike bytes of S_next[b][n]
+// The readout (K3, spec R9) is a small kernel over the statistics after the last step.
 #include <stdlib.h>
 
 #include <new>
@@ -34,23 +38,27 @@
 
 namespace {
 
-constexpr int kTile = 128;                  // utterances per CTA = neurons per CTA = bytes of K per ring slot
-constexpr int kThreads = 192;
-constexpr int kTileBytes = kTile * kTile;   // one 128 x 128 u8 tile
+constexpr int kTile = 128;                  // utterances per CTA (MMA M) = bytes of K per ring slot
+constexpr int kNT = 64;                     // neurons per CTA (MMA N): 64 columns x <= 4 digit planes = 256 TMEM columns, two CTAs per SM
+constexpr int kEpiWarps = 8;                // epilogue warps: TMEM lane quarter = warp & 3, column half = warp >> 2
+constexpr int kThreads = (kEpiWarps + 2) * 32;
+constexpr int kATileBytes = kTile * kTile;  // 128 utterances x 128 bytes of K
+constexpr int kBTileBytes = kNT * kTile;    // 64 neurons x 128 bytes of K
+constexpr int kStages = 2;
 
 struct DenseArgs {
     double *V;               // [NP][Bp]
     uint8_t *ref;            // [NP][Bp]
     uint8_t *s_next;         // [Bp][NK] spikes of this step (next step's A operand)
     const uint8_t *in_t;     // [T][C][Bp] input level bytes, time-major
-    int *stat;               // [6][NP][Bp] count, sum t, first, last, sum isi^2, bursts
+    int4 *stat;              // [NP][Bp][2]: {count, sum t, first, last}, {sum isi^2, bursts, -, -}
     const int32_t *in_row;   // [NP] internal neuron -> its input row, -1 none
     const double *gain;      // [NP]
     const double *leak;      // [NP]
     const int32_t *ext_id;   // [NP] internal -> external neuron index (>= N: padding)
     uint8_t *raster;         // optional [B][T][N]
     int32_t *probe;          // optional [Bp][NP]: write the recombined integer sums and do nothing else (diagnostic)
-    int B, Bp, N, NP, NK, C, T, t, refractory, planes, top_signed, stages;
+    int B, Bp, N, NP, NK, C, T, t, refractory, planes, top_signed;
     double theta, scale;
 };
 
@@ -85,10 +93,10 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr)
     return (unsigned long long)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((unsigned long long)(1024 >> 4) << 32) |
            (1ull << 46) | (2ull << 61);
 }
-// Instruction descriptor, kind::i8: D = s32, A = u8, B = u8 or s8, both K-major, N = 128, M = 128.
+// Instruction descriptor, kind::i8: D = s32, A = u8, B = u8 or s8, both K-major, N = kNT, M = 128.
 __device__ __forceinline__ unsigned umma_idesc(bool b_signed)
 {
-    return (2u << 4) | (0u << 7) | ((b_signed ? 1u : 0u) << 10) | ((unsigned)(kTile >> 3) << 17) | ((unsigned)(kTile >> 4) << 24);
+    return (2u << 4) | (0u << 7) | ((b_signed ? 1u : 0u) << 10) | ((unsigned)(kNT >> 3) << 17) | ((unsigned)(kTile >> 4) << 24);
 }
 __device__ __forceinline__ void umma_i8(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned accumulate)
 {
@@ -99,37 +107,36 @@ __device__ __forceinline__ void umma_commit(unsigned long long *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&r)[16])
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, unsigned (&r)[8])
 {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 1) dense_step_kernel(const DenseArgs a, const __grid_constant__ CUtensorMap map_s,
+__global__ void __launch_bounds__(kThreads, 2) dense_step_kernel(const DenseArgs a, const __grid_constant__ CUtensorMap map_s,
                                                                  const __grid_constant__ CUtensorMap map_w)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long s_full[4], s_empty[4], s_acc;
+    __shared__ __align__(8) unsigned long long s_full[kStages], s_empty[kStages], s_acc;
     __shared__ unsigned s_tmem;
 
     // the swizzle pattern is a function of the shared-memory address: tiles start on 1024-byte boundaries
     unsigned char *const ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kTile, n0 = blockIdx.y * kTile;
+    const int m0 = blockIdx.x * kTile, n0 = blockIdx.y * kNT;
     const int P = a.planes;
-    const unsigned stage_bytes = (unsigned)(1 + P) * kTileBytes;
+    const unsigned stage_bytes = (unsigned)kATileBytes + (unsigned)P * kBTileBytes;
     const int n_chunks = a.NK / kTile;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < a.stages; ++s) { mbar_init(s_full + s, 1); mbar_init(s_empty + s, 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(s_full + s, 1); mbar_init(s_empty + s, 1); }
         mbar_init(&s_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
-        // 512 columns: up to four accumulator blocks of 128; one CTA per SM (launch bounds), so the allocation cannot starve
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem)) : "memory");
+    if (warp == kEpiWarps + 1) {
+        // 256 columns = up to four accumulator blocks of 64; two CTAs per SM share the 512 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&s_tmem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -137,23 +144,23 @@ __global__ void __launch_bounds__(kThreads, 1) dense_step_kernel(const DenseArgs
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem = s_tmem;
 
-    if (warp == 4) {
+    if (warp == kEpiWarps) {
         // ---- producer
         if (lane == 0) {
             for (int c = 0; c < n_chunks; ++c) {
-                const int s = c % a.stages, round = c / a.stages;
+                const int s = c % kStages, round = c / kStages;
                 if (round > 0) mbar_wait(s_empty + s, (unsigned)(round - 1) & 1u);
                 unsigned char *slot = ring + (size_t)s * stage_bytes;
                 mbar_expect_tx(s_full + s, stage_bytes);
                 tma_tile_g2s(slot, &map_s, c * kTile, m0, s_full + s);
-                for (int p = 0; p < P; ++p) tma_tile_g2s(slot + (size_t)(1 + p) * kTileBytes, &map_w, c * kTile, p * a.NP + n0, s_full + s);
+                for (int p = 0; p < P; ++p) tma_tile_g2s(slot + kATileBytes + (size_t)p * kBTileBytes, &map_w, c * kTile, p * a.NP + n0, s_full + s);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == kEpiWarps + 1) {
         // ---- MMA issuer
         if (lane == 0) {
             for (int c = 0; c < n_chunks; ++c) {
-                const int s = c % a.stages, round = c / a.stages;
+                const int s = c % kStages, round = c / kStages;
                 mbar_wait(s_full + s, (unsigned)round & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const unsigned slot = smem_u32(ring + (size_t)s * stage_bytes);
@@ -161,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_step_kernel(const DenseArgs
                     const unsigned idesc = umma_idesc(a.top_signed && p == P - 1);
 #pragma unroll
                     for (int kk = 0; kk < kTile / 32; ++kk)
-                        umma_i8(tmem + (unsigned)p * kTile, umma_desc(slot + kk * 32), umma_desc(slot + (1 + p) * kTileBytes + kk * 32),
+                        umma_i8(tmem + (unsigned)p * kNT, umma_desc(slot + kk * 32), umma_desc(slot + kATileBytes + p * kBTileBytes + kk * 32),
                                 idesc, (c > 0 || kk > 0) ? 1u : 0u);
                 }
                 umma_commit(s_empty + s);                  // the slot may be refilled once these MMAs have read it
@@ -169,24 +176,47 @@ __global__ void __launch_bounds__(kThreads, 1) dense_step_kernel(const DenseArgs
             umma_commit(&s_acc);                           // all accumulators complete
         }
     } else {
-        // ---- epilogue: thread = utterance row of the tile = TMEM lane
+        // ---- epilogue: thread = utterance row of the tile = TMEM lane (quarter = warp & 3); warps 0-3 take the first 32
+        //      neuron columns of the tile, warps 4-7 the second
+        const int q = warp & 3, half = warp >> 2;
+        const int u = m0 + q * 32 + lane;
+        const bool valid = u < a.B;
+        const unsigned lane_base = tmem + ((unsigned)(q * 32) << 16);
+        const size_t Bp = (size_t)a.Bp;
+        const int nb = n0 + half * 32;                      // first neuron of this thread's 32
+        // state of the first block, requested before the accumulators are complete (it does not depend on them)
+        double v0[8];
+        unsigned rf[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const size_t idx = (size_t)(nb + j) * Bp + u;
+            v0[j] = (valid && !a.probe) ? __ldcg(a.V + idx) : 0.0;
+            rf[j] = (valid && !a.probe) ? (unsigned)__ldcg(a.ref + idx) : 0u;
+        }
         mbar_wait(&s_acc, 0u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int u = m0 + warp * 32 + lane;
-        const bool valid = u < a.B;
-        const unsigned lane_base = tmem + ((unsigned)(warp * 32) << 16);
-        const size_t Bp = (size_t)a.Bp;
-        const size_t plane = (size_t)a.NP * Bp;
-        for (int cb = 0; cb < kTile / 16; ++cb) {
-            unsigned d[4][16];
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+            const int nc = nb + cb * 8;
+            unsigned d[4][8];
 #pragma unroll
             for (int p = 0; p < 4; ++p)
-                if (p < P) tmem_ld16(lane_base + (unsigned)(p * kTile + cb * 16), d[p]);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            unsigned out_w[4] = {0u, 0u, 0u, 0u};
+                if (p < P) tmem_ld8(lane_base + (unsigned)(p * kNT + half * 32 + cb * 8), d[p]);
+            // next block's state while the tensor-memory loads are in flight
+            double v1[8];
+            unsigned rf1[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int n = n0 + cb * 16 + j;
+            for (int j = 0; j < 8; ++j) {
+                const bool more = valid && !a.probe && cb < 3;
+                const size_t idx = (size_t)(nc + 8 + j) * Bp + u;
+                v1[j] = more ? __ldcg(a.V + idx) : 0.0;
+                rf1[j] = more ? (unsigned)__ldcg(a.ref + idx) : 0u;
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            unsigned out_lo = 0u, out_hi = 0u, fired = 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = nc + j;
                 unsigned accu = d[0][j];
                 if (P > 1) accu += d[1][j] << 8;
                 if (P > 2) accu += d[2][j] << 16;
@@ -199,36 +229,39 @@ __global__ void __launch_bounds__(kThreads, 1) dense_step_kernel(const DenseArgs
                 double i_in = 0.0;
                 if (r >= 0 && __ldg(a.in_t + ((size_t)a.t * a.C + r) * Bp + u)) i_in = add64(0.0, __ldg(a.gain + n));
                 const double cur = add64(i_in, mul64((double)acc, a.scale));
-                const size_t idx = (size_t)n * Bp + u;
-                const double v0 = a.V[idx];
-                const int rf = a.ref[idx];
-                const double v = add64(sub64(v0, mul64(__ldg(a.leak + n), v0)), cur);
-                const bool active = rf == 0;
+                const double v = add64(sub64(v0[j], mul64(__ldg(a.leak + n), v0[j])), cur);
+                const bool active = rf[j] == 0u;
                 const bool fire = active && (v >= a.theta) && (ext < a.N);
-                a.V[idx] = (active && !fire) ? v : 0.0;
-                a.ref[idx] = (uint8_t)(fire ? a.refractory : (active ? 0 : rf - 1));
-                if (fire) {
-                    out_w[j >> 2] |= 1u << (8 * (j & 3));
-                    int *st = a.stat + idx;
-                    const int c = st[0];
-                    if (c > 0) {
-                        const int isi = a.t - st[3 * plane];
-                        st[4 * plane] += isi * isi;
-                        if (isi <= a.refractory + 1) st[5 * plane] += 1;
-                    } else st[2 * plane] = a.t;
-                    st[0] = c + 1;
-                    st[plane] += a.t;
-                    st[3 * plane] = a.t;
-                }
+                const size_t idx = (size_t)n * Bp + u;
+                __stcg(a.V + idx, (active && !fire) ? v : 0.0);
+                a.ref[idx] = (uint8_t)(fire ? (unsigned)a.refractory : (active ? 0u : rf[j] - 1u));
+                if (fire) { fired |= 1u << j; if (j < 4) out_lo |= 1u << (8 * j); else out_hi |= 1u << (8 * (j - 4)); }
                 if (a.raster && ext < a.N) a.raster[((size_t)u * a.T + a.t) * a.N + ext] = fire ? 1 : 0;
             }
-            if (!a.probe && valid)
-                *reinterpret_cast<uint4 *>(a.s_next + (size_t)u * a.NK + n0 + cb * 16) = make_uint4(out_w[0], out_w[1], out_w[2], out_w[3]);
+            // spikes are rare: statistics of the readout (spec R9) only for the neurons that fired
+            while (fired) {
+                const int j = __ffs(fired) - 1;
+                fired &= fired - 1u;
+                int4 *st = a.stat + ((size_t)(nc + j) * Bp + u) * 2;
+                int4 s0 = st[0];                        // count, sum t, first, last
+                if (s0.x > 0) {
+                    int4 s1 = st[1];                    // sum isi^2, bursts
+                    const int isi = a.t - s0.w;
+                    s1.x += isi * isi;
+                    if (isi <= a.refractory + 1) s1.y += 1;
+                    st[1] = s1;
+                } else s0.z = a.t;
+                s0.x += 1; s0.y += a.t; s0.w = a.t;
+                st[0] = s0;
+            }
+            if (!a.probe && valid) *reinterpret_cast<uint2 *>(a.s_next + (size_t)u * a.NK + nc) = make_uint2(out_lo, out_hi);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v0[j] = v1[j]; rf[j] = rf1[j]; }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    if (warp == kEpiWarps + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
 // Digit planes of the weights, K-major: Wd[p][n][k] = digit p of wt[k][n] (wt = presynaptic-major int32 plane of the reservoir)
@@ -268,23 +301,24 @@ __global__ void dense_input_kernel(const uint8_t *spikes, int B, int C, int T, i
     }
 }
 
-__global__ void dense_init_stat_kernel(int *stat, size_t plane)
+__global__ void dense_init_stat_kernel(int4 *stat, size_t plane)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= plane) return;
-    stat[i] = 0; stat[plane + i] = 0; stat[2 * plane + i] = -1; stat[3 * plane + i] = -1; stat[4 * plane + i] = 0; stat[5 * plane + i] = 0;
+    stat[2 * i] = make_int4(0, 0, -1, -1);
+    stat[2 * i + 1] = make_int4(0, 0, 0, 0);
 }
 
 // K3 (spec R9; the same formulas as the event-driven kernel's epilogue in reservoir_core.cuh): one thread per (utterance, output neuron)
-__global__ void dense_readout_kernel(const int *stat, size_t plane, int Bp, int B, const int32_t *out_int, int n_out, int T,
+__global__ void dense_readout_kernel(const int4 *stat, size_t plane, int Bp, int B, const int32_t *out_int, int n_out, int T,
                                      unsigned feature_mask, int nkeys, int nan_to_num, double *features, int *diag, int N,
                                      const int32_t *ext_id, int NP)
 {
     const int o = blockIdx.x * blockDim.x + threadIdx.x, u = blockIdx.y;
     if (o >= n_out || u >= B) return;
     const size_t idx = (size_t)__ldg(out_int + o) * Bp + u;
-    const int cnt = stat[idx], sumt = stat[plane + idx], first = stat[2 * plane + idx], last = stat[3 * plane + idx];
-    const int s2 = stat[4 * plane + idx], burst = stat[5 * plane + idx];
+    const int4 s0 = stat[2 * idx], s1 = stat[2 * idx + 1];
+    const int cnt = s0.x, sumt = s0.y, first = s0.z, last = s0.w, s2 = s1.x, burst = s1.y;
     const double c = (double)cnt, nan = __longlong_as_double(0x7ff8000000000000LL);
     double *f = features + (size_t)u * nkeys * n_out;
     int slot = 0;
@@ -327,14 +361,14 @@ encode_tiled_fn encode_tiled()
     return fn;
 }
 
-// u8 matrix [rows][cols] (cols contiguous) as a 2-D tensor with 128 x 128 boxes, 128-byte swizzle
-int make_map(lsm_ctx *ctx, CUtensorMap *map, const void *base, size_t rows, size_t cols)
+// u8 matrix [rows][cols] (cols contiguous) as a 2-D tensor with box_rows x 128-byte boxes, 128-byte swizzle
+int make_map(lsm_ctx *ctx, CUtensorMap *map, const void *base, size_t rows, size_t cols, int box_rows)
 {
     encode_tiled_fn fn = encode_tiled();
     if (!fn) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available in this driver");
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)cols};
-    const cuuint32_t box[2] = {kTile, kTile}, estr[2] = {1, 1};
+    const cuuint32_t box[2] = {kTile, (cuuint32_t)box_rows}, estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -353,7 +387,7 @@ struct lsm_dense_ws {
     int cap = 0;                    // utterances the state buffers hold (multiple of 128)
     double *d_V = nullptr;
     uint8_t *d_ref = nullptr, *d_S = nullptr /* [2][cap][NK] */, *d_in_t = nullptr;
-    int *d_stat = nullptr;
+    int4 *d_stat = nullptr;
 };
 
 void lsm_dense_ws_free(lsm_dense_ws *w)
@@ -415,7 +449,7 @@ static int dense_prepare(lsm_ctx *ctx, lsm_reservoir *res, int B, cudaStream_t s
         if (cudaMalloc(&w->d_V, plane * sizeof(double)) != cudaSuccess || cudaMalloc(&w->d_ref, plane) != cudaSuccess ||
             cudaMalloc(&w->d_S, 2 * (size_t)need * w->NK) != cudaSuccess ||
             cudaMalloc(&w->d_in_t, (size_t)p.num_steps * p.num_inputs * need) != cudaSuccess ||
-            cudaMalloc(&w->d_stat, 6 * plane * sizeof(int)) != cudaSuccess) {
+            cudaMalloc(&w->d_stat, 2 * plane * sizeof(int4)) != cudaSuccess) {
             cudaGetLastError();
             LSM_FAIL(ctx, LSM_ERR_NOMEM, "dense reservoir arm: out of device memory for %d utterances x %d neurons", need, w->NP);
         }
@@ -432,8 +466,6 @@ static void dense_fill(const lsm_reservoir *res, const lsm_dense_ws *w, int B, i
     a->raster = nullptr; a->probe = nullptr;
     a->B = B; a->Bp = Bp; a->N = p.num_neurons; a->NP = w->NP; a->NK = w->NK; a->C = p.num_inputs; a->T = p.num_steps; a->t = 0;
     a->refractory = p.refractory; a->planes = w->planes; a->top_signed = w->top_signed;
-    a->stages = (200 * 1024) / ((1 + w->planes) * kTileBytes);
-    if (a->stages > 4) a->stages = 4;
     a->theta = p.theta; a->scale = ldexp(1.0, -p.w_shift);
 }
 
@@ -466,11 +498,11 @@ int lsm_launch_reservoir_dense(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *
         }
         alignas(64) CUtensorMap map_s[2], map_w;
         for (int k = 0; k < 2; ++k)
-            if ((rc = make_map(ctx, &map_s[k], w->d_S + (size_t)k * Bp * w->NK, (size_t)Bp, (size_t)w->NK)) != LSM_OK) return rc;
-        if ((rc = make_map(ctx, &map_w, w->d_wd, (size_t)w->planes * w->NP, (size_t)w->NK)) != LSM_OK) return rc;
-        const size_t smem = (size_t)a.stages * (1 + w->planes) * kTileBytes + 1024;
+            if ((rc = make_map(ctx, &map_s[k], w->d_S + (size_t)k * Bp * w->NK, (size_t)Bp, (size_t)w->NK, kTile)) != LSM_OK) return rc;
+        if ((rc = make_map(ctx, &map_w, w->d_wd, (size_t)w->planes * w->NP, (size_t)w->NK, kNT)) != LSM_OK) return rc;
+        const size_t smem = (size_t)kStages * (kATileBytes + w->planes * kBTileBytes) + 1024;
         LSM_CUDA(ctx, cudaFuncSetAttribute(dense_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const dim3 grid((n + kTile - 1) / kTile, w->NP / kTile);
+        const dim3 grid((n + kTile - 1) / kTile, w->NP / kNT);
         for (int t = 0; t < p.num_steps; ++t) {
             a.t = t;
             a.s_next = w->d_S + (size_t)((t + 1) & 1) * Bp * w->NK;          // step t reads S[t & 1] (spikes of t-1), writes S[(t+1) & 1]
@@ -525,11 +557,11 @@ int lsm_reservoir_dense_probe_launch(lsm_ctx *ctx, lsm_reservoir *res, const uin
     LSM_CUDA(ctx, cudaMemsetAsync(w->d_S, 0, (size_t)Bp * w->NK, st));
     dense_probe_in_kernel<<<dim3((w->NK + 255) / 256, B), 256, 0, st>>>(d_s, B, p.num_neurons, res->d_ext_id, w->NK, w->d_S);
     alignas(64) CUtensorMap map_s, map_w;
-    if ((rc = make_map(ctx, &map_s, w->d_S, (size_t)Bp, (size_t)w->NK)) != LSM_OK) return rc;
-    if ((rc = make_map(ctx, &map_w, w->d_wd, (size_t)w->planes * w->NP, (size_t)w->NK)) != LSM_OK) return rc;
-    const size_t smem = (size_t)a.stages * (1 + w->planes) * kTileBytes + 1024;
+    if ((rc = make_map(ctx, &map_s, w->d_S, (size_t)Bp, (size_t)w->NK, kTile)) != LSM_OK) return rc;
+    if ((rc = make_map(ctx, &map_w, w->d_wd, (size_t)w->planes * w->NP, (size_t)w->NK, kNT)) != LSM_OK) return rc;
+    const size_t smem = (size_t)kStages * (kATileBytes + w->planes * kBTileBytes) + 1024;
     LSM_CUDA(ctx, cudaFuncSetAttribute(dense_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dense_step_kernel<<<dim3((B + kTile - 1) / kTile, w->NP / kTile), kThreads, smem, st>>>(a, map_s, map_w);
+    dense_step_kernel<<<dim3((B + kTile - 1) / kTile, w->NP / kNT), kThreads, smem, st>>>(a, map_s, map_w);
     dense_probe_out_kernel<<<dim3((w->NP + 255) / 256, B), 256, 0, st>>>(a.probe, B, p.num_neurons, res->d_ext_id, w->NP, d_acc);
     ctx->launches += 3;
     LSM_CUDA(ctx, cudaGetLastError());
