@@ -280,7 +280,8 @@ int lsm_standardize_transform(lsm_ctx *ctx, const double *d_X, int32_t n, int32_
 
 /* Multinomial logistic regression readout on the device (train_classifier.py:36-47: LogisticRegression(max_iter=1000).fit /
  * .predict).  scikit-learn's lbfgs objective: mean multinomial log-loss + ||W||^2 / (2 C n), intercept unpenalised; L-BFGS until
- * max|grad| <= tol.  d_X: double[n][F] (standardised features), d_y: int32[n] class indices 0..n_classes-1 (<= 16 classes).
+ * max|grad| <= tol.  d_X: double[n][F] (standardised features), d_y: int32[n] class indices 0..n_classes-1 (3..64 classes; beyond 16 the
+ * passes run per block of 16 classes).
  * h_coef: double[n_classes][F], h_intercept: double[n_classes] (host, scikit-learn's coef_ / intercept_ layout).
  * The unique optimum is reached to solver tolerance, not scikit-learn's iterates bit for bit: the parity bar is the reference's
  * own metric, test accuracy (tests/test_gpu_readout.py: within 0.5 points and >= 99 % identical predictions).                    */

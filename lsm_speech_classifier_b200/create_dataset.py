@@ -13,7 +13,7 @@ from pathlib import Path
 
 import numpy as np
 
-from . import _lib
+from . import _lib, npzio
 from .frontend import (DURATION, HYSTERESIS_GAP, REDUNDANCY_FACTOR, SAMPLE_RATE, SPIKE_THRESHOLDS,  # noqa: F401
                        TIME_BINS, Frontend)
 
@@ -135,7 +135,7 @@ def save_packed_spikes(filename, X_spikes: np.ndarray, y_labels: np.ndarray):
     X = np.asarray(X_spikes)
     if X.dtype != np.uint8 or X.ndim != 3 or (X > 1).any():
         raise ValueError("X_spikes must be uint8[S, C, T] of zeros and ones")
-    np.savez_compressed(filename, X_spikes_bits=np.packbits(X, axis=2), n_steps=np.int32(X.shape[2]),
+    npzio.savez_compressed(filename, X_spikes_bits=np.packbits(X, axis=2), n_steps=np.int32(X.shape[2]),
                         y_labels=np.asarray(y_labels, dtype=np.int32))
 
 
@@ -181,7 +181,7 @@ def create_dataset(n_filters: int, filterbank: str, synthetic: tuple | None = No
         save_packed_spikes(PACKED_FILE, X_spikes, y_labels)
         print(f"Saved to '{PACKED_FILE}' (bit-packed)")
         return
-    np.savez_compressed(OUTPUT_FILE, X_spikes=X_spikes, y_labels=y_labels)
+    npzio.savez_compressed(OUTPUT_FILE, X_spikes=X_spikes, y_labels=y_labels)
     print(f"Saved to '{OUTPUT_FILE}'")
 
 

@@ -5,7 +5,10 @@
 #include <stdlib.h>
 
 #include <complex>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "lsm_common.cuh"
@@ -50,6 +53,7 @@ extern "C" void lsm_ctx_destroy(lsm_ctx *ctx)
     for (int i = 0; i < 4; ++i) { if (ctx->ev_stage_full[i]) cudaEventDestroy(ctx->ev_stage_full[i]); if (ctx->ev_stage_free[i]) cudaEventDestroy(ctx->ev_stage_free[i]); }
     for (int i = 0; i < 2; ++i) if (ctx->copy_stream[i]) cudaStreamDestroy(ctx->copy_stream[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    lsm_copy_pool_free(ctx->copy_pool);
     delete ctx;
 }
 
@@ -737,6 +741,77 @@ static bool device_visible(const void *h, void **d)
     return false;
 }
 
+
+// ------------------------------------------------------------------------------------ host copy workers
+// Pageable caller buffers (plain numpy arrays: what create_dataset / extract_all_features style callers hand over) reach the
+// zero-copy kernel through a ring of pinned staging buffers; the copies into and out of the ring are split over a few host
+// threads (one thread moves ~10 GB/s, the kernel consumes 25 GB/s of PCM), created on first use and owned by the ctx.
+struct lsm_copy_pool {
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cv_work, cv_done;
+    char *dst = nullptr;
+    const char *src = nullptr;
+    size_t bytes = 0;
+    unsigned generation = 0;
+    int pending = 0;
+    bool stop = false;
+
+    explicit lsm_copy_pool(int n)
+    {
+        for (int i = 0; i < n; ++i) threads.emplace_back([this, i, n] { run(i, n); });
+    }
+    ~lsm_copy_pool()
+    {
+        { std::lock_guard<std::mutex> l(m); stop = true; }
+        cv_work.notify_all();
+        for (auto &t : threads) t.join();
+    }
+    void run(int i, int n)
+    {
+        unsigned seen = 0;
+        for (;;) {
+            char *d; const char *s_; size_t b;
+            {
+                std::unique_lock<std::mutex> l(m);
+                cv_work.wait(l, [&] { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation; d = dst; s_ = src; b = bytes;
+            }
+            // 4 KiB-aligned slices
+            const size_t per = ((b / n) + 4095) & ~(size_t)4095;
+            const size_t lo = (size_t)i * per < b ? (size_t)i * per : b, hi = lo + per < b ? lo + per : b;
+            if (hi > lo) memcpy(d + lo, s_ + lo, hi - lo);
+            {
+                std::lock_guard<std::mutex> l(m);
+                if (--pending == 0) cv_done.notify_all();
+            }
+        }
+    }
+    // blocking: returns when all slices have been copied
+    void copy(void *d, const void *s_, size_t b)
+    {
+        if (b < (1u << 20) || threads.empty()) { memcpy(d, s_, b); return; }
+        std::unique_lock<std::mutex> l(m);
+        dst = (char *)d; src = (const char *)s_; bytes = b; pending = (int)threads.size(); ++generation;
+        cv_work.notify_all();
+        cv_done.wait(l, [&] { return pending == 0; });
+    }
+};
+
+void lsm_copy_pool_free(lsm_copy_pool *p) { delete p; }
+
+static lsm_copy_pool *copy_pool(lsm_ctx *ctx)
+{
+    if (!ctx->copy_pool) {
+        int n = (int)std::thread::hardware_concurrency() / 2;
+        if (const char *e = getenv("LSM_COPY_THREADS")) n = atoi(e);
+        n = n < 1 ? 1 : (n > 8 ? 8 : n);
+        ctx->copy_pool = new (std::nothrow) lsm_copy_pool(n);
+    }
+    return ctx->copy_pool;
+}
+
 // ------------------------------------------------------------------------------------ whole path
 static cudaStream_t lane_stream(lsm_ctx *ctx, int lane) { return lane == 0 ? ctx->own_stream : ctx->copy_stream[0]; }
 
@@ -938,6 +1013,46 @@ extern "C" int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservo
             LSM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             return LSM_OK;
         }
+    }
+    // Pageable buffers, fused pair: a ring of four pinned pieces.  Host threads copy piece k into the ring while the kernels of
+    // pieces k-1 and k-2 run on the two launch lanes reading their pieces over PCIe (zero-copy) and writing their feature rows
+    // into the pinned half of the same slot; finished rows are copied out to the caller's array two pieces later.
+    if (lsm_fused_npt(fe, res) && !h_spikes_or_null && !getenv("LSM_NO_PAGEABLE_RING")) {
+        lsm_copy_pool *pool = copy_pool(ctx);
+        if (!pool) LSM_FAIL(ctx, LSM_ERR_NOMEM, "out of host memory");
+        int piece = lsm_fused_wave(ctx, fe, res);
+        if (piece <= 0) piece = 512;
+        while (piece > 1024) piece /= 2;                         // ~600 utterances: 38 MB of PCM per slot
+        if (piece > B) piece = B;
+        const size_t in_bytes = (size_t)piece * L * sizeof(float), out_bytes = (size_t)piece * feat_per * sizeof(double);
+        const size_t slot_bytes = ((in_bytes + 255) & ~(size_t)255) + out_bytes;
+        void *ringp;
+        int rc;
+        if ((rc = lsm_stage_pinned(ctx, 0, 4 * slot_bytes, &ringp)) != LSM_OK) return rc;
+        const int n_pieces = (B + piece - 1) / piece;
+        auto slot_in = [&](int k) { return (char *)ringp + (size_t)(k & 3) * slot_bytes; };
+        auto slot_out = [&](int k) { return slot_in(k) + ((in_bytes + 255) & ~(size_t)255); };
+        auto count = [&](int k) { return k + 1 < n_pieces ? piece : B - k * piece; };
+        for (int k = 0; k < n_pieces + 2; ++k) {
+            if (k >= 2) {
+                // piece k-2 is complete: its rows leave the ring (and its slot is free for piece k+2)
+                const int j = k - 2;
+                LSM_CUDA(ctx, cudaEventSynchronize(ctx->ev_stage_free[j & 3]));
+                pool->copy(h_features + (size_t)j * piece * feat_per, slot_out(j), (size_t)count(j) * feat_per * sizeof(double));
+            }
+            if (k < n_pieces) {
+                const int n = count(k);
+                pool->copy(slot_in(k), h_pcm + (size_t)k * piece * L, (size_t)n * L * sizeof(float));
+                void *dv_in = nullptr, *dv_out = nullptr;
+                if (!device_visible(slot_in(k), &dv_in) || !device_visible(slot_out(k), &dv_out))
+                    LSM_FAIL(ctx, LSM_ERR_CUDA, "pinned staging ring is not device-visible");
+                cudaStream_t ls = lane_stream(ctx, k & 1);
+                if ((rc = lsm_launch_fused(ctx, fe, res, (const float *)dv_in, n, nullptr, feature_mask, nan_to_num, (double *)dv_out, ls,
+                                           (long long)k * piece)) != LSM_OK) return rc;
+                LSM_CUDA(ctx, cudaEventRecord(ctx->ev_stage_free[k & 3], ls));
+            }
+        }
+        return LSM_OK;
     }
     // chunked, three legs on three streams: H2D(c+1) | kernels(c) | D2H(c-1).  A chunk is one full wave of the
     // persistent front-end grid (every CTA gets exactly one utterance, so a chunk has no drain tail); a short

@@ -8,6 +8,9 @@
 
 #include "lsm_b200.h"
 
+struct lsm_copy_pool;
+void lsm_copy_pool_free(lsm_copy_pool *p);
+
 struct lsm_ctx {
     int device = 0;
     int sm_count = 0;
@@ -19,6 +22,7 @@ struct lsm_ctx {
     cudaEvent_t ev_stage_full[4] = {}, ev_stage_free[4] = {};   // copy-engine feed: staging ring hand-over
     int stage_busy[4] = {};
     unsigned stage_next = 0;
+    struct lsm_copy_pool *copy_pool = nullptr;   // host threads that move pageable caller buffers through the pinned ring (api.cu)
     int host_feed = 0;                   // lsm_ctx_set_host_feed: 0 = the kernel reads pinned host PCM itself, 1 = copy engine first
     char err[512] = {0};
     // staging owned by the ctx for the *_host entry points (grown on demand)

@@ -64,10 +64,24 @@ def sharded_features(lsm, spike_data: np.ndarray, feature_keys, compute=None) ->
     rank, ws = world()
     n = len(spike_data)
     lo, hi, per = shard_bounds(n, rank, ws)
+    default_compute = compute is None
     if compute is None:
         def compute(block):
             return lsm.simulate_batch(block, feature_keys, nan_to_num=True)
     width = len(feature_keys) * lsm.num_output_neurons
+    d = _dist()
+    if default_compute and ws > 1 and d.get_backend() == "nccl":
+        # GPU ranks: the block goes to the device once, the feature rows stay there for the all-gather, and only the gathered
+        # matrix comes back (no numpy round trip between the kernel and the collective)
+        import torch
+        dev = torch.device("cuda", lsm.ctx.device)
+        out = torch.zeros((ws * per, width), dtype=torch.float64, device=dev)
+        mine = out[rank * per: rank * per + (hi - lo)]
+        if hi > lo:
+            block = torch.from_numpy(np.ascontiguousarray(spike_data[lo:hi], dtype=np.uint8)).to(dev)
+            mine.copy_(lsm.simulate_batch(block, feature_keys, nan_to_num=True))
+        d.all_gather_into_tensor(out, out[rank * per: (rank + 1) * per].clone())
+        return out.cpu().numpy()[:n]
     local = compute(spike_data[lo:hi]) if hi > lo else np.zeros((0, width))
     local = np.ascontiguousarray(local, dtype=np.float64)
     if ws == 1:

@@ -13,6 +13,7 @@ from pathlib import Path
 
 import numpy as np
 
+from . import npzio
 from .snn import SNN, SimulationParams
 
 NUM_NEURONS = 1000
@@ -161,7 +162,7 @@ def main(feature_set: str, multiplier: float, leak_variance_divisor: float = Non
     scaler = StandardScaler()
     X_train_scaled = scaler.fit_transform(X_train_feat)
     X_test_scaled = scaler.transform(X_test_feat)
-    np.savez_compressed(FEATURE_FILE, X_train_features=X_train_scaled, y_train=y_train,
+    npzio.savez_compressed(FEATURE_FILE, X_train_features=X_train_scaled, y_train=y_train,
                         X_test_features=X_test_scaled, y_test=y_test, feature_set=feature_set,
                         leak_variance_divisor=leak_variance_divisor)
     print(f"Extraction complete. Features saved to '{FEATURE_FILE}'")
@@ -195,7 +196,7 @@ def main_fused(pcm, y_labels, n_filters: int, filterbank: str, feature_set: str,
     scaler = StandardScaler()
     X_train_scaled = scaler.fit_transform(X_train_feat)
     X_test_scaled = scaler.transform(X_test_feat)
-    np.savez_compressed(FEATURE_FILE, X_train_features=X_train_scaled, y_train=y_train,
+    npzio.savez_compressed(FEATURE_FILE, X_train_features=X_train_scaled, y_train=y_train,
                         X_test_features=X_test_scaled, y_test=y_test, feature_set=feature_set,
                         leak_variance_divisor=leak_variance_divisor)
     print(f"Extraction complete. Features saved to '{FEATURE_FILE}'")

@@ -74,7 +74,7 @@ def _blobs(n, F, K, seed, sep=1.2):
     return X, y
 
 
-@pytest.mark.parametrize("n,F,K", [(1920, 400, 12), (320, 2000, 4), (600, 96, 3)])
+@pytest.mark.parametrize("n,F,K", [(1920, 400, 12), (320, 2000, 4), (600, 96, 3), (2100, 300, 35), (900, 64, 17)])
 def test_logistic_regression_matches_sklearn(env, n, F, K):
     import time
     from sklearn.linear_model import LogisticRegression as SkLR
@@ -147,4 +147,4 @@ def test_logistic_regression_errors(env):
     with pytest.raises(ValueError):
         clf.fit(np.zeros((4, 3)), np.arange(4) % 2)                  # two classes: scikit-learn's binary objective is a different one
     with pytest.raises(_lib.LsmError):
-        clf.fit(np.random.default_rng(0).random((40, 3)), np.arange(40) % 17)      # > 16 classes
+        clf.fit(np.random.default_rng(0).random((140, 3)), np.arange(140) % 65)    # > 64 classes

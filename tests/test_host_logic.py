@@ -113,3 +113,36 @@ def test_packed_spike_file_round_trip(tmp_path, monkeypatch):
     assert np.array_equal(cd.load_packed_spikes("odd.npz")[0], Xo)
     with pytest.raises(ValueError):
         cd.save_packed_spikes("bad.npz", X * 2, y)
+
+
+def test_parallel_npz_writer_is_a_drop_in_for_savez_compressed(tmp_path):
+    """npzio.savez_compressed: same container, keys, dtypes, shapes and array bytes as
+    np.savez_compressed (create_dataset.py:176, extract_lsm_features.py:204), readable by np.load and zipfile."""
+    import zipfile
+    from lsm_speech_classifier_b200 import npzio
+    rs = np.random.RandomState(0)
+    X = (rs.random_sample((700, 128, 400)) < 0.04).astype(np.uint8)          # 36 MB: several deflate segments
+    y = rs.randint(0, 12, 700).astype(np.int32)
+    F = np.asfortranarray(rs.standard_normal((300, 2000)))
+    ref, got = tmp_path / "ref.npz", tmp_path / "got"                          # extension added like numpy does
+    kw = dict(X_spikes=X, y_labels=y, X_train_features=F, feature_set="original", leak_variance_divisor=None,
+              empty=np.zeros((0, 5)), scalar=np.float64(3.5))
+    np.savez_compressed(ref, **kw)
+    npzio.savez_compressed(got, **kw)
+    a, b = np.load(ref, allow_pickle=True), np.load(str(got) + ".npz", allow_pickle=True)
+    assert a.files == b.files
+    for k in a.files:
+        assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape, k
+        assert a[k].tobytes() == b[k].tobytes() if a[k].dtype != object else a[k].item() == b[k].item(), k
+    assert b["X_train_features"].flags.f_contiguous
+    with zipfile.ZipFile(str(got) + ".npz") as z:
+        assert z.testzip() is None
+        assert all(i.compress_type == zipfile.ZIP_DEFLATED for i in z.infolist())
+    # CRC combination over many segments
+    import zlib
+    data = rs.bytes(5_000_000)
+    crc = 0
+    for lo in range(0, len(data), 700_001):
+        part = data[lo:lo + 700_001]
+        crc = npzio._crc32_combine(crc, zlib.crc32(part), len(part)) if lo else zlib.crc32(part)
+    assert crc == zlib.crc32(data)
