@@ -177,6 +177,73 @@ def workload_config():
                               else "by the kernel's readout epilogue (NVLink stores into every rank's matrix; no collective kernel)")}
 
 
+# mel front end (BASELINE.json configs[2]): fp64 lane-operations per utterance in K1m - per frame 2048 window products, 5120
+# radix-2 butterflies x 10, 1025 untangle + magnitude bins x 20; 101 frames; + ~45 per dB value of the 101 x C plane
+MEL_FP64_OPS_PER_UTT = 101 * (2048 + 5120 * 10 + 1025 * 20) + 101 * 128 * 45
+
+
+def mel_numbers(pcm_np, steps, warmup, cpu_sample=96):
+    """The same step through the mel front end (librosa branch of create_dataset.py:43-48), one GPU: the fused
+    audio -> features kernel, K1m and K2 alone, host buffers end to end, parity with the C oracle on a sample."""
+    import torch
+    from lsm_speech_classifier_b200 import _lib, filterbank as fb
+    from lsm_speech_classifier_b200.extract_lsm_features import FEATURE_SETS, build_lsm
+    from lsm_speech_classifier_b200.frontend import Frontend
+    from lsm_speech_classifier_b200.snn import AudioToFeatures
+    from oracle import coracle
+    keys = FEATURE_SETS[FEATURE_SET]
+    B = len(pcm_np)
+    fe = Frontend(N_FILTERS, "mel")
+    d_pcm = torch.from_numpy(pcm_np).cuda()
+    head = fe.encode(d_pcm[:500]).cpu().numpy()
+    lsm = build_lsm(head, MULTIPLIER, verbose=False)
+    path = AudioToFeatures(fe, lsm)
+    F = len(keys) * lsm.num_output_neurons
+    d_feat = torch.empty((B, F), dtype=torch.float64, device="cuda")
+    d_spk = fe.encode(d_pcm)
+
+    def timed(fn, reps):
+        for _ in range(max(1, warmup)):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    step_ms = timed(lambda: path.run(d_pcm, keys, out=d_feat, want_spikes=False), steps)
+    k1_ms = timed(lambda: fe.encode(d_pcm), max(2, steps // 2))
+    k2_ms = timed(lambda: lsm.simulate_batch(d_spk, keys), max(2, steps // 2))
+    out_np = np.empty((B, F), dtype=np.float64)
+    path.run_host(pcm_np, keys, out=out_np)
+    t0 = time.perf_counter()
+    n_e2e = max(2, min(steps, 5))
+    for _ in range(n_e2e):
+        path.run_host(pcm_np, keys, out=out_np)
+    e2e = B * n_e2e / (time.perf_counter() - t0)
+    same_as_device = bool(np.array_equal(out_np, d_feat.cpu().numpy()))
+    sample = np.ascontiguousarray(pcm_np[:: max(1, B // cpu_sample)][:cpu_sample])
+    t0 = time.perf_counter()
+    spk = coracle.mel_encode(sample, fe.table, fe.window, fe.tw, fe.tw2, fb.pack_mel_basis(fe.table), fe.params.mel_hop, fe.time_bins,
+                             fe.zoom_i0, fe.zoom_f, [0.70, 0.80, 0.90, 0.95], 0.1)
+    want, _ = coracle.reservoir_run(lsm.reservoir, spk, _lib.feature_mask(keys), True, False)
+    cpu = len(sample) / (time.perf_counter() - t0)
+    got = path.run_host(sample, keys)
+    peak = fe.ctx.fp64_peak_gops()
+    gops = MEL_FP64_OPS_PER_UTT * B / (k1_ms / 1e3) / 1e9
+    return {"filterbank": "mel", "value": B / (step_ms / 1e3), "unit": "utterances/s", "ms_per_step": step_ms, "fused_one_kernel": bool(path.fused),
+            "kernel_ms": {"K1m_mel_encode": k1_ms, "K2_reservoir_features": k2_ms},
+            "e2e": {"value": e2e, "unit": "utterances/s", "note": "pageable numpy arrays through lsm_pipeline_run_host (chunked H2D | kernel | D2H)",
+                    "same_rows_as_device_path": same_as_device},
+            "roofline": {"kernel": "mel_encode_kernel (K1m)", "bound": "fp64", "achieved": gops, "peak": peak,
+                         "unit": "G fp64 lane-ops/s", "frac": gops / peak, "lane_ops_per_utterance": MEL_FP64_OPS_PER_UTT,
+                         "note": "fp64 radix-2 FFT in shared memory: barrier / shared-memory bound, not pipe bound (DESIGN.md K1m)"},
+            "cpu_baseline": {"value": cpu, "unit": "utterances/s", "cores": coracle.num_threads(), "kind": "port",
+                             "sample": f"{len(sample)} utterances, oracle C port (mel)", "gpu_matches_cpu_bit_exact": bool(np.array_equal(got, want))}}
+
+
 _REAL_STDOUT = None
 
 
@@ -204,6 +271,8 @@ def main():
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-times", action="store_true", help="(kept for compatibility; per-kernel times are always reported)")
+    ap.add_argument("--filterbank", type=str, default="gammatone", choices=["gammatone", "mel"],
+                    help="mel: the same step through the mel front end (one GPU), printed as its own line")
     ap.add_argument("--filter-mode", type=str, default="speculative", choices=["speculative", "exact"],
                     help="gammatone filter evaluation (include/lsm_b200.h): both give the reference-order spike trains")
     args = ap.parse_args()
@@ -218,6 +287,15 @@ def main():
 
     # synthesise the inputs first: the generator forks worker processes, which must happen before CUDA is initialised
     pcm_np, _ = make_inputs(rank)
+    if args.filterbank == "mel":
+        if rank == 0:
+            m = mel_numbers(pcm_np, args.steps, max(args.warmup, 3))
+            cfg = workload_config()
+            cfg["workload"] = cfg["workload"].replace("128-ch gammatone", "128-ch mel (configs[2] front end)")
+            cfg["filterbank"] = "mel"
+            emit({"metric": METRIC, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "higher_is_better": True,
+                  "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32", "data": "synthetic", "config": cfg, **m})
+        return
 
     import torch
     import torch.distributed as dist
@@ -491,8 +569,8 @@ def main():
     hbm_peak = float(peaks["hbm_gbs"])
     step_ms = ms_total / args.steps
     fused = bool(path.fused)
-    # Dominant kernel: pipeline_kernel (warp-specialised audio -> features; two launches share the SMs, so the per-launch figure
-    # is taken over the timed steps: kernels run back to back on the two launch lanes for the whole region).  Binding resource:
+    # Dominant kernel: the fused audio -> features kernel (two launches share the SMs, so the per-launch figure is taken over
+    # the timed steps: kernels run back to back on the two streams for the whole region).  Binding resource:
     # the fp64 pipe (13 DFMA per channel-sample); HBM is the secondary key.
     dom_bytes = FUSED_BYTES_PER_UTT * B
     dom_gbs = dom_bytes / (step_ms / 1e3) / 1e9
@@ -532,7 +610,7 @@ def main():
                          "note": "pageable numpy arrays through the synchronous lsm_pipeline_run_host (the reference-style call)"},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
-        "roofline": {"kernel": "pipeline_kernel (warp-specialised audio->features: lane = utterance filter warps + encoder/reservoir units)"
+        "roofline": {"kernel": "gammatone_encode_kernel<128,6,8,1> (fused audio->features, lane = channel: filter + encoder + reservoir + readout)"
                                if fused else "gammatone_encode_kernel (K1)",
                      "bound": "fp64", "achieved": step_gops, "peak": fp64_peak, "unit": "G fp64 lane-ops/s (DFMA = 1)",
                      "frac": step_gops / fp64_peak, "traffic": traffic,
@@ -584,6 +662,11 @@ def main():
                                "stage23_reservoir_features": len(sample) / (tc - tb),
                                "neuron_steps_per_s": len(sample) / dt * N_NEURONS * T_STEPS,
                                "gpu_matches_cpu_bit_exact": bool(np.array_equal(got, ref))}
+    if world == 1 and not os.environ.get("LSM_BENCH_NO_MEL"):
+        try:
+            out["mel_arm"] = mel_numbers(pcm_np, max(3, args.steps // 2), 3)
+        except Exception as e:          # the mel arm is a secondary line: never lose the headline over it
+            out["mel_arm"] = {"error": repr(e)}
     emit(out)
     if world > 1:
         dist.destroy_process_group()

@@ -238,8 +238,9 @@ int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, co
                           int32_t B, uint32_t feature_mask, int32_t nan_to_num, double *h_features,
                           uint8_t *h_spikes_or_null);
 /* Device-resident variant: d_pcm -> d_features on the ctx's stream.  Runs as ONE fused kernel when the pair
- * allows it (gammatone, redundancy 1, reservoir width = channels x {4,8,16}); d_spikes_or_null then only
- * receives a copy of the spike trains if non-NULL.  Otherwise two kernels, and d_spikes is required.      */
+ * allows it (gammatone: redundancy 1, reservoir width = channels x {4,8,16}; mel: redundancy 1, channels a multiple of
+ * 32, reservoir of at most 1024 neurons); d_spikes_or_null then only receives a copy of the spike trains if non-NULL.
+ * Otherwise two kernels, and d_spikes is required.                                                         */
 int lsm_pipeline_run(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm,
                      int32_t B, uint32_t feature_mask, int32_t nan_to_num, uint8_t *d_spikes_or_null,
                      double *d_features);

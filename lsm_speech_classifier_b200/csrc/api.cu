@@ -954,6 +954,8 @@ extern "C" int lsm_pipeline_run(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *r
     // one fused kernel when the pair allows it (spikes handed over in shared memory; d_spikes optional)
     if (lsm_fused_npt(fe, res))
         return lsm_launch_fused(ctx, fe, res, d_pcm, B, d_spikes, feature_mask, nan_to_num, d_features, ctx->stream, 0);
+    if (lsm_mel_fused_ok(fe, res))
+        return lsm_launch_mel_fused(ctx, fe, res, d_pcm, B, d_spikes, feature_mask, nan_to_num, d_features, ctx->stream, 0);
     if (!d_spikes) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_pipeline_run: this configuration runs as two kernels and needs a d_spikes buffer");
     int rc = frontend_launch(ctx, fe, d_pcm, B, d_spikes, nullptr, ctx->stream);
     if (rc != LSM_OK) return rc;
@@ -962,7 +964,7 @@ extern "C" int lsm_pipeline_run(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *r
 
 extern "C" int lsm_pipeline_is_fused(const lsm_frontend *fe, const lsm_reservoir *res)
 {
-    return (fe && res && lsm_fused_npt(fe, res)) ? 1 : 0;
+    return (fe && res && (lsm_fused_npt(fe, res) || lsm_mel_fused_ok(fe, res))) ? 1 : 0;
 }
 
 extern "C" int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *h_pcm,
@@ -1059,6 +1061,7 @@ extern "C" int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservo
     // remainder is folded into the last chunk.  The first chunk's H2D and the last chunk's D2H are the only
     // copies that are not hidden.
     const bool fused = lsm_fused_npt(fe, res) != 0;
+    const bool mel_fused = !fused && lsm_mel_fused_ok(fe, res);
     int wave = fe->grid > 0 ? fe->grid : 1024;
     if (fused) { const int w = lsm_fused_wave(ctx, fe, res); if (w > 0) wave = w; }
     int n_chunks = B / wave;
@@ -1089,6 +1092,9 @@ extern "C" int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservo
         if (fused) {
             if ((rc = lsm_launch_fused(ctx, fe, res, (const float *)d_pcm[b], n, h_spikes_or_null ? (uint8_t *)d_spk[b] : nullptr,
                                        feature_mask, nan_to_num, (double *)d_feat[b], s_k, (long long)off)) != LSM_OK) return rc;
+        } else if (mel_fused) {
+            if ((rc = lsm_launch_mel_fused(ctx, fe, res, (const float *)d_pcm[b], n, h_spikes_or_null ? (uint8_t *)d_spk[b] : nullptr,
+                                           feature_mask, nan_to_num, (double *)d_feat[b], s_k, (long long)off)) != LSM_OK) return rc;
         } else {
             if ((rc = frontend_launch(ctx, fe, (const float *)d_pcm[b], n, (uint8_t *)d_spk[b], nullptr, s_k)) != LSM_OK) return rc;
             if ((rc = lsm_launch_reservoir(ctx, res, (const uint8_t *)d_spk[b], n, feature_mask, nan_to_num,

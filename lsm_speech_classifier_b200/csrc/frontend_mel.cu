@@ -18,7 +18,7 @@
 #include <math.h>
 #include <vector>
 
-#include "lsm_common.cuh"
+#include "reservoir_core.cuh"
 
 namespace {
 
@@ -38,6 +38,7 @@ struct MelArgs {
     double *spec_norm;       // optional [B][C][nbins]
     int B, L, C, hop, ncols, nbins, K, R;
     double thr[8], lower[8];
+    ResArgs res;             // fused variants: the reservoir + readout that follow the encoder in the same CTA
 };
 
 __device__ __forceinline__ float block_reduce_f32(float v, bool want_max, float *s_red)
@@ -71,29 +72,38 @@ __device__ __forceinline__ void bfly(double &pr, double &pi, double &qr, double 
     qr = __dsub_rn(ur, tr); qi = __dsub_rn(ui, ti);
 }
 
-__global__ void __launch_bounds__(kThreads) mel_encode_kernel(const MelArgs a, int *next_utt)
+// FUSED: 0 = front end only (spike trains to global memory); 1 / 2 = the reservoir (lean / generic layout, 4 neurons per thread:
+// reservoirs of up to 1024 neurons) and the readout follow in the same CTA, the spike train handed over as bits in shared
+// memory (one ballot word per warp of 32 channels and time step), exactly as the fused gammatone kernel does.  The FFT
+// buffers and the reservoir's shared-memory plan share one dynamic allocation; the twiddle tables are reloaded per utterance.
+constexpr size_t kMelSmemBytes = sizeof(double) * 2 * kHalf + sizeof(double2) * kHalf + sizeof(float) * (kHalf + 8);
+
+template <int FUSED>
+__global__ void __launch_bounds__(kThreads, FUSED ? 3 : 5) mel_encode_kernel(const MelArgs a, int *next_utt)
 {
-    __shared__ double s_re[kHalf], s_im[kHalf];
-    __shared__ double2 s_tw[kHalf];       // per-stage twiddle tables, stage s at offset 2^(s-1) - 1: T_s[j] = tw[j * (1024 >> s)], j < 2^(s-1)
-                                          // (contiguous in j: the strided reads of one shared table were up to 16-way bank conflicted)
-    __shared__ float s_S[kHalf + 8];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_re = reinterpret_cast<double *>(smem_raw), *s_im = s_re + kHalf;
+    double2 *s_tw = reinterpret_cast<double2 *>(s_im + kHalf);   // per-stage twiddle tables, stage s at offset 2^(s-1) - 1: T_s[j] = tw[j * (1024 >> s)], j < 2^(s-1)
+                                                                 // (contiguous in j: the strided reads of one shared table were up to 16-way bank conflicted)
+    float *s_S = reinterpret_cast<float *>(s_tw + kHalf);
     __shared__ float s_red[kThreads / 32];
     __shared__ int s_utt;
+    __shared__ int s_cnt[5];
 
     const int tid = threadIdx.x;
     const int C = a.C, ncols = a.ncols;
     float *plane = a.scratch + (size_t)blockIdx.x * ncols * C;     // mel power / dB plane [ncols][C]
-    for (int q = tid; q < kHalf - 1; q += kThreads) {
-        const int s = 32 - __clz(q + 1);                 // stage whose table holds entry q
-        const int j = q + 1 - (1 << (s - 1));
-        s_tw[q] = __ldg(a.tw + j * (kHalf >> s));
-    }
 
     for (;;) {
         if (tid == 0) s_utt = atomicAdd(next_utt, 1);
         __syncthreads();
         const int utt = s_utt;
         if (utt >= a.B) break;
+        for (int q = tid; q < kHalf - 1; q += kThreads) {
+            const int s = 32 - __clz(q + 1);                 // stage whose table holds entry q
+            const int j = q + 1 - (1 << (s - 1));
+            s_tw[q] = __ldg(a.tw + j * (kHalf >> s));
+        }
         const float *pcm = a.pcm + (size_t)utt * a.L;
 
         for (int t = 0; t < ncols; ++t) {
@@ -178,9 +188,12 @@ __global__ void __launch_bounds__(kThreads) mel_encode_kernel(const MelArgs a, i
         const bool degenerate = (double)diff < 1e-8;                                    // create_dataset.py:64-65
         const float den = (float)__dadd_rn((double)diff, 1e-8);
 
-        for (int m = tid; m < C; m += kThreads) {
+        if (FUSED) __syncthreads();                         // every thread is done with the FFT buffers: the bit plane takes their place
+        unsigned *s_bits = reinterpret_cast<unsigned *>(smem_raw);
+        const int CW = (C + 31) >> 5;
+        for (int m = tid; m < C; m += kThreads) {             // whole warps (fused pairs have C % 32 == 0)
             const int T = a.nbins * a.K;
-            uint8_t *row0 = a.spikes + ((size_t)utt * C * a.R + (size_t)m * a.R) * T;
+            uint8_t *row0 = a.spikes ? a.spikes + ((size_t)utt * C * a.R + (size_t)m * a.R) * T : nullptr;
             double *dump = a.spec_norm ? a.spec_norm + ((size_t)utt * C + m) * a.nbins : nullptr;
             for (int c = 0; c < ncols; ++c) {
                 const float v = fmaxf(plane[(size_t)c * C + m], floor_db);
@@ -207,16 +220,28 @@ __global__ void __launch_bounds__(kThreads) mel_encode_kernel(const MelArgs a, i
                         else if (is_on && v < (float)a.lower[k]) on &= ~(1u << k);
                     }
                 }
-                for (int r = 0; r < a.R; ++r) {
-                    uint8_t *row = row0 + (size_t)r * T + (size_t)j * a.K;
-                    if (a.K == 4) {
-                        const unsigned w = (on & 1u) | ((on & 2u) << 7) | ((on & 4u) << 14) | ((on & 8u) << 21);
-                        *reinterpret_cast<uint32_t *>(row) = w;
-                    } else {
-                        for (int k = 0; k < a.K; ++k) row[k] = (on >> k) & 1u;
+                if (FUSED) {
+                    for (int k = 0; k < a.K; ++k) {
+                        const unsigned word = __ballot_sync(0xffffffffu, (on >> k) & 1u);
+                        if ((m & 31) == 0) s_bits[(j * a.K + k) * CW + (m >> 5)] = word;
+                    }
+                }
+                if (row0) {
+                    for (int r = 0; r < a.R; ++r) {
+                        uint8_t *row = row0 + (size_t)r * T + (size_t)j * a.K;
+                        if (a.K == 4) {
+                            const unsigned w = (on & 1u) | ((on & 2u) << 7) | ((on & 4u) << 14) | ((on & 8u) << 21);
+                            *reinterpret_cast<uint32_t *>(row) = w;
+                        } else {
+                            for (int k = 0; k < a.K; ++k) row[k] = (on >> k) & 1u;
+                        }
                     }
                 }
             }
+        }
+        if (FUSED) {
+            __syncthreads();                                 // the bit plane is complete
+            reservoir_simulate<4, FUSED == 1, false, 0>(a.res, utt, smem_raw, s_cnt, tid, kThreads);
         }
         __syncthreads();
     }
@@ -271,7 +296,7 @@ int lsm_mel_create(lsm_ctx *ctx, lsm_frontend *fe, const float *h_basis)
     if (rc == LSM_OK) rc = up(ctx, (double **)&fe->d_twiddle2, tw2.data(), tw2.size());
     if (rc != LSM_OK) return rc;
     int per_sm = 0;
-    LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_encode_kernel, kThreads, 0));
+    LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_encode_kernel<0>, kThreads, kMelSmemBytes));
     if (per_sm < 1) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "mel kernel does not fit on an SM");
     fe->grid = per_sm * ctx->sm_count;
     rc = up<float>(ctx, &fe->d_mel_scratch, nullptr, (size_t)fe->grid * fe->ncols * C);
@@ -285,12 +310,58 @@ void lsm_mel_destroy(lsm_frontend *fe)
     cudaFree(fe->d_window); cudaFree(fe->d_twiddle); cudaFree(fe->d_twiddle2); cudaFree(fe->d_mel_scratch);
 }
 
-int lsm_launch_mel(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, uint8_t *d_spikes, double *d_spec_norm,
-                   cudaStream_t st)
+// Can this mel front end hand its spike trains to this reservoir inside one kernel?  Whole warps of channels, no redundancy,
+// a reservoir of at most 1024 neurons (4 per thread of the 256-thread CTA) whose shared-memory plan fits beside nothing else.
+bool lsm_mel_fused_ok(const lsm_frontend *fe, const lsm_reservoir *res)
 {
     const lsm_frontend_params &p = fe->p;
+    if (getenv("LSM_NO_FUSE")) return false;
+    if (p.kind != LSM_FILTERBANK_MEL || p.redundancy != 1 || (p.channels & 31) || p.channels > 256) return false;
+    if (res->p.num_inputs != p.channels || res->p.num_steps != p.n_bins * p.n_thresholds) return false;
+    if (res->n_pad != 4 * kThreads) return false;
+    return lsm_res_smem_bytes(res->p.num_steps, (p.channels + 31) / 32, 4 * kThreads, res->p.num_neurons) <= 100 * 1024;
+}
+
+static void mel_fill(const lsm_frontend *fe, const float *d_pcm, int B, uint8_t *d_spikes, double *d_spec_norm, MelArgs *out);
+
+// audio -> features in one launch (mel): features as lsm_launch_reservoir writes them, spike trains optional
+int lsm_launch_mel_fused(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B, uint8_t *d_spikes_or_null,
+                         uint32_t feature_mask, int nan_to_num, double *d_features, cudaStream_t st, long long row0)
+{
     if (B <= 0) return LSM_OK;
     MelArgs a;
+    mel_fill(fe, d_pcm, B, d_spikes_or_null, nullptr, &a);
+    lsm_reservoir_fill_args(res, nullptr, B, feature_mask, nan_to_num, d_features, nullptr, &a.res);
+    a.res.gather_row0 += row0;
+    size_t smem = lsm_res_smem_bytes(a.res.T, a.res.CW, 4 * kThreads, a.res.N);
+    if (smem < kMelSmemBytes) smem = kMelSmemBytes;
+    int rc = lsm_frontend_order_before(ctx, fe, st);
+    if (rc != LSM_OK) return rc;
+    int *counter = fe->d_counters + (fe->counter_next++ % 64);
+    LSM_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), st));
+    int per_sm = 0;
+    if (res->lean) {
+        LSM_CUDA(ctx, cudaFuncSetAttribute(mel_encode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_encode_kernel<1>, kThreads, smem));
+    } else {
+        LSM_CUDA(ctx, cudaFuncSetAttribute(mel_encode_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_encode_kernel<2>, kThreads, smem));
+    }
+    if (per_sm < 1) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "fused mel kernel does not fit on an SM");
+    int grid = per_sm * ctx->sm_count;
+    if (grid > fe->grid) grid = fe->grid;                    // the per-CTA dB planes were sized for the front end's own grid
+    if (grid > B) grid = B;
+    if (res->lean) mel_encode_kernel<1><<<grid, kThreads, smem, st>>>(a, counter);
+    else mel_encode_kernel<2><<<grid, kThreads, smem, st>>>(a, counter);
+    ctx->launches += 1;
+    LSM_CUDA(ctx, cudaGetLastError());
+    return lsm_frontend_order_after(ctx, fe, st);
+}
+
+static void mel_fill(const lsm_frontend *fe, const float *d_pcm, int B, uint8_t *d_spikes, double *d_spec_norm, MelArgs *out)
+{
+    const lsm_frontend_params &p = fe->p;
+    MelArgs &a = *out;
     a.pcm = d_pcm; a.win = fe->d_window; a.tw = fe->d_twiddle; a.tw2 = fe->d_twiddle2;
     a.mel_w = fe->d_mel_w; a.mel_lo = fe->d_mel_lo; a.mel_n = fe->d_mel_n; a.mel_off = fe->d_mel_off;
     a.zoom_i0 = fe->d_zoom_i0; a.zoom_f = fe->d_zoom_f; a.scratch = fe->d_mel_scratch;
@@ -298,12 +369,21 @@ int lsm_launch_mel(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, ui
     a.B = B; a.L = p.n_samples; a.C = p.channels; a.hop = p.mel_hop; a.ncols = fe->ncols; a.nbins = p.n_bins;
     a.K = p.n_thresholds; a.R = p.redundancy;
     for (int k = 0; k < 8; ++k) { a.thr[k] = p.thresholds_desc[k]; a.lower[k] = p.lower_bounds[k]; }
+    memset(&a.res, 0, sizeof(a.res));
+}
+
+int lsm_launch_mel(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, uint8_t *d_spikes, double *d_spec_norm,
+                   cudaStream_t st)
+{
+    if (B <= 0) return LSM_OK;
+    MelArgs a;
+    mel_fill(fe, d_pcm, B, d_spikes, d_spec_norm, &a);
     int rc = lsm_frontend_order_before(ctx, fe, st);
     if (rc != LSM_OK) return rc;
     int *counter = fe->d_counters + (fe->counter_next++ % 64);
     LSM_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), st));
     const int grid = B < fe->grid ? B : fe->grid;
-    mel_encode_kernel<<<grid, kThreads, 0, st>>>(a, counter);
+    mel_encode_kernel<0><<<grid, kThreads, kMelSmemBytes, st>>>(a, counter);
     ctx->launches += 1;
     LSM_CUDA(ctx, cudaGetLastError());
     return lsm_frontend_order_after(ctx, fe, st);

@@ -154,6 +154,9 @@ int lsm_launch_mel(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, ui
 int lsm_launch_reservoir(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spikes, int B,
                          uint32_t feature_mask, int nan_to_num, double *d_features, uint8_t *d_raster,
                          cudaStream_t st, int *d_diag = nullptr, long long row0 = 0);
+bool lsm_mel_fused_ok(const lsm_frontend *fe, const lsm_reservoir *res);
+int lsm_launch_mel_fused(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B, uint8_t *d_spikes_or_null,
+                         uint32_t feature_mask, int nan_to_num, double *d_features, cudaStream_t st, long long row0);
 void lsm_reservoir_geometry(int N, int *npt, int *threads, int *n_pad);
 // dense arm (reservoir_dense.cu)
 const char *lsm_dense_unsupported(const lsm_reservoir *res);

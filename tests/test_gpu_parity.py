@@ -272,6 +272,42 @@ def test_mel_spikes_and_spectrogram_bit_exact(env, small_set, n_filters, redunda
     assert got[24].sum() == 0      # silent clip
 
 
+@pytest.mark.parametrize("n_filters,kw", [(128, {}), (64, {}), (256, {}), (128, dict(leak_variance_divisor=4.0)),
+                                          (128, dict(num_neurons=2500, small_world_graph_k=500))])
+def test_mel_fused_kernel_equals_two_kernel_path_and_oracle(env, small_set, n_filters, kw, monkeypatch):
+    """mel audio -> features as ONE kernel (spike train handed over as bits in shared memory, reservoir + readout in the same CTA)
+    vs K1m then K2 vs the oracle; 256 channels and a heterogeneous leak take the generic reservoir layout; 2500 neurons do not fuse."""
+    import torch
+    from lsm_speech_classifier_b200.frontend import Frontend
+    from lsm_speech_classifier_b200.snn import AudioToFeatures
+    from oracle import coracle
+    pcm, _ = small_set
+    fe = Frontend(n_filters, "mel")
+    X = oracle_mel(pcm, fe)
+    lsm = build_snn(X, **kw)
+    want, _ = coracle.reservoir_run(lsm.reservoir, X, 0xFF, True, False)
+    keys = list(lsm_keys())
+    path = AudioToFeatures(fe, lsm)
+    assert path.fused == (kw.get("num_neurons", 1000) == 1000)
+    d_pcm = torch.from_numpy(pcm).cuda()
+    fused, spk = path.run(d_pcm, keys)
+    fused_nospk, none = path.run(d_pcm, keys, want_spikes=False)
+    torch.cuda.synchronize()
+    assert (none is None) == path.fused
+    monkeypatch.setenv("LSM_NO_FUSE", "1")
+    unfused, spk2 = path.run(d_pcm, keys)
+    torch.cuda.synchronize()
+    monkeypatch.delenv("LSM_NO_FUSE")
+    assert np.array_equal(spk.cpu().numpy(), X) and np.array_equal(spk2.cpu().numpy(), X)
+    for got in (fused, fused_nospk, unfused):
+        assert np.array_equal(got.cpu().numpy(), want)
+    # host buffers (chunked copy / kernel / copy pipeline), with and without the spike trains, ragged multi-chunk batch
+    h_spk = np.empty_like(X)
+    assert np.array_equal(path.run_host(pcm, keys, spikes_out=h_spk), want) and np.array_equal(h_spk, X)
+    big = np.concatenate([pcm] * 70)[:1931]
+    assert np.array_equal(path.run_host(big, keys), np.concatenate([want] * 70)[:1931])
+
+
 def test_mel_golden_vectors(env, golden):
     from lsm_speech_classifier_b200.frontend import Frontend
     g = golden("frontend_mel64.npz")
