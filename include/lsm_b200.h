@@ -271,6 +271,16 @@ int lsm_pipeline_is_fused(const lsm_frontend *fe, const lsm_reservoir *res);
  * reduces over X_train[:500] (extract_lsm_features.py:40-44).  h_out: int64[2].            */
 int lsm_spike_density(lsm_ctx *ctx, const uint8_t *d_spikes, int64_t n_bytes, int64_t *h_out);
 
+/* ---------------------------------------------------------------- upstream of the path
+ * Sample-rate conversion of the ingest step: the resampling inside librosa.load(filepath, sr=16000) at create_dataset.py:26, as
+ * librosa's res_type="polyphase" = scipy.signal.resample_poly(y, up, down) (default Kaiser window), bit for bit.
+ * d_in: float[B][n_in]; up / down: the reduced rate ratio; h_taps: host float[up][taps_per_phase], the low-pass designed as scipy
+ * does (firwin(2 * 10 * max(up, down) + 1, 1 / max(up, down), window=("kaiser", 5.0)) in float32, times up, zero-padded in front by
+ * n_pre_pad), transposed and flipped per phase (scipy.signal._upfirdn._pad_h); n_pre_remove: leading outputs to drop
+ * ((half_len + n_pre_pad) / down); d_out: float[B][n_out], n_out = ceil(n_in * up / down).  ingest.py builds these arguments.   */
+int lsm_resample_poly(lsm_ctx *ctx, const float *d_in, int32_t B, int32_t n_in, int32_t up, int32_t down, const float *h_taps,
+                      int32_t taps_per_phase, int32_t n_pre_remove, int32_t n_out, float *d_out);
+
 /* ---------------------------------------------------------------- downstream of the path
  * sklearn.preprocessing.StandardScaler on the device, bit-exact with scikit-learn's dense float64 path
  * (extract_lsm_features.py:199-201).  d_X: double[n][F] row-major; d_mean/d_var/d_scale: double[F].

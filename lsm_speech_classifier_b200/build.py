@@ -10,7 +10,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SO = os.path.join(PKG, os.environ.get("LSM_SO_NAME", "liblsmb200.so"))
-SOURCES = ["api.cu", "error_bound.cu", "frontend_gammatone.cu", "pipeline_lanes.cu", "frontend_mel.cu", "reservoir.cu", "reservoir_dense.cu", "standardize.cu", "logreg.cu"]
+SOURCES = ["api.cu", "error_bound.cu", "frontend_gammatone.cu", "pipeline_lanes.cu", "frontend_mel.cu", "reservoir.cu", "reservoir_dense.cu", "standardize.cu", "logreg.cu", "resample.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "--fmad=false",            # never contract a*b+c: bit parity with the CPU oracle
          "-Xcompiler", "-fPIC", "-cudart", "static"]

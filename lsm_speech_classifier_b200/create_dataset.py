@@ -34,28 +34,12 @@ def _frontend(n_filters: int, filterbank: str, redundancy: int = REDUNDANCY_FACT
 
 
 def load_audio_file(filepath: Path):
-    """reference :22-36 contract: float32 mono at 16 kHz, exactly 16000 samples (zero padded or
-    truncated), None on failure.  Decoding/resampling is outside the accelerated path: PCM WAV at
-    16 kHz is read with the standard library; anything else is reported and skipped."""
-    import wave
+    """reference :22-36 contract: float32 mono at 16 kHz, exactly 16000 samples (zero padded or truncated), None on failure
+    (with the reference's message).  PCM and float WAV files of any rate and channel count (ingest.py: RIFF parser, channel
+    mean, polyphase resampler on the GPU pinned to scipy.signal.resample_poly); other containers are reported and skipped."""
+    from . import ingest
     try:
-        with wave.open(str(filepath), "rb") as w:
-            if w.getframerate() != SAMPLE_RATE:
-                raise ValueError(f"sample rate {w.getframerate()} != {SAMPLE_RATE} (resampling is out of scope)")
-            n = min(w.getnframes(), int(SAMPLE_RATE * DURATION))
-            raw = w.readframes(n)
-            width, ch = w.getsampwidth(), w.getnchannels()
-        if width != 2:
-            raise ValueError("only 16-bit PCM WAV is supported")
-        audio = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
-        if ch > 1:
-            audio = audio.reshape(-1, ch).mean(axis=1).astype(np.float32)
-        target_length = int(SAMPLE_RATE * DURATION)
-        if len(audio) < target_length:
-            audio = np.pad(audio, (0, target_length - len(audio)))
-        else:
-            audio = audio[:target_length]
-        return audio
+        return ingest.load_audio(filepath, SAMPLE_RATE, DURATION)
     except Exception as e:
         print(f"Error loading {filepath}: {e}")
         return None

@@ -291,3 +291,26 @@ def features_from_raster(raster, out_idx, refractory):
             f['isi_variances'][o] = float(n_isi * s2 - s1 * s1) / float(n_isi * n_isi)
             f['burst_counts'][o] = float(int((isi <= refractory + 1).sum()))
     return f
+
+
+# ---------------------------------------------------------------------------------------------
+# Ingest: sample-rate conversion.  The reference resamples inside librosa.load
+# (/root/reference/create_dataset.py:26); librosa's res_type="polyphase" is scipy.signal.resample_poly, whose arithmetic
+# (scipy/signal/_upfirdn_apply.pyx _apply_impl) is restated here sample by sample: for every kept output one float32 multiply and
+# one float32 add per tap, in ascending input order, zero padding outside the signal.  Pinned: equals scipy's output bit for bit
+# (tests/test_oracle_frontend.py).  Small signals only - this is a Python loop.
+def resample_poly_ref(x, up, down, taps, hpp, n_pre_remove, n_out):
+    """x float32[n_in]; (up, down, taps[up][hpp], hpp, n_pre_remove, n_out) as ingest.polyphase_design returns them."""
+    x = np.asarray(x, dtype=np.float32)
+    n_in = len(x)
+    out = np.zeros(n_out, dtype=np.float32)
+    for o in range(n_out):
+        pos = (o + n_pre_remove) * down
+        t, xi = pos % up, pos // up
+        acc = np.float32(0.0)
+        for j in range(hpp):
+            k = xi - hpp + 1 + j
+            if 0 <= k < n_in:
+                acc = np.float32(acc + np.float32(x[k] * taps[t, j]))
+        out[o] = acc
+    return out

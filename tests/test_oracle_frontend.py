@@ -166,3 +166,65 @@ def test_c_oracle_mel_vs_scipy_restatement(golden):
     s256 = coracle.mel_encode(pcm[:1], b256, filterbank.hann_periodic(2048), tw, tw2, filterbank.pack_mel_basis(b256),
                               160, 100, i0, f, THR, GAP)
     assert s256.shape == (1, 256, 400)
+
+
+def test_polyphase_resampler_restatement_is_scipy_bit_for_bit():
+    """ingest.polyphase_design + pyref.resample_poly_ref (what the GPU kernel repeats) against scipy.signal.resample_poly =
+    librosa.resample(res_type="polyphase"): the resampling step of load_audio_file (create_dataset.py:26)."""
+    from scipy.signal import resample_poly
+    from lsm_speech_classifier_b200 import ingest
+    from oracle import pyref
+    rs = np.random.RandomState(1)
+    for sr, n in ((44100, 1500), (48000, 1400), (8000, 700), (22050, 900), (11025, 400), (16001, 300), (44100, 1), (48000, 7)):
+        x = (rs.standard_normal(n) * 0.3).astype(np.float32)
+        want = resample_poly(x, 16000, sr)
+        got = pyref.resample_poly_ref(x, *ingest.polyphase_design(n, 16000, sr))
+        assert want.dtype == np.float32 and np.array_equal(got, want), sr
+
+
+def _write_wav(path, tag, bits, rate, frames, extensible=False):
+    """frames: float array [n, ch] in [-1, 1); returns the float32 array a libsndfile-style decoder yields."""
+    import struct
+    n, ch = frames.shape
+    if tag == 1 and bits == 8:
+        q = np.clip(np.round(frames * 128.0) + 128, 0, 255).astype(np.uint8); body = q.tobytes(); dec = (q.astype(np.float32) - 128.0) / 128.0
+    elif tag == 1 and bits == 16:
+        q = np.clip(np.round(frames * 32768.0), -32768, 32767).astype("<i2"); body = q.tobytes(); dec = q.astype(np.float32) / 32768.0
+    elif tag == 1 and bits == 24:
+        q = np.clip(np.round(frames * 8388608.0), -8388608, 8388607).astype(np.int32)
+        b = np.stack([(q & 0xFF), (q >> 8) & 0xFF, (q >> 16) & 0xFF], axis=-1).astype(np.uint8); body = b.tobytes(); dec = q.astype(np.float32) / 8388608.0
+    elif tag == 1 and bits == 32:
+        q = np.clip(np.round(frames.astype(np.float64) * 2147483648.0), -2147483648, 2147483647).astype("<i4"); body = q.tobytes()
+        dec = (q.astype(np.float64) / 2147483648.0).astype(np.float32)
+    elif tag == 3 and bits == 32:
+        q = frames.astype("<f4"); body = q.tobytes(); dec = q.astype(np.float32)
+    else:
+        q = frames.astype("<f8"); body = q.tobytes(); dec = q.astype(np.float32)
+    align = ch * bits // 8
+    if extensible:
+        fmt = struct.pack("<HHIIHHHHIH", 0xFFFE, ch, rate, rate * align, align, bits, 22, bits, 0, tag) + b"\x00" * 14
+    else:
+        fmt = struct.pack("<HHIIHH", tag, ch, rate, rate * align, align, bits)
+    chunks = b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"LIST" + struct.pack("<I", 4) + b"abcd" + b"data" + struct.pack("<I", len(body)) + body
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 4 + len(chunks)) + b"WAVE" + chunks)
+    return dec.reshape(n, ch)
+
+
+def test_wav_reader_formats(tmp_path):
+    """ingest.read_wav: the decode half of librosa.load (create_dataset.py:26) for RIFF/WAVE files."""
+    from lsm_speech_classifier_b200 import ingest
+    rs = np.random.RandomState(2)
+    for tag, bits, ch, ext in ((1, 8, 1, False), (1, 16, 1, False), (1, 16, 2, False), (1, 24, 2, False), (1, 32, 1, False),
+                               (3, 32, 2, False), (3, 64, 1, False), (1, 16, 2, True), (3, 32, 1, True)):
+        frames = np.clip(rs.standard_normal((501, ch)) * 0.3, -0.99, 0.99)
+        p = tmp_path / f"t{tag}_{bits}_{ch}_{int(ext)}.wav"
+        want = _write_wav(p, tag, bits, 22050, frames, ext)
+        got, rate = ingest.read_wav(p)
+        assert rate == 22050 and got.dtype == np.float32 and np.array_equal(got, want), (tag, bits, ch, ext)
+    bad = tmp_path / "bad.wav"
+    bad.write_bytes(b"RIFF\x00\x00\x00\x00WAVEnope")
+    with pytest.raises(ValueError):
+        ingest.read_wav(bad)
+    with pytest.raises(ValueError):
+        ingest.read_wav(__file__)
