@@ -13,7 +13,7 @@ from pathlib import Path
 
 import numpy as np
 
-from . import _lib, npzio
+from . import _lib, npzio, timing
 from .frontend import (DURATION, HYSTERESIS_GAP, REDUNDANCY_FACTOR, SAMPLE_RATE, SPIKE_THRESHOLDS,  # noqa: F401
                        TIME_BINS, Frontend)
 
@@ -150,10 +150,12 @@ def create_dataset(n_filters: int, filterbank: str, synthetic: tuple | None = No
     init_from_env()             # under torchrun (also when this stage is run on its own): one rank per GPU, utterances sharded
     if is_main():
         print(f"Creating dataset with filterbank: {filterbank}, filters: {n_filters}")
-    pcm, labels = collect_pcm(synthetic)
+    with timing.stage("audio: synthesis / WAV decode"):
+        pcm, labels = collect_pcm(synthetic)
     if pcm is None:
         return
-    X_spikes = encode_batch(pcm, n_filters, filterbank)
+    with timing.stage("stage 1 compute: audio -> spike trains (GPU, host buffers)", len(pcm)):
+        X_spikes = encode_batch(pcm, n_filters, filterbank)
     y_labels = np.array(labels, dtype=np.int32)
     if not is_main():
         return
@@ -161,12 +163,12 @@ def create_dataset(n_filters: int, filterbank: str, synthetic: tuple | None = No
     print("\nDataset created successfully.")
     print(f"  Shape: {X_spikes.shape}")
     print(f"  Avg spikes per sample: {np.mean(counts):.1f}")
-    if packed:
-        save_packed_spikes(PACKED_FILE, X_spikes, y_labels)
-        print(f"Saved to '{PACKED_FILE}' (bit-packed)")
-        return
-    npzio.savez_compressed(OUTPUT_FILE, X_spikes=X_spikes, y_labels=y_labels)
-    print(f"Saved to '{OUTPUT_FILE}'")
+    with timing.stage("stage 1 write: spike file (parallel deflate)"):
+        if packed:
+            save_packed_spikes(PACKED_FILE, X_spikes, y_labels)
+        else:
+            npzio.savez_compressed(OUTPUT_FILE, X_spikes=X_spikes, y_labels=y_labels)
+    print(f"Saved to '{PACKED_FILE}' (bit-packed)" if packed else f"Saved to '{OUTPUT_FILE}'")
 
 
 def _cli(argv=None):

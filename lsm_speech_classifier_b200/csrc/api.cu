@@ -6,6 +6,7 @@
 
 #include <complex>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -123,6 +124,13 @@ static int upload(lsm_ctx *ctx, T **dst, const T *src, size_t n)
     if (src) LSM_CUDA(ctx, cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
     return LSM_OK;
 }
+
+// Pageable host buffers for one kernel stage: pieces of the batch flow through a ring of four pinned slots (filled and emptied by
+// the ctx's host copy threads) and double-buffered device staging on the two launch lanes; defined with the copy pool below.
+typedef std::function<int(const void *d_in, void *d_out, int n, cudaStream_t st, long long off)> lsm_piece_fn;
+static int host_ring_staged(lsm_ctx *ctx, int B, int piece, size_t in_per, size_t out_per, const void *h_in, void *h_out,
+                            int lanes, const lsm_piece_fn &launch);
+static bool is_pageable(const void *p);
 
 // ------------------------------------------------------------------------------------ stage 1
 extern "C" int lsm_frontend_create(lsm_ctx *ctx, const lsm_frontend_params *p, const void *h_table,
@@ -316,6 +324,11 @@ extern "C" int lsm_frontend_encode_host(lsm_ctx *ctx, lsm_frontend *fe, const fl
     const size_t spk_bytes = (size_t)B * fe->p.channels * fe->p.redundancy * fe->p.n_bins * fe->p.n_thresholds;
     void *d_pcm, *d_spk;
     int rc;
+    if (B >= 512 && is_pageable(h_pcm) && is_pageable(h_spikes) && !getenv("LSM_NO_PAGEABLE_RING"))
+        return host_ring_staged(ctx, B, 768, pcm_bytes / B, spk_bytes / B, h_pcm, h_spikes, 2,
+                                [&](const void *d_in, void *d_out, int n, cudaStream_t st, long long) {
+                                    return frontend_launch(ctx, fe, (const float *)d_in, n, (uint8_t *)d_out, nullptr, st);
+                                });
     if ((rc = lsm_stage_device(ctx, 0, pcm_bytes, &d_pcm)) != LSM_OK) return rc;
     if ((rc = lsm_stage_device(ctx, 1, spk_bytes, &d_spk)) != LSM_OK) return rc;
     LSM_CUDA(ctx, cudaMemcpyAsync(d_pcm, h_pcm, pcm_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -717,6 +730,16 @@ extern "C" int lsm_reservoir_run_host(lsm_ctx *ctx, lsm_reservoir *res, const ui
     const size_t ras_bytes = (size_t)B * p.num_steps * p.num_neurons;
     void *d_spk = nullptr, *d_feat = nullptr, *d_ras = nullptr;
     int rc;
+    if (B >= 512 && h_features && !h_raster_or_null && res->mode == LSM_RESERVOIR_EVENT && is_pageable(h_spikes) && is_pageable(h_features) &&
+        !getenv("LSM_NO_PAGEABLE_RING")) {
+        // reservoirs whose statistics live in a global slab (one slab per ctx) keep to one lane
+        const int lanes = p.num_neurons > 8192 ? 1 : 2;
+        return host_ring_staged(ctx, B, 1024, spk_bytes / B, feat_bytes / B, h_spikes, h_features, lanes,
+                                [&](const void *d_in, void *d_out, int n, cudaStream_t st, long long off) {
+                                    return lsm_launch_reservoir(ctx, res, (const uint8_t *)d_in, n, feature_mask, nan_to_num, (double *)d_out,
+                                                                nullptr, st, nullptr, off);
+                                });
+    }
     if ((rc = lsm_stage_device(ctx, 1, spk_bytes, &d_spk)) != LSM_OK) return rc;
     if (h_features && (rc = lsm_stage_device(ctx, 2, feat_bytes, &d_feat)) != LSM_OK) return rc;
     if (h_raster_or_null && (rc = lsm_stage_device(ctx, 3, ras_bytes, &d_ras)) != LSM_OK) return rc;
@@ -814,6 +837,51 @@ static lsm_copy_pool *copy_pool(lsm_ctx *ctx)
 
 // ------------------------------------------------------------------------------------ whole path
 static cudaStream_t lane_stream(lsm_ctx *ctx, int lane) { return lane == 0 ? ctx->own_stream : ctx->copy_stream[0]; }
+
+static bool is_pageable(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+static int host_ring_staged(lsm_ctx *ctx, int B, int piece, size_t in_per, size_t out_per, const void *h_in, void *h_out,
+                            int lanes, const lsm_piece_fn &launch)
+{
+    lsm_copy_pool *pool = copy_pool(ctx);
+    if (!pool) LSM_FAIL(ctx, LSM_ERR_NOMEM, "out of host memory");
+    if (piece > B) piece = B;
+    const size_t in_bytes = ((size_t)piece * in_per + 255) & ~(size_t)255, out_bytes = ((size_t)piece * out_per + 255) & ~(size_t)255;
+    const size_t slot_bytes = in_bytes + out_bytes;
+    void *ringp, *devp;
+    int rc;
+    if ((rc = lsm_stage_pinned(ctx, 1, 4 * slot_bytes, &ringp)) != LSM_OK) return rc;
+    if ((rc = lsm_stage_device(ctx, 0, 2 * slot_bytes, &devp)) != LSM_OK) return rc;
+    const int n_pieces = (B + piece - 1) / piece;
+    auto pin_in = [&](int k) { return (char *)ringp + (size_t)(k & 3) * slot_bytes; };
+    auto pin_out = [&](int k) { return pin_in(k) + in_bytes; };
+    auto dev_in = [&](int k) { return (char *)devp + (size_t)(k % lanes) * slot_bytes; };
+    auto dev_out = [&](int k) { return dev_in(k) + in_bytes; };
+    auto count = [&](int k) { return k + 1 < n_pieces ? piece : B - k * piece; };
+    for (int k = 0; k < n_pieces + 2; ++k) {
+        if (k >= 2) {
+            const int j = k - 2;
+            LSM_CUDA(ctx, cudaEventSynchronize(ctx->ev_stage_free[j & 3]));
+            pool->copy((char *)h_out + (size_t)j * piece * out_per, pin_out(j), (size_t)count(j) * out_per);
+        }
+        if (k < n_pieces) {
+            const int n = count(k);
+            pool->copy(pin_in(k), (const char *)h_in + (size_t)k * piece * in_per, (size_t)n * in_per);
+            cudaStream_t ls = lane_stream(ctx, k % lanes);
+            LSM_CUDA(ctx, cudaMemcpyAsync(dev_in(k), pin_in(k), (size_t)n * in_per, cudaMemcpyHostToDevice, ls));
+            if ((rc = launch(dev_in(k), dev_out(k), n, ls, (long long)k * piece)) != LSM_OK) return rc;
+            LSM_CUDA(ctx, cudaMemcpyAsync(pin_out(k), dev_out(k), (size_t)n * out_per, cudaMemcpyDeviceToHost, ls));
+            LSM_CUDA(ctx, cudaEventRecord(ctx->ev_stage_free[k & 3], ls));
+        }
+    }
+    return LSM_OK;
+}
+
 
 // The warp-specialised kernel's units give up (and say so) if a group never completes; surfaced at the synchronous calls.
 static int check_pipe_error(lsm_ctx *ctx, lsm_frontend *fe)

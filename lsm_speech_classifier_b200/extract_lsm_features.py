@@ -13,7 +13,7 @@ from pathlib import Path
 
 import numpy as np
 
-from . import npzio
+from . import npzio, timing
 from .snn import SNN, SimulationParams
 
 NUM_NEURONS = 1000
@@ -144,27 +144,33 @@ def main(feature_set: str, multiplier: float, leak_variance_divisor: float = Non
     init_from_env()             # under torchrun (also when this stage is run on its own): one rank per GPU, samples sharded
     if _dist() is not None:
         _dist().barrier()       # the spike file is written by rank 0 of the previous stage
-    X_spikes, y_labels = load_spike_dataset()
+    with timing.stage("stage 2 read: spike file (inflate, one core)"):
+        X_spikes, y_labels = load_spike_dataset()
     if X_spikes is None:
         return
-    X_train, X_test, y_train, y_test = train_test_split(
-        X_spikes, y_labels, test_size=0.2, random_state=42, stratify=y_labels)
-    lsm = build_lsm(X_train, multiplier, leak_variance_divisor, num_neurons, verbose=is_main())
-    if is_main():
-        run_network_diagnostics(lsm, X_train)
+    with timing.stage("stage 2 split (train_test_split copies)"):
+        X_train, X_test, y_train, y_test = train_test_split(
+            X_spikes, y_labels, test_size=0.2, random_state=42, stratify=y_labels)
+    with timing.stage("stage 2 setup: w_critico, reservoir build + upload, diagnostics"):
+        lsm = build_lsm(X_train, multiplier, leak_variance_divisor, num_neurons, verbose=is_main())
+        if is_main():
+            run_network_diagnostics(lsm, X_train)
     feature_keys = FEATURE_SETS[feature_set]
     if is_main():
         print(f"Extracting feature set: '{feature_set}'")
-    X_train_feat = extract_all_features(lsm, X_train, feature_keys, "Training")
-    X_test_feat = extract_all_features(lsm, X_test, feature_keys, "Testing")
+    with timing.stage("stage 2 compute: spike trains -> features (GPU, host buffers)", len(X_train) + len(X_test)):
+        X_train_feat = extract_all_features(lsm, X_train, feature_keys, "Training")
+        X_test_feat = extract_all_features(lsm, X_test, feature_keys, "Testing")
     if not is_main():
         return
-    scaler = StandardScaler()
-    X_train_scaled = scaler.fit_transform(X_train_feat)
-    X_test_scaled = scaler.transform(X_test_feat)
-    npzio.savez_compressed(FEATURE_FILE, X_train_features=X_train_scaled, y_train=y_train,
-                        X_test_features=X_test_scaled, y_test=y_test, feature_set=feature_set,
-                        leak_variance_divisor=leak_variance_divisor)
+    with timing.stage("stage 2 scaler (sklearn, host)"):
+        scaler = StandardScaler()
+        X_train_scaled = scaler.fit_transform(X_train_feat)
+        X_test_scaled = scaler.transform(X_test_feat)
+    with timing.stage("stage 2 write: feature file (parallel deflate)"):
+        npzio.savez_compressed(FEATURE_FILE, X_train_features=X_train_scaled, y_train=y_train,
+                               X_test_features=X_test_scaled, y_test=y_test, feature_set=feature_set,
+                               leak_variance_divisor=leak_variance_divisor)
     print(f"Extraction complete. Features saved to '{FEATURE_FILE}'")
 
 
@@ -184,21 +190,27 @@ def main_fused(pcm, y_labels, n_filters: int, filterbank: str, feature_set: str,
     y_labels = np.asarray(y_labels, dtype=np.int32)
     idx = np.arange(len(pcm))
     tr, te, y_train, y_test = train_test_split(idx, y_labels, test_size=0.2, random_state=42, stratify=y_labels)
-    fe = Frontend(n_filters, filterbank)
-    head = fe.encode(pcm[tr[:500]])
-    lsm = build_lsm(head, multiplier, leak_variance_divisor, num_neurons)
-    run_network_diagnostics(lsm, head)
+    with timing.stage("fused setup: w_critico head, reservoir build + upload, diagnostics"):
+        fe = Frontend(n_filters, filterbank)
+        head = fe.encode(pcm[tr[:500]])
+        lsm = build_lsm(head, multiplier, leak_variance_divisor, num_neurons)
+        run_network_diagnostics(lsm, head)
     feature_keys = FEATURE_SETS[feature_set]
     print(f"Extracting feature set: '{feature_set}' (fused audio -> features)")
     path = AudioToFeatures(fe, lsm)
-    X_train_feat = path.run_host(np.ascontiguousarray(pcm[tr]), feature_keys)
-    X_test_feat = path.run_host(np.ascontiguousarray(pcm[te]), feature_keys)
-    scaler = StandardScaler()
-    X_train_scaled = scaler.fit_transform(X_train_feat)
-    X_test_scaled = scaler.transform(X_test_feat)
-    npzio.savez_compressed(FEATURE_FILE, X_train_features=X_train_scaled, y_train=y_train,
-                        X_test_features=X_test_scaled, y_test=y_test, feature_set=feature_set,
-                        leak_variance_divisor=leak_variance_divisor)
+    with timing.stage("fused gather of the split rows (numpy fancy indexing)"):
+        pcm_tr, pcm_te = np.ascontiguousarray(pcm[tr]), np.ascontiguousarray(pcm[te])
+    with timing.stage("fused compute: audio -> features (GPU, host buffers)", len(pcm)):
+        X_train_feat = path.run_host(pcm_tr, feature_keys)
+        X_test_feat = path.run_host(pcm_te, feature_keys)
+    with timing.stage("scaler (sklearn, host)"):
+        scaler = StandardScaler()
+        X_train_scaled = scaler.fit_transform(X_train_feat)
+        X_test_scaled = scaler.transform(X_test_feat)
+    with timing.stage("write: feature file (parallel deflate)"):
+        npzio.savez_compressed(FEATURE_FILE, X_train_features=X_train_scaled, y_train=y_train,
+                               X_test_features=X_test_scaled, y_test=y_test, feature_set=feature_set,
+                               leak_variance_divisor=leak_variance_divisor)
     print(f"Extraction complete. Features saved to '{FEATURE_FILE}'")
 
 

@@ -7,16 +7,18 @@ import argparse
 
 
 def run_pipeline(n_filters: int, filterbank: str, feature_set: str, multiplier: float, synthetic=None,
-                 train: bool = True, readout: str = "sklearn", fused: bool = False, packed: bool = False):
-    from . import create_dataset as cd, extract_lsm_features as ex
+                 train: bool = True, readout: str = "sklearn", fused: bool = False, packed: bool = False, show_timing: bool = False):
+    from . import create_dataset as cd, extract_lsm_features as ex, timing
     from .distributed import init_from_env, is_main
     init_from_env()
+    timing.enabled = bool(show_timing)
     if is_main():
         print("--- Running Pipeline ---")
     if fused:
         # (extension) no spike file between the stages: audio -> features in one pass
         print("\n--- Steps 1+2: Audio -> LSM Features (fused) ---")
-        pcm, labels = cd.collect_pcm(synthetic)
+        with timing.stage("audio: synthesis / WAV decode"):
+            pcm, labels = cd.collect_pcm(synthetic)
         if pcm is not None:
             ex.main_fused(pcm, labels, n_filters, filterbank, feature_set, multiplier)
     else:
@@ -34,6 +36,8 @@ def run_pipeline(n_filters: int, filterbank: str, feature_set: str, multiplier: 
         train_and_evaluate_classifier(readout=readout)
     if is_main():
         print("\n--- Pipeline Finished ---")
+        if show_timing:
+            print("\nWall-clock breakdown:\n" + timing.report())
 
 
 def _barrier():
@@ -59,10 +63,11 @@ def _cli(argv=None):
     parser.add_argument("--fused", action="store_true",
                         help="(extension) audio -> features in one pass, no spike file between the stages (same feature file)")
     parser.add_argument("--packed", action="store_true", help="(extension) bit-packed spike file between the stages")
+    parser.add_argument("--timing", action="store_true", help="(extension) print a wall-clock breakdown of the stages")
     args = parser.parse_args(argv)
     run_pipeline(n_filters=args.n_filters, filterbank=args.filterbank, feature_set=args.feature_set,
                  multiplier=args.multiplier, synthetic=args.synthetic, train=not args.no_train, readout=args.readout,
-                 fused=args.fused, packed=args.packed)
+                 fused=args.fused, packed=args.packed, show_timing=args.timing)
 
 
 if __name__ == "__main__":
