@@ -544,6 +544,19 @@ def main():
     if world > 1:
         dist.all_reduce(h2d_s, op=dist.ReduceOp.MAX)
     h2d_ceiling_gbs = world * B * L * 4 / float(h2d_s.item()) / 1e9
+    # ... and with the feature rows of the previous step going the other way at the same time, as every e2e step has it
+    side = torch.cuda.Stream()
+    fence()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        d_stage.copy_(h_pcm, non_blocking=True)
+        with torch.cuda.stream(side):
+            h_feats[1].copy_(d_feats[1], non_blocking=True)
+    torch.cuda.synchronize()
+    both_s = torch.tensor([(time.perf_counter() - t0) / 5], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(both_s, op=dist.ReduceOp.MAX)
+    both_ceiling_gbs = world * (B * L * 4 + B * F * 8) / float(both_s.item()) / 1e9
     del d_stage
     # the same step from PAGEABLE numpy arrays through the synchronous public call (what create_dataset / extract_all_features
     # style callers hand over): the copies are staged by the driver
@@ -612,8 +625,11 @@ def main():
                         "of the two on this box - both are in e2e_feeds"},
         "e2e_feeds": {**feeds, "h2d_copy_engine_ceiling_gbs": h2d_ceiling_gbs,
                       "e2e_h2d_gbs": e2e_val * L * 4 / 1e9,
+                      "h2d_plus_d2h_ceiling_gbs": both_ceiling_gbs, "e2e_h2d_plus_d2h_gbs": e2e_val * (L * 4 + F * 8) / 1e9,
+                      "e2e_fraction_of_copy_ceiling": e2e_val * (L * 4 + F * 8) / 1e9 / both_ceiling_gbs,
                       "note": "utterances/s per feed and sample format; ceiling = all ranks copying their 153.6 MB batch from pinned host "
-                              "memory at once with cudaMemcpyAsync (aggregate GB/s, max over ranks)"},
+                              "memory at once with cudaMemcpyAsync (aggregate GB/s, max over ranks); h2d_plus_d2h = the same with every rank's feature "
+                              "matrix going device -> pinned host concurrently (what an e2e step moves), and the e2e figure as a fraction of it"},
         "e2e_pcm16": {"value": e2e_i16_val, "unit": "utterances/s", "h2d_bytes_per_step": B * L * 2, "d2h_bytes_per_step": B * F * 8,
                       "note": "same steps with int16 PCM host buffers (lsm_pipeline_run_host_async_i16): the WAV-file sample format, "
                               "converted exactly in the kernel; e2e above keeps the float32 contract of load_audio_file"},

@@ -154,6 +154,11 @@ def create_dataset(n_filters: int, filterbank: str, synthetic: tuple | None = No
         pcm, labels = collect_pcm(synthetic)
     if pcm is None:
         return
+    if timing.enabled:
+        # attribute the one-time costs (CUDA context, library load, filter tables, pinned staging ring, host copy threads) to their
+        # own line: a warm-up call on silence sized like one piece of the real run
+        with timing.stage("GPU init (one-time): CUDA context, tables, pinned staging"):
+            _frontend(n_filters, filterbank).encode(np.zeros((min(len(pcm), 768), pcm.shape[1]), np.float32))
     with timing.stage("stage 1 compute: audio -> spike trains (GPU, host buffers)", len(pcm)):
         X_spikes = encode_batch(pcm, n_filters, filterbank)
     y_labels = np.array(labels, dtype=np.int32)
