@@ -207,6 +207,102 @@ __global__ void __launch_bounds__(MAXT, MINB) gammatone_encode_kernel(const GtAr
     }
 }
 
+
+// ---- Warp-specialised form of the fused kernel (default shape: 128 channels, 8 neurons per thread, speculative mode).
+//      In gammatone_encode_kernel the same 128 threads take turns between the filter (fp64-pipe bound) and the reservoir
+//      (issue / latency bound), so whenever some of an SM's CTAs are in their reservoir phase the fp64 pipe runs short of
+//      filter warps.  Here a CTA carries both kinds of work side by side:
+//        threads   0..127  FILTER group (named barrier 1): lane = channel, gt_filter_fast on utterance after utterance without
+//                          ever leaving the filter; window energies go to one of the CTA's two scratch planes
+//        threads 128..255  UNIT group (named barrier 2): speculative encoder epilogue with the derived bound on the plane the
+//                          filter group just finished, spike bits to shared memory, reservoir (8 neurons per thread), readout
+//      The groups hand planes over through named barriers (full[slot]: filter arrives, unit syncs; empty[slot]: the other way
+//      round), two planes deep.  Utterances the bound cannot settle go to a work list; the exact pass (gammatone_encode_kernel,
+//      mode 0, over that list) follows on the same stream.
+constexpr int kWsFilter = 128, kWsUnit = 128, kWsThreads = kWsFilter + kWsUnit;
+constexpr int kBarFilter = 1, kBarUnit = 2, kBarFull = 3 /* +slot */, kBarEmpty = 5 /* +slot */;
+
+__device__ __forceinline__ void bar_arrive(int id, int count)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_sync(int id, int count)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+template <bool LEAN>
+__global__ void __launch_bounds__(kWsThreads, 3) gammatone_ws_kernel(const GtArgs a, int *next_utt, const int unit_smem_off)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_x = reinterpret_cast<double *>(smem_raw);            // filter group: [2][kChunkBlocks*hop] PCM as fp64
+    unsigned char *usmem = smem_raw + unit_smem_off;               // unit group: the reservoir's shared-memory plan
+    __shared__ double s_red[6 * 8];
+    __shared__ double s_out[6];
+    __shared__ float s_xm[4];
+    __shared__ int s_utt_f;
+    __shared__ int s_slot_utt[2];
+    __shared__ float s_slot_xm[2];
+    __shared__ int s_cnt3[5];
+
+    double *planes = a.scratch + (size_t)blockIdx.x * 2 * a.ncols * a.C;
+    if (threadIdx.x < kWsFilter) {
+        const int tid = threadIdx.x;
+        int i = 0;
+        for (;; ++i) {
+            const int slot = i & 1;
+            if (tid == 0) {
+                const int k = atomicAdd(next_utt, 1);
+                s_utt_f = k < a.B ? k : -1;
+            }
+            bar_sync(kBarFilter, kWsFilter);
+            const int utt = s_utt_f;
+            if (i >= 2) bar_sync(kBarEmpty + slot, kWsThreads);      // the unit group has released this slot's plane
+            if (utt < 0) {
+                if (tid == 0) s_slot_utt[slot] = -1;
+                bar_arrive(kBarFull + slot, kWsThreads);
+                break;
+            }
+            const PcmRow pcm = {a.pcm ? a.pcm + (size_t)utt * a.L : nullptr, a.pcm16 ? a.pcm16 + (size_t)utt * a.L : nullptr};
+            float xm = 0.0f;
+            gt_filter_fast<kBarFilter>(a, pcm, s_x, planes + (size_t)slot * a.ncols * a.C, xm, tid, kWsFilter);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) xm = fmaxf(xm, __shfl_xor_sync(0xffffffffu, xm, o));
+            if ((tid & 31) == 0) s_xm[tid >> 5] = xm;
+            bar_sync(kBarFilter, kWsFilter);
+            if (tid == 0) {
+                s_slot_xm[slot] = fmaxf(fmaxf(s_xm[0], s_xm[1]), fmaxf(s_xm[2], s_xm[3]));
+                s_slot_utt[slot] = utt;
+            }
+            __threadfence_block();
+            bar_arrive(kBarFull + slot, kWsThreads);                 // plane, peak level and utterance index are the unit group's
+        }
+        // the unit group's release of the slot used last (i - 1) has no taker yet: take it, so no barrier is left half-way
+        if (i >= 1) bar_sync(kBarEmpty + ((i - 1) & 1), kWsThreads);
+    } else {
+        const int tid = threadIdx.x - kWsFilter;
+        for (int i = 0;; ++i) {
+            const int slot = i & 1;
+            bar_sync(kBarFull + slot, kWsThreads);
+            const int utt = s_slot_utt[slot];
+            if (utt < 0) break;
+            const float xm = s_slot_xm[slot];
+            const bool near = spec_epilogue<8, kBarUnit>(a, utt, planes + (size_t)slot * a.ncols * a.C, tid, kWsUnit, xm, s_red, s_out, usmem);
+            bar_arrive(kBarEmpty + slot, kWsThreads);                // the plane may be overwritten
+            // too close to call on the speculative plane: finish it like the others, and list it for the exact pass
+            unsigned any;
+            asm volatile("{ .reg .pred p, q; setp.ne.u32 q, %1, 0; bar.red.or.pred p, %2, %3, q; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(any) : "r"((unsigned)near), "r"(kBarUnit), "r"(kWsUnit) : "memory");
+            if (any && tid == 0) {
+                a.rerun_list[1 + atomicAdd(a.rerun_list, 1)] = utt;
+                atomicAdd(a.reruns, 1);
+            }
+            reservoir_simulate<8, LEAN, false, kBarUnit>(a.res, utt, usmem, s_cnt3, tid, kWsUnit);
+            bar_sync(kBarUnit, kWsUnit);                             // shared memory is reused by the next utterance
+        }
+    }
+}
+
 // ---- audit: both arrangements of the filter on the same utterance (diagnostic; lsm_frontend_audit).  Per utterance:
 //      out[0] largest |dB_speculative - dB_exact| over all cells         out[1] largest such distance / its cell's bound
 //      out[2] |max_speculative - max_exact| / its bound                  out[3] |min_speculative - min_exact| / its bound
@@ -489,6 +585,52 @@ int lsm_launch_fused_args(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, Gt
     return launch_fused_t<128, 4, 16>(ctx, fe, res, a, threads, smem, st, launch, wave, max_grid, forced_slot);
 }
 
+
+// Can the pair run as the warp-specialised kernel?  The reference's default shape in speculative mode.
+bool lsm_ws_eligible(const lsm_frontend *fe, const lsm_reservoir *res)
+{
+    if (getenv("LSM_NO_WS")) return false;
+    return fe->p.channels == kWsFilter && lsm_fused_npt(fe, res) == 8 && fe->mode == LSM_FILTER_SPECULATIVE;
+}
+
+// The warp-specialised kernel on utterances [0, B) + the exact pass over the utterances it could not settle.
+int lsm_launch_fused_ws(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, GtArgs &a, cudaStream_t st, int *wave, bool launch)
+{
+    int rc;
+    const size_t smem_f = (sizeof(double) * 2 * kChunkBlocks * fe->p.hop + 127) & ~(size_t)127;
+    const size_t smem = smem_f + lsm_res_smem_bytes(a.res.T, a.res.CW, kWsUnit * 8, a.res.N);
+    int per_sm = 0;
+    if (res->lean) {
+        LSM_CUDA(ctx, cudaFuncSetAttribute(gammatone_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gammatone_ws_kernel<true>, kWsThreads, smem));
+    } else {
+        LSM_CUDA(ctx, cudaFuncSetAttribute(gammatone_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gammatone_ws_kernel<false>, kWsThreads, smem));
+    }
+    if (per_sm < 1) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "warp-specialised kernel does not fit on an SM (%zu B shared memory)", smem);
+    int grid = per_sm * ctx->sm_count;
+    if (grid > fe->grid / 2) grid = fe->grid / 2;          // two scratch planes per CTA out of a slot sized for fe->grid planes
+    if (wave) *wave = 2 * grid;                            // utterances in flight: one per group
+    if (!launch) return LSM_OK;
+    if (grid > a.B) grid = a.B;
+    if ((rc = lsm_frontend_ensure_rerun(ctx, fe, a.B)) != LSM_OK) return rc;
+    int *counter;
+    const int slot = (int)(fe->slot_next++ & 1u);
+    if ((rc = next_counter(ctx, fe, st, &counter, &a, slot)) != LSM_OK) return rc;
+    a.rerun_list = fe->d_rerun + (size_t)slot * (fe->rerun_cap + 1);
+    LSM_CUDA(ctx, cudaMemsetAsync(a.rerun_list, 0, sizeof(int), st));
+    if (res->lean) gammatone_ws_kernel<true><<<grid, kWsThreads, smem, st>>>(a, counter, (int)smem_f);
+    else gammatone_ws_kernel<false><<<grid, kWsThreads, smem, st>>>(a, counter, (int)smem_f);
+    ctx->launches += 1;
+    LSM_CUDA(ctx, cudaGetLastError());
+    if ((rc = lsm_frontend_order_after(ctx, fe, st, slot)) != LSM_OK) return rc;
+    // exact pass over the device work list (typically empty; a few CTAs suffice), same scratch slot, same stream
+    GtArgs x = a;
+    x.mode = 0; x.rerun_list = nullptr;
+    x.utt_list = a.rerun_list + 1; x.utt_count = a.rerun_list;
+    return lsm_launch_fused_args(ctx, fe, res, x, st, true, nullptr, 8, slot);
+}
+
 // row0: index of utterance 0 of this launch within the API call (offsets the fused all-gather's destination rows)
 int lsm_launch_fused(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B,
                      uint8_t *d_spikes_or_null, uint32_t feature_mask, int nan_to_num, double *d_features, cudaStream_t st,
@@ -499,6 +641,7 @@ int lsm_launch_fused(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const f
     lsm_gammatone_fill_args(fe, d_pcm, B, d_spikes_or_null, nullptr, &a);
     lsm_reservoir_fill_args(res, nullptr, B, feature_mask, nan_to_num, d_features, nullptr, &a.res);
     a.res.gather_row0 += row0;
+    if (a.mode == 1 && lsm_ws_eligible(fe, res)) return lsm_launch_fused_ws(ctx, fe, res, a, st, nullptr, true);
     return lsm_launch_fused_args(ctx, fe, res, a, st, true, nullptr, 0, -2);
 }
 

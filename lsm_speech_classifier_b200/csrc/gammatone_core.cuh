@@ -84,10 +84,18 @@ struct PcmRow {
 
 // PCM -> fp64 in shared memory; buffer element i of chunk k holds sample k*chunk + i + kSkew.  xm collects max |sample|
 // (float32 holds every sample exactly, so the maximum is exact; NaN samples are skipped here and caught by the bound test).
-__device__ __forceinline__ void stage_pcm(double *dst, const PcmRow pcm, int base, int chunk, int L, float &xm)
+// Barrier of a thread group: the whole CTA (BAR = 0, __syncthreads) or the nthr threads that own named barrier BAR.
+template <int BAR>
+__device__ __forceinline__ void group_sync(int nthr)
+{
+    if (BAR == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(BAR), "r"(nthr) : "memory");
+}
+
+__device__ __forceinline__ void stage_pcm(double *dst, const PcmRow pcm, int base, int chunk, int L, float &xm, int tid, int nthr)
 {
     // streaming loads (evict-first): every PCM sample is read once and must not push the CTAs' scratch planes out of L2
-    for (int i = threadIdx.x; i < chunk; i += blockDim.x) {
+    for (int i = tid; i < chunk; i += nthr) {
         const double v = (base + i < L) ? pcm.at(base + i) : 0.0;
         dst[i] = v;
         xm = fmaxf(xm, fabsf((float)v));
@@ -136,7 +144,7 @@ __device__ __forceinline__ void gt_filter_exact(const GtArgs &a, const PcmRow pc
     double y1 = 0, y2 = 0, y3 = 0, y4 = 0;
     double acc_new = 0, acc_mid = 0, acc_old = 0;
 
-    stage_pcm(s_x, pcm, kSkew, chunk, a.L, xm_unused);
+    stage_pcm(s_x, pcm, kSkew, chunk, a.L, xm_unused, threadIdx.x, blockDim.x);
     if (live) {
         // prologue: iterations s = -3, -2, -1 fill the skewed pipeline (outputs belong to no sample)
 #pragma unroll
@@ -155,7 +163,7 @@ __device__ __forceinline__ void gt_filter_exact(const GtArgs &a, const PcmRow pc
     for (int ck = 0; ck < n_chunks; ++ck) {
         const double *xs = s_x + (ck & 1) * chunk;
         // prefetch the next chunk into the other buffer while this one is filtered
-        if (ck + 1 < n_chunks) stage_pcm(s_x + ((ck + 1) & 1) * chunk, pcm, (ck + 1) * chunk + kSkew, chunk, a.L, xm_unused);
+        if (ck + 1 < n_chunks) stage_pcm(s_x + ((ck + 1) & 1) * chunk, pcm, (ck + 1) * chunk + kSkew, chunk, a.L, xm_unused, threadIdx.x, blockDim.x);
         if (live) {
             for (int bl = 0; bl < kChunkBlocks; ++bl) {
                 const int m = ck * kChunkBlocks + bl;       // hop-block index = index of the window that starts here
@@ -211,9 +219,11 @@ __device__ __forceinline__ void gt_filter_exact(const GtArgs &a, const PcmRow pc
 //      error_bound.cu; spec_epilogue flags every utterance in which that bound could change one of the
 //      encoder's comparisons, and those utterances are filtered again by gt_filter_exact: the spike trains that leave the
 //      kernel are the exact path's, byte for byte.
-__device__ __forceinline__ void gt_filter_fast(const GtArgs &a, const PcmRow pcm, double *s_x, double *plane, float &xm)
+template <int BAR = 0>
+__device__ __forceinline__ void gt_filter_fast(const GtArgs &a, const PcmRow pcm, double *s_x, double *plane, float &xm,
+                                               const int tid = threadIdx.x, const int nthr = blockDim.x)
 {
-    const int ch = threadIdx.x;
+    const int ch = tid;
     const int C = a.C;
     const bool live = ch < C;
     const int hop = a.hop, nwin = a.nwin, ncols = a.ncols;
@@ -247,7 +257,7 @@ __device__ __forceinline__ void gt_filter_fast(const GtArgs &a, const PcmRow pcm
         acc = fma(n4, n4, acc);                                                    \
     }
 
-    stage_pcm(s_x, pcm, kSkew, chunk, a.L, xm);
+    stage_pcm(s_x, pcm, kSkew, chunk, a.L, xm, tid, nthr);
     if (live) {
 #pragma unroll
         for (int s = 0; s < kSkew; ++s) {
@@ -257,11 +267,11 @@ __device__ __forceinline__ void gt_filter_fast(const GtArgs &a, const PcmRow pcm
         }
         acc = 0.0;   // (already zero: stage 4 has seen no sample yet)
     }
-    __syncthreads();
+    group_sync<BAR>(nthr);
 
     for (int ck = 0; ck < n_chunks; ++ck) {
         const double *xs = s_x + (ck & 1) * chunk;
-        if (ck + 1 < n_chunks) stage_pcm(s_x + ((ck + 1) & 1) * chunk, pcm, (ck + 1) * chunk + kSkew, chunk, a.L, xm);
+        if (ck + 1 < n_chunks) stage_pcm(s_x + ((ck + 1) & 1) * chunk, pcm, (ck + 1) * chunk + kSkew, chunk, a.L, xm, tid, nthr);
         if (live) {
             for (int bl = 0; bl < kChunkBlocks; ++bl) {
                 const int m = ck * kChunkBlocks + bl;
@@ -280,7 +290,7 @@ __device__ __forceinline__ void gt_filter_fast(const GtArgs &a, const PcmRow pcm
                 full1 = acc;
             }
         }
-        __syncthreads();
+        group_sync<BAR>(nthr);
     }
 #undef LSM_FAST_SAMPLE
 }
@@ -288,13 +298,6 @@ __device__ __forceinline__ void gt_filter_fast(const GtArgs &a, const PcmRow pcm
 // ------------------------------------------------------------------------------------------------------------------
 // Block-wide reductions for a group of NTHR threads that owns named barrier BAR (0 = the whole CTA, __syncthreads).
 // s_red: double[6][8] scratch, s_out: double[6].  Every thread of the group gets all results.
-template <int BAR>
-__device__ __forceinline__ void group_sync(int nthr)
-{
-    if (BAR == 0) __syncthreads();
-    else asm volatile("bar.sync %0, %1;" ::"r"(BAR), "r"(nthr) : "memory");
-}
-
 // vmax[k] -> maximum over the group, vmin[k] -> minimum over the group, k < NV
 template <int NV, int BAR>
 __device__ __forceinline__ void group_maxmin(double *vmax, double *vmin, int tid, int nthr, double *s_red, double *s_out)

@@ -146,6 +146,8 @@ int lsm_launch_fused(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const f
 int lsm_launch_fused_args(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, GtArgs &a, cudaStream_t st, bool launch, int *wave,
                           int max_grid, int forced_slot);
 int lsm_fused_wave(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res);
+bool lsm_ws_eligible(const lsm_frontend *fe, const lsm_reservoir *res);
+int lsm_launch_fused_ws(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, GtArgs &a, cudaStream_t st, int *wave, bool launch);
 struct ResArgs;
 void lsm_reservoir_fill_args(const lsm_reservoir *res, const uint8_t *d_spikes, int B, uint32_t feature_mask,
                              int nan_to_num, double *d_features, uint8_t *d_raster, ResArgs *out);
