@@ -212,13 +212,14 @@ __global__ void __launch_bounds__(MAXT, MINB) gammatone_encode_kernel(const GtAr
 //      In gammatone_encode_kernel the same 128 threads take turns between the filter (fp64-pipe bound) and the reservoir
 //      (issue / latency bound), so whenever some of an SM's CTAs are in their reservoir phase the fp64 pipe runs short of
 //      filter warps.  Here a CTA carries both kinds of work side by side:
-//        threads   0..127  FILTER group (named barrier 1): lane = channel, gt_filter_fast on utterance after utterance without
-//                          ever leaving the filter; window energies go to one of the CTA's two scratch planes
-//        threads 128..255  UNIT group (named barrier 2): speculative encoder epilogue with the derived bound on the plane the
-//                          filter group just finished, spike bits to shared memory, reservoir (8 neurons per thread), readout
-//      The groups hand planes over through named barriers (full[slot]: filter arrives, unit syncs; empty[slot]: the other way
-//      round), two planes deep.  Utterances the bound cannot settle go to a work list; the exact pass (gammatone_encode_kernel,
-//      mode 0, over that list) follows on the same stream.
+//        threads   0..127  FILTER group (named barrier 1): lane = channel; gt_filter_fast and the speculative encoder epilogue
+//                          (both fp64 work) on utterance after utterance; the spike train goes, as ballot words, into one of two
+//                          bit-plane buffers in shared memory
+//        threads 128..255  UNIT group (named barrier 2): reservoir (8 neurons per thread) and readout on the bit plane the
+//                          filter group finished last
+//      The groups hand bit planes over through named barriers (full[slot]: filter arrives, unit syncs; empty[slot]: the other
+//      way round), two deep.  Utterances the derived bound cannot settle go to a work list; the exact pass
+//      (gammatone_encode_kernel, mode 0, over that list) follows on the same stream and overwrites their rows.
 constexpr int kWsFilter = 128, kWsUnit = 128, kWsThreads = kWsFilter + kWsUnit;
 constexpr int kBarFilter = 1, kBarUnit = 2, kBarFull = 3 /* +slot */, kBarEmpty = 5 /* +slot */;
 
@@ -232,22 +233,21 @@ __device__ __forceinline__ void bar_sync(int id, int count)
 }
 
 template <bool LEAN>
-__global__ void __launch_bounds__(kWsThreads, 3) gammatone_ws_kernel(const GtArgs a, int *next_utt, const int unit_smem_off)
+__global__ void __launch_bounds__(kWsThreads, 3) gammatone_ws_kernel(const GtArgs a, int *next_utt, const int bits_off, const int bits_bytes,
+                                                                     const int unit_off)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_x = reinterpret_cast<double *>(smem_raw);            // filter group: [2][kChunkBlocks*hop] PCM as fp64
-    unsigned char *usmem = smem_raw + unit_smem_off;               // unit group: the reservoir's shared-memory plan
     __shared__ double s_red[6 * 8];
     __shared__ double s_out[6];
     __shared__ float s_xm[4];
     __shared__ int s_utt_f;
     __shared__ int s_slot_utt[2];
-    __shared__ float s_slot_xm[2];
     __shared__ int s_cnt3[5];
 
-    double *planes = a.scratch + (size_t)blockIdx.x * 2 * a.ncols * a.C;
     if (threadIdx.x < kWsFilter) {
         const int tid = threadIdx.x;
+        double *plane = a.scratch + (size_t)blockIdx.x * a.ncols * a.C;
         int i = 0;
         for (;; ++i) {
             const int slot = i & 1;
@@ -257,27 +257,40 @@ __global__ void __launch_bounds__(kWsThreads, 3) gammatone_ws_kernel(const GtArg
             }
             bar_sync(kBarFilter, kWsFilter);
             const int utt = s_utt_f;
-            if (i >= 2) bar_sync(kBarEmpty + slot, kWsThreads);      // the unit group has released this slot's plane
+            bar_sync(kBarFilter, kWsFilter);                         // everyone has read s_utt_f before it is written again
             if (utt < 0) {
+                if (i >= 2) bar_sync(kBarEmpty + slot, kWsThreads);
                 if (tid == 0) s_slot_utt[slot] = -1;
+                __threadfence_block();
                 bar_arrive(kBarFull + slot, kWsThreads);
                 break;
             }
             const PcmRow pcm = {a.pcm ? a.pcm + (size_t)utt * a.L : nullptr, a.pcm16 ? a.pcm16 + (size_t)utt * a.L : nullptr};
             float xm = 0.0f;
-            gt_filter_fast<kBarFilter>(a, pcm, s_x, planes + (size_t)slot * a.ncols * a.C, xm, tid, kWsFilter);
+            gt_filter_fast<kBarFilter>(a, pcm, s_x, plane, xm, tid, kWsFilter);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) xm = fmaxf(xm, __shfl_xor_sync(0xffffffffu, xm, o));
             if ((tid & 31) == 0) s_xm[tid >> 5] = xm;
             bar_sync(kBarFilter, kWsFilter);
+            xm = fmaxf(fmaxf(s_xm[0], s_xm[1]), fmaxf(s_xm[2], s_xm[3]));
+            if (i >= 2) bar_sync(kBarEmpty + slot, kWsThreads);      // the unit group is done with this slot's bit plane
+            const bool near = a.ws_debug == 2 ? false
+                : spec_epilogue<8, kBarFilter>(a, utt, plane, tid, kWsFilter, xm, s_red, s_out, smem_raw + bits_off + slot * bits_bytes);
+            // too close to call on the speculative plane: finish it like the others, and list it for the exact pass
+            unsigned any;
+            asm volatile("{ .reg .pred p, q; setp.ne.u32 q, %1, 0; bar.red.or.pred p, %2, %3, q; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(any) : "r"((unsigned)near), "r"(kBarFilter), "r"(kWsFilter) : "memory");
             if (tid == 0) {
-                s_slot_xm[slot] = fmaxf(fmaxf(s_xm[0], s_xm[1]), fmaxf(s_xm[2], s_xm[3]));
+                if (any) {
+                    a.rerun_list[1 + atomicAdd(a.rerun_list, 1)] = utt;
+                    atomicAdd(a.reruns, 1);
+                }
                 s_slot_utt[slot] = utt;
             }
             __threadfence_block();
-            bar_arrive(kBarFull + slot, kWsThreads);                 // plane, peak level and utterance index are the unit group's
+            bar_arrive(kBarFull + slot, kWsThreads);                 // bit plane and utterance index are the unit group's
         }
-        // the unit group's release of the slot used last (i - 1) has no taker yet: take it, so no barrier is left half-way
+        // the unit group's release after the last real item (i - 1) has no taker yet: take it, so no barrier is left half-way
         if (i >= 1) bar_sync(kBarEmpty + ((i - 1) & 1), kWsThreads);
     } else {
         const int tid = threadIdx.x - kWsFilter;
@@ -286,19 +299,11 @@ __global__ void __launch_bounds__(kWsThreads, 3) gammatone_ws_kernel(const GtArg
             bar_sync(kBarFull + slot, kWsThreads);
             const int utt = s_slot_utt[slot];
             if (utt < 0) break;
-            const float xm = s_slot_xm[slot];
-            const bool near = spec_epilogue<8, kBarUnit>(a, utt, planes + (size_t)slot * a.ncols * a.C, tid, kWsUnit, xm, s_red, s_out, usmem);
-            bar_arrive(kBarEmpty + slot, kWsThreads);                // the plane may be overwritten
-            // too close to call on the speculative plane: finish it like the others, and list it for the exact pass
-            unsigned any;
-            asm volatile("{ .reg .pred p, q; setp.ne.u32 q, %1, 0; bar.red.or.pred p, %2, %3, q; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(any) : "r"((unsigned)near), "r"(kBarUnit), "r"(kWsUnit) : "memory");
-            if (any && tid == 0) {
-                a.rerun_list[1 + atomicAdd(a.rerun_list, 1)] = utt;
-                atomicAdd(a.reruns, 1);
-            }
-            reservoir_simulate<8, LEAN, false, kBarUnit>(a.res, utt, usmem, s_cnt3, tid, kWsUnit);
-            bar_sync(kBarUnit, kWsUnit);                             // shared memory is reused by the next utterance
+            if (a.ws_debug == 0)
+                reservoir_simulate<8, LEAN, false, kBarUnit>(a.res, utt, smem_raw + unit_off, s_cnt3, tid, kWsUnit, 0,
+                                                             reinterpret_cast<unsigned *>(smem_raw + bits_off + slot * bits_bytes));
+            bar_sync(kBarUnit, kWsUnit);                             // every unit thread is done with the bit plane and the staging area
+            bar_arrive(kBarEmpty + slot, kWsThreads);
         }
     }
 }
@@ -399,7 +404,7 @@ void lsm_gammatone_fill_args(const lsm_frontend *fe, const float *d_pcm, int B, 
     // the normalised-spectrogram dump is defined as the exact path's: asking for it selects the exact filter
     a.mode = d_spec_norm ? 0 : fe->mode;
     a.energy_in = nullptr; a.xmax_in = nullptr;
-    a.utt_list = nullptr; a.utt_count = nullptr; a.rerun_list = nullptr;
+    a.utt_list = nullptr; a.utt_count = nullptr; a.rerun_list = nullptr; a.ws_debug = 0;
     a.spec_delta = fe->spec_delta;
     a.bound_scale = (float)fe->bound_scale;
     a.reruns = fe->d_counters + 64;
@@ -589,41 +594,50 @@ int lsm_launch_fused_args(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, Gt
 // Can the pair run as the warp-specialised kernel?  The reference's default shape in speculative mode.
 bool lsm_ws_eligible(const lsm_frontend *fe, const lsm_reservoir *res)
 {
-    if (getenv("LSM_NO_WS")) return false;
+    // Opt-in (LSM_WS=1): measured on B200 at 6.0 ms per 2400-utterance step against 5.9 ms for the phases-in-turn kernel
+    // (profiles/r2_ws_exp.md: the filter group alone runs at the three-register DFMA ceiling, 4.6 ms, but the encoder epilogue
+    // and the reservoir cost 0.6 + 0.8 ms wherever they run - the SM's issue / operand bandwidth is shared, not idle).
+    if (!getenv("LSM_WS")) return false;
     return fe->p.channels == kWsFilter && lsm_fused_npt(fe, res) == 8 && fe->mode == LSM_FILTER_SPECULATIVE;
 }
 
 // The warp-specialised kernel on utterances [0, B) + the exact pass over the utterances it could not settle.
-int lsm_launch_fused_ws(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, GtArgs &a, cudaStream_t st, int *wave, bool launch)
+template <bool LEAN>
+static int launch_ws_t(lsm_ctx *ctx, lsm_frontend *fe, GtArgs &a, cudaStream_t st, int *wave, bool launch, int *slot_out)
 {
     int rc;
     const size_t smem_f = (sizeof(double) * 2 * kChunkBlocks * fe->p.hop + 127) & ~(size_t)127;
-    const size_t smem = smem_f + lsm_res_smem_bytes(a.res.T, a.res.CW, kWsUnit * 8, a.res.N);
+    const size_t bits = (sizeof(unsigned) * (size_t)a.res.T * a.res.CW + 127) & ~(size_t)127;
+    const size_t smem_u = lsm_res_smem_bytes(a.res.T, a.res.CW, kWsUnit * 8, a.res.N);
+    const size_t smem = smem_f + 2 * bits + smem_u;
     int per_sm = 0;
-    if (res->lean) {
-        LSM_CUDA(ctx, cudaFuncSetAttribute(gammatone_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gammatone_ws_kernel<true>, kWsThreads, smem));
-    } else {
-        LSM_CUDA(ctx, cudaFuncSetAttribute(gammatone_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gammatone_ws_kernel<false>, kWsThreads, smem));
-    }
+    LSM_CUDA(ctx, cudaFuncSetAttribute(gammatone_ws_kernel<LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gammatone_ws_kernel<LEAN>, kWsThreads, smem));
     if (per_sm < 1) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "warp-specialised kernel does not fit on an SM (%zu B shared memory)", smem);
     int grid = per_sm * ctx->sm_count;
-    if (grid > fe->grid / 2) grid = fe->grid / 2;          // two scratch planes per CTA out of a slot sized for fe->grid planes
+    if (grid > fe->grid) grid = fe->grid;                  // one scratch plane per CTA out of a slot sized for fe->grid planes
     if (wave) *wave = 2 * grid;                            // utterances in flight: one per group
     if (!launch) return LSM_OK;
     if (grid > a.B) grid = a.B;
     if ((rc = lsm_frontend_ensure_rerun(ctx, fe, a.B)) != LSM_OK) return rc;
     int *counter;
     const int slot = (int)(fe->slot_next++ & 1u);
+    *slot_out = slot;
     if ((rc = next_counter(ctx, fe, st, &counter, &a, slot)) != LSM_OK) return rc;
     a.rerun_list = fe->d_rerun + (size_t)slot * (fe->rerun_cap + 1);
     LSM_CUDA(ctx, cudaMemsetAsync(a.rerun_list, 0, sizeof(int), st));
-    if (res->lean) gammatone_ws_kernel<true><<<grid, kWsThreads, smem, st>>>(a, counter, (int)smem_f);
-    else gammatone_ws_kernel<false><<<grid, kWsThreads, smem, st>>>(a, counter, (int)smem_f);
+    gammatone_ws_kernel<LEAN><<<grid, kWsThreads, smem, st>>>(a, counter, (int)smem_f, (int)bits, (int)(smem_f + 2 * bits));
     ctx->launches += 1;
     LSM_CUDA(ctx, cudaGetLastError());
-    if ((rc = lsm_frontend_order_after(ctx, fe, st, slot)) != LSM_OK) return rc;
+    return lsm_frontend_order_after(ctx, fe, st, slot);
+}
+
+int lsm_launch_fused_ws(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, GtArgs &a, cudaStream_t st, int *wave, bool launch)
+{
+    int rc, slot = 0;
+    { const char *e = getenv("LSM_WS_DEBUG"); a.ws_debug = e ? atoi(e) : 0; }
+    rc = res->lean ? launch_ws_t<true>(ctx, fe, a, st, wave, launch, &slot) : launch_ws_t<false>(ctx, fe, a, st, wave, launch, &slot);
+    if (rc != LSM_OK || !launch) return rc;
     // exact pass over the device work list (typically empty; a few CTAs suffice), same scratch slot, same stream
     GtArgs x = a;
     x.mode = 0; x.rerun_list = nullptr;

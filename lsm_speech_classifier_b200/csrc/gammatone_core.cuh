@@ -50,6 +50,7 @@ struct GtArgs {
     int *reruns;            // number of utterances filtered twice (speculative mode)
     const int *utt_list;    // optional indirection: work item i is utterance utt_list[i], i < *utt_count (exact re-execution pass)
     const int *utt_count;
+    int ws_debug;           // warp-specialised kernel, timing experiments: 1 = no reservoir, 2 = filter group alone (LSM_WS_DEBUG)
     int *rerun_list;        // kernels without the exact path: utterances whose speculative plane was too close to call; [0] = count
     double thr[8], lower[8];
     ResArgs res;            // fused mode only: the reservoir this utterance's spikes feed

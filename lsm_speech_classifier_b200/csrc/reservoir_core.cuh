@@ -73,18 +73,21 @@ __device__ __forceinline__ void res_sync(int nthr)
 // LEAN = uniform leak, uniform input gain, at most one input row per neuron, relabelled neurons (see above).
 // STAT_GLOBAL = per-neuron statistics in a.stat_global instead of shared memory (reservoirs too large for it).
 // tid / nthr: this thread's index in the group and the group's size (whole warps); slab: the group's index for STAT_GLOBAL.
+// bits_ext: the input bit plane when it lives outside the group's own shared-memory plan (a buffer another thread group filled);
+// the plan keeps its layout, its own bit-plane area is then simply unused.
 template <int NPT, bool LEAN, bool STAT_GLOBAL = false, int BAR = 0>
 __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int utt, unsigned char *smem_raw, int *s_cnt,
-                                                   const int tid, const int nthr, const int slab = 0)
+                                                   const int tid, const int nthr, const int slab = 0, unsigned *bits_ext = nullptr)
 {
     const int lane = tid & 31;
     const int N = a.N, T = a.T, CW = a.CW;
     const int S = nthr * NPT;
     const int NL = (N + 7) & ~3;                       // list capacity, multiple of 4
-    unsigned *s_bits = reinterpret_cast<unsigned *>(smem_raw);
+    unsigned *s_plan = reinterpret_cast<unsigned *>(smem_raw);
+    unsigned *s_bits = bits_ext ? bits_ext : s_plan;
     const size_t bits_words = ((size_t)T * CW + 1) & ~(size_t)1;      // lsm_res_smem_bytes: 8-byte aligned list
-    int *s_stat = STAT_GLOBAL ? a.stat_global + (size_t)slab * 6 * S : reinterpret_cast<int *>(s_bits + bits_words);
-    unsigned short *s_list = reinterpret_cast<unsigned short *>(reinterpret_cast<int *>(s_bits + bits_words) +
+    int *s_stat = STAT_GLOBAL ? a.stat_global + (size_t)slab * 6 * S : reinterpret_cast<int *>(s_plan + bits_words);
+    unsigned short *s_list = reinterpret_cast<unsigned short *>(reinterpret_cast<int *>(s_plan + bits_words) +
                                                                 (STAT_GLOBAL ? 0 : 6 * (size_t)S));
 
     for (int i = tid; i < S; i += nthr) {
@@ -286,7 +289,7 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
     //      run: full 128-byte lines whether the destination is HBM or pinned host memory across PCIe.
     if (a.features) {
         double *f = a.features + (size_t)utt * a.nkeys * a.n_out;
-        double *s_buf = reinterpret_cast<double *>(smem_raw);
+        double *s_buf = reinterpret_cast<double *>(s_bits);
         const int cap = (T * CW * (int)sizeof(unsigned)) / (int)sizeof(double);   // doubles that fit in the bit plane
         const double nan = __longlong_as_double(0x7ff8000000000000LL);
         int o_k[NPT];

@@ -225,6 +225,45 @@ def lsm_keys():
     return _lib.FEATURE_KEYS
 
 
+@pytest.mark.parametrize("kw", [{}, dict(leak_variance_divisor=4.0)])
+def test_warp_specialised_lane_channel_kernel_equals_the_oracle(env, small_set, kw, monkeypatch):
+    """LSM_WS=1: filter + encoder group and reservoir group side by side in one CTA, bit planes handed over through named barriers
+    (gammatone_ws_kernel); more utterances than resident groups, device and pinned-host PCM, PCM16, and a widened near-tie test
+    so that the exact pass over the work list runs too."""
+    import torch
+    from lsm_speech_classifier_b200.frontend import Frontend
+    from lsm_speech_classifier_b200.snn import AudioToFeatures
+    from oracle import coracle
+    pcm, _ = small_set
+    fe = Frontend(128, "gammatone")
+    X = oracle_spikes(pcm, fe)
+    lsm = build_snn(X, **kw)
+    want, _ = coracle.reservoir_run(lsm.reservoir, X, 0xFF, True, False)
+    keys = list(lsm_keys())
+    path = AudioToFeatures(fe, lsm)
+    big = np.concatenate([pcm] * 40)[:1403]
+    want_big = np.concatenate([want] * 40)[:1403]
+    monkeypatch.setenv("LSM_WS", "1")
+    launches = fe.ctx.launches
+    got, spk = path.run(torch.from_numpy(big).cuda(), keys)
+    torch.cuda.synchronize()
+    assert fe.ctx.launches - launches == 2                       # the warp-specialised kernel + the exact pass over its work list
+    assert np.array_equal(got.cpu().numpy(), want_big) and np.array_equal(spk.cpu().numpy()[:len(pcm)], X)
+    h_in = torch.from_numpy(big).pin_memory()
+    h_out = torch.zeros((len(big), want.shape[1]), dtype=torch.float64).pin_memory()
+    path.run_host(h_in.numpy(), keys, out=h_out.numpy())
+    assert np.array_equal(h_out.numpy(), want_big)
+    i16 = np.clip(np.round(pcm * 32768.0), -32768, 32767).astype(np.int16)
+    want16 = path.run_host((i16.astype(np.float32) / 32768.0), keys)
+    got16, _ = path.run(torch.from_numpy(i16).cuda(), keys)
+    assert np.array_equal(got16.cpu().numpy(), want16)
+    fe.set_mode("speculative", delta_db=1e-3)                    # many near-ties: the exact pass has work to do
+    fe.reruns(reset=True)
+    got2, _ = path.run(torch.from_numpy(big).cuda(), keys)
+    assert np.array_equal(got2.cpu().numpy(), want_big)
+    assert 0 < fe.reruns() < len(big)
+
+
 def test_spike_density_matches_w_critico_inputs(env, small_set):
     import ctypes as C
     import torch
