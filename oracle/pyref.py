@@ -314,3 +314,66 @@ def resample_poly_ref(x, up, down, taps, hpp, n_pre_remove, n_out):
                 acc = np.float32(acc + np.float32(x[k] * taps[t, j]))
         out[o] = acc
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Reservoir construction, second implementation (the product's builder, reservoir.py, had no independent
+# counterpart).  The reference builds its liquid with SNN(simulation_params=...) (/root/reference/extract_lsm_features.py:164-188,
+# snnpy un-vendored); the frozen spec R1-R7 is restated here with plain Python loops over neurons and edges - no
+# adjacency matrix, no vectorised draws beyond the ones the spec names - and tests/test_oracle_reservoir.py requires every
+# array of reservoir.build_reservoir to equal this one's.
+def build_reservoir_ref(num_neurons, k, p, mean_weight, weight_variance, num_inputs, num_outputs, theta, leak_coefficient,
+                        leak_variance_divisor=None, input_gain=None, seed=42, w_shift=24):
+    n = int(num_neurons)
+    rs = np.random.RandomState(seed)                                   # R1: one generator, fixed order of use
+    half = k // 2
+    nb = [set() for _ in range(n)]                                     # R2: ring lattice, k/2 neighbours each side
+    for u in range(n):
+        for j in range(1, half + 1):
+            v = (u + j) % n
+            nb[u].add(v)
+            nb[v].add(u)
+    if p > 0:
+        for j in range(1, half + 1):                                   # right-hand edges (u, u+j), one distance at a time
+            draw = rs.random_sample(n)
+            for u in range(n):
+                if not draw[u] < p:
+                    continue
+                v = (u + j) % n
+                if len(nb[u]) >= n - 1 or v not in nb[u]:
+                    continue
+                while True:                                            # uniformly random non-neighbour
+                    w = int(rs.randint(n))
+                    if w != u and w not in nb[u]:
+                        break
+                nb[u].discard(v); nb[v].discard(u)
+                nb[u].add(w); nb[w].add(u)
+    edges = [(i, j) for i in range(n) for j in sorted(nb[i])]          # directed, (post, pre) row-major
+    sd = abs(mean_weight) / weight_variance if weight_variance else 0.0
+    if sd > 0:                                                         # R3: one normal draw per directed edge, rounded to 2^-w_shift
+        w = rs.normal(mean_weight, sd, size=len(edges))
+    else:
+        w = np.full(len(edges), float(mean_weight))
+    w_q = [int(np.rint(x * float(1 << w_shift))) for x in w]
+    w_rowptr = [0]
+    for i in range(n):
+        w_rowptr.append(w_rowptr[-1] + len(nb[i]))
+    if num_inputs <= n:                                                # R4: input row r -> one neuron, distinct while rows <= n
+        in_neuron = [int(v) for v in rs.permutation(n)[:num_inputs]]
+    else:
+        in_neuron = [int(v) for v in rs.randint(n, size=num_inputs)]
+    gain = float(theta if input_gain is None else input_gain)
+    in_rowptr, in_col = [0], []
+    for i in range(n):
+        rows = [r for r in range(num_inputs) if in_neuron[r] == i]     # ascending input row inside a neuron's list
+        in_col += rows
+        in_rowptr.append(len(in_col))
+    n_out = min(int(num_outputs), n)
+    out_idx = sorted(int(v) for v in rs.permutation(n)[:n_out])        # R5
+    if leak_variance_divisor:                                          # R7
+        leak = np.clip(rs.normal(leak_coefficient, leak_coefficient / leak_variance_divisor, size=n), 0.0, 1.0)
+    else:
+        leak = np.full(n, float(leak_coefficient))
+    return dict(w_rowptr=np.array(w_rowptr, np.int32), w_col=np.array([j for _, j in edges], np.int32), w_q=np.array(w_q, np.int32),
+                in_rowptr=np.array(in_rowptr, np.int32), in_col=np.array(in_col, np.int32), in_val=np.full(len(in_col), gain),
+                out_idx=np.array(out_idx, np.int32), leak=np.asarray(leak, np.float64))

@@ -98,3 +98,22 @@ def test_default_multiplier_sits_in_the_reference_health_band(golden):
         part[mult] = np.mean([(ras.sum(0) > 0).mean() * 100 for ras in raster])
     assert part[0.4] < 40 < part[0.6] < 98 < part[1.0] + 1e-9 or part[0.4] < part[0.6] < part[1.0]
     assert 40 <= part[0.6] <= 98
+
+
+def test_reservoir_builder_equals_the_loop_restatement_of_the_spec():
+    """reservoir.build_reservoir (product, vectorised numpy) against pyref.build_reservoir_ref (plain loops over the frozen spec
+    R1-R7): every array identical, for the reference's shape, a small heterogeneous-leak one, more input rows than neurons, no
+    rewiring and a zero weight spread."""
+    X = np.zeros((128, 400), np.uint8)
+    cases = [dict(), dict(num_neurons=256, small_world_graph_k=50, num_output_neurons=100, leak_variance_divisor=4.0),
+             dict(num_neurons=90, small_world_graph_k=12, num_output_neurons=400), dict(num_neurons=300, small_world_graph_k=40, small_world_graph_p=0.0),
+             dict(num_neurons=200, small_world_graph_k=30, weight_variance=0.0, small_world_graph_p=0.5, input_gain=1.25, seed=7)]
+    for kw in cases:
+        p = SimulationParams(mean_weight=0.0123, input_spike_times=X, **kw)
+        r = build_reservoir(p)
+        ref = pyref.build_reservoir_ref(p.num_neurons, p.small_world_graph_k, p.small_world_graph_p, p.mean_weight, p.weight_variance,
+                                        X.shape[0], p.num_output_neurons, p.membrane_threshold, p.leak_coefficient,
+                                        p.leak_variance_divisor, p.input_gain, p.seed)
+        for name, want in ref.items():
+            got = getattr(r, name)
+            assert got.dtype == want.dtype and np.array_equal(got, want), (kw, name)
