@@ -23,6 +23,7 @@
 namespace {
 
 constexpr int kFft = 2048, kHalf = 1024, kThreads = 256;
+constexpr int kFR = 1;       // frames per trip through the FFT's barriers (2 was measured: half the barriers per frame, but 4 instead of 5 CTAs per SM: 4.12 vs 3.83 ms)
 
 struct MelArgs {
     const float *pcm;        // [B][L]
@@ -76,14 +77,14 @@ __device__ __forceinline__ void bfly(double &pr, double &pi, double &qr, double 
 // reservoirs of up to 1024 neurons) and the readout follow in the same CTA, the spike train handed over as bits in shared
 // memory (one ballot word per warp of 32 channels and time step), exactly as the fused gammatone kernel does.  The FFT
 // buffers and the reservoir's shared-memory plan share one dynamic allocation; the twiddle tables are reloaded per utterance.
-constexpr size_t kMelSmemBytes = sizeof(double) * 2 * kHalf + sizeof(double2) * kHalf + sizeof(float) * (kHalf + 8);
+constexpr size_t kMelSmemBytes = sizeof(double) * 2 * kHalf * kFR + sizeof(double2) * kHalf + sizeof(float) * (kHalf + 8) * kFR;
 
 template <int FUSED>
 __global__ void __launch_bounds__(kThreads, FUSED ? 3 : 5) mel_encode_kernel(const MelArgs a, int *next_utt)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_re = reinterpret_cast<double *>(smem_raw), *s_im = s_re + kHalf;
-    double2 *s_tw = reinterpret_cast<double2 *>(s_im + kHalf);   // per-stage twiddle tables, stage s at offset 2^(s-1) - 1: T_s[j] = tw[j * (1024 >> s)], j < 2^(s-1)
+    double *s_re = reinterpret_cast<double *>(smem_raw), *s_im = s_re + kFR * kHalf;      // [kFR][kHalf] each
+    double2 *s_tw = reinterpret_cast<double2 *>(s_im + kFR * kHalf);   // per-stage twiddle tables, stage s at offset 2^(s-1) - 1: T_s[j] = tw[j * (1024 >> s)], j < 2^(s-1)
                                                                  // (contiguous in j: the strided reads of one shared table were up to 16-way bank conflicted)
     float *s_S = reinterpret_cast<float *>(s_tw + kHalf);
     __shared__ float s_red[kThreads / 32];
@@ -106,15 +107,23 @@ __global__ void __launch_bounds__(kThreads, FUSED ? 3 : 5) mel_encode_kernel(con
         }
         const float *pcm = a.pcm + (size_t)utt * a.L;
 
-        for (int t = 0; t < ncols; ++t) {
-            const int start = t * a.hop - kHalf;                   // centre padding: n_fft/2 zeros each side
-            // ---- windowed frame, packed z[j] = x[2j] + i x[2j+1], stored bit-reversed for the DIT FFT
-            for (int j = tid; j < kHalf; j += kThreads) {
-                const int i0 = start + 2 * j, i1 = i0 + 1;
-                const double x0 = (i0 >= 0 && i0 < a.L) ? __dmul_rn(__ldg(a.win + 2 * j), (double)__ldg(pcm + i0)) : 0.0;
-                const double x1 = (i1 >= 0 && i1 < a.L) ? __dmul_rn(__ldg(a.win + 2 * j + 1), (double)__ldg(pcm + i1)) : 0.0;
-                const int r = phys((int)(__brev((unsigned)j) >> 22));
-                s_re[r] = x0; s_im[r] = x1;
+        // kFR frames per trip through the barriers: the same butterflies, half the barriers per frame and twice the
+        // independent work between two of them
+        for (int t0 = 0; t0 < ncols; t0 += kFR) {
+            // ---- windowed frames, packed z[j] = x[2j] + i x[2j+1], stored bit-reversed for the DIT FFT
+#pragma unroll
+            for (int f = 0; f < kFR; ++f) {
+                const int t = t0 + f;
+                if (t >= ncols) break;
+                const int start = t * a.hop - kHalf;               // centre padding: n_fft/2 zeros each side
+                double *re = s_re + f * kHalf, *im = s_im + f * kHalf;
+                for (int j = tid; j < kHalf; j += kThreads) {
+                    const int i0 = start + 2 * j, i1 = i0 + 1;
+                    const double x0 = (i0 >= 0 && i0 < a.L) ? __dmul_rn(__ldg(a.win + 2 * j), (double)__ldg(pcm + i0)) : 0.0;
+                    const double x1 = (i1 >= 0 && i1 < a.L) ? __dmul_rn(__ldg(a.win + 2 * j + 1), (double)__ldg(pcm + i1)) : 0.0;
+                    const int r = phys((int)(__brev((unsigned)j) >> 22));
+                    re[r] = x0; im[r] = x1;
+                }
             }
             __syncthreads();
             // ---- 10 radix-2 stages as 5 passes of two stages each: a thread owns the 4 points p, p+h, p+2h, p+3h
@@ -126,43 +135,57 @@ __global__ void __launch_bounds__(kThreads, FUSED ? 3 : 5) mel_encode_kernel(con
                 const int j = tid & (h - 1);
                 const int p = ((tid >> (s - 1)) << (s + 1)) + j;
                 const int i0 = phys(p), i1 = phys(p + h), i2 = phys(p + 2 * h), i3 = phys(p + 3 * h);
-                double r0 = s_re[i0], m0 = s_im[i0], r1 = s_re[i1], m1 = s_im[i1];
-                double r2 = s_re[i2], m2 = s_im[i2], r3 = s_re[i3], m3 = s_im[i3];
                 const double2 ws = s_tw[h - 1 + j];
-                bfly(r0, m0, r1, m1, ws);
-                bfly(r2, m2, r3, m3, ws);
                 const double2 wa = s_tw[2 * h - 1 + j], wb = s_tw[2 * h - 1 + j + h];
-                bfly(r0, m0, r2, m2, wa);
-                bfly(r1, m1, r3, m3, wb);
-                s_re[i0] = r0; s_im[i0] = m0; s_re[i1] = r1; s_im[i1] = m1;
-                s_re[i2] = r2; s_im[i2] = m2; s_re[i3] = r3; s_im[i3] = m3;
+#pragma unroll
+                for (int f = 0; f < kFR; ++f) {
+                    if (t0 + f >= ncols) break;
+                    double *re = s_re + f * kHalf, *im = s_im + f * kHalf;
+                    double r0 = re[i0], m0 = im[i0], r1 = re[i1], m1 = im[i1];
+                    double r2 = re[i2], m2 = im[i2], r3 = re[i3], m3 = im[i3];
+                    bfly(r0, m0, r1, m1, ws);
+                    bfly(r2, m2, r3, m3, ws);
+                    bfly(r0, m0, r2, m2, wa);
+                    bfly(r1, m1, r3, m3, wb);
+                    re[i0] = r0; im[i0] = m0; re[i1] = r1; im[i1] = m1;
+                    re[i2] = r2; im[i2] = m2; re[i3] = r3; im[i3] = m3;
+                }
                 __syncthreads();
             }
             // ---- real-input untangle, complex64 rounding, |.|^2 in float32
             for (int k = tid; k <= kHalf; k += kThreads) {
                 const int k1 = k & (kHalf - 1), k2 = (kHalf - k) & (kHalf - 1);
-                const double zr = s_re[phys(k1)], zi = s_im[phys(k1)], cr = s_re[phys(k2)], ci = -s_im[phys(k2)];
-                const double ar = __dmul_rn(0.5, __dadd_rn(zr, cr)), ai = __dmul_rn(0.5, __dadd_rn(zi, ci));
-                const double br = __dmul_rn(0.5, __dsub_rn(zr, cr)), bi = __dmul_rn(0.5, __dsub_rn(zi, ci));
                 const double2 w = __ldg(a.tw2 + k);
                 const double c_re = w.y, c_im = -w.x;                                   // -i * W
-                const double xr = __dadd_rn(ar, __dsub_rn(__dmul_rn(c_re, br), __dmul_rn(c_im, bi)));
-                const double xi = __dadd_rn(ai, __dadd_rn(__dmul_rn(c_re, bi), __dmul_rn(c_im, br)));
-                const float r32 = (float)xr, i32 = (float)xi;
-                const double r64 = (double)r32, i64 = (double)i32;
-                const float mag = (float)__dsqrt_rn(__dadd_rn(__dmul_rn(r64, r64), __dmul_rn(i64, i64)));
-                s_S[k] = __fmul_rn(mag, mag);
+                const int p1 = phys(k1), p2 = phys(k2);
+#pragma unroll
+                for (int f = 0; f < kFR; ++f) {
+                    if (t0 + f >= ncols) break;
+                    const double *re = s_re + f * kHalf, *im = s_im + f * kHalf;
+                    const double zr = re[p1], zi = im[p1], cr = re[p2], ci = -im[p2];
+                    const double ar = __dmul_rn(0.5, __dadd_rn(zr, cr)), ai = __dmul_rn(0.5, __dadd_rn(zi, ci));
+                    const double br = __dmul_rn(0.5, __dsub_rn(zr, cr)), bi = __dmul_rn(0.5, __dsub_rn(zi, ci));
+                    const double xr = __dadd_rn(ar, __dsub_rn(__dmul_rn(c_re, br), __dmul_rn(c_im, bi)));
+                    const double xi = __dadd_rn(ai, __dadd_rn(__dmul_rn(c_re, bi), __dmul_rn(c_im, br)));
+                    const float r32 = (float)xr, i32 = (float)xi;
+                    const double r64 = (double)r32, i64 = (double)i32;
+                    const float mag = (float)__dsqrt_rn(__dadd_rn(__dmul_rn(r64, r64), __dmul_rn(i64, i64)));
+                    s_S[f * (kHalf + 8) + k] = __fmul_rn(mag, mag);
+                }
             }
             __syncthreads();
-            // ---- mel projection: one band per thread, ascending bins, float32 multiply then add
-            for (int m = tid; m < C; m += kThreads) {
+            // ---- mel projection: one band per thread and frame, ascending bins, float32 multiply then add
+            for (int q = tid; q < C * kFR; q += kThreads) {
+                const int f = q / C, m = q - f * C;
+                if (t0 + f >= ncols) continue;
                 const float *w = a.mel_w + __ldg(a.mel_off + m);
                 const int lo = __ldg(a.mel_lo + m), n = __ldg(a.mel_n + m);
+                const float *S = s_S + f * (kHalf + 8);
                 float acc = 0.0f;
-                for (int q = 0; q < n; ++q) acc = __fadd_rn(acc, __fmul_rn(__ldg(w + q), s_S[lo + q]));
-                plane[(size_t)t * C + m] = acc;
+                for (int qq = 0; qq < n; ++qq) acc = __fadd_rn(acc, __fmul_rn(__ldg(w + qq), S[lo + qq]));
+                plane[(size_t)(t0 + f) * C + m] = acc;
             }
-            // the next frame's loads touch s_re/s_im only, and ten barriers separate this read of s_S from its next write
+            // the next trip's loads touch s_re/s_im only, and ten barriers separate this read of s_S from its next write
         }
 
         // ---- power_to_db(ref=np.max, amin=1e-10, top_db=80), create_dataset.py:48
@@ -296,6 +319,7 @@ int lsm_mel_create(lsm_ctx *ctx, lsm_frontend *fe, const float *h_basis)
     if (rc == LSM_OK) rc = up(ctx, (double **)&fe->d_twiddle2, tw2.data(), tw2.size());
     if (rc != LSM_OK) return rc;
     int per_sm = 0;
+    LSM_CUDA(ctx, cudaFuncSetAttribute(mel_encode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMelSmemBytes));
     LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_encode_kernel<0>, kThreads, kMelSmemBytes));
     if (per_sm < 1) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "mel kernel does not fit on an SM");
     fe->grid = per_sm * ctx->sm_count;
