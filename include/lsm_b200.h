@@ -180,6 +180,17 @@ int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
                          const double *h_leak,            /* double[N] */
                          const int32_t *h_out_idx,        /* int32[n_out], ascending */
                          lsm_reservoir **out);
+/* Strict reservoir: the weights as fp64 numbers (snnpy-style normal draws) instead of int32 multiples of
+ * 2^-w_shift, and every neuron's recurrent current formed as SURVEY.md 8c S6 words it: the fp64 sum of the weights of its spiking
+ * presynaptic neurons, added one by one in ascending presynaptic index (h_w_col strictly ascending inside a row; w_shift is
+ * ignored).  Same calls afterwards; such a reservoir runs on the event-driven arm as its own kernel (no fusion with a front end,
+ * no dense arm), about twice the time of a quantised one.  The quantised form (lsm_reservoir_create) stays the default of the
+ * Python layer because its sums are exact in any order; this form exists so that "computed in its fp64 accumulation order"
+ * (BASELINE.json north star) can be had literally.                                                                          */
+int lsm_reservoir_create_f64(lsm_ctx *ctx, const lsm_reservoir_params *p,
+                             const int32_t *h_w_rowptr, const int32_t *h_w_col, const double *h_w_val,
+                             const int32_t *h_in_rowptr, const int32_t *h_in_col, const double *h_in_val,
+                             const double *h_leak, const int32_t *h_out_idx, lsm_reservoir **out);
 void lsm_reservoir_destroy(lsm_reservoir *res);
 /* d_spikes: uint8[B][num_inputs][num_steps].  d_features: double[B][popcount(mask)*n_out], RAW
  * (un-standardised).  nan_to_num != 0 applies extract_lsm_features.py:85's np.nan_to_num on device.

@@ -25,7 +25,7 @@ EXPORTS = [
     "lsm_hysteresis_encode", "lsm_fp64_peak_gops", "lsm_pipeline_is_fused", "lsm_frontend_mel_tables", "lsm_reservoir_diagnostics", "lsm_gammatone_design", "lsm_zoom_table", "lsm_standardize_fit", "lsm_standardize_transform",
     "lsm_frontend_set_mode", "lsm_frontend_reruns", "lsm_pipeline_run_host_async", "lsm_sync_all", "lsm_lane_stream", "lsm_logreg_fit", "lsm_logreg_predict", "lsm_pipeline_run_i16", "lsm_pipeline_run_host_async_i16", "lsm_reservoir_set_gather",
     "lsm_frontend_set_bound_scale", "lsm_frontend_audit", "lsm_gammatone_error_bound",
-    "lsm_reservoir_set_mode", "lsm_reservoir_dense_probe", "lsm_resample_poly",
+    "lsm_reservoir_set_mode", "lsm_reservoir_dense_probe", "lsm_resample_poly", "lsm_reservoir_create_f64",
     "lsm_ctx_set_host_feed", "lsm_peer_buffer_create", "lsm_peer_buffer_open", "lsm_peer_buffer_close", "lsm_peer_buffer_destroy",
 ]
 
@@ -77,6 +77,7 @@ def load():
     lib.lsm_frontend_encode.argtypes = [vp, vp, vp, i32, vp, vp]
     lib.lsm_frontend_encode_host.argtypes = [vp, vp, vp, i32, vp]
     lib.lsm_reservoir_create.argtypes = [vp, C.POINTER(ReservoirParams)] + [vp] * 8 + [C.POINTER(vp)]
+    lib.lsm_reservoir_create_f64.argtypes = [vp, C.POINTER(ReservoirParams)] + [vp] * 8 + [C.POINTER(vp)]
     lib.lsm_reservoir_destroy.argtypes = [vp]
     lib.lsm_reservoir_destroy.restype = None
     lib.lsm_reservoir_run.argtypes = [vp, vp, vp, i32, u32, i32, vp, vp]

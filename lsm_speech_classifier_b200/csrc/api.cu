@@ -434,10 +434,11 @@ extern "C" int lsm_hysteresis_encode(lsm_ctx *ctx, const void *d_spec, int32_t i
 }
 
 // ------------------------------------------------------------------------------------ stage 2+3
-extern "C" int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
-                                    const int32_t *h_w_rowptr, const int32_t *h_w_col, const int32_t *h_w_q,
-                                    const int32_t *h_in_rowptr, const int32_t *h_in_col, const double *h_in_val,
-                                    const double *h_leak, const int32_t *h_out_idx, lsm_reservoir **out)
+// h_w_q: integer weights (multiples of 2^-w_shift), or h_w_val: fp64 weights of a strict reservoir - exactly one of the two
+static int reservoir_create_impl(lsm_ctx *ctx, const lsm_reservoir_params *p,
+                                 const int32_t *h_w_rowptr, const int32_t *h_w_col, const int32_t *h_w_q, const double *h_w_val,
+                                 const int32_t *h_in_rowptr, const int32_t *h_in_col, const double *h_in_val,
+                                 const double *h_leak, const int32_t *h_out_idx, lsm_reservoir **out)
 {
     if (!ctx) return LSM_ERR_INVALID;
     if (!p || !h_w_rowptr || !h_in_rowptr || !h_leak || !h_out_idx || !out)
@@ -448,7 +449,8 @@ extern "C" int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
         p->w_shift < 0 || p->w_shift > 52)
         LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_create: bad dimensions");
     const int64_t nnz = h_w_rowptr[N];
-    if (nnz > 0 && (!h_w_col || !h_w_q)) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_create: null weights");
+    const bool strict = h_w_val != nullptr;
+    if (nnz > 0 && (!h_w_col || (!h_w_q && !h_w_val))) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_create: null weights");
     LSM_CUDA(ctx, cudaSetDevice(ctx->device));
     lsm_reservoir *res = new (std::nothrow) lsm_reservoir();
     if (!res) LSM_FAIL(ctx, LSM_ERR_NOMEM, "out of host memory");
@@ -470,7 +472,8 @@ extern "C" int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
     // lean kernel variant (reservoir_core.cuh): uniform leak, uniform input gain (and no -0.0), every driven neuron has exactly
     // one input row and no row drives two neurons, the rows fit the "internal neuron 8r" slots, theta > 0, refractory period
     // fits a 4-bit counter, and the input gain is a multiple of the weight quantum (so the folded constant is exact)
-    res->lean = res->max_in_per_neuron <= 1 && !getenv("LSM_NO_LEAN");
+    res->lean = res->max_in_per_neuron <= 1 && !getenv("LSM_NO_LEAN") && !strict;     // strict reservoirs keep the caller's neuron order
+    res->w64 = strict ? 1 : 0;
     res->leak0 = h_leak[0];
     res->gain0 = nin > 0 ? h_in_val[0] + 0.0 : 0.0;
     for (int i = 1; i < N && res->lean; ++i)
@@ -514,12 +517,21 @@ extern "C" int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
     res->c_off = ldexp(1.0, 52 - p->w_shift) + ldexp(1.0, 31 - p->w_shift);
     res->c_on = res->c_off - res->gain0;
     // dense presynaptic-major plane: wt[j][i] = weight of j -> i (internal labels); one extra all-zero row pads spike lists
-    std::vector<int32_t> wt((size_t)(res->zero_row + 1) * n_pad, 0);
+    std::vector<int32_t> wt(strict ? 1 : (size_t)(res->zero_row + 1) * n_pad, 0);
+    std::vector<double> wt64(strict ? (size_t)N * n_pad : 0, 0.0);
     std::vector<int64_t> rowabs(N, 0);
     for (int i = 0; i < N; ++i) {
+        int prev = -1;
         for (int64_t q = h_w_rowptr[i]; q < h_w_rowptr[i + 1]; ++q) {
             const int j = h_w_col[q];
             if (j < 0 || j >= N) { delete res; LSM_FAIL(ctx, LSM_ERR_INVALID, "presynaptic index out of range"); }
+            if (strict) {
+                // one edge per (post, pre) pair, ascending inside a row: the order of the sum is part of the definition
+                if (j <= prev) { delete res; LSM_FAIL(ctx, LSM_ERR_INVALID, "row %d: presynaptic indices must be strictly ascending", i); }
+                prev = j;
+                wt64[(size_t)j * n_pad + i] = h_w_val[q];
+                continue;
+            }
             wt[(size_t)perm[j] * n_pad + perm[i]] += h_w_q[q];
             rowabs[i] += h_w_q[q] < 0 ? -(int64_t)h_w_q[q] : (int64_t)h_w_q[q];
         }
@@ -552,7 +564,9 @@ extern "C" int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
         if (lo < 0 || hi >= (1 << 24)) { res->dense_planes = 4; res->dense_top_signed = 1; }
         else res->dense_planes = hi >= (1 << 16) ? 3 : (hi >= (1 << 8) ? 2 : 1);
     }
+    if (strict) res->dense_planes = 0;                    // the dense arm contracts integer digit planes
     int rc = upload(ctx, &res->d_wt, wt.data(), wt.size());
+    if (rc == LSM_OK && strict) rc = upload(ctx, &res->d_wt64, wt64.data(), wt64.size());
     if (rc == LSM_OK) rc = upload(ctx, &res->d_in_rowptr, h_in_rowptr, (size_t)N + 1);
     if (rc == LSM_OK) rc = upload(ctx, &res->d_in_col, h_in_col, (size_t)nin);
     if (rc == LSM_OK) rc = upload(ctx, &res->d_in_val, h_in_val, (size_t)nin);
@@ -565,10 +579,30 @@ extern "C" int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
     return LSM_OK;
 }
 
+extern "C" int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
+                                    const int32_t *h_w_rowptr, const int32_t *h_w_col, const int32_t *h_w_q,
+                                    const int32_t *h_in_rowptr, const int32_t *h_in_col, const double *h_in_val,
+                                    const double *h_leak, const int32_t *h_out_idx, lsm_reservoir **out)
+{
+    if (ctx && h_w_rowptr && p && p->num_neurons > 0 && h_w_rowptr[p->num_neurons] > 0 && !h_w_q)
+        LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_create: null weights");
+    return reservoir_create_impl(ctx, p, h_w_rowptr, h_w_col, h_w_q, nullptr, h_in_rowptr, h_in_col, h_in_val, h_leak, h_out_idx, out);
+}
+
+extern "C" int lsm_reservoir_create_f64(lsm_ctx *ctx, const lsm_reservoir_params *p,
+                                        const int32_t *h_w_rowptr, const int32_t *h_w_col, const double *h_w_val,
+                                        const int32_t *h_in_rowptr, const int32_t *h_in_col, const double *h_in_val,
+                                        const double *h_leak, const int32_t *h_out_idx, lsm_reservoir **out)
+{
+    if (!ctx) return LSM_ERR_INVALID;
+    if (!h_w_val) LSM_FAIL(ctx, LSM_ERR_INVALID, "lsm_reservoir_create_f64: null weights");
+    return reservoir_create_impl(ctx, p, h_w_rowptr, h_w_col, nullptr, h_w_val, h_in_rowptr, h_in_col, h_in_val, h_leak, h_out_idx, out);
+}
+
 extern "C" void lsm_reservoir_destroy(lsm_reservoir *res)
 {
     if (!res) return;
-    cudaFree(res->d_wt); cudaFree(res->d_in_rowptr); cudaFree(res->d_in_col); cudaFree(res->d_in_val);
+    cudaFree(res->d_wt); cudaFree(res->d_wt64); cudaFree(res->d_in_rowptr); cudaFree(res->d_in_col); cudaFree(res->d_in_val);
     cudaFree(res->d_leak); cudaFree(res->d_out_slot); cudaFree(res->d_in_row); cudaFree(res->d_ext_id);
     free(res->h_dense_in_row); free(res->h_dense_gain); free(res->h_dense_leak); free(res->h_dense_out_int);
     lsm_dense_ws_free(res->dense);

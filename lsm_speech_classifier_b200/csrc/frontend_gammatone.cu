@@ -537,7 +537,7 @@ int lsm_launch_gammatone(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int
 int lsm_fused_npt(const lsm_frontend *fe, const lsm_reservoir *res)
 {
     const lsm_frontend_params &p = fe->p;
-    if (getenv("LSM_NO_FUSE")) return 0;
+    if (getenv("LSM_NO_FUSE") || res->w64) return 0;      // strict reservoirs run as their own kernel
     if (p.kind != LSM_FILTERBANK_GAMMATONE || p.redundancy != 1 || (p.channels & 31) || p.channels > 256) return 0;
     if (res->p.num_inputs != p.channels || res->p.num_steps != p.n_bins * p.n_thresholds) return 0;
     if (res->n_pad % p.channels) return 0;

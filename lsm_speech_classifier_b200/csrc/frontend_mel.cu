@@ -339,7 +339,7 @@ void lsm_mel_destroy(lsm_frontend *fe)
 bool lsm_mel_fused_ok(const lsm_frontend *fe, const lsm_reservoir *res)
 {
     const lsm_frontend_params &p = fe->p;
-    if (getenv("LSM_NO_FUSE")) return false;
+    if (getenv("LSM_NO_FUSE") || res->w64) return false;
     if (p.kind != LSM_FILTERBANK_MEL || p.redundancy != 1 || (p.channels & 31) || p.channels > 256) return false;
     if (res->p.num_inputs != p.channels || res->p.num_steps != p.n_bins * p.n_thresholds) return false;
     if (res->n_pad != 4 * kThreads) return false;

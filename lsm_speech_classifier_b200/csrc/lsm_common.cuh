@@ -77,6 +77,8 @@ struct lsm_reservoir {
     lsm_reservoir_params p;
     int n_pad = 0;                 // row pitch of the dense weight plane (multiple of 32)
     int32_t *d_wt = nullptr;       // dense [N][n_pad]: row = PRESYNAPTIC j, column = postsynaptic i
+    double *d_wt64 = nullptr;      // strict reservoirs (lsm_reservoir_create_f64): the same plane in fp64, summed in ascending presynaptic order
+    int w64 = 0;
     int32_t *d_in_rowptr = nullptr, *d_in_col = nullptr;
     double *d_in_val = nullptr;
     double *d_leak = nullptr;

@@ -17,7 +17,7 @@
 
 namespace {
 
-template <int NPT, bool LEAN, bool STAT_GLOBAL>
+template <int NPT, bool LEAN, bool STAT_GLOBAL, bool W64 = false>
 __global__ void __launch_bounds__(1024) reservoir_kernel(const ResArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(1024) reservoir_kernel(const ResArgs a)
         }
     }
     __syncthreads();
-    reservoir_simulate<NPT, LEAN, STAT_GLOBAL>(a, utt, smem_raw, s_cnt, threadIdx.x, blockDim.x, blockIdx.x);
+    reservoir_simulate<NPT, LEAN, STAT_GLOBAL, 0, W64>(a, utt, smem_raw, s_cnt, threadIdx.x, blockDim.x, blockIdx.x);
 }
 
 }  // namespace
@@ -74,7 +74,7 @@ void lsm_reservoir_fill_args(const lsm_reservoir *res, const uint8_t *d_spikes, 
 {
     const lsm_reservoir_params &p = res->p;
     ResArgs &a = *out;
-    a.spikes = d_spikes; a.wt = res->d_wt; a.in_rowptr = res->d_in_rowptr; a.in_col = res->d_in_col;
+    a.spikes = d_spikes; a.wt = res->d_wt; a.wt64 = res->d_wt64; a.in_rowptr = res->d_in_rowptr; a.in_col = res->d_in_col;
     a.in_val = res->d_in_val; a.in_row = res->d_in_row; a.leak = res->d_leak; a.out_slot = res->d_out_slot;
     a.features = d_features; a.raster = d_raster; a.stat_global = nullptr; a.diag = nullptr;
     a.ext_id = res->d_ext_id; a.c_off = res->c_off; a.c_on = res->c_on; a.hi_magic = res->hi_magic; a.zero_row = res->zero_row;
@@ -123,6 +123,19 @@ int lsm_launch_reservoir(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spik
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         reservoir_kernel<NPT, LEAN, SG><<<B, threads, smem, st>>>(a);                                \
     } while (0)
+#define LSM_RES_LAUNCH64(NPT, SG)                                                                    \
+    do {                                                                                             \
+        if (smem > 48 * 1024)                                                                        \
+            LSM_CUDA(ctx, cudaFuncSetAttribute(reservoir_kernel<NPT, false, SG, true>,               \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        reservoir_kernel<NPT, false, SG, true><<<B, threads, smem, st>>>(a);                         \
+    } while (0)
+    if (res->w64) {                 // strict reservoir: fp64 weights, ordered sums
+        if (a.stat_global) LSM_RES_LAUNCH64(16, true);
+        else if (npt == 4) LSM_RES_LAUNCH64(4, false);
+        else if (npt == 8) LSM_RES_LAUNCH64(8, false);
+        else LSM_RES_LAUNCH64(16, false);
+    } else
     if (a.stat_global) {            // only the 16-neurons-per-thread shapes are large enough to need the slab
         if (res->lean) LSM_RES_LAUNCH(16, true, true);
         else LSM_RES_LAUNCH(16, false, true);
@@ -136,6 +149,7 @@ int lsm_launch_reservoir(lsm_ctx *ctx, lsm_reservoir *res, const uint8_t *d_spik
         else LSM_RES_LAUNCH(16, false, false);
     }
 #undef LSM_RES_LAUNCH
+#undef LSM_RES_LAUNCH64
     ctx->launches += 1;
     LSM_CUDA(ctx, cudaGetLastError());
     return LSM_OK;

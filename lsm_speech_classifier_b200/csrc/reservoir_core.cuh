@@ -8,6 +8,7 @@
 struct ResArgs {
     const uint8_t *spikes;    // [B][C][T]  level signal: any non-zero byte is "on"
     const int32_t *wt;        // [zero_row+1][n_pad]  row = presynaptic neuron, last row = zeros (list padding)
+    const double *wt64;       // strict reservoirs: [N][n_pad] fp64 weights, same orientation
     const int32_t *in_rowptr; // [N+1]
     const int32_t *in_col;
     const double *in_val;
@@ -75,10 +76,15 @@ __device__ __forceinline__ void res_sync(int nthr)
 // tid / nthr: this thread's index in the group and the group's size (whole warps); slab: the group's index for STAT_GLOBAL.
 // bits_ext: the input bit plane when it lives outside the group's own shared-memory plan (a buffer another thread group filled);
 // the plan keeps its layout, its own bit-plane area is then simply unused.
-template <int NPT, bool LEAN, bool STAT_GLOBAL = false, int BAR = 0>
+// W64: strict reservoir (SURVEY.md 8c S3/S6 as written): fp64 weights, and the recurrent current of a neuron is their sum added one
+// by one in ascending presynaptic index.  The spike list is then built in ascending neuron order (a block-wide prefix sum instead
+// of per-warp atomics) and consumed one row at a time; generic layout (identity labelling) and whole-CTA groups only.
+template <int NPT, bool LEAN, bool STAT_GLOBAL = false, int BAR = 0, bool W64 = false>
 __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int utt, unsigned char *smem_raw, int *s_cnt,
                                                    const int tid, const int nthr, const int slab = 0, unsigned *bits_ext = nullptr)
 {
+    static_assert(!W64 || (!LEAN && BAR == 0), "strict reservoirs use the generic layout and one group per CTA");
+    __shared__ int s_wsum[W64 ? 32 : 1];               // W64: spikes per warp of the current step (ordered compaction)
     const int lane = tid & 31;
     const int N = a.N, T = a.T, CW = a.CW;
     const int S = nthr * NPT;
@@ -154,10 +160,25 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
         // ---- recurrent current: exact integer sum over the neurons that fired at t-1; one 16-byte
         //      load per (presynaptic row, 4 consecutive postsynaptic neurons)
         int acc[NPT];
+        double accd[W64 ? NPT : 1];
 #pragma unroll
         for (int k = 0; k < NPT; ++k) acc[k] = 0;
+        if (W64) {
+#pragma unroll
+            for (int k = 0; k < NPT; ++k) accd[k] = 0.0;
+#pragma unroll 1
+            for (int q = 0; q < n_prev; ++q) {                       // ascending presynaptic index: one rounded addition per spike
+                const double2 *row = reinterpret_cast<const double2 *>(a.wt64 + (size_t)list[q] * a.n_pad + i0);
+#pragma unroll
+                for (int u = 0; u < NPT / 2; ++u) {
+                    const double2 w = __ldg(row + u);
+                    accd[2 * u] = add64(accd[2 * u], w.x);
+                    accd[2 * u + 1] = add64(accd[2 * u + 1], w.y);
+                }
+            }
+        }
 #pragma unroll 1   // keep the step loop small: the unrolled form (16 rows per trip) made instruction fetch a top stall
-        for (int q = 0; q < n_prev; q += 4) {
+        for (int q = 0; !W64 && q < n_prev; q += 4) {
             const uint2 jj = *reinterpret_cast<const uint2 *>(list + q);
             // entries past the end of the list select the all-zero weight row (index N)
             const int j0 = jj.x & 0xffff;
@@ -222,7 +243,7 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
                         i_in = add64(i_in, mul64(__ldg(a.in_val + p), on));
                     }
                 }
-                const double cur = add64(i_in, mul64((double)acc[k], a.scale));
+                const double cur = W64 ? add64(i_in, accd[k]) : add64(i_in, mul64((double)acc[k], a.scale));
                 const double v = add64(sub64(V[k], mul64(lk[k], V[k])), cur);
                 const bool active = ref[k] == 0;
                 const bool fire = active && (v >= a.theta) && (i < N);
@@ -255,7 +276,7 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
                     s_stat[S + sl] += t;
                     s_stat[3 * S + sl] = t;
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, fire);
+                const unsigned m = W64 ? 0u : __ballot_sync(0xffffffffu, fire);
                 if (m) {
                     int base = 0;
                     if (lane == 0) base = atomicAdd(&s_cnt[c_nxt], __popc(m));
@@ -263,6 +284,25 @@ __device__ __forceinline__ void reservoir_simulate(const ResArgs &a, const int u
                     if (fire) list_next[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(i0 + k);
                 }
             }
+        }
+        if (W64) {
+            // ordered compaction: position = spikes of lower threads + this thread's lower neurons (neuron index = tid * NPT + k)
+            const int mine = __popc(fired);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) s_wsum[tid >> 5] = incl;
+            res_sync<BAR>(nthr);
+            int base = 0;
+            for (int w = 0; w < (tid >> 5); ++w) base += s_wsum[w];
+            int pos = base + incl - mine;
+#pragma unroll
+            for (int k = 0; k < NPT; ++k)
+                if ((fired >> k) & 1u) list_next[pos++] = (unsigned short)(i0 + k);
+            if (tid == nthr - 1) s_cnt[c_nxt] = base + incl;
         }
         res_sync<BAR>(nthr);
         const int tmp = c_cur; c_cur = c_nxt; c_nxt = c_zero; c_zero = tmp;

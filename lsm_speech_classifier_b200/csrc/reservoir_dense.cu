@@ -401,6 +401,7 @@ void lsm_dense_ws_free(lsm_dense_ws *w)
 // Why the dense arm cannot serve this reservoir, or nullptr.
 const char *lsm_dense_unsupported(const lsm_reservoir *res)
 {
+    if (res->w64) return "strict reservoirs (fp64 weights, ordered sums) have no integer digit planes";
     if (res->max_in_per_neuron > 1) return "a neuron is driven by several input rows";
     if (res->p.refractory > 255) return "refractory period > 255";
     if (res->n_gather > 0) return "the fused all-gather is an epilogue of the event-driven kernel";

@@ -53,6 +53,8 @@ class SimulationParams:
     # not in the reference's call: ours, with defaults that keep its behaviour
     input_gain: Optional[float] = None   # None -> membrane_threshold: an active input step makes its neuron fire
     seed: int = 42
+    quantize_weights: bool = True        # R3: weights rounded to 2**-24 (int32, order-free sums).  False: SURVEY.md 8c S3/S6 as
+                                         # written - fp64 normals, row sums in ascending presynaptic order ("strict" reservoirs)
 
 
 @dataclass
@@ -71,6 +73,7 @@ class ReservoirDef:
     in_val: np.ndarray     # float64[nin]
     out_idx: np.ndarray    # int32[N_out] ascending
     leak: np.ndarray       # float64[N]
+    w_val: Optional[np.ndarray] = None   # float64[nnz]: strict reservoirs (quantize_weights=False) carry their weights here, w_q is zeros
     w_shift: int = W_SHIFT
     meta: dict = field(default_factory=dict)
 
@@ -115,10 +118,15 @@ def build_reservoir(p: SimulationParams) -> ReservoirDef:
     nnz = len(post)
     sd = abs(p.mean_weight) / p.weight_variance if p.weight_variance else 0.0
     w = rs.normal(p.mean_weight, sd, size=nnz) if sd > 0 else np.full(nnz, float(p.mean_weight))
-    wq = np.rint(w * float(1 << W_SHIFT))
-    if np.any(np.abs(wq) >= 2 ** 31):
-        raise ValueError("weight out of Q7.24 range")
-    wq = wq.astype(np.int32)                                              # R3
+    if p.quantize_weights:
+        wq = np.rint(w * float(1 << W_SHIFT))
+        if np.any(np.abs(wq) >= 2 ** 31):
+            raise ValueError("weight out of Q7.24 range")
+        wq = wq.astype(np.int32)                                          # R3
+        w_val = None
+    else:
+        wq = np.zeros(nnz, dtype=np.int32)                                # S3: the fp64 draws themselves
+        w_val = np.ascontiguousarray(w, dtype=np.float64)
     rowptr = np.zeros(n + 1, dtype=np.int32)
     np.cumsum(np.bincount(post, minlength=n), out=rowptr[1:])
     # worst-case row sum must stay inside int32 so any integer accumulator is exact
@@ -147,7 +155,7 @@ def build_reservoir(p: SimulationParams) -> ReservoirDef:
         theta=float(p.membrane_threshold), refractory=int(p.refractory_period),
         w_rowptr=rowptr, w_col=pre.astype(np.int32), w_q=wq,
         in_rowptr=in_rowptr, in_col=in_col, in_val=in_val, out_idx=out_idx,
-        leak=np.ascontiguousarray(leak, dtype=np.float64),
+        leak=np.ascontiguousarray(leak, dtype=np.float64), w_val=w_val,
         meta=dict(seed=p.seed, k=int(p.small_world_graph_k), p=float(p.small_world_graph_p),
                   mean_weight=float(p.mean_weight), weight_variance=float(p.weight_variance),
                   input_gain=gain),

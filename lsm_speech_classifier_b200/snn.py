@@ -49,11 +49,14 @@ class SNN:
         p.num_neurons, p.num_inputs, p.num_steps = r.num_neurons, r.num_inputs, r.num_steps
         p.refractory, p.w_shift, p.n_out, p.theta = r.refractory, r.w_shift, len(r.out_idx), r.theta
         self._p = p
-        arrs = [_lib.as_host(r.w_rowptr, np.int32), _lib.as_host(r.w_col, np.int32), _lib.as_host(r.w_q, np.int32),
+        strict = getattr(r, "w_val", None) is not None        # fp64 weights, ordered sums (SimulationParams.quantize_weights=False)
+        arrs = [_lib.as_host(r.w_rowptr, np.int32), _lib.as_host(r.w_col, np.int32),
+                _lib.as_host(r.w_val, np.float64) if strict else _lib.as_host(r.w_q, np.int32),
                 _lib.as_host(r.in_rowptr, np.int32), _lib.as_host(r.in_col, np.int32), _lib.as_host(r.in_val, np.float64),
                 _lib.as_host(r.leak, np.float64), _lib.as_host(r.out_idx, np.int32)]
         h = C.c_void_p()
-        self.ctx.check(self.ctx.lib.lsm_reservoir_create(self.ctx.h, C.byref(p), *[_lib._np_ptr(a) for a in arrs], C.byref(h)))
+        create = self.ctx.lib.lsm_reservoir_create_f64 if strict else self.ctx.lib.lsm_reservoir_create
+        self.ctx.check(create(self.ctx.h, C.byref(p), *[_lib._np_ptr(a) for a in arrs], C.byref(h)))
         self.h = h
         self._sample = None
         self.spike_matrix = None

@@ -123,6 +123,8 @@ def reservoir_run(r, spikes, feature_mask=0xFF, nan_to_num=False, want_raster=Fa
     B, Cc, T = spikes.shape
     N = r.num_neurons
     t_rowptr, t_col, t_q = transpose_csr(r.w_rowptr, r.w_col, r.w_q, N)
+    w_val = getattr(r, "w_val", None)
+    t_val = transpose_csr(r.w_rowptr, r.w_col, np.ascontiguousarray(w_val, dtype=np.float64), N)[2] if w_val is not None else None
     nkeys = bin(feature_mask & 0xFF).count("1")
     n_out = len(r.out_idx)
     feats = np.zeros((B, nkeys * n_out), dtype=np.float64)
@@ -130,7 +132,7 @@ def reservoir_run(r, spikes, feature_mask=0xFF, nan_to_num=False, want_raster=Fa
     f = lib().oracle_reservoir_run
     f.argtypes = None
     rc = f(C.c_int(N), C.c_int(Cc), C.c_int(T), C.c_double(r.theta), C.c_int(r.refractory), C.c_int(r.w_shift),
-           _p(t_rowptr, C.c_int32), _p(t_col, C.c_int32), _p(t_q, C.c_int32),
+           _p(t_rowptr, C.c_int32), _p(t_col, C.c_int32), _p(t_q, C.c_int32), _p(t_val, C.c_double),
            _p(r.in_rowptr, C.c_int32), _p(r.in_col, C.c_int32), _p(r.in_val, C.c_double),
            _p(r.leak, C.c_double), _p(r.out_idx, C.c_int32), C.c_int(n_out),
            _p(spikes, C.c_uint8), C.c_int(B), C.c_uint32(feature_mask), C.c_int(int(nan_to_num)),

@@ -544,14 +544,17 @@ typedef struct {
     int w_shift;
 } oracle_res_dims;
 
+/* wt_val != NULL: strict reservoir: fp64 weights, and the recurrent current of a neuron is their sum taken
+ * one by one in ascending presynaptic index - the spike list is ascending, so scattering it row by row adds in that order. */
 static void simulate_one(const oracle_res_dims *d, const uint8_t *x,
-                         const int32_t *wt_rowptr, const int32_t *wt_col, const int32_t *wt_q,
+                         const int32_t *wt_rowptr, const int32_t *wt_col, const int32_t *wt_q, const double *wt_val,
                          const int32_t *in_rowptr, const int32_t *in_col, const double *in_val,
                          const double *leak, const int32_t *out_idx, uint32_t feature_mask,
                          int nan_to_num, double *features, uint8_t *raster,
                          double *V, int32_t *ref, int32_t *spk, int64_t *acc, int32_t *st)
 {
     const int N = d->N, T = d->T;
+    double *accd = (double *)acc;                        /* strict reservoirs reuse the accumulator array as doubles */
     const double scale = ldexp(1.0, -d->w_shift);
     int nspk = 0;
     /* per-neuron streaming statistics: count, sum t, first, last, sum isi^2, bursts */
@@ -561,17 +564,25 @@ static void simulate_one(const oracle_res_dims *d, const uint8_t *x,
         V[i] = 0.0; ref[i] = 0; cnt[i] = 0; sumt[i] = 0; first[i] = -1; last[i] = -1; burst[i] = 0; s2[i] = 0;
     }
     for (int t = 0; t < T; ++t) {
-        for (int i = 0; i < N; ++i) acc[i] = 0;
-        for (int q = 0; q < nspk; ++q) {
-            int j = spk[q];
-            for (int p = wt_rowptr[j]; p < wt_rowptr[j + 1]; ++p) acc[wt_col[p]] += wt_q[p];
+        if (wt_val) {
+            for (int i = 0; i < N; ++i) accd[i] = 0.0;
+            for (int q = 0; q < nspk; ++q) {
+                int j = spk[q];
+                for (int p = wt_rowptr[j]; p < wt_rowptr[j + 1]; ++p) accd[wt_col[p]] = accd[wt_col[p]] + wt_val[p];
+            }
+        } else {
+            for (int i = 0; i < N; ++i) acc[i] = 0;
+            for (int q = 0; q < nspk; ++q) {
+                int j = spk[q];
+                for (int p = wt_rowptr[j]; p < wt_rowptr[j + 1]; ++p) acc[wt_col[p]] += wt_q[p];
+            }
         }
         nspk = 0;
         for (int i = 0; i < N; ++i) {
             double i_in = 0.0;
             for (int p = in_rowptr[i]; p < in_rowptr[i + 1]; ++p)
                 i_in = i_in + in_val[p] * (x[(size_t)in_col[p] * T + t] ? 1.0 : 0.0);  /* level signal: non-zero = on */
-            double cur = i_in + (double)acc[i] * scale;
+            double cur = wt_val ? i_in + accd[i] : i_in + (double)acc[i] * scale;
             int fire = 0;
             if (ref[i] == 0) {
                 double v = (V[i] - leak[i] * V[i]) + cur;
@@ -623,7 +634,7 @@ static void simulate_one(const oracle_res_dims *d, const uint8_t *x,
 
 typedef struct {
     oracle_res_dims d;
-    const int32_t *wt_rowptr, *wt_col, *wt_q, *in_rowptr, *in_col; const double *in_val, *leak;
+    const int32_t *wt_rowptr, *wt_col, *wt_q; const double *wt_val; const int32_t *in_rowptr, *in_col; const double *in_val, *leak;
     const int32_t *out_idx; const uint8_t *spikes; uint32_t feature_mask; int nan_to_num, nkeys;
     double *features; uint8_t *raster;
 } rs_ctx;
@@ -643,20 +654,20 @@ static void rs_one(void *vc, int b, void *scratch)
     double *V = (double *)scratch;
     int64_t *acc = (int64_t *)(V + N);
     int32_t *ref = (int32_t *)(acc + N), *spk = ref + N, *st = spk + N + (N & 1);
-    simulate_one(&c->d, c->spikes + (size_t)b * c->d.C * c->d.T, c->wt_rowptr, c->wt_col, c->wt_q,
+    simulate_one(&c->d, c->spikes + (size_t)b * c->d.C * c->d.T, c->wt_rowptr, c->wt_col, c->wt_q, c->wt_val,
                  c->in_rowptr, c->in_col, c->in_val, c->leak, c->out_idx, c->feature_mask, c->nan_to_num,
                  c->features ? c->features + (size_t)b * c->nkeys * c->d.n_out : NULL,
                  c->raster ? c->raster + (size_t)b * c->d.T * N : NULL, V, ref, spk, acc, st);
 }
 
 int oracle_reservoir_run(int N, int C, int T, double theta, int refractory, int w_shift,
-                         const int32_t *wt_rowptr, const int32_t *wt_col, const int32_t *wt_q,
+                         const int32_t *wt_rowptr, const int32_t *wt_col, const int32_t *wt_q, const double *wt_val_or_null,
                          const int32_t *in_rowptr, const int32_t *in_col, const double *in_val,
                          const double *leak, const int32_t *out_idx, int n_out,
                          const uint8_t *spikes, int B, uint32_t feature_mask, int nan_to_num,
                          double *features, uint8_t *raster, int nthreads)
 {
-    rs_ctx c = {{N, C, T, refractory, n_out, theta, w_shift}, wt_rowptr, wt_col, wt_q, in_rowptr, in_col,
+    rs_ctx c = {{N, C, T, refractory, n_out, theta, w_shift}, wt_rowptr, wt_col, wt_q, wt_val_or_null, in_rowptr, in_col,
                 in_val, leak, out_idx, spikes, feature_mask, nan_to_num, 0, features, raster};
     for (int k = 0; k < 8; ++k) c.nkeys += (feature_mask >> k) & 1;
     pf_job j = {rs_one, &c, B, 0, rs_mk, free};

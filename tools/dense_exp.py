@@ -107,3 +107,18 @@ for N in [int(v) for v in args.sizes.split(",")]:
         else:
             print(f"| {N} | {mult:.1f} | {avg.mean() * N / 400:.1f} | {ms_e:.2f} | - | - | - |", flush=True)
         l4.close()
+
+# ---- 4. strict reservoirs (fp64 weights, ascending-order sums) against the quantised default, event-driven arm
+from lsm_speech_classifier_b200.snn import SNN, SimulationParams  # noqa: E402
+from lsm_speech_classifier_b200.extract_lsm_features import calculate_theoretical_w_critico  # noqa: E402
+print(f"\n| N = 1000, multiplier | quantised ms / {B} utt | strict (fp64, ordered) ms / {B} utt |")
+print("|---|---|---|")
+for mult in (0.6, 1.0):
+    row = []
+    for q in (True, False):
+        prm = SimulationParams(input_spike_times=X[0], quantize_weights=q)
+        prm.mean_weight = calculate_theoretical_w_critico(prm, X[:500], verbose=False) * mult
+        l5 = SNN(simulation_params=prm)
+        row.append(timed(lambda: l5.simulate_batch(spk, keys)))
+        l5.close()
+    print(f"| {mult:.1f} | {row[0]:.2f} | {row[1]:.2f} |", flush=True)
