@@ -184,7 +184,7 @@ int lsm_reservoir_create(lsm_ctx *ctx, const lsm_reservoir_params *p,
  * 2^-w_shift, and every neuron's recurrent current formed as SURVEY.md 8c S6 words it: the fp64 sum of the weights of its spiking
  * presynaptic neurons, added one by one in ascending presynaptic index (h_w_col strictly ascending inside a row; w_shift is
  * ignored).  Same calls afterwards; such a reservoir runs on the event-driven arm as its own kernel (no fusion with a front end,
- * no dense arm), about twice the time of a quantised one.  The quantised form (lsm_reservoir_create) stays the default of the
+ * no dense arm), 2.8 x the time of a quantised one (profiles/r2_config4.md).  The quantised form (lsm_reservoir_create) stays the default of the
  * Python layer because its sums are exact in any order; this form exists so that "computed in its fp64 accumulation order"
  * (BASELINE.json north star) can be had literally.                                                                          */
 int lsm_reservoir_create_f64(lsm_ctx *ctx, const lsm_reservoir_params *p,
