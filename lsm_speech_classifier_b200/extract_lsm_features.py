@@ -117,14 +117,16 @@ def run_network_diagnostics(lsm: SNN, X_sample_batch):
     return avg_part
 
 
-def build_lsm(X_train, multiplier: float, leak_variance_divisor=None, num_neurons: int = NUM_NEURONS, verbose=True) -> SNN:
-    """reference :164-188: parameter record, w_critico, weight, then the one reservoir."""
+def build_lsm(X_train, multiplier: float, leak_variance_divisor=None, num_neurons: int = NUM_NEURONS, verbose=True,
+              strict_weights: bool = False) -> SNN:
+    """reference :164-188: parameter record, w_critico, weight, then the one reservoir.  strict_weights: fp64 weights summed in
+    ascending presynaptic order (SURVEY.md 8c S3/S6 as written) instead of the order-free 2^-24 quantisation."""
     k = int(0.10 * num_neurons * 2)
     base_params = SimulationParams(
         num_neurons=num_neurons, mean_weight=0.0, num_output_neurons=NUM_OUTPUT_NEURONS,
         membrane_threshold=MEMBRANE_THRESHOLD, leak_coefficient=LEAK_COEFFICIENT,
         refractory_period=REFRACTORY_PERIOD, small_world_graph_p=SMALL_WORLD_P, small_world_graph_k=k,
-        input_spike_times=X_train[0], leak_variance_divisor=leak_variance_divisor)
+        input_spike_times=X_train[0], leak_variance_divisor=leak_variance_divisor, quantize_weights=not strict_weights)
     w = calculate_theoretical_w_critico(base_params, X_train, verbose=verbose)
     optimal_weight = w * multiplier
     if verbose:
@@ -136,7 +138,8 @@ def build_lsm(X_train, multiplier: float, leak_variance_divisor=None, num_neuron
     return SNN(simulation_params=base_params)
 
 
-def main(feature_set: str, multiplier: float, leak_variance_divisor: float = None, num_neurons: int = NUM_NEURONS):
+def main(feature_set: str, multiplier: float, leak_variance_divisor: float = None, num_neurons: int = NUM_NEURONS,
+         strict_weights: bool = False):
     from sklearn.model_selection import train_test_split
     from sklearn.preprocessing import StandardScaler
     from .distributed import _dist, init_from_env, is_main
@@ -152,7 +155,7 @@ def main(feature_set: str, multiplier: float, leak_variance_divisor: float = Non
         X_train, X_test, y_train, y_test = train_test_split(
             X_spikes, y_labels, test_size=0.2, random_state=42, stratify=y_labels)
     with timing.stage("stage 2 setup: w_critico, reservoir build + upload, diagnostics"):
-        lsm = build_lsm(X_train, multiplier, leak_variance_divisor, num_neurons, verbose=is_main())
+        lsm = build_lsm(X_train, multiplier, leak_variance_divisor, num_neurons, verbose=is_main(), strict_weights=strict_weights)
         if is_main():
             run_network_diagnostics(lsm, X_train)
     feature_keys = FEATURE_SETS[feature_set]
@@ -226,9 +229,11 @@ def _cli(argv=None):
     parser.add_argument("--multiplier", type=float, default=0.6)
     parser.add_argument("--leak-variance-divisor", type=float, default=None)
     parser.add_argument("--n-neurons", type=int, default=NUM_NEURONS, help="(extension) reservoir size; k = 0.2*N")
+    parser.add_argument("--strict-weights", action="store_true",
+                        help="(extension) fp64 weights summed in ascending presynaptic order instead of order-free 2^-24 multiples")
     args = parser.parse_args(argv)
     main(feature_set=args.feature_set, multiplier=args.multiplier, leak_variance_divisor=args.leak_variance_divisor,
-         num_neurons=args.n_neurons)
+         num_neurons=args.n_neurons, strict_weights=args.strict_weights)
 
 
 if __name__ == "__main__":
