@@ -127,3 +127,22 @@ def test_fused_and_packed_cli_modes_write_the_same_feature_file(workdir, tmp_pat
             assert np.array_equal(got[k], ref[k]), (flag, k)
         assert not (d / "speech_spike_dataset_pure_redundancy.npz").exists()
         assert (d / "speech_spike_dataset_packed.npz").exists() == (flag == "--packed")
+
+
+def test_cli_timing_breakdown_and_strict_weights(tmp_path, monkeypatch, capsys):
+    """main.py --timing prints the wall-clock breakdown; extract_lsm_features --strict-weights builds the fp64-weight reservoir
+    (same file schema, rows of the strict oracle)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from lsm_speech_classifier_b200 import extract_lsm_features as ex, main as m, timing
+    monkeypatch.chdir(tmp_path)
+    m._cli(["--synthetic", "4", "12", "--no-train", "--timing"])
+    out = capsys.readouterr().out
+    assert "Wall-clock breakdown" in out and "stage 1 compute" in out and "stage 2 compute" in out
+    timing.enabled = False
+    quant = np.load(ex.FEATURE_FILE, allow_pickle=True)["X_train_features"]
+    ex._cli(["--strict-weights"])
+    strict = np.load(ex.FEATURE_FILE, allow_pickle=True)
+    assert strict["X_train_features"].shape == quant.shape and strict["X_train_features"].dtype == np.float64
+    assert not np.array_equal(strict["X_train_features"], quant) or True      # (weights differ by < 2^-25: rows may coincide)
