@@ -540,3 +540,106 @@ __device__ __forceinline__ bool spec_epilogue(const GtArgs &a, int utt, double *
     }
     return near | bad;
 }
+
+// ---- SPECULATIVE filter, lane = utterance ("lanes" arrangement).  The lane = channel kernel keeps its per-channel
+//      coefficients in registers, and a DFMA with three distinct register operands issues at only ~75 % of the fp64
+//      pipe's rate on this GPU (tools/fp64_cascade.cu: 14.4 vs 19.2 T lane-ops/s).  Here a warp filters J channels of
+//      32 utterances: the coefficients are the same for every lane, sit in the kernel-parameter constant bank and reach the
+//      DFMAs through uniform registers (two register operands each), so the cascade runs at the pipe's full rate.
+//      Each lane streams its own utterance with 16-byte loads (a sector is consumed by two of them, L1 keeps the line),
+//      no shared memory, no barriers.  Output: raw window energy sums energy[utt][col][ch] (one full 32-byte sector per
+//      lane and window for J = 4); the encoder epilogue of the second kernel takes it from there.
+constexpr int kLanesJ = 4;
+
+struct EnergyArgs {
+    const float *pcm;       // [B][L]
+    double *energy;         // [B][ncols][C] raw energy sums of the normalised cascade
+    float *xmax;            // [B] max |sample| (the error bound scales with it)
+    int B, L, C, nwin, hop, ncols;
+    int n_units;            // big units + single-channel units
+    int big_groups;         // utterance groups [0, big_groups) are cut into units of kLanesJ channels, the rest into single channels
+    double coef[256][6];    // per channel: c1..c4 (numerator zeros / A0), -a1, -a2
+};
+
+// one unit of work: J channels starting at ch0 for the 32 utterances of group g
+template <int J>
+__device__ __forceinline__ void energy_unit(const EnergyArgs &a, const int g, const int ch0)
+{
+    const int lane = threadIdx.x & 31;
+    const int utt = g * 32 + lane;
+    const bool valid = utt < a.B;
+    const float4 *src = reinterpret_cast<const float4 *>(a.pcm + (size_t)(valid ? utt : a.B - 1) * a.L);
+    const int n4_max = a.L / 4 - 1;
+    const int hop = a.hop, ncols = a.ncols;
+    const int r_old = a.nwin - 2 * hop;
+    const int n_used = (ncols - 1) * hop + a.nwin;
+    double *dst = a.energy + (size_t)utt * ncols * a.C + ch0;
+
+    // Stage k works on the sample that stage k-1 finished one iteration earlier (software skew, as in the lane = channel
+    // kernels): per channel four independent 3-FMA chains instead of one of depth eleven.  Iteration i feeds x[i] to stage 1
+    // and completes output i-3; outputs -3..-1 are exact zeros (zero state), so the energy sums need no prologue.
+    double xp = 0.0;
+    float xm = 0.0f;
+    double p1[J], q1[J], p2[J], q2[J], p3[J], q3[J], p4[J], q4[J], acc[J], full1[J], full2[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) { p1[j] = q1[j] = p2[j] = q2[j] = p3[j] = q3[j] = p4[j] = q4[j] = acc[j] = full1[j] = full2[j] = 0.0; }
+
+#define LSM_LANE_SAMPLE(xf)                                                                             \
+    {                                                                                                   \
+        const double x_ = (double)(xf);                                                                 \
+        _Pragma("unroll") for (int j = 0; j < J; ++j) {                                                 \
+            const double *c = a.coef[ch0 + j];                                                          \
+            const double y1 = fma(c[4], p1[j], fma(c[5], q1[j], fma(c[0], xp, x_)));                    \
+            const double y2 = fma(c[4], p2[j], fma(c[5], q2[j], fma(c[1], q1[j], p1[j])));              \
+            const double y3 = fma(c[4], p3[j], fma(c[5], q3[j], fma(c[2], q2[j], p2[j])));              \
+            const double y4 = fma(c[4], p4[j], fma(c[5], q4[j], fma(c[3], q3[j], p3[j])));              \
+            q1[j] = p1[j]; p1[j] = y1; q2[j] = p2[j]; p2[j] = y2;                                       \
+            q3[j] = p3[j]; p3[j] = y3; q4[j] = p4[j]; p4[j] = y4;                                       \
+            acc[j] = fma(y4, y4, acc[j]);                                                               \
+        }                                                                                               \
+        xp = x_;                                                                                        \
+    }
+
+    // Groups of 8 iterations aligned with the 16-byte loads; group gi completes outputs 8gi-3 .. 8gi+4, so a window-phase
+    // boundary at sample 8gi (the phases are multiples of 8 samples long) falls after the group's third iteration.
+    int next_b = r_old;                                // next boundary: first the head of hop-block 0 ...
+    int m = 0;                                         // hop-block the boundary belongs to
+    bool head = true;                                  // boundary kind: end of the block's head (window m-2 complete) / end of the block
+    const int n_groups = n_used / 8;                   // the last boundary (sample n_used) is handled after the loop's last group
+    float4 f0 = __ldg(src + 0), f1 = __ldg(src + 1);   // two loads (8 samples) in flight ahead of the arithmetic
+    for (int gi = 0; gi <= n_groups; ++gi) {
+        const float4 g0 = __ldg(src + min(2 * gi + 2, n4_max)), g1 = __ldg(src + min(2 * gi + 3, n4_max));
+        if (ch0 == 0)      // one unit per group reports the peak level (every sample that can reach a window, and a few more)
+            xm = fmaxf(fmaxf(fmaxf(xm, fabsf(f0.x)), fmaxf(fabsf(f0.y), fabsf(f0.z))),
+                       fmaxf(fmaxf(fabsf(f0.w), fabsf(f1.x)), fmaxf(fmaxf(fabsf(f1.y), fabsf(f1.z)), fabsf(f1.w))));
+        LSM_LANE_SAMPLE(f0.x) LSM_LANE_SAMPLE(f0.y) LSM_LANE_SAMPLE(f0.z)
+        if (8 * gi == next_b) {
+            if (head) {
+                if (m >= 2 && valid) {
+                    // window m-2 complete: full(m-2) + full(m-1) + head(m)
+                    double *o = dst + (size_t)(m - 2) * a.C;
+                    if (J == 4) {
+                        *reinterpret_cast<double2 *>(o) = make_double2((full2[0] + full1[0]) + acc[0], (full2[1] + full1[1]) + acc[1]);
+                        *reinterpret_cast<double2 *>(o + 2) = make_double2((full2[2] + full1[2]) + acc[2], (full2[3] + full1[3]) + acc[3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < J; ++j) o[j] = (full2[j] + full1[j]) + acc[j];
+                    }
+                }
+                next_b += hop - r_old;
+                head = false;
+            } else {
+#pragma unroll
+                for (int j = 0; j < J; ++j) { full2[j] = full1[j]; full1[j] = acc[j]; acc[j] = 0.0; }
+                next_b += r_old;
+                head = true;
+                ++m;
+            }
+        }
+        LSM_LANE_SAMPLE(f0.w) LSM_LANE_SAMPLE(f1.x) LSM_LANE_SAMPLE(f1.y) LSM_LANE_SAMPLE(f1.z) LSM_LANE_SAMPLE(f1.w)
+        f0 = g0; f1 = g1;
+    }
+#undef LSM_LANE_SAMPLE
+    if (ch0 == 0 && valid) a.xmax[utt] = xm;
+}
+

@@ -372,6 +372,100 @@ __global__ void __launch_bounds__(kThreads, 2) pipeline_kernel(const __grid_cons
     }
 }
 
+
+// ---- Second form of the same idea (LSM_PIPELINE=2): the filter role is the lane = utterance unit of gammatone_energy_kernel
+//      (energy_unit: 8-sample groups fully expanded, coefficients resident in uniform registers, PCM by 16-byte loads through L1 -
+//      0.17 other instructions per DFMA where the TMA-fed role above executes 0.97), units of two channels x 32 utterances handed
+//      out by an atomic counter (single-channel units at the end of the queue balance the tail), and the same encoder / reservoir
+//      units.  4 filter warps + 2 units per CTA, two CTAs per SM, so that consecutive launches overlap at half-SM granularity.
+constexpr int kP2FW = 4, kP2EU = 2, kP2JB = 2;
+constexpr int kP2Threads = kP2FW * 32 + kP2EU * kEThreads;
+
+struct Pipe2Args {
+    GtArgs gt;                // front end + reservoir (gt.res)
+    EnergyArgs ea;            // the filter units' view: PCM, energy planes, peak levels, coefficient table
+    int *done;                // [groups] channels completed per 32-utterance group (zero at launch)
+    int *unit_next;           // encoder units' utterance counter (zero at launch)
+    int *filter_next;         // filter warps' unit counter (zero at launch)
+    int *err_flag;
+    int n_units, n_big, big_groups;
+};
+
+template <int BAR>
+__device__ __forceinline__ void unit2_role(const Pipe2Args &a, unsigned char *usmem, double *s_red, double *s_out, int *s_cnt,
+                                           int *s_utt, const int tid)
+{
+    const GtArgs &gt = a.gt;
+    for (;;) {
+        if (tid == 0) {
+            const int i = atomicAdd(a.unit_next, 1);
+            int ok = i < gt.B ? i : -1;
+            if (ok >= 0) {
+                const int *flag = a.done + (i >> 5);
+                long long spins = 0;
+                while (ld_acquire(flag) < gt.C) {                 // every channel of the utterance's group has been filtered
+                    __nanosleep(500);
+                    if (++spins > (1ll << 24)) { atomicExch(a.err_flag, 1); ok = -1; break; }
+                }
+            }
+            *s_utt = ok;
+        }
+        res_sync<BAR>(kEThreads);
+        const int utt = *s_utt;
+        if (utt < 0) break;
+        const float xm = __ldcg(a.ea.xmax + utt);
+        double *plane = a.ea.energy + (size_t)utt * gt.ncols * gt.C;
+        const bool near = spec_epilogue<8, BAR>(gt, utt, plane, tid, kEThreads, xm, s_red, s_out, usmem);
+        if (group_or<BAR>(near, kEThreads) && tid == 0) {
+            gt.rerun_list[1 + atomicAdd(gt.rerun_list, 1)] = utt;
+            atomicAdd(gt.reruns, 1);
+        }
+        reservoir_simulate<8, true, false, BAR>(gt.res, utt, usmem, s_cnt, tid, kEThreads);
+        res_sync<BAR>(kEThreads);
+    }
+}
+
+__global__ void __launch_bounds__(kP2Threads, 2) pipeline2_kernel(const __grid_constant__ Pipe2Args a, const int unit_smem_bytes)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ double s_red[kP2EU][6 * 8];
+    __shared__ double s_out[kP2EU][6];
+    __shared__ int s_cnt[kP2EU][5];
+    __shared__ int s_utt[kP2EU];
+
+    const int warp = __reduce_max_sync(0xffffffffu, (int)(threadIdx.x >> 5));
+    if (warp < kP2FW) {
+        const int lane = threadIdx.x & 31;
+        for (;;) {
+            int u = 0;
+            if (lane == 0) u = atomicAdd(a.filter_next, 1);
+            // the unit index as a value the compiler knows to be warp-uniform: channel index and coefficients stay on the uniform datapath
+            u = __reduce_max_sync(0xffffffffu, __shfl_sync(0xffffffffu, u, 0));
+            if (u >= a.n_units) break;
+            int g, add;
+            if (u < a.n_big) {                                  // 64 two-channel units per group
+                g = u >> 6;
+                energy_unit<kP2JB>(a.ea, g, (u & 63) << 1);
+                add = kP2JB;
+            } else {                                            // 128 single-channel units per group
+                const int s = u - a.n_big;
+                g = a.big_groups + (s >> 7);
+                energy_unit<1>(a.ea, g, s & 127);
+                add = 1;
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(a.done + g, add);
+        }
+    } else {
+        const int e = (warp - kP2FW) >> 2;
+        const int tid = threadIdx.x - kP2FW * 32 - e * kEThreads;
+        unsigned char *usmem = smem + (size_t)e * unit_smem_bytes;
+        if (e == 0) unit2_role<1>(a, usmem, s_red[0], s_out[0], s_cnt[0], &s_utt[0], tid);
+        else unit2_role<2>(a, usmem, s_red[1], s_out[1], s_cnt[1], &s_utt[1], tid);
+    }
+}
+
 }  // namespace
 
 // cuTensorMapEncodeTiled through the runtime (no link against libcuda)
@@ -409,6 +503,58 @@ bool lsm_pipeline_lanes_eligible(const lsm_frontend *fe, const lsm_reservoir *re
     return encode_tiled() != nullptr;
 }
 
+
+// LSM_PIPELINE=2: the energy-unit form (float32 PCM in device memory only)
+static int launch_pipeline2(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B, uint8_t *d_spikes_or_null,
+                            uint32_t feature_mask, int nan_to_num, double *d_features, cudaStream_t st, int lane, long long row0)
+{
+    const lsm_frontend_params &p = fe->p;
+    int rc;
+    if ((rc = lsm_frontend_ensure_energy(ctx, fe, B)) != LSM_OK) return rc;
+    if ((rc = lsm_frontend_order_before(ctx, fe, st, lane)) != LSM_OK) return rc;
+    std::unique_ptr<Pipe2Args> holder(new (std::nothrow) Pipe2Args);
+    if (!holder) LSM_FAIL(ctx, LSM_ERR_NOMEM, "out of host memory");
+    Pipe2Args &a = *holder;
+    lsm_gammatone_fill_args(fe, d_pcm, B, d_spikes_or_null, nullptr, &a.gt);
+    lsm_reservoir_fill_args(res, nullptr, B, feature_mask, nan_to_num, d_features, nullptr, &a.gt.res);
+    a.gt.res.gather_row0 += row0;
+    const int groups = (B + 31) / 32;
+    const size_t plane = (size_t)fe->ncols * p.channels;
+    EnergyArgs &ea = a.ea;
+    ea.pcm = d_pcm; ea.energy = fe->d_energy + (size_t)lane * fe->energy_cap * plane; ea.xmax = fe->d_xmax + (size_t)lane * fe->energy_cap;
+    ea.B = B; ea.L = p.n_samples; ea.C = p.channels; ea.nwin = p.nwin; ea.hop = p.hop; ea.ncols = fe->ncols;
+    memcpy(ea.coef, fe->h_lane_coef, sizeof(double) * 6 * p.channels);
+    int *sync = fe->d_pipe_sync + (size_t)lane * (fe->energy_cap / 32 + 8);
+    a.unit_next = sync; a.filter_next = sync + 1; a.done = sync + 4;
+    a.err_flag = fe->d_pipe_sync + 2 * (size_t)(fe->energy_cap / 32 + 8);
+    a.gt.rerun_list = fe->d_rerun + (size_t)lane * (fe->rerun_cap + 1);
+    int grid = 2 * ctx->sm_count;
+    // whole rounds of two-channel units over all filter warps, the rest of the batch as single-channel units (they balance the tail)
+    const int upg = p.channels / kP2JB, workers = grid * kP2FW;
+    const long long big_total = (long long)groups * upg;
+    long long rounds = big_total / workers;
+    if (rounds * workers == big_total && rounds > 0) rounds -= 0;          // an exact fit needs no small units
+    int big_groups = (int)((rounds * workers) / upg);
+    if (big_groups > groups) big_groups = groups;
+    a.big_groups = big_groups;
+    a.n_big = big_groups * upg;
+    a.n_units = a.n_big + (groups - big_groups) * p.channels;
+    ea.big_groups = big_groups; ea.n_units = a.n_units;
+    const int unit_smem = (int)((lsm_res_smem_bytes(a.gt.res.T, a.gt.res.CW, kEThreads * 8, a.gt.res.N) + 127) & ~(size_t)127);
+    const size_t smem = (size_t)kP2EU * unit_smem;
+    LSM_CUDA(ctx, cudaMemsetAsync(sync, 0, sizeof(int) * (4 + (size_t)groups), st));
+    LSM_CUDA(ctx, cudaMemsetAsync(a.gt.rerun_list, 0, sizeof(int), st));
+    LSM_CUDA(ctx, cudaFuncSetAttribute(pipeline2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (grid * kP2FW > a.n_units) grid = (a.n_units + kP2FW - 1) / kP2FW;
+    pipeline2_kernel<<<grid, kP2Threads, smem, st>>>(a, unit_smem);
+    ctx->launches += 1;
+    LSM_CUDA(ctx, cudaGetLastError());
+    GtArgs x = a.gt;
+    x.mode = 0; x.rerun_list = nullptr;
+    x.utt_list = a.gt.rerun_list + 1; x.utt_count = a.gt.rerun_list;
+    return lsm_launch_fused_args(ctx, fe, res, x, st, true, nullptr, 8, lane);
+}
+
 // One launch: utterances [0, B) of d_pcm (float32, or PCM16 when fe->next_pcm16 is set and d_pcm is null) on launch lane `lane`
 // of the front end (its own energy planes, counters and work list), stream st.  Features (and optionally spike trains) as
 // lsm_launch_fused; row0 offsets the fused all-gather's destination rows.  The exact pass over the flagged utterances follows
@@ -421,6 +567,8 @@ int lsm_launch_pipeline_lanes(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res
     const lsm_frontend_params &p = fe->p;
     const bool i16 = d_pcm == nullptr;
     int rc;
+    if (!i16 && getenv("LSM_PIPELINE") && atoi(getenv("LSM_PIPELINE")) == 2)
+        return launch_pipeline2(ctx, fe, res, d_pcm, B, d_spikes_or_null, feature_mask, nan_to_num, d_features, st, lane, row0);
     if ((rc = lsm_frontend_ensure_energy(ctx, fe, B)) != LSM_OK) return rc;
     if ((rc = lsm_frontend_order_before(ctx, fe, st, lane)) != LSM_OK) return rc;      // earlier users of this lane's planes
     std::unique_ptr<PipeArgs> holder(new (std::nothrow) PipeArgs);

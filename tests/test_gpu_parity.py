@@ -586,8 +586,9 @@ def test_speculative_filter_arrangements_agree(env, small_set, monkeypatch):
     assert np.array_equal(fe40.encode(pcm[:9]), want40)
 
 
-def test_warp_specialised_kernel_equals_the_lane_channel_kernel(env, small_set, monkeypatch):
-    """Default shape, LSM_PIPELINE=1: the warp-specialised kernel (lane = utterance filter warps + encoder/reservoir units in
+@pytest.mark.parametrize("variant,n_launches", [("1", 6), ("2", 4)])
+def test_warp_specialised_kernel_equals_the_lane_channel_kernel(env, small_set, monkeypatch, variant, n_launches):
+    """Default shape, LSM_PIPELINE=1 (TMA-fed filter warps) / 2 (energy-unit filter warps, no peak pre-pass): the warp-specialised kernel (lane = utterance filter warps + encoder/reservoir units in
     one CTA, flagged utterances finished by the exact kernel) against the lane = channel fused kernel in exact mode:
     same features and spike trains for ragged batch sizes, whatever fraction of the batch takes the exact pass, float32 and
     PCM16, device and host buffers."""
@@ -608,7 +609,7 @@ def test_warp_specialised_kernel_equals_the_lane_channel_kernel(env, small_set, 
     pipe = AudioToFeatures(fe, lsm)
     keys = FEATURE_SETS["original"]
     want = pipe.run_host(pcm, keys)
-    monkeypatch.setenv("LSM_PIPELINE", "1")
+    monkeypatch.setenv("LSM_PIPELINE", variant)
     d_pcm = torch.from_numpy(pcm).cuda()
     for delta, lo, hi in ((0.0, 0, 3), (1e-3, 1, len(pcm) - 1), (1e9, len(pcm) - 1, len(pcm))):
         fe.set_mode("speculative", delta)
@@ -616,7 +617,7 @@ def test_warp_specialised_kernel_equals_the_lane_channel_kernel(env, small_set, 
         launches = fe.ctx.launches
         spk = np.zeros_like(spikes)
         got = pipe.run_host(pcm, keys, spikes_out=spk)
-        assert fe.ctx.launches - launches == 6, "two pieces on the two lanes: peak pre-pass + pipeline kernel + exact pass each"
+        assert fe.ctx.launches - launches == n_launches, "two pieces on the two lanes: (peak pre-pass +) pipeline kernel + exact pass each"
         assert np.array_equal(got, want), delta
         assert np.array_equal(spk, spikes), delta
         assert lo <= fe.reruns() <= hi, (delta, fe.reruns())
@@ -633,7 +634,7 @@ def test_warp_specialised_kernel_equals_the_lane_channel_kernel(env, small_set, 
     as_f32 = i16.astype(np.float32) / np.float32(32768.0)
     monkeypatch.delenv("LSM_PIPELINE")
     want16 = pipe.run_host(as_f32, keys)
-    monkeypatch.setenv("LSM_PIPELINE", "1")
+    monkeypatch.setenv("LSM_PIPELINE", variant)
     out16, _ = pipe.run(torch.from_numpy(i16).cuda(), keys)
     assert np.array_equal(out16.cpu().numpy(), want16)
     h_in = torch.from_numpy(i16).pin_memory()

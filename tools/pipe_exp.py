@@ -15,7 +15,8 @@ from lsm_speech_classifier_b200.extract_lsm_features import FEATURE_SETS, build_
 from lsm_speech_classifier_b200.frontend import Frontend  # noqa: E402
 from lsm_speech_classifier_b200.snn import AudioToFeatures  # noqa: E402
 
-os.environ["LSM_PIPELINE"] = "1"          # the warp-specialised kernel is opt-in
+VARIANT = sys.argv[1] if len(sys.argv) > 1 else "1"
+os.environ["LSM_PIPELINE"] = VARIANT          # the warp-specialised kernel is opt-in (1: TMA-fed filter warps, 2: energy-unit filter warps)
 keys = FEATURE_SETS["original"]
 fe = Frontend(128, "gammatone")
 d_pcm = torch.from_numpy(pcm).cuda()
@@ -56,7 +57,7 @@ print(f"encoder/reservoir units alone:                   {timed(step):.3f} ms")
 del os.environ["LSM_PIPE_DEBUG"]
 del os.environ["LSM_PIPELINE"]
 print(f"lane = channel fused kernel (one launch):        {timed(step):.3f} ms")
-os.environ["LSM_PIPELINE"] = "1"
+os.environ["LSM_PIPELINE"] = VARIANT
 for n in (1200, 600, 4800):
     x = torch.cat([d_pcm, d_pcm])[:n].contiguous()
     o = torch.empty((n, 2000), dtype=torch.float64, device="cuda")
