@@ -949,14 +949,18 @@ int lsm_pipeline_lanes_device(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res
     const int16_t *pcm16 = d_pcm ? nullptr : fe->next_pcm16;
     cudaStream_t l0 = lane_stream(ctx, 0), l1 = lane_stream(ctx, 1);
     const bool on_lane = st == l0 || st == l1;
-    const int piece = on_lane ? (B > 8192 ? 8192 : B) : lanes_piece(B);
+    // variant 2 (energy-unit filter role, dynamic unit queue): whole calls on the caller's stream, alternating the two resource
+    // lanes from call to call, so that callers with two streams have two launches in flight
+    const bool whole_calls = !on_lane && getenv("LSM_PIPELINE") && atoi(getenv("LSM_PIPELINE")) == 2 && !pcm16;
+    const int piece = (on_lane || whole_calls) ? (B > 8192 ? 8192 : B) : lanes_piece(B);
     int rc = LSM_OK, used = 0;
-    if (!on_lane && B > piece) LSM_CUDA(ctx, cudaEventRecord(ctx->ev[8], st));
+    if (!on_lane && !whole_calls && B > piece) LSM_CUDA(ctx, cudaEventRecord(ctx->ev[8], st));
     for (int off = 0, k = 0; off < B && rc == LSM_OK; off += piece, ++k) {
         const int n = B - off < piece ? B - off : piece;
         int lane = k & 1;
         cudaStream_t ls = lane == 0 ? l0 : l1;
         if (on_lane) { lane = st == l1 ? 1 : 0; ls = st; }
+        else if (whole_calls) { lane = (int)(fe->slot_next++ & 1u); ls = st; }
         else if (B <= piece) { lane = 0; ls = st; }          // a single small launch stays on the caller's stream
         else if (k < 2) LSM_CUDA(ctx, cudaStreamWaitEvent(ls, ctx->ev[8], 0));
         fe->next_pcm16 = pcm16 ? pcm16 + (size_t)off * L : nullptr;

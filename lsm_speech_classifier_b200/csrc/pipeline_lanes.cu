@@ -427,7 +427,7 @@ __device__ __forceinline__ void unit2_role(const Pipe2Args &a, unsigned char *us
 
 __global__ void __launch_bounds__(kP2Threads, 2) pipeline2_kernel(const __grid_constant__ Pipe2Args a, const int unit_smem_bytes)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];      // one declaration per translation unit: pipeline_kernel needs 1024
     __shared__ double s_red[kP2EU][6 * 8];
     __shared__ double s_out[kP2EU][6];
     __shared__ int s_cnt[kP2EU][5];
