@@ -225,6 +225,35 @@ def lsm_keys():
     return _lib.FEATURE_KEYS
 
 
+def test_odd_number_of_steps_and_one_word_of_channels(env, small_set):
+    """T * CW odd (297 steps, 32 channels): the reservoir's spike list sits behind the bit plane and is read with 8-byte loads, so
+    the plane is padded to whole 8-byte words (round-1 advisor finding).  Stand-alone reservoir, fused kernel (one warp per CTA)
+    and host path against the oracle."""
+    import torch
+    from lsm_speech_classifier_b200.frontend import Frontend
+    from lsm_speech_classifier_b200.snn import SNN, AudioToFeatures, SimulationParams
+    from oracle import coracle, pyref
+    pcm, _ = small_set
+    thr = [0.5, 0.7, 0.9]
+    fe = Frontend(32, "gammatone", thresholds=thr, hysteresis_gap=0.15, time_bins=99)      # hop 162, 97 columns zoomed to 99
+    assert fe.steps == 297 and fe.rows == 32
+    X = coracle.gammatone_encode(pcm, fe.table, fe.params.nwin, fe.params.hop, fe.time_bins, fe.zoom_i0, fe.zoom_f, thr, 0.15)
+    assert np.array_equal(fe.encode(pcm), X) and X.shape == (len(pcm), 32, 297)
+    wc = pyref.w_critico(50, 2.0, 2, list(X))
+    lsm = SNN(SimulationParams(mean_weight=wc * 0.8, input_spike_times=X[0], num_neurons=250, small_world_graph_k=50,
+                               num_output_neurons=100))
+    fo, ro = coracle.reservoir_run(lsm.reservoir, X, 0xFF, False, True)
+    fg, rg = lsm.simulate_batch(X, nan_to_num=False, return_raster=True)
+    assert ro.sum() > 0 and np.array_equal(rg, ro) and np.array_equal(fg, fo, equal_nan=True)
+    path = AudioToFeatures(fe, lsm)
+    assert path.fused
+    keys = list(lsm_keys())
+    want = np.nan_to_num(fo)
+    got, spk = path.run(torch.from_numpy(pcm).cuda(), keys)
+    assert np.array_equal(got.cpu().numpy(), want) and np.array_equal(spk.cpu().numpy(), X)
+    assert np.array_equal(path.run_host(pcm, keys), want)
+
+
 @pytest.mark.parametrize("kw", [{}, dict(leak_variance_divisor=4.0)])
 def test_warp_specialised_lane_channel_kernel_equals_the_oracle(env, small_set, kw, monkeypatch):
     """LSM_WS=1: filter + encoder group and reservoir group side by side in one CTA, bit planes handed over through named barriers
