@@ -18,6 +18,7 @@ from lsm_speech_classifier_b200.distributed import shard_bounds  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--total", type=int, default=105000)
 ap.add_argument("--classes", type=int, default=35)
+ap.add_argument("--nccl", action="store_true", help="round-1 form: zero-copy feed, one NCCL all-gather after the kernels")
 args = ap.parse_args()
 
 rank = int(os.environ.get("RANK", "0"))
@@ -66,23 +67,49 @@ h_pcm = torch.from_numpy(pcm).pin_memory()
 d_local = torch.zeros((per, F), dtype=torch.float64, device="cuda")
 path.run_host(h_pcm[:256].numpy(), keys, out=d_local[:256])            # warm-up
 torch.cuda.synchronize()
+fused = world > 1 and not args.nccl
+if fused:
+    # round-2 form: PCM by the copy engine in batches of 2400 on alternating launch lanes, and the all-gather fused into the
+    # readout epilogue (every rank's kernel stores its rows into all ranks' matrices over NVLink)
+    from lsm_speech_classifier_b200.distributed import PeerAllGather
+    pag = PeerAllGather(per, F, torch.float64, torch.device("cuda", local_rank), n_buffers=1, ctx=fe.ctx)
+    pag.bufs[0].zero_()
+    fe.ctx.set_host_feed("copy_engine")
+    lsm.set_gather(pag.pointers(0), rank * per)
+    path.run_host_async(h_pcm[:256], keys, out=d_local[:256], lane=0)  # staging buffers of this feed
+    fe.ctx.sync_all()
+    torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 t0 = time.perf_counter()
-path.run_host(h_pcm.numpy(), keys, out=d_local[:hi - lo])              # pinned PCM in (zero-copy), feature rows stay on the device
+if fused:
+    step = 2400
+    for k, off in enumerate(range(0, hi - lo, step)):
+        n = min(step, hi - lo - off)
+        lsm.set_gather(pag.pointers(0), rank * per + off)
+        path.run_host_async(h_pcm[off:off + n], keys, out=d_local[off:off + n], lane=k & 1)
+    fe.ctx.sync_all()
+else:
+    path.run_host(h_pcm.numpy(), keys, out=d_local[:hi - lo])          # pinned PCM in (zero-copy), feature rows stay on the device
 torch.cuda.synchronize()
 t_compute = time.perf_counter() - t0
-d_all = torch.empty((world * per, F), dtype=torch.float64, device="cuda")
-if world > 1:
-    dist.barrier()
-    torch.cuda.synchronize()
-t0 = time.perf_counter()
-if world > 1:
-    dist.all_gather_into_tensor(d_all, d_local)
+if fused:
+    lsm.set_gather([], 0)
+    dist.barrier()                                                     # every rank's stores have landed
+    d_all = pag.bufs[0]
+    t_gather = 0.0
 else:
-    d_all.copy_(d_local)
-torch.cuda.synchronize()
-t_gather = time.perf_counter() - t0
+    d_all = torch.empty((world * per, F), dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    if world > 1:
+        dist.all_gather_into_tensor(d_all, d_local)
+    else:
+        d_all.copy_(d_local)
+    torch.cuda.synchronize()
+    t_gather = time.perf_counter() - t0
 times = torch.tensor([t_synth, t_compute, t_gather], dtype=torch.float64, device="cuda")
 if world > 1:
     dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -104,8 +131,12 @@ if rank == 0:
     print(f"* synthesis on the host (not part of the path): {t_synth:.1f} s per rank, {workers} worker processes each")
     print(f"* audio -> raw features, pinned host PCM in, feature rows in device memory: **{t_compute * 1e3:.1f} ms** for the slowest rank "
           f"= **{S / t_compute / 1e6:.2f} M utterances/s** over the box ({S / t_compute / world / 1e3:.0f} k per GPU)")
-    print(f"* one NCCL all-gather of the float64[{per}, {F}] blocks -> float64[{world * per}, {F}] ({gb:.2f} GB on every rank): "
-          f"{t_gather * 1e3:.1f} ms ({gb / max(t_gather, 1e-9):.0f} GB/s into each GPU)")
+    if fused:
+        print(f"* the all-gather of the float64[{per}, {F}] blocks -> float64[{world * per}, {F}] ({gb:.2f} GB on every rank) is inside that time: the "
+              f"readout epilogue of every rank's kernel stores its rows into all {world} matrices over NVLink (PCM by the copy engine in batches of 2400)")
+    else:
+        print(f"* one NCCL all-gather of the float64[{per}, {F}] blocks -> float64[{world * per}, {F}] ({gb:.2f} GB on every rank): "
+              f"{t_gather * 1e3:.1f} ms ({gb / max(t_gather, 1e-9):.0f} GB/s into each GPU)")
     print(f"* spot check on rank 0: {checked} rows out of all {world} blocks recomputed locally and compared with the gathered matrix: "
           f"bit-identical **{ok}**; exact re-executions of the speculative filter on this rank: {fe.reruns()}")
 if world > 1:
