@@ -76,7 +76,9 @@ if fused:
     pag.bufs[0].zero_()
     fe.ctx.set_host_feed("copy_engine")
     lsm.set_gather(pag.pointers(0), rank * per)
-    path.run_host_async(h_pcm[:256], keys, out=d_local[:256], lane=0)  # staging buffers of this feed
+    w = min(2400, hi - lo)
+    for ln in (0, 1):                                                  # staging buffers of this feed, both lanes, full batch size
+        path.run_host_async(h_pcm[:w], keys, out=d_local[:w], lane=ln)
     fe.ctx.sync_all()
     torch.cuda.synchronize()
 if world > 1:
