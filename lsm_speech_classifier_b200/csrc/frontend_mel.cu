@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "reservoir_core.cuh"
+#include "sqrt_rn.cuh"
 
 namespace {
 
@@ -35,10 +36,13 @@ struct MelArgs {
     const int32_t *zoom_i0;
     const double *zoom_f;
     float *scratch;          // [grid][ncols][C]
+    float *power;            // [B][ncols][C] mel power: mel_power_kernel -> mel_finish_kernel (which works in place)
+    int mel_w_len;
     uint8_t *spikes;
     double *spec_norm;       // optional [B][C][nbins]
     int B, L, C, hop, ncols, nbins, K, R;
     double thr[8], lower[8];
+    double2 tw1[31];         // twiddles of stages 1-5, stage s at offset 2^(s-1) - 1 (warp-per-frame kernel: constant-bank operands)
     ResArgs res;             // fused variants: the reservoir + readout that follow the encoder in the same CTA
 };
 
@@ -71,6 +75,89 @@ __device__ __forceinline__ void bfly(double &pr, double &pi, double &qr, double 
     const double ur = pr, ui = pi;
     pr = __dadd_rn(ur, tr); pi = __dadd_rn(ui, ti);
     qr = __dsub_rn(ur, tr); qi = __dsub_rn(ui, ti);
+}
+
+// Per-utterance epilogue shared by both mel kernels: power_to_db, floor, min-max, zoom, Schmitt triggers; spikes to global rows
+// and / or (FUSED) to the reservoir's bit plane at the start of smem_plan.  Called by all nthr threads of the CTA.
+template <int FUSED>
+__device__ __forceinline__ void mel_epilogue(const MelArgs &a, const int utt, float *plane, unsigned char *smem_plan, float *s_red,
+                                             const int tid, const int nthr)
+{
+    const int C = a.C, ncols = a.ncols;
+    // ---- power_to_db(ref=np.max, amin=1e-10, top_db=80), create_dataset.py:48
+    float tmax = -INFINITY;
+    for (int m = tid; m < C; m += nthr)
+        for (int t = 0; t < ncols; ++t) tmax = fmaxf(tmax, plane[(size_t)t * C + m]);
+    const float ref = block_reduce_f32(tmax, true, s_red);
+    const double refd = ((double)ref > 1e-10) ? (double)ref : 1e-10;               // scalar path is float64 (numpy 1.26)
+    const float ref_db = (float)__dmul_rn(10.0, lsm_log10(refd));
+    float dmax = -INFINITY, dmin = INFINITY;
+    for (int m = tid; m < C; m += nthr)
+        for (int t = 0; t < ncols; ++t) {
+            const float v = fmaxf(plane[(size_t)t * C + m], 1e-10f);
+            const float d = __fsub_rn(__fmul_rn(10.0f, (float)lsm_log10((double)v)), ref_db);
+            plane[(size_t)t * C + m] = d;
+            dmax = fmaxf(dmax, d); dmin = fminf(dmin, d);
+        }
+    const float mx = block_reduce_f32(dmax, true, s_red);
+    const float rawmin = block_reduce_f32(dmin, false, s_red);
+    const float floor_db = (float)__dsub_rn((double)mx, 80.0);
+    const float mn = fmaxf(rawmin, floor_db);                                       // min of the clamped plane
+    const float diff = __fsub_rn(mx, mn);
+    const bool degenerate = (double)diff < 1e-8;                                    // create_dataset.py:64-65
+    const float den = (float)__dadd_rn((double)diff, 1e-8);
+
+    if (FUSED) __syncthreads();                         // every thread is done with the FFT buffers: the bit plane takes their place
+    unsigned *s_bits = reinterpret_cast<unsigned *>(smem_plan);
+    const int CW = (C + 31) >> 5;
+    for (int m = tid; m < C; m += nthr) {             // whole warps (fused pairs have C % 32 == 0)
+        const int T = a.nbins * a.K;
+        uint8_t *row0 = a.spikes ? a.spikes + ((size_t)utt * C * a.R + (size_t)m * a.R) * T : nullptr;
+        double *dump = a.spec_norm ? a.spec_norm + ((size_t)utt * C + m) * a.nbins : nullptr;
+        for (int c = 0; c < ncols; ++c) {
+            const float v = fmaxf(plane[(size_t)c * C + m], floor_db);
+            plane[(size_t)c * C + m] = __fdiv_rn(__fsub_rn(v, mn), den);
+        }
+        unsigned on = 0;
+        for (int j = 0; j < a.nbins; ++j) {
+            float v;
+            if (degenerate) v = 0.0f;
+            else if (ncols == a.nbins) v = plane[(size_t)j * C + m];
+            else {
+                const int i0 = a.zoom_i0[j];
+                const double f = a.zoom_f[j];
+                double vd = __dmul_rn((double)plane[(size_t)i0 * C + m], __dsub_rn(1.0, f));
+                if (i0 + 1 < ncols) vd = __dadd_rn(vd, __dmul_rn((double)plane[(size_t)(i0 + 1) * C + m], f));
+                v = (float)vd;
+            }
+            if (dump) dump[j] = (double)v;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (k < a.K) {
+                    const bool is_on = (on >> k) & 1u;
+                    if (!is_on && v > (float)a.thr[k]) on |= (1u << k);
+                    else if (is_on && v < (float)a.lower[k]) on &= ~(1u << k);
+                }
+            }
+            if (FUSED) {
+                for (int k = 0; k < a.K; ++k) {
+                    const unsigned word = __ballot_sync(0xffffffffu, (on >> k) & 1u);
+                    if ((m & 31) == 0) s_bits[(j * a.K + k) * CW + (m >> 5)] = word;
+                }
+            }
+            if (row0) {
+                for (int r = 0; r < a.R; ++r) {
+                    uint8_t *row = row0 + (size_t)r * T + (size_t)j * a.K;
+                    if (a.K == 4) {
+                        const unsigned w = (on & 1u) | ((on & 2u) << 7) | ((on & 4u) << 14) | ((on & 8u) << 21);
+                        *reinterpret_cast<uint32_t *>(row) = w;
+                    } else {
+                        for (int k = 0; k < a.K; ++k) row[k] = (on >> k) & 1u;
+                    }
+                }
+            }
+        }
+    }
 }
 
 // FUSED: 0 = front end only (spike trains to global memory); 1 / 2 = the reservoir (lean / generic layout, 4 neurons per thread:
@@ -188,80 +275,196 @@ __global__ void __launch_bounds__(kThreads, FUSED ? 3 : 5) mel_encode_kernel(con
             // the next trip's loads touch s_re/s_im only, and ten barriers separate this read of s_S from its next write
         }
 
-        // ---- power_to_db(ref=np.max, amin=1e-10, top_db=80), create_dataset.py:48
-        float tmax = -INFINITY;
-        for (int m = tid; m < C; m += kThreads)
-            for (int t = 0; t < ncols; ++t) tmax = fmaxf(tmax, plane[(size_t)t * C + m]);
-        const float ref = block_reduce_f32(tmax, true, s_red);
-        const double refd = ((double)ref > 1e-10) ? (double)ref : 1e-10;               // scalar path is float64 (numpy 1.26)
-        const float ref_db = (float)__dmul_rn(10.0, lsm_log10(refd));
-        float dmax = -INFINITY, dmin = INFINITY;
-        for (int m = tid; m < C; m += kThreads)
-            for (int t = 0; t < ncols; ++t) {
-                const float v = fmaxf(plane[(size_t)t * C + m], 1e-10f);
-                const float d = __fsub_rn(__fmul_rn(10.0f, (float)lsm_log10((double)v)), ref_db);
-                plane[(size_t)t * C + m] = d;
-                dmax = fmaxf(dmax, d); dmin = fminf(dmin, d);
-            }
-        const float mx = block_reduce_f32(dmax, true, s_red);
-        const float rawmin = block_reduce_f32(dmin, false, s_red);
-        const float floor_db = (float)__dsub_rn((double)mx, 80.0);
-        const float mn = fmaxf(rawmin, floor_db);                                       // min of the clamped plane
-        const float diff = __fsub_rn(mx, mn);
-        const bool degenerate = (double)diff < 1e-8;                                    // create_dataset.py:64-65
-        const float den = (float)__dadd_rn((double)diff, 1e-8);
+        mel_epilogue<FUSED>(a, utt, plane, smem_raw, s_red, tid, kThreads);
+        if (FUSED) {
+            __syncthreads();                                 // the bit plane is complete
+            reservoir_simulate<4, FUSED == 1, false, 0>(a.res, utt, smem_raw, s_cnt, tid, kThreads);
+        }
+        __syncthreads();
+    }
+}
 
-        if (FUSED) __syncthreads();                         // every thread is done with the FFT buffers: the bit plane takes their place
-        unsigned *s_bits = reinterpret_cast<unsigned *>(smem_raw);
-        const int CW = (C + 31) >> 5;
-        for (int m = tid; m < C; m += kThreads) {             // whole warps (fused pairs have C % 32 == 0)
-            const int T = a.nbins * a.K;
-            uint8_t *row0 = a.spikes ? a.spikes + ((size_t)utt * C * a.R + (size_t)m * a.R) * T : nullptr;
-            double *dump = a.spec_norm ? a.spec_norm + ((size_t)utt * C + m) * a.nbins : nullptr;
-            for (int c = 0; c < ncols; ++c) {
-                const float v = fmaxf(plane[(size_t)c * C + m], floor_db);
-                plane[(size_t)c * C + m] = __fdiv_rn(__fsub_rn(v, mn), den);
-            }
-            unsigned on = 0;
-            for (int j = 0; j < a.nbins; ++j) {
-                float v;
-                if (degenerate) v = 0.0f;
-                else if (ncols == a.nbins) v = plane[(size_t)j * C + m];
-                else {
-                    const int i0 = a.zoom_i0[j];
-                    const double f = a.zoom_f[j];
-                    double vd = __dmul_rn((double)plane[(size_t)i0 * C + m], __dsub_rn(1.0, f));
-                    if (i0 + 1 < ncols) vd = __dadd_rn(vd, __dmul_rn((double)plane[(size_t)(i0 + 1) * C + m], f));
-                    v = (float)vd;
-                }
-                if (dump) dump[j] = (double)v;
+// ---- warp-per-frame arrangement (default): mel_power_kernel (STFT power -> mel power, frames are independent) followed by
+//      mel_finish_kernel (per-utterance epilogue, optionally the reservoir).  The same butterflies, untangle and projection as
+//      mel_encode_kernel - every output of a radix-2 butterfly depends only on its two inputs and its twiddle, so the schedule is
+//      free - but one warp owns a frame and the 1024 complex points live in its registers, 32 per lane:
+//        stages 1-5   lane l holds positions 32 l .. 32 l + 31 (a closed group of the first five stages); the twiddles depend on the
+//                     register slot only and come from the kernel-parameter constant bank
+//        transpose    through the warp's own 16 KB of shared memory (XOR-swizzled 16-byte slots, conflict-free both ways)
+//        stages 6-10  lane l holds positions l, l + 32, ..: twiddle T_s[l + 32 kk], one conflict-free 16-byte load per 16 / 2^(s-6)
+//                     butterflies
+//        untangle     bins l, l + 32, ..: own value from registers, the mirrored bin from shared memory
+//        projection   the power spectrum in shared memory, bands l, l + 32, .. per lane, four bands interleaved
+//      No block barrier at all in the power kernel: the block kernel spent 5.7 stall cycles per issue at its six barriers per
+//      frame (profiles/r2_summary.md, capture L).  A frame needs ~250 registers per lane, i.e. 8 warps per SM, so everything that
+//      is latency-bound (dB conversion, normalisation, Schmitt triggers, the reservoir) runs in the second kernel at full occupancy.
+constexpr int kPT = 256, kPW = kPT / 32;
+constexpr int kMelWMax = 2560;                                               // packed triangle weights held in shared memory (2 x 1025 + edges)
+constexpr size_t kMelPowerSmem = sizeof(double2) * kHalf * (2 + kPW) + sizeof(double2) * (kHalf + 2) + sizeof(float) * kMelWMax;
+
+__host__ __device__ constexpr int brev5(int r) { return ((r & 1) << 4) | ((r & 2) << 2) | (r & 4) | ((r & 8) >> 2) | ((r & 16) >> 4); }
+
+__device__ __forceinline__ void warp_frame(const MelArgs &a, const float *pcm, const int t, const double2 *s_win, const double2 *s_tw,
+                                           const double2 *s_tw2, const float *s_melw, double2 *buf, float *plane_row, const int lane)
+{
+    double re[32], im[32];
+    const int start = t * a.hop - kHalf;                           // centre padding: n_fft/2 zeros each side
+    const int jl = (int)(__brev((unsigned)lane) >> 27);
+    // ---- windowed frame, packed z[j] = x[2j] + i x[2j+1]; position 32 l + r of the bit-reversed order holds j = 32 brev5(r) + brev5(l)
+    if (start >= 0 && start + kFft <= a.L && ((reinterpret_cast<uintptr_t>(pcm + start) & 7) == 0)) {
+        const float2 *x2 = reinterpret_cast<const float2 *>(pcm + start);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if (k < a.K) {
-                        const bool is_on = (on >> k) & 1u;
-                        if (!is_on && v > (float)a.thr[k]) on |= (1u << k);
-                        else if (is_on && v < (float)a.lower[k]) on &= ~(1u << k);
-                    }
-                }
-                if (FUSED) {
-                    for (int k = 0; k < a.K; ++k) {
-                        const unsigned word = __ballot_sync(0xffffffffu, (on >> k) & 1u);
-                        if ((m & 31) == 0) s_bits[(j * a.K + k) * CW + (m >> 5)] = word;
-                    }
-                }
-                if (row0) {
-                    for (int r = 0; r < a.R; ++r) {
-                        uint8_t *row = row0 + (size_t)r * T + (size_t)j * a.K;
-                        if (a.K == 4) {
-                            const unsigned w = (on & 1u) | ((on & 2u) << 7) | ((on & 4u) << 14) | ((on & 8u) << 21);
-                            *reinterpret_cast<uint32_t *>(row) = w;
-                        } else {
-                            for (int k = 0; k < a.K; ++k) row[k] = (on >> k) & 1u;
-                        }
-                    }
-                }
+        for (int r = 0; r < 32; ++r) {
+            const int j = 32 * brev5(r) + jl;
+            const double2 w = s_win[j];
+            const float2 x = __ldg(x2 + j);
+            re[r] = __dmul_rn(w.x, (double)x.x);
+            im[r] = __dmul_rn(w.y, (double)x.y);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const int j = 32 * brev5(r) + jl;
+            const double2 w = s_win[j];
+            const int i0 = start + 2 * j, i1 = i0 + 1;
+            re[r] = (i0 >= 0 && i0 < a.L) ? __dmul_rn(w.x, (double)__ldg(pcm + i0)) : 0.0;
+            im[r] = (i1 >= 0 && i1 < a.L) ? __dmul_rn(w.y, (double)__ldg(pcm + i1)) : 0.0;
+        }
+    }
+    // ---- stages 1-5 in registers
+#pragma unroll
+    for (int s = 1; s <= 5; ++s) {
+        const int h = 1 << (s - 1);
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            if (r & h) continue;
+            bfly(re[r], im[r], re[r + h], im[r + h], a.tw1[h - 1 + (r & (h - 1))]);
+        }
+    }
+    // ---- transpose: position P = 32 g + r lives in 16-byte slot 32 g + (r ^ g)
+#pragma unroll
+    for (int r = 0; r < 32; ++r) buf[32 * lane + (r ^ lane)] = make_double2(re[r], im[r]);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const double2 v = buf[32 * k + (lane ^ k)];
+        re[k] = v.x; im[k] = v.y;
+    }
+    // ---- stages 6-10: slot k holds position 32 k + lane; stage s pairs slots k, k + 2^(s-6); twiddle index (32 k + lane) mod 2^(s-1)
+#pragma unroll
+    for (int s = 6; s <= 10; ++s) {
+        const int hk = 1 << (s - 6), h = 32 * hk;
+#pragma unroll
+        for (int kk = 0; kk < hk; ++kk) {
+            const double2 w = s_tw[h - 1 + lane + 32 * kk];
+#pragma unroll
+            for (int b = 0; b < 16 / hk; ++b) {
+                const int k = kk + 2 * hk * b;
+                bfly(re[k], im[k], re[k + hk], im[k + hk], w);
             }
         }
+    }
+    // ---- real-input untangle, complex64 rounding, |.|^2 in float32: bins lane + 32 i (own slot i) and, on lane 0, bin 1024
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) buf[32 * k + (lane ^ k)] = make_double2(re[k], im[k]);
+    __syncwarp();
+    float pw[33];
+#pragma unroll
+    for (int i = 0; i <= 32; ++i) {
+        const int kb = i < 32 ? lane + 32 * i : kHalf;
+        const int k2 = (kHalf - kb) & (kHalf - 1);
+        const double2 w = s_tw2[kb];
+        const double c_re = w.y, c_im = -w.x;                                   // -i * W
+        const double2 mz = buf[(k2 & ~31) | ((k2 ^ (k2 >> 5)) & 31)];
+        const double zr = i < 32 ? re[i] : re[0], zi = i < 32 ? im[i] : im[0], cr = mz.x, ci = -mz.y;
+        const double ar = __dmul_rn(0.5, __dadd_rn(zr, cr)), ai = __dmul_rn(0.5, __dadd_rn(zi, ci));
+        const double br = __dmul_rn(0.5, __dsub_rn(zr, cr)), bi = __dmul_rn(0.5, __dsub_rn(zi, ci));
+        const double xr = __dadd_rn(ar, __dsub_rn(__dmul_rn(c_re, br), __dmul_rn(c_im, bi)));
+        const double xi = __dadd_rn(ai, __dadd_rn(__dmul_rn(c_re, bi), __dmul_rn(c_im, br)));
+        const float r32 = (float)xr, i32 = (float)xi;
+        const double r64 = (double)r32, i64 = (double)i32;
+        const float mag = (float)sqrt_rn_inline(__dadd_rn(__dmul_rn(r64, r64), __dmul_rn(i64, i64)));
+        pw[i] = __fmul_rn(mag, mag);
+    }
+    __syncwarp();                                                   // every lane has read its mirrored bins: the spectrum takes the buffer
+    float *S = reinterpret_cast<float *>(buf);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) S[lane + 32 * i] = pw[i];
+    if (lane == 0) S[kHalf] = pw[32];
+    __syncwarp();
+    // ---- mel projection: ascending bins, float32 multiply then add; four of the lane's bands at a time for independent chains
+    for (int m0 = lane; m0 < a.C; m0 += 128) {
+        int lo[4], n[4], off[4];
+        float acc[4];
+        int nmax = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int m = m0 + 32 * u;
+            const bool ok = m < a.C;
+            lo[u] = ok ? __ldg(a.mel_lo + m) : 0;
+            n[u] = ok ? __ldg(a.mel_n + m) : 0;
+            off[u] = ok ? __ldg(a.mel_off + m) : 0;
+            acc[u] = 0.0f;
+            nmax = max(nmax, n[u]);
+        }
+        for (int qq = 0; qq < nmax; ++qq) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                           // branch-free: past a band's end the sum is kept, the loads stay in range
+                const bool on = qq < n[u];
+                const int q = on ? qq : 0;
+                const float nacc = __fadd_rn(acc[u], __fmul_rn(s_melw[off[u] + q], S[lo[u] + q]));
+                acc[u] = on ? nacc : acc[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (m0 + 32 * u < a.C) plane_row[m0 + 32 * u] = acc[u];
+    }
+    __syncwarp();                                                   // the next frame's transpose overwrites S
+}
+
+__global__ void __launch_bounds__(kPT, 1) mel_power_kernel(const __grid_constant__ MelArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *s_win = reinterpret_cast<double2 *>(smem_raw);          // [1024] (win[2j], win[2j+1])
+    double2 *s_tw = s_win + kHalf;                                   // per-stage tables as in mel_encode_kernel
+    double2 *s_tw2 = s_tw + kHalf;                                   // [1025] (+ 1 pad)
+    double2 *s_x = s_tw2 + kHalf + 2;                                // [kPW][1024]
+    float *s_melw = reinterpret_cast<float *>(s_x + (size_t)kPW * kHalf);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int j = tid; j < kHalf; j += kPT) s_win[j] = make_double2(__ldg(a.win + 2 * j), __ldg(a.win + 2 * j + 1));
+    for (int q = tid; q < kHalf - 1; q += kPT) {
+        const int s = 32 - __clz(q + 1);
+        s_tw[q] = __ldg(a.tw + (q + 1 - (1 << (s - 1))) * (kHalf >> s));
+    }
+    for (int k = tid; k <= kHalf; k += kPT) s_tw2[k] = __ldg(a.tw2 + k);
+    for (int q = tid; q < a.mel_w_len; q += kPT) s_melw[q] = __ldg(a.mel_w + q);
+    __syncthreads();
+    const long long frames = (long long)a.B * a.ncols;
+    for (long long f = (long long)blockIdx.x * kPW + warp; f < frames; f += (long long)gridDim.x * kPW) {
+        const int utt = (int)(f / a.ncols), t = (int)(f - (long long)utt * a.ncols);
+        warp_frame(a, a.pcm + (size_t)utt * a.L, t, s_win, s_tw, s_tw2, s_melw, s_x + (size_t)warp * kHalf,
+                   a.power + (size_t)f * a.C, lane);
+    }
+}
+
+// second kernel: one CTA per utterance in flight; FUSED as in mel_encode_kernel (the reservoir plan is the whole dynamic allocation)
+template <int FUSED>
+__global__ void __launch_bounds__(kThreads, FUSED ? 3 : 5) mel_finish_kernel(const MelArgs a, int *next_utt)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float s_red[kThreads / 32];
+    __shared__ int s_utt;
+    __shared__ int s_cnt[5];
+    const int tid = threadIdx.x;
+    for (;;) {
+        if (tid == 0) s_utt = atomicAdd(next_utt, 1);
+        __syncthreads();
+        const int utt = s_utt;
+        if (utt >= a.B) break;
+        mel_epilogue<FUSED>(a, utt, a.power + (size_t)utt * a.ncols * a.C, smem_raw, s_red, tid, kThreads);
         if (FUSED) {
             __syncthreads();                                 // the bit plane is complete
             reservoir_simulate<4, FUSED == 1, false, 0>(a.res, utt, smem_raw, s_cnt, tid, kThreads);
@@ -281,11 +484,23 @@ int up(lsm_ctx *ctx, T **dst, const T *src, size_t n)
 
 }  // namespace
 
+// stages 1-5 of the FFT use twiddles tw[j * (1024 >> s)], j < 2^(s-1): 31 values, kept on the host for the kernel parameters
+static void mel_host_tw1(lsm_frontend *fe, const double *h_tw)
+{
+    for (int s = 1; s <= 5; ++s)
+        for (int j = 0; j < (1 << (s - 1)); ++j) {
+            const int q = j * (kHalf >> s), o = (1 << (s - 1)) - 1 + j;
+            fe->mel_tw1[2 * o] = h_tw[2 * q];
+            fe->mel_tw1[2 * o + 1] = h_tw[2 * q + 1];
+        }
+}
+
 int lsm_mel_set_tables(lsm_ctx *ctx, lsm_frontend *fe, const double *h_win, const double *h_tw, const double *h_tw2)
 {
     LSM_CUDA(ctx, cudaMemcpy(fe->d_window, h_win, sizeof(double) * kFft, cudaMemcpyHostToDevice));
     LSM_CUDA(ctx, cudaMemcpy(fe->d_twiddle, h_tw, sizeof(double) * 2 * (kHalf / 2), cudaMemcpyHostToDevice));
     LSM_CUDA(ctx, cudaMemcpy(fe->d_twiddle2, h_tw2, sizeof(double) * 2 * (kHalf + 1), cudaMemcpyHostToDevice));
+    mel_host_tw1(fe, h_tw);
     return LSM_OK;
 }
 
@@ -318,7 +533,14 @@ int lsm_mel_create(lsm_ctx *ctx, lsm_frontend *fe, const float *h_basis)
     if (rc == LSM_OK) rc = up(ctx, (double **)&fe->d_twiddle, tw.data(), tw.size());
     if (rc == LSM_OK) rc = up(ctx, (double **)&fe->d_twiddle2, tw2.data(), tw2.size());
     if (rc != LSM_OK) return rc;
+    mel_host_tw1(fe, tw.data());
     int per_sm = 0;
+    fe->mel_w_len = (int)w.size();
+    if (fe->mel_w_len <= kMelWMax) {
+        LSM_CUDA(ctx, cudaFuncSetAttribute(mel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMelPowerSmem));
+        LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_finish_kernel<0>, kThreads, 0));
+        fe->grid_warp = per_sm * ctx->sm_count;
+    }
     LSM_CUDA(ctx, cudaFuncSetAttribute(mel_encode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMelSmemBytes));
     LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_encode_kernel<0>, kThreads, kMelSmemBytes));
     if (per_sm < 1) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "mel kernel does not fit on an SM");
@@ -332,6 +554,7 @@ void lsm_mel_destroy(lsm_frontend *fe)
 {
     cudaFree(fe->d_mel_w); cudaFree(fe->d_mel_lo); cudaFree(fe->d_mel_n); cudaFree(fe->d_mel_off);
     cudaFree(fe->d_window); cudaFree(fe->d_twiddle); cudaFree(fe->d_twiddle2); cudaFree(fe->d_mel_scratch);
+    cudaFree(fe->d_mel_power);
 }
 
 // Can this mel front end hand its spike trains to this reservoir inside one kernel?  Whole warps of channels, no redundancy,
@@ -348,6 +571,37 @@ bool lsm_mel_fused_ok(const lsm_frontend *fe, const lsm_reservoir *res)
 
 static void mel_fill(const lsm_frontend *fe, const float *d_pcm, int B, uint8_t *d_spikes, double *d_spec_norm, MelArgs *out);
 
+// Warp-per-frame arrangement unless LSM_MEL_BLOCK is set (the block-per-frame kernels of round 1, kept selectable) or the packed
+// weights do not fit in shared memory.
+static bool mel_use_warp(const lsm_frontend *fe)
+{
+    static const bool block_fft = getenv("LSM_MEL_BLOCK") != nullptr;
+    return !block_fft && fe->grid_warp > 0;
+}
+
+static int mel_power_reserve(lsm_ctx *ctx, lsm_frontend *fe, int B)
+{
+    if (B <= fe->mel_power_cap) return LSM_OK;
+    const int cap = (B + 255) & ~255;
+    LSM_CUDA(ctx, cudaDeviceSynchronize());
+    cudaFree(fe->d_mel_power);
+    fe->d_mel_power = nullptr; fe->mel_power_cap = 0;
+    LSM_CUDA(ctx, cudaMalloc((void **)&fe->d_mel_power, sizeof(float) * (size_t)cap * fe->ncols * fe->p.channels));
+    fe->mel_power_cap = cap;
+    return LSM_OK;
+}
+
+static int mel_power_launch(lsm_ctx *ctx, const MelArgs &a, cudaStream_t st)
+{
+    const long long warps = (long long)a.B * a.ncols;
+    long long grid = (warps + kPW - 1) / kPW;
+    if (grid > ctx->sm_count) grid = ctx->sm_count;
+    mel_power_kernel<<<(int)grid, kPT, kMelPowerSmem, st>>>(a);
+    ctx->launches += 1;
+    LSM_CUDA(ctx, cudaGetLastError());
+    return LSM_OK;
+}
+
 // audio -> features in one launch (mel): features as lsm_launch_reservoir writes them, spike trains optional
 int lsm_launch_mel_fused(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, const float *d_pcm, int B, uint8_t *d_spikes_or_null,
                          uint32_t feature_mask, int nan_to_num, double *d_features, cudaStream_t st, long long row0)
@@ -358,12 +612,33 @@ int lsm_launch_mel_fused(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, con
     lsm_reservoir_fill_args(res, nullptr, B, feature_mask, nan_to_num, d_features, nullptr, &a.res);
     a.res.gather_row0 += row0;
     size_t smem = lsm_res_smem_bytes(a.res.T, a.res.CW, 4 * kThreads, a.res.N);
-    if (smem < kMelSmemBytes) smem = kMelSmemBytes;
-    int rc = lsm_frontend_order_before(ctx, fe, st);
+    const bool warp = mel_use_warp(fe);
+    int rc = warp ? mel_power_reserve(ctx, fe, B) : LSM_OK;
     if (rc != LSM_OK) return rc;
+    a.power = fe->d_mel_power;
+    if (!warp && smem < kMelSmemBytes) smem = kMelSmemBytes;
+    if ((rc = lsm_frontend_order_before(ctx, fe, st)) != LSM_OK) return rc;
     int *counter = fe->d_counters + (fe->counter_next++ % 64);
     LSM_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), st));
     int per_sm = 0;
+    if (warp) {
+        if ((rc = mel_power_launch(ctx, a, st)) != LSM_OK) return rc;
+        if (res->lean) {
+            LSM_CUDA(ctx, cudaFuncSetAttribute(mel_finish_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_finish_kernel<1>, kThreads, smem));
+        } else {
+            LSM_CUDA(ctx, cudaFuncSetAttribute(mel_finish_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_finish_kernel<2>, kThreads, smem));
+        }
+        if (per_sm < 1) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "fused mel kernel does not fit on an SM");
+        int grid = per_sm * ctx->sm_count;
+        if (grid > B) grid = B;
+        if (res->lean) mel_finish_kernel<1><<<grid, kThreads, smem, st>>>(a, counter);
+        else mel_finish_kernel<2><<<grid, kThreads, smem, st>>>(a, counter);
+        ctx->launches += 1;
+        LSM_CUDA(ctx, cudaGetLastError());
+        return lsm_frontend_order_after(ctx, fe, st);
+    }
     if (res->lean) {
         LSM_CUDA(ctx, cudaFuncSetAttribute(mel_encode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_encode_kernel<1>, kThreads, smem));
@@ -389,10 +664,11 @@ static void mel_fill(const lsm_frontend *fe, const float *d_pcm, int B, uint8_t 
     a.pcm = d_pcm; a.win = fe->d_window; a.tw = fe->d_twiddle; a.tw2 = fe->d_twiddle2;
     a.mel_w = fe->d_mel_w; a.mel_lo = fe->d_mel_lo; a.mel_n = fe->d_mel_n; a.mel_off = fe->d_mel_off;
     a.zoom_i0 = fe->d_zoom_i0; a.zoom_f = fe->d_zoom_f; a.scratch = fe->d_mel_scratch;
-    a.spikes = d_spikes; a.spec_norm = d_spec_norm;
+    a.spikes = d_spikes; a.spec_norm = d_spec_norm; a.power = fe->d_mel_power; a.mel_w_len = fe->mel_w_len;
     a.B = B; a.L = p.n_samples; a.C = p.channels; a.hop = p.mel_hop; a.ncols = fe->ncols; a.nbins = p.n_bins;
     a.K = p.n_thresholds; a.R = p.redundancy;
     for (int k = 0; k < 8; ++k) { a.thr[k] = p.thresholds_desc[k]; a.lower[k] = p.lower_bounds[k]; }
+    for (int o = 0; o < 31; ++o) a.tw1[o] = make_double2(fe->mel_tw1[2 * o], fe->mel_tw1[2 * o + 1]);
     memset(&a.res, 0, sizeof(a.res));
 }
 
@@ -401,13 +677,20 @@ int lsm_launch_mel(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, ui
 {
     if (B <= 0) return LSM_OK;
     MelArgs a;
-    mel_fill(fe, d_pcm, B, d_spikes, d_spec_norm, &a);
-    int rc = lsm_frontend_order_before(ctx, fe, st);
+    int rc = mel_use_warp(fe) ? mel_power_reserve(ctx, fe, B) : LSM_OK;
     if (rc != LSM_OK) return rc;
+    mel_fill(fe, d_pcm, B, d_spikes, d_spec_norm, &a);
+    if ((rc = lsm_frontend_order_before(ctx, fe, st)) != LSM_OK) return rc;
     int *counter = fe->d_counters + (fe->counter_next++ % 64);
     LSM_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), st));
-    const int grid = B < fe->grid ? B : fe->grid;
-    mel_encode_kernel<0><<<grid, kThreads, kMelSmemBytes, st>>>(a, counter);
+    if (mel_use_warp(fe)) {
+        if ((rc = mel_power_launch(ctx, a, st)) != LSM_OK) return rc;
+        const int grid = B < fe->grid_warp ? B : fe->grid_warp;
+        mel_finish_kernel<0><<<grid, kThreads, 0, st>>>(a, counter);
+    } else {
+        const int grid = B < fe->grid ? B : fe->grid;
+        mel_encode_kernel<0><<<grid, kThreads, kMelSmemBytes, st>>>(a, counter);
+    }
     ctx->launches += 1;
     LSM_CUDA(ctx, cudaGetLastError());
     return lsm_frontend_order_after(ctx, fe, st);

@@ -71,6 +71,11 @@ struct lsm_frontend {
     double2 *d_twiddle = nullptr;  // [n_fft/4]  exp(-2 pi i q / (n_fft/2))
     double2 *d_twiddle2 = nullptr; // [n_fft/2 + 1]  exp(-2 pi i k / n_fft)
     float *d_mel_scratch = nullptr; // per-CTA [ncols][C] mel power / dB plane
+    double mel_tw1[62] = {0};      // host copy of the twiddles of FFT stages 1-5 (kernel-parameter constants of the warp-per-frame kernel)
+    int grid_warp = 0;             // grid of mel_finish_kernel<0> (warp-per-frame arrangement; 0: packed weights too long, block kernel only)
+    int mel_w_len = 0;             // packed mel weights (floats)
+    float *d_mel_power = nullptr;  // [mel_power_cap][ncols][C] mel power between the two kernels of the warp-per-frame arrangement
+    int mel_power_cap = 0;
 };
 
 struct lsm_reservoir {

@@ -24,3 +24,9 @@ for _ in range(3):
     out, _ = path.run(d_pcm, keys, want_spikes=False)
 torch.cuda.synchronize()
 print("ok fused" if path.fused else "ok two-kernel", float(out.sum()))
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(5):
+    path.run(d_pcm, keys, want_spikes=False)
+b.record(); torch.cuda.synchronize()
+print("ms per batch", a.elapsed_time(b) / 5)
