@@ -16,6 +16,8 @@
 // explicit *_rn intrinsics, no FMA contraction.  librosa's own FFT (pocketfft) has a different internal order;
 // the oracle documents that and is itself compared with scipy.fft.
 #include <math.h>
+#include <string.h>
+#include <algorithm>
 #include <vector>
 
 #include "reservoir_core.cuh"
@@ -37,7 +39,8 @@ struct MelArgs {
     const double *zoom_f;
     float *scratch;          // [grid][ncols][C]
     float *power;            // [B][ncols][C] mel power: mel_power_kernel -> mel_finish_kernel (which works in place)
-    int mel_w_len;
+    const uint2 *sched;      // [sched_len][32] projection schedule of the warp-per-frame kernel: (weight bits, bin | (band + 1) << 16)
+    int sched_len;
     uint8_t *spikes;
     double *spec_norm;       // optional [B][C][nbins]
     int B, L, C, hop, ncols, nbins, K, R;
@@ -299,13 +302,14 @@ __global__ void __launch_bounds__(kThreads, FUSED ? 3 : 5) mel_encode_kernel(con
 //      frame (profiles/r2_summary.md, capture L).  A frame needs ~250 registers per lane, i.e. 8 warps per SM, so everything that
 //      is latency-bound (dB conversion, normalisation, Schmitt triggers, the reservoir) runs in the second kernel at full occupancy.
 constexpr int kPT = 256, kPW = kPT / 32;
-constexpr int kMelWMax = 2560;                                               // packed triangle weights held in shared memory (2 x 1025 + edges)
-constexpr size_t kMelPowerSmem = sizeof(double2) * kHalf * (2 + kPW) + sizeof(double2) * (kHalf + 2) + sizeof(float) * kMelWMax;
+constexpr int kSchedMax = 160;                                               // longest projection schedule held in shared memory (steps)
+constexpr int kZeroBin = kHalf + 2;                                          // a spectrum slot that always holds 0 (schedule padding)
+constexpr size_t kMelPowerSmemBase = sizeof(double2) * kHalf * (2 + kPW) + sizeof(double2) * (kHalf + 2);
 
 __host__ __device__ constexpr int brev5(int r) { return ((r & 1) << 4) | ((r & 2) << 2) | (r & 4) | ((r & 8) >> 2) | ((r & 16) >> 4); }
 
 __device__ __forceinline__ void warp_frame(const MelArgs &a, const float *pcm, const int t, const double2 *s_win, const double2 *s_tw,
-                                           const double2 *s_tw2, const float *s_melw, double2 *buf, float *plane_row, const int lane)
+                                           const double2 *s_tw2, const uint2 *s_sched, double2 *buf, float *plane_row, const int lane)
 {
     double re[32], im[32];
     const int start = t * a.hop - kHalf;                           // centre padding: n_fft/2 zeros each side
@@ -392,34 +396,19 @@ __device__ __forceinline__ void warp_frame(const MelArgs &a, const float *pcm, c
 #pragma unroll
     for (int i = 0; i < 32; ++i) S[lane + 32 * i] = pw[i];
     if (lane == 0) S[kHalf] = pw[32];
+    if (lane == 1) S[kZeroBin] = 0.0f;
     __syncwarp();
-    // ---- mel projection: ascending bins, float32 multiply then add; four of the lane's bands at a time for independent chains
-    for (int m0 = lane; m0 < a.C; m0 += 128) {
-        int lo[4], n[4], off[4];
-        float acc[4];
-        int nmax = 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int m = m0 + 32 * u;
-            const bool ok = m < a.C;
-            lo[u] = ok ? __ldg(a.mel_lo + m) : 0;
-            n[u] = ok ? __ldg(a.mel_n + m) : 0;
-            off[u] = ok ? __ldg(a.mel_off + m) : 0;
-            acc[u] = 0.0f;
-            nmax = max(nmax, n[u]);
-        }
-        for (int qq = 0; qq < nmax; ++qq) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {                           // branch-free: past a band's end the sum is kept, the loads stay in range
-                const bool on = qq < n[u];
-                const int q = on ? qq : 0;
-                const float nacc = __fadd_rn(acc[u], __fmul_rn(s_melw[off[u] + q], S[lo[u] + q]));
-                acc[u] = on ? nacc : acc[u];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (m0 + 32 * u < a.C) plane_row[m0 + 32 * u] = acc[u];
+    // ---- mel projection: ascending bins, float32 multiply then add.  The host deals the bands out to the 32 lanes so that every
+    //      lane has the same number of terms (lsm_mel_create): step k of a lane is one term of one of its bands, a band's last term
+    //      carries the band's index and the sum is stored; lanes that run out of terms add 0 x 0 to a sum nobody reads.
+    float acc = 0.0f;
+#pragma unroll 4
+    for (int k = 0; k < a.sched_len; ++k) {
+        const uint2 e = s_sched[k * 32 + lane];
+        const float nacc = __fadd_rn(acc, __fmul_rn(__uint_as_float(e.x), S[e.y & 0xffffu]));
+        const unsigned out = e.y >> 16;
+        if (out) plane_row[out - 1] = nacc;
+        acc = out ? 0.0f : nacc;
     }
     __syncwarp();                                                   // the next frame's transpose overwrites S
 }
@@ -431,7 +420,7 @@ __global__ void __launch_bounds__(kPT, 1) mel_power_kernel(const __grid_constant
     double2 *s_tw = s_win + kHalf;                                   // per-stage tables as in mel_encode_kernel
     double2 *s_tw2 = s_tw + kHalf;                                   // [1025] (+ 1 pad)
     double2 *s_x = s_tw2 + kHalf + 2;                                // [kPW][1024]
-    float *s_melw = reinterpret_cast<float *>(s_x + (size_t)kPW * kHalf);
+    uint2 *s_sched = reinterpret_cast<uint2 *>(s_x + (size_t)kPW * kHalf);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int j = tid; j < kHalf; j += kPT) s_win[j] = make_double2(__ldg(a.win + 2 * j), __ldg(a.win + 2 * j + 1));
@@ -440,12 +429,22 @@ __global__ void __launch_bounds__(kPT, 1) mel_power_kernel(const __grid_constant
         s_tw[q] = __ldg(a.tw + (q + 1 - (1 << (s - 1))) * (kHalf >> s));
     }
     for (int k = tid; k <= kHalf; k += kPT) s_tw2[k] = __ldg(a.tw2 + k);
-    for (int q = tid; q < a.mel_w_len; q += kPT) s_melw[q] = __ldg(a.mel_w + q);
+    for (int q = tid; q < a.sched_len * 32; q += kPT) s_sched[q] = __ldg(a.sched + q);
     __syncthreads();
+    // a CTA owns a contiguous run of frames and its warps walk it side by side: consecutive frames share 92 % of their samples, so
+    // the run streams through L1 once; each warp prefetches the hop its next frame adds
     const long long frames = (long long)a.B * a.ncols;
-    for (long long f = (long long)blockIdx.x * kPW + warp; f < frames; f += (long long)gridDim.x * kPW) {
+    const long long f0 = frames * blockIdx.x / gridDim.x, f1 = frames * (blockIdx.x + 1) / gridDim.x;
+    for (long long f = f0 + warp; f < f1; f += kPW) {
         const int utt = (int)(f / a.ncols), t = (int)(f - (long long)utt * a.ncols);
-        warp_frame(a, a.pcm + (size_t)utt * a.L, t, s_win, s_tw, s_tw2, s_melw, s_x + (size_t)warp * kHalf,
+        if (f + kPW < f1 && lane < 8) {
+            const long long fn = f + kPW;
+            const int un = (int)(fn / a.ncols), tn = (int)(fn - (long long)un * a.ncols);
+            long long i = (long long)tn * a.hop + kHalf - a.hop + 32 * lane;        // the last hop of the next frame, 128 bytes per lane
+            i = i < 0 ? 0 : (i > a.L - 1 ? a.L - 1 : i);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.pcm + (size_t)un * a.L + i));
+        }
+        warp_frame(a, a.pcm + (size_t)utt * a.L, t, s_win, s_tw, s_tw2, s_sched, s_x + (size_t)warp * kHalf,
                    a.power + (size_t)f * a.C, lane);
     }
 }
@@ -464,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, FUSED ? 3 : 5) mel_finish_kernel(con
         __syncthreads();
         const int utt = s_utt;
         if (utt >= a.B) break;
-        mel_epilogue<FUSED>(a, utt, a.power + (size_t)utt * a.ncols * a.C, smem_raw, s_red, tid, kThreads);
+        mel_epilogue<FUSED>(a, utt, a.power + (size_t)utt * a.ncols * a.C, smem_raw, s_red, tid, (int)blockDim.x);
         if (FUSED) {
             __syncthreads();                                 // the bit plane is complete
             reservoir_simulate<4, FUSED == 1, false, 0>(a.res, utt, smem_raw, s_cnt, tid, kThreads);
@@ -535,11 +534,43 @@ int lsm_mel_create(lsm_ctx *ctx, lsm_frontend *fe, const float *h_basis)
     if (rc != LSM_OK) return rc;
     mel_host_tw1(fe, tw.data());
     int per_sm = 0;
-    fe->mel_w_len = (int)w.size();
-    if (fe->mel_w_len <= kMelWMax) {
-        LSM_CUDA(ctx, cudaFuncSetAttribute(mel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMelPowerSmem));
-        LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_finish_kernel<0>, kThreads, 0));
-        fe->grid_warp = per_sm * ctx->sm_count;
+    // projection schedule of the warp-per-frame kernel: bands dealt to 32 lanes, longest first, each to the lane with the fewest terms
+    {
+        std::vector<int> order(C), total(32, 0);
+        std::vector<std::vector<int>> mine(32);
+        for (int m = 0; m < C; ++m) order[m] = m;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return n[x] > n[y]; });
+        for (int m : order) {
+            int best = 0;
+            for (int l = 1; l < 32; ++l) if (total[l] < total[best]) best = l;
+            mine[best].push_back(m);
+            total[best] += n[m] > 0 ? n[m] : 1;
+        }
+        int len = 0;
+        for (int l = 0; l < 32; ++l) len = total[l] > len ? total[l] : len;
+        fe->mel_sched_len = len;
+        if (len <= kSchedMax) {
+            std::vector<uint32_t> sched((size_t)len * 32 * 2);
+            for (int l = 0; l < 32; ++l) {
+                int k = 0;
+                auto put = [&](float wv, uint32_t bin, uint32_t out) {
+                    uint32_t bits; memcpy(&bits, &wv, 4);
+                    sched[((size_t)k * 32 + l) * 2] = bits; sched[((size_t)k * 32 + l) * 2 + 1] = bin | (out << 16); ++k;
+                };
+                for (int m : mine[l]) {
+                    if (n[m] == 0) put(0.0f, kZeroBin, (uint32_t)m + 1);               // an empty triangle: the sum is 0
+                    for (int q = 0; q < n[m]; ++q) put(w[off[m] + q], (uint32_t)(lo[m] + q), q == n[m] - 1 ? (uint32_t)m + 1 : 0u);
+                }
+                while (k < len) put(0.0f, kZeroBin, 0u);
+            }
+            if ((rc = up(ctx, &fe->d_mel_sched, sched.data(), sched.size())) != LSM_OK) return rc;
+            const size_t smem = kMelPowerSmemBase + sizeof(uint2) * 32 * (size_t)len;
+            LSM_CUDA(ctx, cudaFuncSetAttribute(mel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            fe->finish_threads = C <= 64 ? 64 : (C + 31) & ~31;
+            if (fe->finish_threads > kThreads) fe->finish_threads = kThreads;
+            LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_finish_kernel<0>, fe->finish_threads, 0));
+            fe->grid_warp = per_sm * ctx->sm_count;
+        }
     }
     LSM_CUDA(ctx, cudaFuncSetAttribute(mel_encode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMelSmemBytes));
     LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_encode_kernel<0>, kThreads, kMelSmemBytes));
@@ -554,7 +585,7 @@ void lsm_mel_destroy(lsm_frontend *fe)
 {
     cudaFree(fe->d_mel_w); cudaFree(fe->d_mel_lo); cudaFree(fe->d_mel_n); cudaFree(fe->d_mel_off);
     cudaFree(fe->d_window); cudaFree(fe->d_twiddle); cudaFree(fe->d_twiddle2); cudaFree(fe->d_mel_scratch);
-    cudaFree(fe->d_mel_power);
+    cudaFree(fe->d_mel_power); cudaFree(fe->d_mel_sched);
 }
 
 // Can this mel front end hand its spike trains to this reservoir inside one kernel?  Whole warps of channels, no redundancy,
@@ -596,7 +627,7 @@ static int mel_power_launch(lsm_ctx *ctx, const MelArgs &a, cudaStream_t st)
     const long long warps = (long long)a.B * a.ncols;
     long long grid = (warps + kPW - 1) / kPW;
     if (grid > ctx->sm_count) grid = ctx->sm_count;
-    mel_power_kernel<<<(int)grid, kPT, kMelPowerSmem, st>>>(a);
+    mel_power_kernel<<<(int)grid, kPT, kMelPowerSmemBase + sizeof(uint2) * 32 * (size_t)a.sched_len, st>>>(a);
     ctx->launches += 1;
     LSM_CUDA(ctx, cudaGetLastError());
     return LSM_OK;
@@ -664,7 +695,8 @@ static void mel_fill(const lsm_frontend *fe, const float *d_pcm, int B, uint8_t 
     a.pcm = d_pcm; a.win = fe->d_window; a.tw = fe->d_twiddle; a.tw2 = fe->d_twiddle2;
     a.mel_w = fe->d_mel_w; a.mel_lo = fe->d_mel_lo; a.mel_n = fe->d_mel_n; a.mel_off = fe->d_mel_off;
     a.zoom_i0 = fe->d_zoom_i0; a.zoom_f = fe->d_zoom_f; a.scratch = fe->d_mel_scratch;
-    a.spikes = d_spikes; a.spec_norm = d_spec_norm; a.power = fe->d_mel_power; a.mel_w_len = fe->mel_w_len;
+    a.spikes = d_spikes; a.spec_norm = d_spec_norm; a.power = fe->d_mel_power;
+    a.sched = reinterpret_cast<const uint2 *>(fe->d_mel_sched); a.sched_len = fe->mel_sched_len;
     a.B = B; a.L = p.n_samples; a.C = p.channels; a.hop = p.mel_hop; a.ncols = fe->ncols; a.nbins = p.n_bins;
     a.K = p.n_thresholds; a.R = p.redundancy;
     for (int k = 0; k < 8; ++k) { a.thr[k] = p.thresholds_desc[k]; a.lower[k] = p.lower_bounds[k]; }
@@ -686,7 +718,7 @@ int lsm_launch_mel(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, ui
     if (mel_use_warp(fe)) {
         if ((rc = mel_power_launch(ctx, a, st)) != LSM_OK) return rc;
         const int grid = B < fe->grid_warp ? B : fe->grid_warp;
-        mel_finish_kernel<0><<<grid, kThreads, 0, st>>>(a, counter);
+        mel_finish_kernel<0><<<grid, fe->finish_threads, 0, st>>>(a, counter);
     } else {
         const int grid = B < fe->grid ? B : fe->grid;
         mel_encode_kernel<0><<<grid, kThreads, kMelSmemBytes, st>>>(a, counter);

@@ -73,7 +73,9 @@ struct lsm_frontend {
     float *d_mel_scratch = nullptr; // per-CTA [ncols][C] mel power / dB plane
     double mel_tw1[62] = {0};      // host copy of the twiddles of FFT stages 1-5 (kernel-parameter constants of the warp-per-frame kernel)
     int grid_warp = 0;             // grid of mel_finish_kernel<0> (warp-per-frame arrangement; 0: packed weights too long, block kernel only)
-    int mel_w_len = 0;             // packed mel weights (floats)
+    uint32_t *d_mel_sched = nullptr; // [mel_sched_len][32][2] projection schedule of the warp-per-frame kernel
+    int mel_sched_len = 0;
+    int finish_threads = 256;      // block size of mel_finish_kernel<0>: the channels rounded up to whole warps
     float *d_mel_power = nullptr;  // [mel_power_cap][ncols][C] mel power between the two kernels of the warp-per-frame arrangement
     int mel_power_cap = 0;
 };
