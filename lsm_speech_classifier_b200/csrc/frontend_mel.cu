@@ -80,28 +80,59 @@ __device__ __forceinline__ void bfly(double &pr, double &pi, double &qr, double 
     qr = __dsub_rn(ur, tr); qi = __dsub_rn(ui, ti);
 }
 
-// Per-utterance epilogue shared by both mel kernels: power_to_db, floor, min-max, zoom, Schmitt triggers; spikes to global rows
+// Per-utterance epilogue shared by the mel kernels: power_to_db, floor, min-max, zoom, Schmitt triggers; spikes to global rows
 // and / or (FUSED) to the reservoir's bit plane at the start of smem_plan.  Called by all nthr threads of the CTA.
+// The passes over the plane (global memory, L2-resident) are latency-bound, so every pass issues its loads in groups:
+// the maximum over eight frames at a time, the dB pass over four, and normalisation is folded into the zoom, four output
+// bins (eight plane values) at a time.
+__device__ __forceinline__ float mel_db(const float p, const float ref_db)
+{
+    return __fsub_rn(__fmul_rn(10.0f, (float)lsm_log10((double)fmaxf(p, 1e-10f))), ref_db);
+}
+
 template <int FUSED>
-__device__ __forceinline__ void mel_epilogue(const MelArgs &a, const int utt, float *plane, unsigned char *smem_plan, float *s_red,
-                                             const int tid, const int nthr)
+__device__ __forceinline__ void mel_epilogue(const MelArgs &a, const int utt, float *__restrict__ plane, unsigned char *smem_plan,
+                                             float *s_red, const int tid, const int nthr)
 {
     const int C = a.C, ncols = a.ncols;
     // ---- power_to_db(ref=np.max, amin=1e-10, top_db=80), create_dataset.py:48
     float tmax = -INFINITY;
-    for (int m = tid; m < C; m += nthr)
-        for (int t = 0; t < ncols; ++t) tmax = fmaxf(tmax, plane[(size_t)t * C + m]);
+    for (int m = tid; m < C; m += nthr) {
+        const float *col = plane + m;
+        int t = 0;
+        for (; t + 8 <= ncols; t += 8) {
+            float p[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) p[u] = col[(size_t)(t + u) * C];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) tmax = fmaxf(tmax, p[u]);
+        }
+        for (; t < ncols; ++t) tmax = fmaxf(tmax, col[(size_t)t * C]);
+    }
     const float ref = block_reduce_f32(tmax, true, s_red);
     const double refd = ((double)ref > 1e-10) ? (double)ref : 1e-10;               // scalar path is float64 (numpy 1.26)
     const float ref_db = (float)__dmul_rn(10.0, lsm_log10(refd));
     float dmax = -INFINITY, dmin = INFINITY;
-    for (int m = tid; m < C; m += nthr)
-        for (int t = 0; t < ncols; ++t) {
-            const float v = fmaxf(plane[(size_t)t * C + m], 1e-10f);
-            const float d = __fsub_rn(__fmul_rn(10.0f, (float)lsm_log10((double)v)), ref_db);
-            plane[(size_t)t * C + m] = d;
+    for (int m = tid; m < C; m += nthr) {
+        float *col = plane + m;
+        int t = 0;
+        for (; t + 4 <= ncols; t += 4) {
+            float p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[u] = col[(size_t)(t + u) * C];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float d = mel_db(p[u], ref_db);
+                col[(size_t)(t + u) * C] = d;
+                dmax = fmaxf(dmax, d); dmin = fminf(dmin, d);
+            }
+        }
+        for (; t < ncols; ++t) {
+            const float d = mel_db(col[(size_t)t * C], ref_db);
+            col[(size_t)t * C] = d;
             dmax = fmaxf(dmax, d); dmin = fminf(dmin, d);
         }
+    }
     const float mx = block_reduce_f32(dmax, true, s_red);
     const float rawmin = block_reduce_f32(dmin, false, s_red);
     const float floor_db = (float)__dsub_rn((double)mx, 80.0);
@@ -113,49 +144,72 @@ __device__ __forceinline__ void mel_epilogue(const MelArgs &a, const int utt, fl
     if (FUSED) __syncthreads();                         // every thread is done with the FFT buffers: the bit plane takes their place
     unsigned *s_bits = reinterpret_cast<unsigned *>(smem_plan);
     const int CW = (C + 31) >> 5;
+    const bool same_grid = ncols == a.nbins;
     for (int m = tid; m < C; m += nthr) {             // whole warps (fused pairs have C % 32 == 0)
         const int T = a.nbins * a.K;
         uint8_t *row0 = a.spikes ? a.spikes + ((size_t)utt * C * a.R + (size_t)m * a.R) * T : nullptr;
         double *dump = a.spec_norm ? a.spec_norm + ((size_t)utt * C + m) * a.nbins : nullptr;
-        for (int c = 0; c < ncols; ++c) {
-            const float v = fmaxf(plane[(size_t)c * C + m], floor_db);
-            plane[(size_t)c * C + m] = __fdiv_rn(__fsub_rn(v, mn), den);
-        }
+        const float *col = plane + m;
         unsigned on = 0;
-        for (int j = 0; j < a.nbins; ++j) {
-            float v;
-            if (degenerate) v = 0.0f;
-            else if (ncols == a.nbins) v = plane[(size_t)j * C + m];
-            else {
-                const int i0 = a.zoom_i0[j];
-                const double f = a.zoom_f[j];
-                double vd = __dmul_rn((double)plane[(size_t)i0 * C + m], __dsub_rn(1.0, f));
-                if (i0 + 1 < ncols) vd = __dadd_rn(vd, __dmul_rn((double)plane[(size_t)(i0 + 1) * C + m], f));
-                v = (float)vd;
-            }
-            if (dump) dump[j] = (double)v;
+        for (int j0 = 0; j0 < a.nbins; j0 += 4) {
+            // normalised (create_dataset.py:62-67) and zoomed (:69-78) values of four bins; the loads first
+            int i0[4];
+            double f[4];
+            float lo[4], hi[4], v4[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (k < a.K) {
-                    const bool is_on = (on >> k) & 1u;
-                    if (!is_on && v > (float)a.thr[k]) on |= (1u << k);
-                    else if (is_on && v < (float)a.lower[k]) on &= ~(1u << k);
+            for (int u = 0; u < 4; ++u) {
+                const int j = min(j0 + u, a.nbins - 1);
+                i0[u] = same_grid ? j : __ldg(a.zoom_i0 + j);
+                f[u] = same_grid ? 0.0 : __ldg(a.zoom_f + j);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                lo[u] = col[(size_t)i0[u] * C];
+                hi[u] = (!same_grid && i0[u] + 1 < ncols) ? col[(size_t)(i0[u] + 1) * C] : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float nlo = __fdiv_rn(__fsub_rn(fmaxf(lo[u], floor_db), mn), den);
+                if (degenerate) v4[u] = 0.0f;
+                else if (same_grid) v4[u] = nlo;
+                else {
+                    double vd = __dmul_rn((double)nlo, __dsub_rn(1.0, f[u]));
+                    if (i0[u] + 1 < ncols) {
+                        const float nhi = __fdiv_rn(__fsub_rn(fmaxf(hi[u], floor_db), mn), den);
+                        vd = __dadd_rn(vd, __dmul_rn((double)nhi, f[u]));
+                    }
+                    v4[u] = (float)vd;
                 }
             }
-            if (FUSED) {
-                for (int k = 0; k < a.K; ++k) {
-                    const unsigned word = __ballot_sync(0xffffffffu, (on >> k) & 1u);
-                    if ((m & 31) == 0) s_bits[(j * a.K + k) * CW + (m >> 5)] = word;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u;
+                if (j >= a.nbins) break;
+                const float v = v4[u];
+                if (dump) dump[j] = (double)v;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (k < a.K) {
+                        const bool is_on = (on >> k) & 1u;
+                        if (!is_on && v > (float)a.thr[k]) on |= (1u << k);
+                        else if (is_on && v < (float)a.lower[k]) on &= ~(1u << k);
+                    }
                 }
-            }
-            if (row0) {
-                for (int r = 0; r < a.R; ++r) {
-                    uint8_t *row = row0 + (size_t)r * T + (size_t)j * a.K;
-                    if (a.K == 4) {
-                        const unsigned w = (on & 1u) | ((on & 2u) << 7) | ((on & 4u) << 14) | ((on & 8u) << 21);
-                        *reinterpret_cast<uint32_t *>(row) = w;
-                    } else {
-                        for (int k = 0; k < a.K; ++k) row[k] = (on >> k) & 1u;
+                if (FUSED) {
+                    for (int k = 0; k < a.K; ++k) {
+                        const unsigned word = __ballot_sync(0xffffffffu, (on >> k) & 1u);
+                        if ((m & 31) == 0) s_bits[(j * a.K + k) * CW + (m >> 5)] = word;
+                    }
+                }
+                if (row0) {
+                    for (int r = 0; r < a.R; ++r) {
+                        uint8_t *row = row0 + (size_t)r * T + (size_t)j * a.K;
+                        if (a.K == 4) {
+                            const unsigned w = (on & 1u) | ((on & 2u) << 7) | ((on & 4u) << 14) | ((on & 8u) << 21);
+                            *reinterpret_cast<uint32_t *>(row) = w;
+                        } else {
+                            for (int k = 0; k < a.K; ++k) row[k] = (on >> k) & 1u;
+                        }
                     }
                 }
             }
