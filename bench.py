@@ -184,7 +184,7 @@ MEL_FP64_OPS_PER_UTT = 101 * (2048 + 5120 * 10 + 1025 * 20) + 101 * 128 * 45
 
 def mel_numbers(pcm_np, steps, warmup, cpu_sample=96):
     """The same step through the mel front end (librosa branch of create_dataset.py:43-48), one GPU: the fused
-    audio -> features kernel, K1m and K2 alone, host buffers end to end, parity with the C oracle on a sample."""
+    audio -> features path (spike trains stay on chip), K1m and K2 alone, host buffers end to end, parity with the C oracle on a sample."""
     import torch
     from lsm_speech_classifier_b200 import _lib, filterbank as fb
     from lsm_speech_classifier_b200.extract_lsm_features import FEATURE_SETS, build_lsm
@@ -237,9 +237,9 @@ def mel_numbers(pcm_np, steps, warmup, cpu_sample=96):
             "kernel_ms": {"K1m_mel_encode": k1_ms, "K2_reservoir_features": k2_ms},
             "e2e": {"value": e2e, "unit": "utterances/s", "note": "pageable numpy arrays through lsm_pipeline_run_host (chunked H2D | kernel | D2H)",
                     "same_rows_as_device_path": same_as_device},
-            "roofline": {"kernel": "mel_encode_kernel (K1m)", "bound": "fp64", "achieved": gops, "peak": peak,
+            "roofline": {"kernel": "mel_power_kernel + mel_finish_kernel (K1m)", "bound": "fp64", "achieved": gops, "peak": peak,
                          "unit": "G fp64 lane-ops/s", "frac": gops / peak, "lane_ops_per_utterance": MEL_FP64_OPS_PER_UTT,
-                         "note": "fp64 radix-2 FFT in shared memory: barrier / shared-memory bound, not pipe bound (DESIGN.md K1m)"},
+                         "note": "warp-per-frame fp64 radix-2 FFT in registers: 8 warps per SM (250 registers per lane), latency / instruction-fetch bound, not pipe bound (DESIGN.md K1m)"},
             "cpu_baseline": {"value": cpu, "unit": "utterances/s", "cores": coracle.num_threads(), "kind": "port",
                              "sample": f"{len(sample)} utterances, oracle C port (mel)", "gpu_matches_cpu_bit_exact": bool(np.array_equal(got, want))}}
 
