@@ -1168,6 +1168,14 @@ extern "C" int lsm_pipeline_run_host(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservo
     // copies that are not hidden.
     const bool fused = lsm_fused_npt(fe, res) != 0;
     const bool mel_fused = !fused && lsm_mel_fused_ok(fe, res);
+    // pageable arrays, fused mel pair: the same pinned ring + host copy threads as the stage calls (cudaMemcpyAsync from pageable
+    // memory is a staged copy inside the driver at 6-8 GB/s, far below what the kernels take)
+    if (mel_fused && !h_spikes_or_null && B >= 512 && is_pageable(h_pcm) && is_pageable(h_features) && !getenv("LSM_NO_PAGEABLE_RING"))
+        return host_ring_staged(ctx, B, 768, (size_t)L * sizeof(float), feat_per * sizeof(double), h_pcm, h_features, 2,
+                                [&](const void *d_in, void *d_out, int n, cudaStream_t st, long long off) {
+                                    return lsm_launch_mel_fused(ctx, fe, res, (const float *)d_in, n, nullptr, feature_mask, nan_to_num,
+                                                                (double *)d_out, st, off);
+                                });
     int wave = fe->grid > 0 ? fe->grid : 1024;
     if (fused) { const int w = lsm_fused_wave(ctx, fe, res); if (w > 0) wave = w; }
     int n_chunks = B / wave;

@@ -376,6 +376,20 @@ def test_mel_fused_kernel_equals_two_kernel_path_and_oracle(env, small_set, n_fi
     assert np.array_equal(path.run_host(big, keys), np.concatenate([want] * 70)[:1931])
 
 
+def test_block_per_frame_kernels_stay_selectable(env):
+    """LSM_MEL_BLOCK=1 selects round 1's block-per-frame kernels (read once per process, hence the child process): the same
+    parity tests pass with them."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-x", "-q", "-m", "gpu", "-k",
+                        "mel_spikes_and_spectrogram_bit_exact or mel_fused_kernel_equals"],
+                       env=dict(os.environ, LSM_MEL_BLOCK="1"), cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
+
+
 def test_mel_golden_vectors(env, golden):
     from lsm_speech_classifier_b200.frontend import Frontend
     g = golden("frontend_mel64.npz")
