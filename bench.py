@@ -235,7 +235,7 @@ def mel_numbers(pcm_np, steps, warmup, cpu_sample=96):
     gops = MEL_FP64_OPS_PER_UTT * B / (k1_ms / 1e3) / 1e9
     return {"filterbank": "mel", "value": B / (step_ms / 1e3), "unit": "utterances/s", "ms_per_step": step_ms, "fused_one_kernel": bool(path.fused),
             "kernel_ms": {"K1m_mel_encode": k1_ms, "K2_reservoir_features": k2_ms},
-            "e2e": {"value": e2e, "unit": "utterances/s", "note": "pageable numpy arrays through lsm_pipeline_run_host (chunked H2D | kernel | D2H)",
+            "e2e": {"value": e2e, "unit": "utterances/s", "note": "pageable numpy arrays through lsm_pipeline_run_host (pinned ring filled by host copy threads | H2D | kernels | D2H on two lanes)",
                     "same_rows_as_device_path": same_as_device},
             "roofline": {"kernel": "mel_power_kernel + mel_finish_kernel (K1m)", "bound": "fp64", "achieved": gops, "peak": peak,
                          "unit": "G fp64 lane-ops/s", "frac": gops / peak, "lane_ops_per_utterance": MEL_FP64_OPS_PER_UTT,

@@ -6,11 +6,13 @@
 //   librosa.power_to_db(spec, ref=np.max)                                     :48     (amin 1e-10, top_db 80)
 //   min-max normalisation :62-67, scipy zoom 101 -> 100 :69-78, encoder :81-98, redundancy :101-104
 //
-// Mapping: one CTA (256 threads) per utterance in flight, persistent grid with dynamic hand-out.  Per frame: the
-// 2048 real samples (fp64 window x float32 PCM) are packed as 1024 complex numbers, transformed by a shared-
-// memory radix-2 FFT in fp64 and untangled to the 1025 real-input bins; power in float32; each thread owns one
-// mel band and sums its (short) triangle in ascending-bin order.  The per-utterance epilogue (dB, floor,
-// normalise, zoom, Schmitt triggers) is the float32 twin of K1's.
+// Mapping (default, "warp-per-frame"): two kernels.  mel_power_kernel: frames are independent; one warp per frame, the 1024
+// packed complex points of the 2048-sample frame (fp64 window x float32 PCM) in its registers, radix-2 FFT in fp64 with one
+// transpose through shared memory, untangle to the 1025 real-input bins, power in float32, mel projection by a lane-balanced
+// schedule (ascending bins per band) -> mel power [B][frames][C] in device memory.  mel_finish_kernel: one CTA per utterance
+// in flight: dB, floor, normalise, zoom, Schmitt triggers (the float32 twin of K1's epilogue) and, fused, the reservoir.
+// LSM_MEL_BLOCK=1 selects round 1's arrangement instead (mel_encode_kernel: one 256-thread CTA per utterance, block-wide
+// shared-memory FFT per frame, one band per thread), which also serves filter banks whose schedule does not fit.
 //
 // Bit-exactness: every operation and its order equals oracle/lsm_oracle.c (fft1024 / frame_power / mel_one);
 // explicit *_rn intrinsics, no FMA contraction.  librosa's own FFT (pocketfft) has a different internal order;
@@ -362,16 +364,14 @@ constexpr size_t kMelPowerSmemBase = sizeof(double2) * kHalf * (2 + kPW) + sizeo
 
 __host__ __device__ constexpr int brev5(int r) { return ((r & 1) << 4) | ((r & 2) << 2) | (r & 4) | ((r & 8) >> 2) | ((r & 16) >> 4); }
 
-// PAIR: the two warps that share an SM sub-partition (warp w and w + 4) meet at a 64-thread named barrier after every phase while
-// both have a frame, so that they walk the ~80 KB of straight-line code together and share its instruction fetches.
-template <int PAIR>
+// The two warps that share an SM sub-partition (warp w and w + 4) meet at a 64-thread named barrier after every phase while both
+// have a frame, so that they walk the ~80 KB of straight-line code together and share its instruction fetches (3.16 -> 3.05 ms;
+// all eight warps in step: 3.06).
 __device__ __forceinline__ void pair_sync(const bool both, const int bar)
 {
-    if (PAIR == 1 && both) asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");
-    if (PAIR == 2 && both) asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (both) asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");
 }
 
-template <int PAIR>
 __device__ __forceinline__ void warp_frame(const MelArgs &a, const float *pcm, const int t, const double2 *s_win, const double2 *s_tw,
                                            const double2 *s_tw2, const uint2 *s_sched, double2 *buf, float *plane_row, const int lane,
                                            const bool both, const int bar)
@@ -400,7 +400,7 @@ __device__ __forceinline__ void warp_frame(const MelArgs &a, const float *pcm, c
             im[r] = (i1 >= 0 && i1 < a.L) ? __dmul_rn(w.y, (double)__ldg(pcm + i1)) : 0.0;
         }
     }
-    pair_sync<PAIR>(both, bar);
+    pair_sync(both, bar);
     // ---- stages 1-5 in registers
 #pragma unroll
     for (int s = 1; s <= 5; ++s) {
@@ -411,7 +411,7 @@ __device__ __forceinline__ void warp_frame(const MelArgs &a, const float *pcm, c
             bfly(re[r], im[r], re[r + h], im[r + h], a.tw1[h - 1 + (r & (h - 1))]);
         }
     }
-    pair_sync<PAIR>(both, bar);
+    pair_sync(both, bar);
     // ---- transpose: position P = 32 g + r lives in 16-byte slot 32 g + (r ^ g)
 #pragma unroll
     for (int r = 0; r < 32; ++r) buf[32 * lane + (r ^ lane)] = make_double2(re[r], im[r]);
@@ -436,7 +436,7 @@ __device__ __forceinline__ void warp_frame(const MelArgs &a, const float *pcm, c
         }
     }
     // ---- real-input untangle, complex64 rounding, |.|^2 in float32: bins lane + 32 i (own slot i) and, on lane 0, bin 1024
-    pair_sync<PAIR>(both, bar);
+    pair_sync(both, bar);
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 32; ++k) buf[32 * k + (lane ^ k)] = make_double2(re[k], im[k]);
@@ -459,7 +459,7 @@ __device__ __forceinline__ void warp_frame(const MelArgs &a, const float *pcm, c
         const float mag = (float)sqrt_rn_inline(__dadd_rn(__dmul_rn(r64, r64), __dmul_rn(i64, i64)));
         pw[i] = __fmul_rn(mag, mag);
     }
-    pair_sync<PAIR>(both, bar);
+    pair_sync(both, bar);
     __syncwarp();                                                   // every lane has read its mirrored bins: the spectrum takes the buffer
     float *S = reinterpret_cast<float *>(buf);
 #pragma unroll
@@ -482,7 +482,6 @@ __device__ __forceinline__ void warp_frame(const MelArgs &a, const float *pcm, c
     __syncwarp();                                                   // the next frame's transpose overwrites S
 }
 
-template <int PAIR>
 __global__ void __launch_bounds__(kPT, 1) mel_power_kernel(const __grid_constant__ MelArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -514,8 +513,8 @@ __global__ void __launch_bounds__(kPT, 1) mel_power_kernel(const __grid_constant
             i = i < 0 ? 0 : (i > a.L - 1 ? a.L - 1 : i);
             asm volatile("prefetch.global.L1 [%0];" ::"l"(a.pcm + (size_t)un * a.L + i));
         }
-        warp_frame<PAIR>(a, a.pcm + (size_t)utt * a.L, t, s_win, s_tw, s_tw2, s_sched, s_x + (size_t)warp * kHalf,
-                         a.power + (size_t)f * a.C, lane, f - warp + (PAIR == 2 ? kPW - 1 : (warp | 4)) < f1, 1 + (warp & 3));
+        warp_frame(a, a.pcm + (size_t)utt * a.L, t, s_win, s_tw, s_tw2, s_sched, s_x + (size_t)warp * kHalf,
+                   a.power + (size_t)f * a.C, lane, f - warp + (warp | 4) < f1, 1 + (warp & 3));
     }
 }
 
@@ -635,9 +634,7 @@ int lsm_mel_create(lsm_ctx *ctx, lsm_frontend *fe, const float *h_basis)
             }
             if ((rc = up(ctx, &fe->d_mel_sched, sched.data(), sched.size())) != LSM_OK) return rc;
             const size_t smem = kMelPowerSmemBase + sizeof(uint2) * 32 * (size_t)len;
-            LSM_CUDA(ctx, cudaFuncSetAttribute(mel_power_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LSM_CUDA(ctx, cudaFuncSetAttribute(mel_power_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LSM_CUDA(ctx, cudaFuncSetAttribute(mel_power_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LSM_CUDA(ctx, cudaFuncSetAttribute(mel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             fe->finish_threads = C <= 64 ? 64 : (C + 31) & ~31;
             if (fe->finish_threads > kThreads) fe->finish_threads = kThreads;
             LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_finish_kernel<0>, fe->finish_threads, 0));
@@ -699,11 +696,7 @@ static int mel_power_launch(lsm_ctx *ctx, const MelArgs &a, cudaStream_t st)
     const long long warps = (long long)a.B * a.ncols;
     long long grid = (warps + kPW - 1) / kPW;
     if (grid > ctx->sm_count) grid = ctx->sm_count;
-    static const int pair = getenv("LSM_MEL_PAIR") ? atoi(getenv("LSM_MEL_PAIR")) : 1;
-    const size_t smem = kMelPowerSmemBase + sizeof(uint2) * 32 * (size_t)a.sched_len;
-    if (pair == 2) mel_power_kernel<2><<<(int)grid, kPT, smem, st>>>(a);
-    else if (pair == 1) mel_power_kernel<1><<<(int)grid, kPT, smem, st>>>(a);
-    else mel_power_kernel<0><<<(int)grid, kPT, smem, st>>>(a);
+    mel_power_kernel<<<(int)grid, kPT, kMelPowerSmemBase + sizeof(uint2) * 32 * (size_t)a.sched_len, st>>>(a);
     ctx->launches += 1;
     LSM_CUDA(ctx, cudaGetLastError());
     return LSM_OK;
