@@ -518,9 +518,11 @@ __global__ void __launch_bounds__(kPT, 1) mel_power_kernel(const __grid_constant
     }
 }
 
-// second kernel: one CTA per utterance in flight; FUSED as in mel_encode_kernel (the reservoir plan is the whole dynamic allocation)
-template <int FUSED>
-__global__ void __launch_bounds__(kThreads, FUSED ? 3 : 5) mel_finish_kernel(const MelArgs a, int *next_utt)
+// second kernel: one CTA per utterance in flight; FUSED as in mel_encode_kernel (the reservoir plan is the whole dynamic allocation).
+// NPT = neurons per thread of the fused reservoir: 8 with 128 threads when the channels fit (every thread has a channel in the
+// epilogue and 8 neurons afterwards, as in the fused gammatone kernel), 4 with 256 threads for wider filter banks.
+template <int FUSED, int NPT>
+__global__ void __launch_bounds__(NPT == 8 ? 128 : kThreads, FUSED == 1 ? (NPT == 8 ? 6 : 4) : FUSED == 2 ? (NPT == 8 ? 5 : 3) : 5) mel_finish_kernel(const MelArgs a, int *next_utt)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float s_red[kThreads / 32];
@@ -535,10 +537,26 @@ __global__ void __launch_bounds__(kThreads, FUSED ? 3 : 5) mel_finish_kernel(con
         mel_epilogue<FUSED>(a, utt, a.power + (size_t)utt * a.ncols * a.C, smem_raw, s_red, tid, (int)blockDim.x);
         if (FUSED) {
             __syncthreads();                                 // the bit plane is complete
-            reservoir_simulate<4, FUSED == 1, false, 0>(a.res, utt, smem_raw, s_cnt, tid, kThreads);
+            reservoir_simulate<NPT, FUSED == 1, false, 0>(a.res, utt, smem_raw, s_cnt, tid, (int)blockDim.x);
         }
         __syncthreads();
     }
+}
+
+template <int FUSED, int NPT>
+static int mel_finish_fused_launch(lsm_ctx *ctx, const MelArgs &a, int *counter, size_t smem, int B, cudaStream_t st)
+{
+    const int threads = NPT == 8 ? 128 : kThreads;
+    int per_sm = 0;
+    LSM_CUDA(ctx, cudaFuncSetAttribute(mel_finish_kernel<FUSED, NPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_finish_kernel<FUSED, NPT>, threads, smem));
+    if (per_sm < 1) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "fused mel kernel does not fit on an SM");
+    int grid = per_sm * ctx->sm_count;
+    if (grid > B) grid = B;
+    mel_finish_kernel<FUSED, NPT><<<grid, threads, smem, st>>>(a, counter);
+    ctx->launches += 1;
+    LSM_CUDA(ctx, cudaGetLastError());
+    return LSM_OK;
 }
 
 template <typename T>
@@ -637,7 +655,7 @@ int lsm_mel_create(lsm_ctx *ctx, lsm_frontend *fe, const float *h_basis)
             LSM_CUDA(ctx, cudaFuncSetAttribute(mel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             fe->finish_threads = C <= 64 ? 64 : (C + 31) & ~31;
             if (fe->finish_threads > kThreads) fe->finish_threads = kThreads;
-            LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_finish_kernel<0>, fe->finish_threads, 0));
+            LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_finish_kernel<0, 4>, fe->finish_threads, 0));
             fe->grid_warp = per_sm * ctx->sm_count;
         }
     }
@@ -723,20 +741,10 @@ int lsm_launch_mel_fused(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoir *res, con
     int per_sm = 0;
     if (warp) {
         if ((rc = mel_power_launch(ctx, a, st)) != LSM_OK) return rc;
-        if (res->lean) {
-            LSM_CUDA(ctx, cudaFuncSetAttribute(mel_finish_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_finish_kernel<1>, kThreads, smem));
-        } else {
-            LSM_CUDA(ctx, cudaFuncSetAttribute(mel_finish_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LSM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_finish_kernel<2>, kThreads, smem));
-        }
-        if (per_sm < 1) LSM_FAIL(ctx, LSM_ERR_UNSUPPORTED, "fused mel kernel does not fit on an SM");
-        int grid = per_sm * ctx->sm_count;
-        if (grid > B) grid = B;
-        if (res->lean) mel_finish_kernel<1><<<grid, kThreads, smem, st>>>(a, counter);
-        else mel_finish_kernel<2><<<grid, kThreads, smem, st>>>(a, counter);
-        ctx->launches += 1;
-        LSM_CUDA(ctx, cudaGetLastError());
+        const bool narrow = a.C <= 128;                       // 128 threads x 8 neurons, else 256 x 4
+        if (res->lean) rc = narrow ? mel_finish_fused_launch<1, 8>(ctx, a, counter, smem, B, st) : mel_finish_fused_launch<1, 4>(ctx, a, counter, smem, B, st);
+        else rc = narrow ? mel_finish_fused_launch<2, 8>(ctx, a, counter, smem, B, st) : mel_finish_fused_launch<2, 4>(ctx, a, counter, smem, B, st);
+        if (rc != LSM_OK) return rc;
         return lsm_frontend_order_after(ctx, fe, st);
     }
     if (res->lean) {
@@ -787,7 +795,7 @@ int lsm_launch_mel(lsm_ctx *ctx, lsm_frontend *fe, const float *d_pcm, int B, ui
     if (mel_use_warp(fe)) {
         if ((rc = mel_power_launch(ctx, a, st)) != LSM_OK) return rc;
         const int grid = B < fe->grid_warp ? B : fe->grid_warp;
-        mel_finish_kernel<0><<<grid, fe->finish_threads, 0, st>>>(a, counter);
+        mel_finish_kernel<0, 4><<<grid, fe->finish_threads, 0, st>>>(a, counter);
     } else {
         const int grid = B < fe->grid ? B : fe->grid;
         mel_encode_kernel<0><<<grid, kThreads, kMelSmemBytes, st>>>(a, counter);
