@@ -23,7 +23,6 @@
 #include <vector>
 
 #include "reservoir_core.cuh"
-#include "sqrt_rn.cuh"
 
 namespace {
 

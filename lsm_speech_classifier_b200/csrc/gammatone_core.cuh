@@ -415,6 +415,20 @@ __device__ __forceinline__ float cell_err(double x_db, float kx, bool &bad)
     return 8.69f * 1.01f * __fdividef(r, 1.0f - r) + 1e-12f;
 }
 
+// 20 log10(sqrt(mean square) + 1e-9) for the speculative plane, without a branch: the library's sqrt and log10 each end their
+// basic block with a slow-path test, which kept the seven columns a thread has in flight from overlapping and costs ~110 more
+// instructions per value than this.  sqrt_rn_inline is exact for 2^-970 <= m < inf and returns 2 m below that (< 1e-290: nothing
+// beside the 1e-9), lsm_log10 is the exact path's own log10 (< 1 ulp; argument >= 1e-9); non-finite energies stay non-finite so
+// that the utterance is flagged as before.  Accuracy is inside what kMiscRel and cell_err's 1e-12 already allow.
+__device__ __forceinline__ double spec_db(const double m)
+{
+    const double arg = sqrt_rn_inline(m) + 1e-9;
+    const double db = 20.0 * lsm_log10(arg);
+    return arg < 1.0e300 ? db : arg;
+}
+
+constexpr int kSpecCols = 5;                  // columns a thread has in flight in spec_db_pass (7 spill at 80 registers)
+
 struct SpecStats {
     double mx, mn;          // speculative plane: maximum, minimum after the floor
     double floor_db, rden;  // mx - 80, 1 / (mx - mn + 1e-8)
@@ -439,22 +453,22 @@ __device__ __forceinline__ SpecStats spec_db_pass(const GtArgs &a, double *col, 
         const double g2n = G * G / (double)a.nwin;      // (A0^4 / gain)^2 / nwin: energy sum -> mean square of the real output
         const float kx = (float)(a.kappa[ch] * (double)xmax) * a.bound_scale;
         int c0 = 0;
-        for (; c0 + 7 <= ncols; c0 += 7) {
-            double e[7];
+        for (; c0 + kSpecCols <= ncols; c0 += kSpecCols) {
+            double e[kSpecCols];
 #pragma unroll
-            for (int u = 0; u < 7; ++u) e[u] = __ldcg(col + (size_t)(c0 + u) * C);
+            for (int u = 0; u < kSpecCols; ++u) e[u] = __ldcg(col + (size_t)(c0 + u) * C);
 #pragma unroll
-            for (int u = 0; u < 7; ++u) {
-                e[u] = 20.0 * log10(sqrt(e[u] * g2n) + 1e-9);
+            for (int u = 0; u < kSpecCols; ++u) {
+                e[u] = spec_db(e[u] * g2n);
                 const double er = (double)cell_err(e[u], kx, bad);
                 vmax[0] = fmax(vmax[0], e[u]); vmax[1] = fmax(vmax[1], e[u] - er); vmax[2] = fmax(vmax[2], e[u] + er);
                 vmin[0] = fmin(vmin[0], e[u]); vmin[1] = fmin(vmin[1], e[u] - er); vmin[2] = fmin(vmin[2], e[u] + er);
             }
 #pragma unroll
-            for (int u = 0; u < 7; ++u) col[(size_t)(c0 + u) * C] = e[u];
+            for (int u = 0; u < kSpecCols; ++u) col[(size_t)(c0 + u) * C] = e[u];
         }
         for (; c0 < ncols; ++c0) {
-            const double e = 20.0 * log10(sqrt(__ldcg(col + (size_t)c0 * C) * g2n) + 1e-9);
+            const double e = spec_db(__ldcg(col + (size_t)c0 * C) * g2n);
             const double er = (double)cell_err(e, kx, bad);
             vmax[0] = fmax(vmax[0], e); vmax[1] = fmax(vmax[1], e - er); vmax[2] = fmax(vmax[2], e + er);
             vmin[0] = fmin(vmin[0], e); vmin[1] = fmin(vmin[1], e - er); vmin[2] = fmin(vmin[2], e + er);

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include "lsm_b200.h"
+#include "sqrt_rn.cuh"
 
 struct lsm_copy_pool;
 void lsm_copy_pool_free(lsm_copy_pool *p);
@@ -213,7 +214,7 @@ __device__ __forceinline__ double lsm_log10(double x)
     k += (i >> 20);
     double f = sub64(x, 1.0);
     double hfsq = mul64(mul64(0.5, f), f);
-    double s = __ddiv_rn(f, add64(2.0, f));
+    double s = div_rn_inline(f, add64(2.0, f));                 // = __ddiv_rn without its slow-path branch (sqrt_rn.cuh)
     double z = mul64(s, s);
     double w = mul64(z, z);
     double t1 = mul64(w, add64(LG2, mul64(w, add64(LG4, mul64(w, LG6)))));
