@@ -376,6 +376,36 @@ def test_mel_fused_kernel_equals_two_kernel_path_and_oracle(env, small_set, n_fi
     assert np.array_equal(path.run_host(big, keys), np.concatenate([want] * 70)[:1931])
 
 
+def test_mel_config3_scale_every_frame_position_of_the_power_kernel(env):
+    """BASELINE config 3 at a size that exercises the power kernel's whole grid: 1500 utterances x 101 frames are dealt to 148 CTAs
+    in contiguous runs, so run boundaries, warp pairs whose partner has no frame left and utterance boundaries inside a run all occur.
+    Spike trains and all eight features against the C oracle; device path, pinned ring (pageable numpy arrays) and a second batch
+    size that moves every boundary."""
+    import torch
+    from lsm_speech_classifier_b200 import synth
+    from lsm_speech_classifier_b200.frontend import Frontend
+    from lsm_speech_classifier_b200.snn import AudioToFeatures
+    from oracle import coracle
+    pcm, _ = synth.synth_dataset(30, 50, workers=8)                       # 1500 utterances
+    pcm[7] = 0.0                                                           # a silent one in the middle of a run
+    pcm[1499, 4000:] = 0.0
+    fe = Frontend(128, "mel")
+    X = oracle_mel(pcm, fe)
+    assert X.sum() > 100000
+    got = fe.encode(torch.from_numpy(pcm).cuda()).cpu().numpy()
+    assert np.array_equal(got, X)
+    assert np.array_equal(fe.encode(torch.from_numpy(pcm[3:1180]).cuda()).cpu().numpy(), X[3:1180])
+    lsm = build_snn(X[:300])
+    want, _ = coracle.reservoir_run(lsm.reservoir, X, 0xFF, True, False)
+    keys = list(lsm_keys())
+    path = AudioToFeatures(fe, lsm)
+    assert path.fused
+    feats, _ = path.run(torch.from_numpy(pcm).cuda(), keys, want_spikes=False)
+    assert np.array_equal(feats.cpu().numpy(), want)
+    assert np.array_equal(path.run_host(pcm, keys), want)                 # pageable: two pieces of 768 through the pinned ring
+    lsm.close()
+
+
 def test_block_per_frame_kernels_stay_selectable(env):
     """LSM_MEL_BLOCK=1 selects round 1's block-per-frame kernels (read once per process, hence the child process): the same
     parity tests pass with them."""
