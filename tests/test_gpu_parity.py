@@ -420,6 +420,23 @@ def test_block_per_frame_kernels_stay_selectable(env):
     assert " passed" in r.stdout and "failed" not in r.stdout
 
 
+def test_diagnostic_switches_give_the_same_bytes(env):
+    """The library's diagnostic switches (read once per process, hence the child process): exact filter from the
+    start, generic reservoir layout, no dead-time skipping, staged copies instead of zero-copy, two host copy threads.  The parity
+    tests of the front end, the reservoir, the host pipeline and the fused kernel pass unchanged."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env2 = dict(os.environ, LSM_EXACT_FILTER="1", LSM_NO_LEAN="1", LSM_NO_DEAD_TIME_SKIP="1", LSM_NO_ZEROCOPY="1", LSM_COPY_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-x", "-q", "-m", "gpu", "-k",
+                        "gammatone_spikes_and_spectrogram_bit_exact or reservoir_raster_and_features_bit_exact or "
+                        "pipeline_host_equals_staged_calls or fused_kernel_equals_two_kernel_path or async_host_calls_on_two_lanes"],
+                       env=env2, cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
+
+
 def test_mel_golden_vectors(env, golden):
     from lsm_speech_classifier_b200.frontend import Frontend
     g = golden("frontend_mel64.npz")
