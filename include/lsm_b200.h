@@ -275,7 +275,9 @@ int lsm_pipeline_run_host_async_i16(lsm_ctx *ctx, lsm_frontend *fe, lsm_reservoi
 /* The cudaStream_t of launch lane 0 / 1, so that a caller can order its own work (an NCCL all-gather of the feature rows, a copy)
  * after an asynchronous call on that lane.  NULL for a bad argument.                                                       */
 void *lsm_lane_stream(lsm_ctx *ctx, int32_t lane);
-/* 1 if lsm_pipeline_run / lsm_pipeline_run_host execute this pair as one fused kernel, else 0. */
+/* 1 if lsm_pipeline_run / lsm_pipeline_run_host execute this pair fused - the spike train is handed to the reservoir inside the
+ * kernel and never written to device memory unless asked for (gammatone: one persistent kernel; mel: the power kernel followed by
+ * one epilogue + reservoir kernel) - else 0 (front-end kernel, spike trains in device memory, reservoir kernel).               */
 int lsm_pipeline_is_fused(const lsm_frontend *fe, const lsm_reservoir *res);
 
 /* Sum of all spike bytes and their count: the two integers calculate_theoretical_w_critico
