@@ -233,6 +233,7 @@ __device__ __forceinline__ void gt_filter_fast(const GtArgs &a, const PcmRow pcm
     const int n_used = (ncols - 1) * hop + nwin;
     const int n_blocks = (n_used + hop - 1) / hop;
     const int n_chunks = (n_blocks + kChunkBlocks - 1) / kChunkBlocks;
+    const bool pairs = !(hop & 1) && !(reinterpret_cast<uintptr_t>(s_x) & 15);
 
     double c1 = 0, c2 = 0, c3 = 0, c4 = 0, na1 = 0, na2 = 0;
     if (live) {
@@ -281,12 +282,23 @@ __device__ __forceinline__ void gt_filter_fast(const GtArgs &a, const PcmRow pcm
                 const int n_here = min(hop, n_used - m * hop);
                 const int n_a = min(n_here, r_old);
                 acc = 0.0;
+                if (pairs && !(n_a & 1)) {
+                    // two samples per 16-byte shared-memory load (the buffers and an even hop keep xb 16-byte aligned)
+                    const double2 *x2 = reinterpret_cast<const double2 *>(xb);
+#pragma unroll 4
+                    for (int p = 0; p < n_a / 2; ++p) { const double2 v = x2[p]; LSM_FAST_SAMPLE(v.x); LSM_FAST_SAMPLE(v.y); }
+                    if (n_a == r_old && m >= 2) plane[(size_t)(m - 2) * C + ch] = (full2 + full1) + acc;
+#pragma unroll 4
+                    for (int p = n_a / 2; p < n_here / 2; ++p) { const double2 v = x2[p]; LSM_FAST_SAMPLE(v.x); LSM_FAST_SAMPLE(v.y); }
+                    if (n_here & 1) LSM_FAST_SAMPLE(xb[n_here - 1]);
+                } else {
 #pragma unroll 8
-                for (int p = 0; p < n_a; ++p) LSM_FAST_SAMPLE(xb[p]);
-                // window m-2 complete: its raw energy sum; dB is taken in the epilogue, where the columns give ILP
-                if (n_a == r_old && m >= 2) plane[(size_t)(m - 2) * C + ch] = (full2 + full1) + acc;
+                    for (int p = 0; p < n_a; ++p) LSM_FAST_SAMPLE(xb[p]);
+                    // window m-2 complete: its raw energy sum; dB is taken in the epilogue, where the columns give ILP
+                    if (n_a == r_old && m >= 2) plane[(size_t)(m - 2) * C + ch] = (full2 + full1) + acc;
 #pragma unroll 8
-                for (int p = n_a; p < n_here; ++p) LSM_FAST_SAMPLE(xb[p]);
+                    for (int p = n_a; p < n_here; ++p) LSM_FAST_SAMPLE(xb[p]);
+                }
                 full2 = full1;
                 full1 = acc;
             }
