@@ -335,11 +335,13 @@ __device__ __forceinline__ void group_maxmin(double *vmax, double *vmin, int tid
 }
 
 // the four (K) Schmitt triggers of one channel for one time bin (create_dataset.py:90-94), bit k of `on` = trigger k
+// KK = the number of triggers when known at compile time (4: the reference's), 0 = a.K
+template <int KK = 0>
 __device__ __forceinline__ void triggers_step(const GtArgs &a, double v, unsigned &on)
 {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        if (k < a.K) {
+    for (int k = 0; k < (KK ? KK : 8); ++k) {
+        if (KK || k < a.K) {
             const bool is_on = (on >> k) & 1u;
             if (!is_on && v > a.thr[k]) on |= (1u << k);
             else if (is_on && v < a.lower[k]) on &= ~(1u << k);
@@ -349,27 +351,31 @@ __device__ __forceinline__ void triggers_step(const GtArgs &a, double v, unsigne
 
 // spikes of time bin j: to the reservoir's bit plane in shared memory (fused kernels) and / or to X_spikes rows.
 // ch = this thread's channel (0 .. C-1, a whole number of warps).
-template <int FNPT>
+template <int FNPT, int KK = 0>
 __device__ __forceinline__ void put_spikes(const GtArgs &a, unsigned on, int j, int ch, uint8_t *row0, unsigned char *smem_raw)
 {
+    const int K = KK ? KK : a.K;
     if (FNPT > 0) {
         // word (t, warp) = ballot over this warp's 32 channels
         unsigned *s_bits = reinterpret_cast<unsigned *>(smem_raw);
         const int CW = a.C >> 5;
-        for (int k = 0; k < a.K; ++k) {
-            const unsigned word = __ballot_sync(0xffffffffu, (on >> k) & 1u);
-            if ((ch & 31) == 0) s_bits[(j * a.K + k) * CW + (ch >> 5)] = word;
+#pragma unroll
+        for (int k = 0; k < (KK ? KK : 8); ++k) {
+            if (KK || k < K) {
+                const unsigned word = __ballot_sync(0xffffffffu, (on >> k) & 1u);
+                if ((ch & 31) == 0) s_bits[(j * K + k) * CW + (ch >> 5)] = word;
+            }
         }
     }
-    const int T = a.nbins * a.K;
+    const int T = a.nbins * K;
     for (int r = 0; row0 && r < a.R; ++r) {
-        uint8_t *row = row0 + (size_t)r * T + (size_t)j * a.K;
-        if (a.K == 4) {
+        uint8_t *row = row0 + (size_t)r * T + (size_t)j * K;
+        if (K == 4) {
             // bytes k = 0..3 of column block j, little endian
             const unsigned w = (on & 1u) | ((on & 2u) << 7) | ((on & 4u) << 14) | ((on & 8u) << 21);
             __stcs(reinterpret_cast<unsigned *>(row), w);        // streaming store: written once, never read here
         } else {
-            for (int k = 0; k < a.K; ++k) row[k] = (on >> k) & 1u;
+            for (int k = 0; k < K; ++k) row[k] = (on >> k) & 1u;
         }
     }
 }
@@ -507,6 +513,25 @@ __device__ __forceinline__ SpecStats spec_db_pass(const GtArgs &a, double *col, 
     return st;
 }
 
+// near-tie test, Schmitt triggers and spike words of four consecutive bins (spec_epilogue's inner block)
+template <int FNPT, int KK>
+__device__ __forceinline__ void spec_bins(const GtArgs &a, const double (&v)[4], const float (&mg)[4], const int j0, const int ch,
+                                          uint8_t *row0, unsigned char *smem_raw, unsigned &on, bool &near)
+{
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u;
+        if (j < a.nbins) {
+            const double m = (double)mg[u];
+#pragma unroll
+            for (int k = 0; k < (KK ? KK : 8); ++k)
+                if (KK || k < a.K) near |= !(fabs(v[u] - a.thr[k]) > m) | !(fabs(v[u] - a.lower[k]) > m);
+            triggers_step<KK>(a, v[u], on);
+            put_spikes<FNPT, KK>(a, on, j, ch, row0, smem_raw);
+        }
+    }
+}
+
 // ---- SPECULATIVE epilogue: the same chain (dB, floor, min-max, zoom, encoder) on the speculative energy plane, arranged
 //      for throughput - independent columns in flight, library log10, reciprocal instead of division - plus the near-tie
 //      test against the derived bound.  Returns true (per thread) if some comparison of the exact path could come out
@@ -551,18 +576,8 @@ __device__ __forceinline__ bool spec_epilogue(const GtArgs &a, int utt, double *
             const float ff = (float)f, vf = fminf(fmaxf((float)v[u], 0.0f), 1.0f);
             mg[u] = ((1.0f - ff) * e0 + ff * e1 + (1.0f - vf) * st.emn + vf * st.emx + deltaf) * rdenf + 1e-13f;
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = j0 + u;
-            if (j < a.nbins) {
-                const double m = (double)mg[u];
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (k < a.K) near |= !(fabs(v[u] - a.thr[k]) > m) | !(fabs(v[u] - a.lower[k]) > m);
-                triggers_step(a, v[u], on);
-                put_spikes<FNPT>(a, on, j, ch, row0, smem_raw);
-            }
-        }
+        if (a.K == 4) spec_bins<FNPT, 4>(a, v, mg, j0, ch, row0, smem_raw, on, near);      // the reference's four triggers: no per-trigger tests
+        else spec_bins<FNPT, 0>(a, v, mg, j0, ch, row0, smem_raw, on, near);
     }
     return near | bad;
 }
